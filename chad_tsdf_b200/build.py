@@ -1,0 +1,44 @@
+"""In-tree build of the CUDA library (sm_100a only) with nvcc.
+
+`python -m chad_tsdf_b200.build` or `build_library()`; the resulting chad_tsdf_b200/libchad_b200.so
+is git-ignored but travels with the tree. nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libchad_b200.so")
+SOURCES = ["radix_sort.cu", "points.cu", "band.cu", "fold.cu", "dag.cu", "context.cu"]
+HEADERS = ["common.cuh", "kernels.cuh", "radix_sort.cuh", "scan.cuh"]
+# -fmad=false / -ffp-contract=off: the reference's strict-IEEE configuration (cmake/options_compiler.cmake:39);
+# the kernels additionally use explicit *_rn intrinsics wherever a result is observable.
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared", "-cudart", "static"]
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "chad_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True))

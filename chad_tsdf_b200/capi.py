@@ -1,0 +1,83 @@
+"""ctypes binding of the C ABI declared in include/chad_b200.h (the drop-in boundary).
+
+There is no CPU fallback: if the shared library has not been built, or no CUDA device exists,
+loading / creating a map raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import LIB
+
+CHAD_OK = 0
+NUM_LEVELS = 21
+LEVEL_CLUSTERS = 20
+
+
+class ChadError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"chad_b200 error {code}: {message}")
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("scans", "points", "updates", "scan_voxels", "batches", "submaps", "kernel_launches",
+                                           "h2d_bytes", "resident_clusters")]
+
+    def as_dict(self) -> dict:
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+# every symbol include/chad_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "chad_create": (C.c_int, [C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(_P)]),
+    "chad_destroy": (None, [_P]),
+    "chad_last_error": (C.c_char_p, [_P]),
+    "chad_insert": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "chad_insert_device": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "chad_flush": (C.c_int, [_P]),
+    "chad_finalize_active": (C.c_int, [_P]),
+    "chad_submap_count": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
+    "chad_submap_roots": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "chad_voxel_count": (C.c_int, [_P, C.POINTER(C.c_size_t)]),
+    "chad_export_voxels": (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "chad_level_words": (C.c_int, [_P, C.c_int, C.POINTER(C.c_size_t)]),
+    "chad_level_counters": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "chad_export_level": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
+    "chad_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "chad_reset_stats": (C.c_int, [_P]),
+    "chad_stage_points": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P, _P, _P]),
+    "chad_stage_pairs": (C.c_int, [_P, _P, _P, C.c_size_t, _P, _P, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "chad_stage_sort": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int]),
+    "chad_stage_morton": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "chad_device_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    "chad_device_free": (C.c_int, [_P, _P]),
+    "chad_upload": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "chad_timer_begin": (C.c_int, [_P]),
+    "chad_timer_end": (C.c_int, [_P, C.POINTER(C.c_float)]),
+}
+
+_LIB: C.CDLL | None = None
+
+
+def load() -> C.CDLL:
+    """Load chad_tsdf_b200/libchad_b200.so and bind every declared symbol; raises if it is missing."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB):
+            raise ChadError(-2, f"{LIB} has not been built (run `python -m chad_tsdf_b200.build`); there is no CPU fallback")
+        lib = C.CDLL(LIB)
+        for name, (restype, argtypes) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _LIB = lib
+    return _LIB
+
+
+def ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)

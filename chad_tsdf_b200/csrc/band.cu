@@ -1,0 +1,137 @@
+// Truncation-band voxel enumeration along every sensor ray and the signed distance of each band
+// voxel: the loop body of Octree::insert(points, normals, position, res, trunc),
+// /root/reference/include/chad/detail/octree.hpp:86-159 (Amanatides-Woo style DDA with the
+// reference's exact operation order, strict-< comparisons and x / z / y / z axis preference).
+// The reference walks the octree for every emitted voxel; here the voxels become a stream of
+// (compact Morton key, sd) pairs in (sorted point, ray step) order -- the order the running
+// average of octree.hpp:161-163 depends on -- that the stable radix sort groups per voxel.
+#include "kernels.cuh"
+
+namespace chadgpu {
+
+namespace {
+
+constexpr int BAND_THREADS = 256;
+
+struct Ray {
+    float px, py, pz;
+    i32 cur[3], vf[3], step[3];
+    float tmax[3], delta[3];
+};
+
+// octree.hpp:92-118
+__device__ __forceinline__ void ray_setup(Ray& r, float px, float py, float pz, const float* pos, float res, float trunc, float recip) {
+    r.px = px; r.py = py; r.pz = pz;
+    const float p[3] = {px, py, pz};
+    float d[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) d[a] = fsub(p[a], pos[a]);
+    const float invl = fdiv(1.0f, fsqrt(dot3(d[0], d[1], d[2], d[0], d[1], d[2])));  // normalize, :92
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float dir = fmul(d[a], invl);
+        const float dir_recip = fdiv(1.0f, dir);                  // :93
+        const float start = fsub(p[a], fmul(dir, trunc));         // :94
+        const float fin = fadd(p[a], fmul(dir, trunc));           // :95
+        const float sv = fmul(start, recip);
+        const i32 vs = (i32)floorf(sv);                           // :96
+        const i32 vf = (i32)floorf(fmul(fin, recip));             // :97
+        const i32 dv = vf - vs;
+        const i32 st = (0 < dv) - (dv < 0);                       // :100
+        r.delta[a] = fabsf(fmul(res, dir_recip));                 // :102
+        float m;                                                  // :104-116
+        if (st < 0) m = fmul(res, floorf(sv));
+        else if (st > 0) m = fmul(res, ceilf(sv));
+        else m = 3.402823466e+38f;
+        m = fsub(m, start);                                       // :117
+        r.tmax[a] = fabsf(fmul(m, dir_recip));                    // :118
+        r.cur[a] = vs; r.vf[a] = vf; r.step[a] = st;
+    }
+}
+// one iteration of the while(true) loop of octree.hpp:125-152; returns false on `break`
+__device__ __forceinline__ bool ray_advance(Ray& r) {
+    int a;
+    if (r.tmax[0] < r.tmax[1]) a = (r.tmax[0] < r.tmax[2]) ? 0 : 2;
+    else a = (r.tmax[1] < r.tmax[2]) ? 1 : 2;
+    // select without dynamic register indexing
+    if (a == 0) { r.cur[0] += r.step[0]; r.tmax[0] = fadd(r.tmax[0], r.delta[0]); return r.cur[0] != r.vf[0] + r.step[0]; }
+    if (a == 1) { r.cur[1] += r.step[1]; r.tmax[1] = fadd(r.tmax[1], r.delta[1]); return r.cur[1] != r.vf[1] + r.step[1]; }
+    r.cur[2] += r.step[2]; r.tmax[2] = fadd(r.tmax[2], r.delta[2]); return r.cur[2] != r.vf[2] + r.step[2];
+}
+
+__global__ void __launch_bounds__(BAND_THREADS) band_count_kernel(const float* __restrict__ xyz_sorted, u32 n_points,
+                                                                  const BatchScans* __restrict__ scans, float res, float trunc, float recip,
+                                                                  u32 max_ray_voxels, const BatchPlan* __restrict__ plan, u32* __restrict__ counts) {
+    const u32 i = blockIdx.x * BAND_THREADS + threadIdx.x;
+    if (i >= n_points) return;
+    const u32 s = scan_of(scans, plan->n_scans, i);
+    const float pos[3] = {scans->pose[s][0], scans->pose[s][1], scans->pose[s][2]};
+    Ray r;
+    ray_setup(r, xyz_sorted[size_t(i) * 3], xyz_sorted[size_t(i) * 3 + 1], xyz_sorted[size_t(i) * 3 + 2], pos, res, trunc, recip);
+    u32 c = 1;  // the start voxel is always emitted (:121-122)
+    while (c < max_ray_voxels && ray_advance(r)) c++;
+    counts[i] = c;
+}
+
+template <bool FULL_KEYS>
+__global__ void __launch_bounds__(BAND_THREADS) band_emit_kernel(const float* __restrict__ xyz_sorted, const float* __restrict__ normals,
+                                                                 u32 n_points, const BatchScans* __restrict__ scans, float res, float trunc,
+                                                                 float recip, u32 max_ray_voxels, BatchPlan* plan,
+                                                                 const u32* __restrict__ offsets, u64* __restrict__ pair_keys,
+                                                                 u32* __restrict__ pair_sd, u32 pair_capacity) {
+    const u32 i = blockIdx.x * BAND_THREADS + threadIdx.x;
+    if (i >= n_points) return;
+    const u32 s = scan_of(scans, plan->n_scans, i);
+    const float pos[3] = {scans->pose[s][0], scans->pose[s][1], scans->pose[s][2]};
+    const u32 k = plan->k;
+    const float nx = normals[size_t(i) * 3], ny = normals[size_t(i) * 3 + 1], nz = normals[size_t(i) * 3 + 2];
+    Ray r;
+    ray_setup(r, xyz_sorted[size_t(i) * 3], xyz_sorted[size_t(i) * 3 + 1], xyz_sorted[size_t(i) * 3 + 2], pos, res, trunc, recip);
+    u32 out = offsets[i];
+    u32 c = 0;
+    u32 err = 0;
+    while (true) {
+        if (out >= pair_capacity) { err |= ERRF_PAIR_CAPACITY; break; }
+        const i32 vx = r.cur[0], vy = r.cur[1], vz = r.cur[2];
+        if (max(rcode(vx), max(rcode(vy), rcode(vz))) >= (1u << k)) err |= ERRF_RANGE;  // outside the batch plan
+        const u64 full = morton_encode(vx, vy, vz);
+        // octree.hpp:157-159: the voxel's LOWER CORNER, decoded from the stored code, projected on the normal
+        i32 dx, dy, dz;
+        morton_decode(full, dx, dy, dz);
+        float sd = dot3(nx, ny, nz, fsub(fmul((float)dx, res), r.px), fsub(fmul((float)dy, res), r.py), fsub(fmul((float)dz, res), r.pz));
+        sd = fclamp(sd, -trunc, trunc);
+        pair_keys[out] = FULL_KEYS ? full : compact_key(full, k);
+        pair_sd[out] = __float_as_uint(sd);
+        out++;
+        c++;
+        if (c >= max_ray_voxels || !ray_advance(r)) break;
+    }
+    if (err) atomicOr(&plan->error, err);
+}
+
+inline unsigned blocks_for(u32 n) { return (n + BAND_THREADS - 1) / BAND_THREADS; }
+
+}  // namespace
+
+int launch_band_count(cudaStream_t s, const float* xyz_sorted, u32 n_points, const BatchScans* scans, const MapParams& mp,
+                      const BatchPlan* plan, u32* counts) {
+    if (!n_points) return 0;
+    band_count_kernel<<<blocks_for(n_points), BAND_THREADS, 0, s>>>(xyz_sorted, n_points, scans, mp.res, mp.trunc, mp.recip, mp.max_ray_voxels, plan,
+                                                                    counts);
+    return 1;
+}
+
+int launch_band_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const BatchScans* scans,
+                     const MapParams& mp, BatchPlan* plan, const u32* offsets, u64* pair_keys, u32* pair_sd, u32 pair_capacity,
+                     bool full_keys) {
+    if (!n_points) return 0;
+    if (full_keys)
+        band_emit_kernel<true><<<blocks_for(n_points), BAND_THREADS, 0, s>>>(xyz_sorted, normals, n_points, scans, mp.res, mp.trunc, mp.recip,
+                                                                             mp.max_ray_voxels, plan, offsets, pair_keys, pair_sd, pair_capacity);
+    else
+        band_emit_kernel<false><<<blocks_for(n_points), BAND_THREADS, 0, s>>>(xyz_sorted, normals, n_points, scans, mp.res, mp.trunc, mp.recip,
+                                                                              mp.max_ray_voxels, plan, offsets, pair_keys, pair_sd, pair_capacity);
+    return 1;
+}
+
+}  // namespace chadgpu

@@ -1,0 +1,920 @@
+// Host side of the C ABI (include/chad_b200.h): the context that owns all device state, the
+// submap bookkeeping of TSDFMap::insert (/root/reference/src/chad/tsdf.cpp:39-75), batching of
+// consecutive scans, and the level-by-level driver of Submap::finalize
+// (/root/reference/include/chad/detail/submap.hpp:10-106).
+//
+// Scheduling. insert() copies the scan into the current batch (pinned staging + async H2D on a
+// copy stream) and returns. When a batch is full, its "front" (plan, point sort, normals, band
+// enumeration, pair sort, segment count) is queued on the compute stream; the "fold" of a batch is
+// queued just before the next batch's front (or at flush), after the host has read the batch's
+// exact distinct-chunk count and grown the resident table if needed. So the device never waits on
+// the host except for one event per batch, and table growth is exact instead of worst-case.
+#include <array>
+#include <cmath>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "chad_b200.h"
+#include "kernels.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+using namespace chadgpu;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct Level {
+    DevBuf raw;            // u32 words (node levels) or u64 words (cluster level)
+    size_t raw_cap = 0;    // capacity in words
+    DevBuf entries, first;
+    DedupTable table{nullptr, nullptr, 0};
+    u32 uniques = 0, dupes = 0, occupied = 0;
+};
+
+size_t next_pow2(size_t v) {
+    size_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+struct chad_ctx {
+    int device = 0, num_sms = 148;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    MapParams mp{};
+    int max_batch = 16;
+    std::string error;
+    int sticky_error = CHAD_OK;
+
+    // submap state (tsdf.cpp:46-61, submap.hpp:108-110)
+    bool has_pose = false;
+    float first_pose[3] = {0, 0, 0};
+    std::vector<std::array<u32, 2>> roots;
+
+    // batch assembly
+    size_t cap_points = 0, cap_pairs = 0;
+    float* h_stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_copied[2] = {nullptr, nullptr};  // last H2D out of h_stage[b] has completed
+    bool stage_busy[2] = {false, false};
+    DevBuf d_xyz[2];
+    cudaEvent_t copy_done[2] = {nullptr, nullptr};
+    int cur = 0;
+    u32 batch_points = 0, batch_scans = 0;
+    BatchScans h_scans{};
+    BatchScans* h_scans_pinned[2] = {nullptr, nullptr};
+    DevBuf d_scans, d_plan;
+    BatchPlan* h_plan = nullptr;  // pinned
+    u32* h_table_count = nullptr; // pinned
+    cudaEvent_t front_done = nullptr;
+    bool fold_pending = false;
+    u32 pending_max_pairs = 0;
+
+    // batch work buffers
+    DevBuf keys_a, keys_b, vals_a, vals_b, sorted_keys, sorted_order, xyz_sorted, normals, seg_info, counts, offsets, radix_ws, scan_ws;
+    RadixWorkspace rws{};
+
+    // resident chunk table of the active submap
+    DevBuf t_keys, t_cells, t_count;
+    ChunkTable table{nullptr, nullptr, 0, nullptr};
+    u64 table_count_known = 0;
+
+    // finalize work buffers
+    size_t cap_chunks = 0;
+    DevBuf f_ids[2], f_slots[2], f_cells, f_tsdf, f_addr[2], f_head, f_head_rank, f_cand, f_slot_of, f_is_new, f_rank, f_radix_ws, f_scan_ws, f_scalars;
+    RadixWorkspace f_rws{};
+    u64* h_scalars = nullptr;  // pinned, 8 x u64
+
+    Level levels[CHAD_NUM_LEVELS];
+    chad_stats stats{};
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+};
+
+namespace {
+
+int fail(chad_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->error = msg; else g_create_error = msg;
+    return code;
+}
+#define CUDA_TRY(ctx, expr)                                                                                   \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess) return fail(ctx, CHAD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+#define TRY(expr)                   \
+    do {                            \
+        int _r = (expr);            \
+        if (_r != CHAD_OK) return _r; \
+    } while (0)
+
+int dev_ensure(chad_ctx* ctx, DevBuf& b, size_t bytes, bool preserve = false) {
+    if (b.bytes >= bytes && b.p) return CHAD_OK;
+    void* np = nullptr;
+    size_t nb = bytes < 256 ? 256 : bytes;
+    CUDA_TRY(ctx, cudaMalloc(&np, nb));
+    if (b.p) {
+        if (preserve) CUDA_TRY(ctx, cudaMemcpyAsync(np, b.p, b.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(ctx, cudaFree(b.p));
+    }
+    b.p = np;
+    b.bytes = nb;
+    return CHAD_OK;
+}
+void dev_free(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+template <typename T> T* plan_field(chad_ctx* ctx, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ctx->d_plan.p) + off); }
+
+int error_from_flags(chad_ctx* ctx, u32 flags) {
+    if (!flags) return CHAD_OK;
+    int code = CHAD_ERR_RANGE;
+    std::string msg = "device error:";
+    if (flags & ERRF_NUMERIC) { msg += " NaN/Inf point coordinate;"; code = CHAD_ERR_NUMERIC; }
+    if (flags & ERRF_RANGE) { msg += " voxel coordinate outside the 21-bit Morton range;"; code = CHAD_ERR_RANGE; }
+    if (flags & ERRF_KEY_BUDGET) { msg += " batch key budget exceeded (reduce max_batch_scans);"; code = CHAD_ERR_RANGE; }
+    if (flags & ERRF_PAIR_CAPACITY) { msg += " band voxel buffer overflow;"; code = CHAD_ERR_CAPACITY; }
+    if (flags & ERRF_TABLE_FULL) { msg += " resident chunk table full;"; code = CHAD_ERR_CAPACITY; }
+    if (flags & ERRF_DEDUP_FULL) { msg += " DAG dedup table full;"; code = CHAD_ERR_CAPACITY; }
+    ctx->sticky_error = code;
+    return fail(ctx, code, msg);
+}
+
+// ---- resident chunk table ---------------------------------------------------------------
+int table_alloc(chad_ctx* ctx, ChunkTable& t, DevBuf& keys, DevBuf& cells, DevBuf& count, u64 capacity) {
+    TRY(dev_ensure(ctx, keys, capacity * 8));
+    TRY(dev_ensure(ctx, cells, capacity * 64));
+    TRY(dev_ensure(ctx, count, 256));
+    t.keys = keys.as<u64>();
+    t.cells = cells.as<uint2>();
+    t.capacity = capacity;
+    t.count = count.as<u32>();
+    launch_table_clear(ctx->stream, t);
+    return CHAD_OK;
+}
+int table_reserve(chad_ctx* ctx, u64 need_chunks) {
+    if (need_chunks * 2 <= ctx->table.capacity) return CHAD_OK;
+    const u64 new_cap = next_pow2(need_chunks * 4);
+    DevBuf nk, nc, ncount;
+    ChunkTable nt{nullptr, nullptr, 0, nullptr};
+    TRY(table_alloc(ctx, nt, nk, nc, ncount, new_cap));
+    ctx->stats.kernel_launches += launch_table_rehash(ctx->stream, ctx->table, nt, ctx->num_sms);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx->t_keys); dev_free(ctx->t_cells); dev_free(ctx->t_count);
+    ctx->t_keys = nk; ctx->t_cells = nc; ctx->t_count = ncount;
+    ctx->table = nt;
+    return CHAD_OK;
+}
+
+// ---- batch buffers ------------------------------------------------------------------------
+int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
+    if (points <= ctx->cap_points) return CHAD_OK;
+    // only called while no batch is in flight
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    const size_t np = points + points / 8 + 1024;
+    const size_t pairs = np * ctx->mp.max_ray_voxels;
+    if (pairs >= (1ull << 30)) return fail(ctx, CHAD_ERR_CAPACITY, "batch too large: more than 2^30 band voxels; lower max_batch_scans");
+    for (int b = 0; b < 2; b++) {
+        if (ctx->h_stage[b]) CUDA_TRY(ctx, cudaFreeHost(ctx->h_stage[b]));
+        CUDA_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_stage[b]), np * 12));
+        ctx->stage_busy[b] = false;
+        TRY(dev_ensure(ctx, ctx->d_xyz[b], np * 12, true));
+    }
+    TRY(dev_ensure(ctx, ctx->keys_a, pairs * 8));
+    TRY(dev_ensure(ctx, ctx->keys_b, pairs * 8));
+    TRY(dev_ensure(ctx, ctx->vals_a, pairs * 4));
+    TRY(dev_ensure(ctx, ctx->vals_b, pairs * 4));
+    TRY(dev_ensure(ctx, ctx->sorted_keys, np * 8));
+    TRY(dev_ensure(ctx, ctx->sorted_order, np * 4));
+    TRY(dev_ensure(ctx, ctx->xyz_sorted, np * 12));
+    TRY(dev_ensure(ctx, ctx->normals, np * 12));
+    TRY(dev_ensure(ctx, ctx->seg_info, np * 4));
+    TRY(dev_ensure(ctx, ctx->counts, np * 4));
+    TRY(dev_ensure(ctx, ctx->offsets, np * 4));
+    TRY(dev_ensure(ctx, ctx->radix_ws, radix_workspace_bytes(pairs)));
+    TRY(dev_ensure(ctx, ctx->scan_ws, scan_workspace_bytes(np)));
+    ctx->rws = radix_workspace_carve(ctx->radix_ws.p, pairs);
+    ctx->cap_points = np;
+    ctx->cap_pairs = pairs;
+    return CHAD_OK;
+}
+
+// launch the fold of the batch whose front has been queued (see the file comment)
+int complete_pending_fold(chad_ctx* ctx) {
+    if (!ctx->fold_pending) return CHAD_OK;
+    ctx->fold_pending = false;
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->front_done));
+    const BatchPlan plan = *ctx->h_plan;
+    ctx->table_count_known = *ctx->h_table_count;
+    ctx->stats.updates += plan.n_pairs;
+    ctx->stats.scan_voxels += plan.n_segments;
+    if (plan.error) {
+        CUDA_TRY(ctx, cudaMemsetAsync(plan_field<u32>(ctx, offsetof(BatchPlan, error)), 0, 4, ctx->stream));
+        return error_from_flags(ctx, plan.error);
+    }
+    TRY(table_reserve(ctx, ctx->table_count_known + plan.n_chunk_heads));
+    ctx->stats.kernel_launches += launch_fold(ctx->stream, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(),
+                                              ctx->pending_max_pairs, ctx->d_plan.as<BatchPlan>(), ctx->table, ctx->num_sms);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_table_count, ctx->table.count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    return CHAD_OK;
+}
+
+// queue everything of the assembled batch up to (not including) the fold
+int process_front(chad_ctx* ctx) {
+    if (ctx->batch_scans == 0) return CHAD_OK;
+    TRY(complete_pending_fold(ctx));  // the previous batch's pairs live in the buffers we are about to reuse
+    const int b = ctx->cur;
+    const u32 n = ctx->batch_points, ns = ctx->batch_scans;
+    cudaStream_t s = ctx->stream;
+    ctx->h_scans.offset[ns] = n;
+    *ctx->h_scans_pinned[b] = ctx->h_scans;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scans.p, ctx->h_scans_pinned[b], sizeof(BatchScans), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[b], ctx->copy_stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->copy_done[b], 0));
+    if (ctx->stage_busy[b]) CUDA_TRY(ctx, cudaEventRecord(ctx->stage_copied[b], ctx->copy_stream));
+
+    BatchPlan* plan = ctx->d_plan.as<BatchPlan>();
+    const BatchScans* scans = ctx->d_scans.as<BatchScans>();
+    const float* xyz = ctx->d_xyz[b].as<float>();
+    u64 launches = 0;
+    launches += launch_plan(s, xyz, n, ns, ctx->mp, plan);
+    launches += launch_point_keys(s, xyz, n, scans, ctx->mp, plan, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>());
+    launches += radix_sort_pairs(s, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), ctx->keys_b.as<u64>(), ctx->vals_b.as<u32>(),
+                                 plan_field<u32>(ctx, offsetof(BatchPlan, n_points)), plan_field<u32>(ctx, offsetof(BatchPlan, nbits_points)), n,
+                                 RS_MAX_PASSES, ctx->rws, ctx->num_sms);
+    launches += launch_point_gather(s, xyz, n, plan, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(),
+                                    ctx->sorted_keys.as<u64>(), ctx->sorted_order.as<u32>(), ctx->xyz_sorted.as<float>());
+    launches += launch_normals(s, ctx->xyz_sorted.as<float>(), ctx->sorted_keys.as<u64>(), n, scans, plan, ctx->seg_info.as<u32>(),
+                               ctx->normals.as<float>());
+    launches += launch_band_count(s, ctx->xyz_sorted.as<float>(), n, scans, ctx->mp, plan, ctx->counts.as<u32>());
+    launches += exclusive_scan<u32, u32>(s, ctx->counts.as<u32>(), ctx->offsets.as<u32>(), n, ctx->scan_ws.p, (u32*)nullptr,
+                                         plan_field<u32>(ctx, offsetof(BatchPlan, n_pairs)));
+    const size_t max_pairs = size_t(n) * ctx->mp.max_ray_voxels;
+    launches += launch_band_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan, ctx->offsets.as<u32>(),
+                                 ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), (u32)ctx->cap_pairs, false);
+    launches += radix_sort_pairs(s, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), ctx->keys_b.as<u64>(), ctx->vals_b.as<u32>(),
+                                 plan_field<u32>(ctx, offsetof(BatchPlan, n_pairs)), plan_field<u32>(ctx, offsetof(BatchPlan, nbits_pairs)), max_pairs,
+                                 RS_MAX_PASSES, ctx->rws, ctx->num_sms);
+    launches += launch_segment_count(s, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), (u32)max_pairs, plan, ctx->num_sms);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_plan, plan, sizeof(BatchPlan), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->front_done, s));
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += launches;
+    ctx->stats.batches++;
+    ctx->fold_pending = true;
+    ctx->pending_max_pairs = (u32)max_pairs;
+    ctx->cur ^= 1;
+    ctx->batch_points = 0;
+    ctx->batch_scans = 0;
+    return CHAD_OK;
+}
+
+int drain(chad_ctx* ctx) {
+    TRY(process_front(ctx));
+    TRY(complete_pending_fold(ctx));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->table_count_known = *ctx->h_table_count;
+    ctx->stats.resident_clusters = ctx->table_count_known;
+    // deferred flags raised by the fold
+    u32 flags = 0;
+    CUDA_TRY(ctx, cudaMemcpy(&flags, plan_field<u32>(ctx, offsetof(BatchPlan, error)), 4, cudaMemcpyDeviceToHost));
+    if (flags) {
+        CUDA_TRY(ctx, cudaMemset(plan_field<u32>(ctx, offsetof(BatchPlan, error)), 0, 4));
+        return error_from_flags(ctx, flags);
+    }
+    return CHAD_OK;
+}
+
+// ---- finalize -----------------------------------------------------------------------------
+enum { SC_COUNT = 0, SC_RMAX = 1, SC_NBITS = 2, SC_PARENTS = 3, SC_NEW32 = 4, SC_ERR = 5, SC_NEW64 = 6 /* u64 slot 6 = words 12,13 */ };
+u32* scalar32(chad_ctx* ctx, int i) { return ctx->f_scalars.as<u32>() + i; }
+u64* scalar64(chad_ctx* ctx) { return ctx->f_scalars.as<u64>() + SC_NEW64; }
+
+int ensure_finalize_capacity(chad_ctx* ctx, size_t chunks) {
+    TRY(dev_ensure(ctx, ctx->f_scalars, 256));
+    if (chunks <= ctx->cap_chunks) return CHAD_OK;
+    const size_t nc = chunks + chunks / 8 + 1024;
+    for (int i = 0; i < 2; i++) {
+        TRY(dev_ensure(ctx, ctx->f_ids[i], nc * 8));
+        TRY(dev_ensure(ctx, ctx->f_slots[i], nc * 4));
+        TRY(dev_ensure(ctx, ctx->f_addr[i], nc * 2 * 4));
+    }
+    TRY(dev_ensure(ctx, ctx->f_cells, nc * 64));
+    TRY(dev_ensure(ctx, ctx->f_tsdf, nc * 8));
+    TRY(dev_ensure(ctx, ctx->f_head, nc * 4));
+    TRY(dev_ensure(ctx, ctx->f_head_rank, nc * 4));
+    TRY(dev_ensure(ctx, ctx->f_cand, nc * 2 * 9 * 4));
+    TRY(dev_ensure(ctx, ctx->f_slot_of, (nc * 2 + 2) * 4));
+    TRY(dev_ensure(ctx, ctx->f_is_new, (nc * 2 + 2) * 8));
+    TRY(dev_ensure(ctx, ctx->f_rank, (nc * 2 + 2) * 8));
+    TRY(dev_ensure(ctx, ctx->f_radix_ws, radix_workspace_bytes(nc)));
+    TRY(dev_ensure(ctx, ctx->f_scan_ws, scan_workspace_bytes(nc * 2 + 2)));
+    ctx->f_rws = radix_workspace_carve(ctx->f_radix_ws.p, nc);
+    ctx->cap_chunks = nc;
+    return CHAD_OK;
+}
+
+int level_reserve(chad_ctx* ctx, Level& L, bool cluster, size_t new_records) {
+    const size_t word = cluster ? 8 : 4;
+    const size_t need_words = cluster ? (size_t(L.uniques) + new_records + 2) : (size_t(L.occupied) + 9 * new_records + 9);
+    if (need_words >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "DAG level exceeds 2^31 words");
+    if (need_words > L.raw_cap) {
+        const size_t cap = next_pow2(need_words * 2);
+        TRY(dev_ensure(ctx, L.raw, cap * word, true));
+        L.raw_cap = cap;
+    }
+    const size_t need_slots = (size_t(L.uniques) + new_records) * 2;
+    if (need_slots > L.table.capacity) {
+        const u64 cap = next_pow2(need_slots * 2);
+        DevBuf ne, nf;
+        TRY(dev_ensure(ctx, ne, cap * 8));
+        TRY(dev_ensure(ctx, nf, cap * 4));
+        DedupTable nt{ne.as<u64>(), nf.as<u32>(), cap};
+        if (L.table.capacity) {
+            ctx->stats.kernel_launches += launch_dedup_rehash(ctx->stream, L.table, nt, ctx->num_sms);
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        } else {
+            launch_dedup_clear(ctx->stream, nt);
+        }
+        dev_free(L.entries); dev_free(L.first);
+        L.entries = ne; L.first = nf; L.table = nt;
+    }
+    return CHAD_OK;
+}
+
+// compact + sort + gather the resident chunks: f_ids[0] = full chunk keys ascending, f_cells = their cells
+int sorted_chunks(chad_ctx* ctx, u32* n_chunks) {
+    TRY(drain(ctx));
+    const size_t C = ctx->table_count_known;
+    *n_chunks = (u32)C;
+    TRY(ensure_finalize_capacity(ctx, C));
+    if (C == 0) return CHAD_OK;
+    cudaStream_t s = ctx->stream;
+    u64 launches = 0;
+    launches += launch_table_compact(s, ctx->table, ctx->f_ids[0].as<u64>(), ctx->f_slots[0].as<u32>(), scalar32(ctx, SC_COUNT), scalar32(ctx, SC_RMAX),
+                                     scalar32(ctx, SC_NBITS), ctx->num_sms);
+    launches += radix_sort_pairs(s, ctx->f_ids[0].as<u64>(), ctx->f_slots[0].as<u32>(), ctx->f_ids[1].as<u64>(), ctx->f_slots[1].as<u32>(),
+                                 scalar32(ctx, SC_COUNT), scalar32(ctx, SC_NBITS), C, RS_MAX_PASSES, ctx->f_rws, ctx->num_sms);
+    u32 nbits = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars, scalar32(ctx, SC_NBITS), 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    nbits = (u32)ctx->h_scalars[0];
+    const u32* sorted_slots = radix_result_in_alt(nbits) ? ctx->f_slots[1].as<u32>() : ctx->f_slots[0].as<u32>();
+    launches += launch_chunk_gather(s, ctx->table, sorted_slots, (u32)C, ctx->f_ids[0].as<u64>(), ctx->f_cells.p);
+    ctx->stats.kernel_launches += launches;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return CHAD_OK;
+}
+
+int finalize_submap(chad_ctx* ctx) {
+    u32 C = 0;
+    TRY(sorted_chunks(ctx, &C));
+    cudaStream_t s = ctx->stream;
+    u64 launches = 0;
+    CUDA_TRY(ctx, cudaMemsetAsync(scalar32(ctx, SC_ERR), 0, 4, s));
+    u64* ids = ctx->f_ids[0].as<u64>();
+    u64* ids_next = ctx->f_ids[1].as<u64>();
+    u32* addr = ctx->f_addr[0].as<u32>();
+    u32* addr_next = ctx->f_addr[1].as<u32>();
+    u32 n_children = C;
+    u32 parents = 0;
+    if (C) {
+        Level& L = ctx->levels[CHAD_LEVEL_CLUSTERS];
+        launches += launch_cluster_build(s, ctx->f_cells.p, C, ctx->mp, ctx->f_tsdf.as<u64>());
+        TRY(level_reserve(ctx, L, true, size_t(C) + 1));
+        launches += launch_cluster_dedup(s, L.table, ctx->f_tsdf.as<u64>(), C, L.raw.as<u64>(), L.uniques, ctx->f_slot_of.as<u32>(),
+                                         ctx->f_is_new.as<u32>(), ctx->f_rank.as<u32>(), ctx->f_scan_ws.p, addr, scalar32(ctx, SC_NEW32),
+                                         scalar32(ctx, SC_ERR));
+        launches += launch_group_heads(s, ids, n_children, ctx->f_head.as<u32>(), ctx->f_head_rank.as<u32>(), ctx->f_scan_ws.p, scalar32(ctx, SC_PARENTS));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->f_scalars.p, 64, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        const u32* hs = reinterpret_cast<const u32*>(ctx->h_scalars);
+        if (hs[SC_ERR]) return error_from_flags(ctx, hs[SC_ERR]);
+        const u32 fresh = hs[SC_NEW32];
+        L.uniques += fresh;
+        L.dupes += 2 * C - fresh;  // levels.hpp:135-138
+        parents = hs[SC_PARENTS];
+    }
+    for (int d = 19; d >= 0; d--) {
+        Level& L = ctx->levels[d];
+        u32 n_records;
+        if (C == 0) {
+            if (d > 0) continue;  // empty octree: only the root is added, twice (submap.hpp:31-46)
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->f_cand.p, 0, 2 * 9 * 4, s));
+            n_records = 2;
+            parents = 1;
+        } else {
+            launches += launch_node_candidates(s, ids, addr, ctx->f_head.as<u32>(), ctx->f_head_rank.as<u32>(), n_children, ctx->f_cand.as<u32>(), ids_next);
+            n_records = 2 * parents;
+        }
+        TRY(level_reserve(ctx, L, false, n_records));
+        launches += launch_node_dedup(s, L.table, ctx->f_cand.as<u32>(), n_records, L.raw.as<u32>(), L.occupied, ctx->f_slot_of.as<u32>(),
+                                      ctx->f_is_new.as<u64>(), ctx->f_rank.as<u64>(), ctx->f_scan_ws.p, addr_next, scalar64(ctx), scalar32(ctx, SC_ERR));
+        std::swap(ids, ids_next);
+        std::swap(addr, addr_next);
+        n_children = parents;
+        if (d > 0 && C) launches += launch_group_heads(s, ids, n_children, ctx->f_head.as<u32>(), ctx->f_head_rank.as<u32>(), ctx->f_scan_ws.p, scalar32(ctx, SC_PARENTS));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->f_scalars.p, 64, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        const u32* hs = reinterpret_cast<const u32*>(ctx->h_scalars);
+        if (hs[SC_ERR]) return error_from_flags(ctx, hs[SC_ERR]);
+        const u64 packed = ctx->h_scalars[SC_NEW64];
+        const u32 fresh = (u32)(packed >> 32), words = (u32)packed;
+        L.uniques += fresh;
+        L.dupes += n_records - fresh;   // levels.hpp:83-86
+        L.occupied += words;            // levels.hpp:79-81
+        parents = hs[SC_PARENTS];
+    }
+    u32 root[2] = {0, 0};
+    CUDA_TRY(ctx, cudaMemcpy(root, addr, 8, cudaMemcpyDeviceToHost));
+    ctx->roots.push_back({root[0], root[1]});
+    launch_table_clear(s, ctx->table);  // octree.clear(), tsdf.cpp:57
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    *ctx->h_table_count = 0;
+    ctx->table_count_known = 0;
+    ctx->stats.kernel_launches += launches;
+    ctx->stats.submaps++;
+    ctx->stats.resident_clusters = 0;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return CHAD_OK;
+}
+
+int begin_scan(chad_ctx* ctx, size_t n, const float position[3], bool* skip) {
+    *skip = false;
+    if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
+    // tsdf.cpp:46-61: a pose more than 5 m (strictly) from the submap's FIRST pose finalises the submap;
+    // the triggering scan goes entirely into the new one
+    if (!ctx->has_pose) {
+        ctx->has_pose = true;
+        std::memcpy(ctx->first_pose, position, 12);
+    } else {
+        const float dx = ctx->first_pose[0] - position[0], dy = ctx->first_pose[1] - position[1], dz = ctx->first_pose[2] - position[2];
+        const float tx = dx * dx, ty = dy * dy, tz = dz * dz;
+        volatile float sum = tx + ty;  // glm::distance = sqrt((x*x + y*y) + z*z), no contraction
+        sum = sum + tz;
+        if (std::sqrt((float)sum) > 5.0f) {
+            TRY(finalize_submap(ctx));
+            std::memcpy(ctx->first_pose, position, 12);
+        }
+    }
+    ctx->stats.scans++;
+    ctx->stats.points += n;
+    if (n == 0) { *skip = true; return CHAD_OK; }
+    if (n >= (1ull << 31)) return fail(ctx, CHAD_ERR_INVALID, "scan too large");
+    if (ctx->batch_scans > 0 && (ctx->batch_scans >= (u32)ctx->max_batch || ctx->batch_points + n > ctx->cap_points)) TRY(process_front(ctx));
+    if (n > ctx->cap_points || ctx->cap_points == 0) {
+        TRY(drain(ctx));
+        TRY(ensure_batch_capacity(ctx, n > ctx->cap_points / 2 ? n * (size_t)ctx->max_batch : ctx->cap_points));
+    }
+    return CHAD_OK;
+}
+
+int end_scan(chad_ctx* ctx, size_t n, const float position[3]) {
+    ctx->h_scans.offset[ctx->batch_scans] = ctx->batch_points;
+    std::memcpy(ctx->h_scans.pose[ctx->batch_scans], position, 12);
+    ctx->batch_scans++;
+    ctx->batch_points += (u32)n;
+    if (ctx->batch_scans >= (u32)ctx->max_batch) TRY(process_front(ctx));
+    return CHAD_OK;
+}
+
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+extern "C" {
+
+const char* chad_last_error(const chad_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans, chad_ctx** out) {
+    if (!out) return fail(nullptr, CHAD_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!(sdf_res > 0.0f) || !(sdf_trunc > 0.0f)) return fail(nullptr, CHAD_ERR_INVALID, "sdf_res and sdf_trunc must be positive");
+    if (max_batch_scans < 0 || max_batch_scans > MAX_BATCH_SCANS) return fail(nullptr, CHAD_ERR_INVALID, "max_batch_scans must be in [0, 64]");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, CHAD_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= count) return fail(nullptr, CHAD_ERR_INVALID, "device ordinal out of range");
+    chad_ctx* ctx = new chad_ctx();
+    ctx->device = device;
+    auto bail = [&](int code) { g_create_error = ctx->error; chad_destroy(ctx); return code; };
+#define CREATE_TRY(expr)                                                                                               \
+    do {                                                                                                               \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess) { ctx->error = std::string(#expr) + ": " + cudaGetErrorString(_e); return bail(CHAD_ERR_CUDA); } \
+    } while (0)
+    CREATE_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CREATE_TRY(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        CREATE_TRY(cudaEventCreateWithFlags(&ctx->stage_copied[b], cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&ctx->copy_done[b], cudaEventDisableTiming));
+        CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_scans_pinned[b]), sizeof(BatchScans)));
+    }
+    CREATE_TRY(cudaEventCreateWithFlags(&ctx->front_done, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreate(&ctx->t0));
+    CREATE_TRY(cudaEventCreate(&ctx->t1));
+    CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_plan), sizeof(BatchPlan)));
+    CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_table_count), 64));
+    CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_scalars), 64));
+    *ctx->h_table_count = 0;
+    CREATE_TRY(radix_sort_init());
+
+    ctx->mp.res = sdf_res;
+    ctx->mp.trunc = sdf_trunc;
+    ctx->mp.recip = float(1.0 / double(sdf_res));
+    ctx->mp.trunc_recip = 1.0f / sdf_trunc;
+    const double ratio = double(sdf_trunc) / double(sdf_res);
+    // a ray crosses at most 1 + sum_a(|dv_a|) voxels with |dv_a| <= 2*ratio*|dir_a| + 1 (octree.hpp:94-97,121-152)
+    ctx->mp.max_ray_voxels = (u32)std::ceil(4.0 + 2.0 * std::sqrt(3.0) * ratio) + 2;
+    ctx->mp.band_margin = (u32)std::ceil(ratio) + 3;
+    ctx->max_batch = max_batch_scans == 0 ? 16 : max_batch_scans;
+
+    int r = dev_ensure(ctx, ctx->d_scans, sizeof(BatchScans));
+    if (r == CHAD_OK) r = dev_ensure(ctx, ctx->d_plan, sizeof(BatchPlan));
+    if (r == CHAD_OK) r = dev_ensure(ctx, ctx->f_scalars, 256);
+    if (r != CHAD_OK) return bail(r);
+    CREATE_TRY(cudaMemsetAsync(ctx->d_plan.p, 0, sizeof(BatchPlan), ctx->stream));
+    r = table_alloc(ctx, ctx->table, ctx->t_keys, ctx->t_cells, ctx->t_count, 1ull << 20);
+    if (r != CHAD_OK) return bail(r);
+    // NodeLevel / LeafClusterLevel constructors reserve index 0 (levels.hpp:52-54,119-120)
+    for (int d = 0; d < CHAD_NUM_LEVELS; d++) {
+        Level& L = ctx->levels[d];
+        const bool cluster = d == CHAD_LEVEL_CLUSTERS;
+        L.occupied = cluster ? 0 : 1;
+        r = level_reserve(ctx, L, cluster, 1024);
+        if (r != CHAD_OK) return bail(r);
+        CREATE_TRY(cudaMemsetAsync(L.raw.p, 0, 64, ctx->stream));
+    }
+    CREATE_TRY(cudaStreamSynchronize(ctx->stream));
+#undef CREATE_TRY
+    *out = ctx;
+    return CHAD_OK;
+}
+
+void chad_destroy(chad_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    DevBuf* bufs[] = {&ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
+                      &ctx->sorted_keys, &ctx->sorted_order, &ctx->xyz_sorted, &ctx->normals, &ctx->seg_info, &ctx->counts, &ctx->offsets,
+                      &ctx->radix_ws, &ctx->scan_ws, &ctx->t_keys, &ctx->t_cells, &ctx->t_count, &ctx->f_ids[0], &ctx->f_ids[1], &ctx->f_slots[0],
+                      &ctx->f_slots[1], &ctx->f_cells, &ctx->f_tsdf, &ctx->f_addr[0], &ctx->f_addr[1], &ctx->f_head, &ctx->f_head_rank, &ctx->f_cand,
+                      &ctx->f_slot_of, &ctx->f_is_new, &ctx->f_rank, &ctx->f_radix_ws, &ctx->f_scan_ws, &ctx->f_scalars};
+    for (DevBuf* b : bufs) dev_free(*b);
+    for (auto& L : ctx->levels) { dev_free(L.raw); dev_free(L.entries); dev_free(L.first); }
+    for (int b = 0; b < 2; b++) {
+        if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
+        if (ctx->h_scans_pinned[b]) cudaFreeHost(ctx->h_scans_pinned[b]);
+        if (ctx->stage_copied[b]) cudaEventDestroy(ctx->stage_copied[b]);
+        if (ctx->copy_done[b]) cudaEventDestroy(ctx->copy_done[b]);
+    }
+    if (ctx->h_plan) cudaFreeHost(ctx->h_plan);
+    if (ctx->h_table_count) cudaFreeHost(ctx->h_table_count);
+    if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    if (ctx->front_done) cudaEventDestroy(ctx->front_done);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int chad_insert(chad_ctx* ctx, const float* xyz, size_t n, const float position[3]) {
+    if (!ctx) return CHAD_ERR_INVALID;
+    if (!position || (n && !xyz)) return fail(ctx, CHAD_ERR_INVALID, "NULL argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    bool skip;
+    TRY(begin_scan(ctx, n, position, &skip));
+    if (skip) return CHAD_OK;
+    const int b = ctx->cur;
+    float* dst = ctx->d_xyz[b].as<float>() + size_t(ctx->batch_points) * 3;
+    if (is_pinned_host(xyz)) {
+        // page-locked caller memory: DMA straight from it and wait for the copy, so the caller may reuse the buffer
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst, xyz, n * 12, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    } else {
+        if (ctx->stage_busy[b] && ctx->batch_scans == 0) {  // first scan of a new batch: the staging buffer may still be draining
+            CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_copied[b]));
+            ctx->stage_busy[b] = false;
+        }
+        float* stage = ctx->h_stage[b] + size_t(ctx->batch_points) * 3;
+        std::memcpy(stage, xyz, n * 12);
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst, stage, n * 12, cudaMemcpyHostToDevice, ctx->copy_stream));
+        ctx->stage_busy[b] = true;
+    }
+    ctx->stats.h2d_bytes += n * 12;
+    return end_scan(ctx, n, position);
+}
+
+int chad_insert_device(chad_ctx* ctx, const float* xyz_device, size_t n, const float position[3]) {
+    if (!ctx) return CHAD_ERR_INVALID;
+    if (!position || (n && !xyz_device)) return fail(ctx, CHAD_ERR_INVALID, "NULL argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    bool skip;
+    TRY(begin_scan(ctx, n, position, &skip));
+    if (skip) return CHAD_OK;
+    float* dst = ctx->d_xyz[ctx->cur].as<float>() + size_t(ctx->batch_points) * 3;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, xyz_device, n * 12, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+    return end_scan(ctx, n, position);
+}
+
+int chad_flush(chad_ctx* ctx) {
+    if (!ctx) return CHAD_ERR_INVALID;
+    if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return drain(ctx);
+}
+
+int chad_finalize_active(chad_ctx* ctx) {
+    if (!ctx) return CHAD_ERR_INVALID;
+    if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->has_pose) return drain(ctx);
+    TRY(finalize_submap(ctx));
+    ctx->has_pose = false;
+    return CHAD_OK;
+}
+
+int chad_submap_count(chad_ctx* ctx, uint32_t* count) {
+    if (!ctx || !count) return CHAD_ERR_INVALID;
+    *count = (uint32_t)ctx->roots.size();
+    return CHAD_OK;
+}
+
+int chad_submap_roots(chad_ctx* ctx, uint32_t i, uint32_t* root_tsdf, uint32_t* root_weight) {
+    if (!ctx || !root_tsdf || !root_weight) return CHAD_ERR_INVALID;
+    if (i >= ctx->roots.size()) return fail(ctx, CHAD_ERR_INVALID, "submap index out of range");
+    *root_tsdf = ctx->roots[i][0];
+    *root_weight = ctx->roots[i][1];
+    return CHAD_OK;
+}
+
+// voxel export: sorted chunks are copied to the host and expanded there (parity / debugging path)
+static int export_voxels_impl(chad_ctx* ctx, uint64_t* keys, uint32_t* sd_bits, uint32_t* weights, size_t capacity, size_t* count) {
+    u32 C = 0;
+    TRY(sorted_chunks(ctx, &C));
+    std::vector<u64> ck(C);
+    std::vector<uint2> cells(size_t(C) * 8);
+    if (C) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ck.data(), ctx->f_ids[0].p, size_t(C) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(cells.data(), ctx->f_cells.p, size_t(C) * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    size_t n = 0;
+    for (size_t c = 0; c < C; c++)
+        for (int s = 0; s < 8; s++) {
+            const uint2 cell = cells[c * 8 + s];
+            if (cell.y == 0) continue;
+            if (keys) {
+                if (n >= capacity) return fail(ctx, CHAD_ERR_INVALID, "export capacity too small");
+                keys[n] = (ck[c] << 3) | (u64)s;
+                sd_bits[n] = cell.x;
+                weights[n] = cell.y;
+            }
+            n++;
+        }
+    *count = n;
+    return CHAD_OK;
+}
+
+int chad_voxel_count(chad_ctx* ctx, size_t* count) {
+    if (!ctx || !count) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return export_voxels_impl(ctx, nullptr, nullptr, nullptr, 0, count);
+}
+
+int chad_export_voxels(chad_ctx* ctx, uint64_t* keys, uint32_t* sd_bits, uint32_t* weights, size_t capacity, size_t* count) {
+    if (!ctx || !count || !keys || !sd_bits || !weights) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return export_voxels_impl(ctx, keys, sd_bits, weights, capacity, count);
+}
+
+int chad_level_words(chad_ctx* ctx, int level, size_t* words) {
+    if (!ctx || !words || level < 0 || level >= CHAD_NUM_LEVELS) return CHAD_ERR_INVALID;
+    const Level& L = ctx->levels[level];
+    *words = (level == CHAD_LEVEL_CLUSTERS) ? size_t(L.uniques) + 1 : size_t(L.occupied);
+    return CHAD_OK;
+}
+
+int chad_level_counters(chad_ctx* ctx, int level, uint32_t* uniques, uint32_t* dupes) {
+    if (!ctx || !uniques || !dupes || level < 0 || level >= CHAD_NUM_LEVELS) return CHAD_ERR_INVALID;
+    *uniques = ctx->levels[level].uniques;
+    *dupes = ctx->levels[level].dupes;
+    return CHAD_OK;
+}
+
+int chad_export_level(chad_ctx* ctx, int level, void* dst, size_t capacity_words) {
+    if (!ctx || !dst || level < 0 || level >= CHAD_NUM_LEVELS) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    size_t words;
+    chad_level_words(ctx, level, &words);
+    if (capacity_words < words) return fail(ctx, CHAD_ERR_INVALID, "export capacity too small");
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpy(dst, ctx->levels[level].raw.p, words * (level == CHAD_LEVEL_CLUSTERS ? 8 : 4), cudaMemcpyDeviceToHost));
+    return CHAD_OK;
+}
+
+int chad_get_stats(chad_ctx* ctx, chad_stats* out) {
+    if (!ctx || !out) return CHAD_ERR_INVALID;
+    *out = ctx->stats;
+    return CHAD_OK;
+}
+
+int chad_reset_stats(chad_ctx* ctx) {
+    if (!ctx) return CHAD_ERR_INVALID;
+    const uint64_t resident = ctx->stats.resident_clusters;
+    ctx->stats = chad_stats{};
+    ctx->stats.resident_clusters = resident;
+    return CHAD_OK;
+}
+
+// ---- stage entry points ---------------------------------------------------------------------
+static int stage_prepare(chad_ctx* ctx, size_t n) {
+    TRY(drain(ctx));
+    if (n > ctx->cap_points || ctx->cap_points == 0) TRY(ensure_batch_capacity(ctx, n ? n : 1));
+    return CHAD_OK;
+}
+static void stage_single_scan(chad_ctx* ctx, size_t n, const float position[3]) {
+    ctx->h_scans.offset[0] = 0;
+    ctx->h_scans.offset[1] = (u32)n;
+    std::memcpy(ctx->h_scans.pose[0], position, 12);
+    *ctx->h_scans_pinned[0] = ctx->h_scans;
+    cudaMemcpyAsync(ctx->d_scans.p, ctx->h_scans_pinned[0], sizeof(BatchScans), cudaMemcpyHostToDevice, ctx->stream);
+}
+static int stage_check(chad_ctx* ctx) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    u32 flags = 0;
+    CUDA_TRY(ctx, cudaMemcpy(&flags, plan_field<u32>(ctx, offsetof(BatchPlan, error)), 4, cudaMemcpyDeviceToHost));
+    if (flags) {
+        CUDA_TRY(ctx, cudaMemset(plan_field<u32>(ctx, offsetof(BatchPlan, error)), 0, 4));
+        int code = error_from_flags(ctx, flags);
+        ctx->sticky_error = CHAD_OK;  // stage calls do not poison the map
+        return code;
+    }
+    return CHAD_OK;
+}
+
+int chad_stage_points(chad_ctx* ctx, const float* xyz, size_t n, const float position[3], float* xyz_sorted, uint64_t* keys, uint32_t* order,
+                      float* normals) {
+    if (!ctx || !position || (n && !xyz)) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(stage_prepare(ctx, n));
+    if (n == 0) return CHAD_OK;
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_xyz[0].p, xyz, n * 12, cudaMemcpyHostToDevice, s));
+    stage_single_scan(ctx, n, position);
+    BatchPlan* plan = ctx->d_plan.as<BatchPlan>();
+    const BatchScans* scans = ctx->d_scans.as<BatchScans>();
+    const float* dxyz = ctx->d_xyz[0].as<float>();
+    u64 launches = 0;
+    launches += launch_plan(s, dxyz, (u32)n, 1, ctx->mp, plan);
+    launches += launch_point_keys(s, dxyz, (u32)n, scans, ctx->mp, plan, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>());
+    launches += radix_sort_pairs(s, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), ctx->keys_b.as<u64>(), ctx->vals_b.as<u32>(),
+                                 plan_field<u32>(ctx, offsetof(BatchPlan, n_points)), plan_field<u32>(ctx, offsetof(BatchPlan, nbits_points)), n,
+                                 RS_MAX_PASSES, ctx->rws, ctx->num_sms);
+    launches += launch_point_gather(s, dxyz, (u32)n, plan, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(),
+                                    ctx->sorted_keys.as<u64>(), ctx->sorted_order.as<u32>(), ctx->xyz_sorted.as<float>());
+    launches += launch_normals(s, ctx->xyz_sorted.as<float>(), ctx->sorted_keys.as<u64>(), (u32)n, scans, plan, ctx->seg_info.as<u32>(),
+                               ctx->normals.as<float>());
+    launches += launch_point_full_keys(s, ctx->sorted_keys.as<u64>(), (u32)n, plan, ctx->keys_a.as<u64>());
+    ctx->stats.kernel_launches += launches;
+    TRY(stage_check(ctx));
+    if (xyz_sorted) CUDA_TRY(ctx, cudaMemcpy(xyz_sorted, ctx->xyz_sorted.p, n * 12, cudaMemcpyDeviceToHost));
+    if (keys) CUDA_TRY(ctx, cudaMemcpy(keys, ctx->keys_a.p, n * 8, cudaMemcpyDeviceToHost));
+    if (order) CUDA_TRY(ctx, cudaMemcpy(order, ctx->sorted_order.p, n * 4, cudaMemcpyDeviceToHost));
+    if (normals) CUDA_TRY(ctx, cudaMemcpy(normals, ctx->normals.p, n * 12, cudaMemcpyDeviceToHost));
+    return CHAD_OK;
+}
+
+int chad_stage_pairs(chad_ctx* ctx, const float* xyz_sorted, const float* normals, size_t n, const float position[3], uint32_t* counts,
+                     uint64_t* keys, float* sd, size_t capacity, size_t* total) {
+    if (!ctx || !position || !total || (n && (!xyz_sorted || !normals))) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(stage_prepare(ctx, n));
+    *total = 0;
+    if (n == 0) return CHAD_OK;
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->xyz_sorted.p, xyz_sorted, n * 12, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->normals.p, normals, n * 12, cudaMemcpyHostToDevice, s));
+    stage_single_scan(ctx, n, position);
+    BatchPlan* plan = ctx->d_plan.as<BatchPlan>();
+    const BatchScans* scans = ctx->d_scans.as<BatchScans>();
+    u64 launches = 0;
+    launches += launch_plan(s, ctx->xyz_sorted.as<float>(), (u32)n, 1, ctx->mp, plan);
+    launches += launch_band_count(s, ctx->xyz_sorted.as<float>(), (u32)n, scans, ctx->mp, plan, ctx->counts.as<u32>());
+    launches += exclusive_scan<u32, u32>(s, ctx->counts.as<u32>(), ctx->offsets.as<u32>(), n, ctx->scan_ws.p, (u32*)nullptr,
+                                         plan_field<u32>(ctx, offsetof(BatchPlan, n_pairs)));
+    launches += launch_band_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), (u32)n, scans, ctx->mp, plan, ctx->offsets.as<u32>(),
+                                 ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), (u32)ctx->cap_pairs, true);
+    ctx->stats.kernel_launches += launches;
+    TRY(stage_check(ctx));
+    u32 U = 0;
+    CUDA_TRY(ctx, cudaMemcpy(&U, plan_field<u32>(ctx, offsetof(BatchPlan, n_pairs)), 4, cudaMemcpyDeviceToHost));
+    *total = U;
+    if (counts) CUDA_TRY(ctx, cudaMemcpy(counts, ctx->counts.p, n * 4, cudaMemcpyDeviceToHost));
+    if (keys || sd) {
+        if (capacity < U) return fail(ctx, CHAD_ERR_INVALID, "pair capacity too small");
+        if (keys) CUDA_TRY(ctx, cudaMemcpy(keys, ctx->keys_a.p, size_t(U) * 8, cudaMemcpyDeviceToHost));
+        if (sd) CUDA_TRY(ctx, cudaMemcpy(sd, ctx->vals_a.p, size_t(U) * 4, cudaMemcpyDeviceToHost));
+    }
+    return CHAD_OK;
+}
+
+int chad_stage_sort(chad_ctx* ctx, uint64_t* keys, uint32_t* values, size_t n, int nbits) {
+    if (!ctx || (n && (!keys || !values)) || nbits < 0 || nbits > 64) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n >= (1ull << 30)) return fail(ctx, CHAD_ERR_INVALID, "n too large");
+    TRY(stage_prepare(ctx, (n + ctx->mp.max_ray_voxels - 1) / ctx->mp.max_ray_voxels));
+    if (n == 0) return CHAD_OK;
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->keys_a.p, keys, n * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->vals_a.p, values, n * 4, cudaMemcpyHostToDevice, s));
+    const u32 scal[2] = {(u32)n, (u32)nbits};
+    CUDA_TRY(ctx, cudaMemcpyAsync(scalar32(ctx, SC_COUNT), &scal[0], 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(scalar32(ctx, SC_NBITS), &scal[1], 4, cudaMemcpyHostToDevice, s));
+    ctx->stats.kernel_launches += radix_sort_pairs(s, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), ctx->keys_b.as<u64>(), ctx->vals_b.as<u32>(),
+                                                   scalar32(ctx, SC_COUNT), scalar32(ctx, SC_NBITS), n, RS_MAX_PASSES, ctx->rws, ctx->num_sms);
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    CUDA_TRY(ctx, cudaGetLastError());
+    const bool alt = radix_result_in_alt((u32)nbits);
+    CUDA_TRY(ctx, cudaMemcpy(keys, alt ? ctx->keys_b.p : ctx->keys_a.p, n * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(ctx, cudaMemcpy(values, alt ? ctx->vals_b.p : ctx->vals_a.p, n * 4, cudaMemcpyDeviceToHost));
+    return CHAD_OK;
+}
+
+int chad_stage_morton(chad_ctx* ctx, const int32_t* voxels, size_t n, uint64_t* keys) {
+    if (!ctx || (n && (!voxels || !keys))) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(stage_prepare(ctx, n));
+    if (n == 0) return CHAD_OK;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->xyz_sorted.p, voxels, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.kernel_launches += launch_morton_encode(ctx->stream, ctx->xyz_sorted.as<i32>(), (u32)n, ctx->keys_a.as<u64>());
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpy(keys, ctx->keys_a.p, n * 8, cudaMemcpyDeviceToHost));
+    return CHAD_OK;
+}
+
+int chad_device_alloc(chad_ctx* ctx, size_t bytes, void** device_ptr) {
+    if (!ctx || !device_ptr) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMalloc(device_ptr, bytes ? bytes : 1));
+    return CHAD_OK;
+}
+int chad_device_free(chad_ctx* ctx, void* device_ptr) {
+    if (!ctx) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaFree(device_ptr));
+    return CHAD_OK;
+}
+int chad_upload(chad_ctx* ctx, void* device_dst, const void* host_src, size_t bytes) {
+    if (!ctx || !device_dst || !host_src) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemcpy(device_dst, host_src, bytes, cudaMemcpyHostToDevice));
+    return CHAD_OK;
+}
+int chad_timer_begin(chad_ctx* ctx) {
+    if (!ctx) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->t0, ctx->stream));
+    return CHAD_OK;
+}
+int chad_timer_end(chad_ctx* ctx, float* milliseconds) {
+    if (!ctx || !milliseconds) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->t1));
+    CUDA_TRY(ctx, cudaEventElapsedTime(milliseconds, ctx->t0, ctx->t1));
+    return CHAD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,327 @@
+// Submap::finalize on the device (/root/reference/include/chad/detail/submap.hpp:10-106): the
+// resident leaf chunks of the active submap are folded bottom-up into the global, hash-deduplicated
+// DAG (NodeLevels, /root/reference/include/chad/detail/levels.hpp:146-200).
+//
+// The reference runs one explicit-stack post-order DFS and calls LeafClusterLevel::add
+// (levels.hpp:123-139) / NodeLevel::add (levels.hpp:57-88) once per record; an address is
+// "number of distinct records added before, over the map's lifetime" (clusters) or "_occupied_n
+// before the add" (nodes). Because the DFS visits children 0..7, every level's add sequence is:
+// for each node of that level in ascending Morton order, TSDF record then weight record, and the
+// sequences of different levels are independent. That makes each level a
+// data-parallel first-occurrence dedup:
+//   probe   : find-or-insert every record of the sequence in the level's resident hash set; records
+//             not yet resident keep the MINIMUM sequence index that carried them (atomicMin);
+//   mark    : a record is new iff it is the first occurrence of a non-resident value;
+//   scan    : exclusive prefix sum of the new records' sizes = the addresses the sequential
+//             reference would have handed out;
+//   commit  : write the new records to the level's raw array, make their set entries resident;
+//   resolve : every sequence element reads its address.
+#include "kernels.cuh"
+#include "scan.cuh"
+
+namespace chadgpu {
+
+namespace {
+
+constexpr int DAG_THREADS = 256;
+constexpr u32 FIRST_IDLE = 0xFFFFFFFFu;
+constexpr u64 WEIGHT_CLUSTER = ~0ull;  // every weight byte is 0xFF
+
+__device__ __forceinline__ u64 mix64(u64 h) {
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull;
+    h ^= h >> 33;
+    return h;
+}
+__device__ __forceinline__ u64 ld_entry(const u64* p) {
+    u64 v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u32 ld_u32_volatile(const u32* p) {
+    u32 v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void note_first(u32* first, u32 e) {
+    if (ld_u32_volatile(first) > e) atomicMin(first, e);
+}
+inline unsigned blocks_for(u32 n) { return (n + DAG_THREADS - 1) / DAG_THREADS; }
+
+// ------------------------------------------------------------------------------------------
+// leaf clusters: cluster.hpp:13-32 (TSDFs::set / set_empty), submap.hpp:83-100
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DAG_THREADS) cluster_build_kernel(const uint2* __restrict__ cells, u32 n_chunks, float trunc_recip,
+                                                                    u64* __restrict__ tsdf_values) {
+    const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (i >= n_chunks) return;
+    u64 v = 0;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        const uint2 c = cells[size_t(i) * 8 + s];
+        u64 byte = 0xFF;  // absent voxel (cluster.hpp:29-32)
+        if (c.y != 0) {
+            float sd = fmul(__uint_as_float(c.x), trunc_recip);  // cluster.hpp:19
+            sd = fclamp(sd, -1.0f, 1.0f);
+            sd = fadd(fmul(sd, 127.0f), 127.0f);                 // cluster.hpp:21
+            byte = (u64)sd;                                      // cluster.hpp:26: truncation toward zero
+        }
+        v |= byte << (8 * s);
+    }
+    tsdf_values[i] = v;
+}
+
+// Sequence of the cluster level: e = 2i -> tsdf cluster of chunk i, e = 2i+1 -> the weight cluster.
+// Only position p = 1 (e = 1) ever needs to add the weight cluster; later weight elements are dupes
+// of it by construction. Work positions: p = 0 -> e 0, p = 1 -> e 1, p >= 2 -> e 2(p-1).
+__device__ __forceinline__ u32 cluster_seq_of(u32 p) { return p < 2 ? p : 2 * (p - 1); }
+__device__ __forceinline__ u64 cluster_value(const u64* __restrict__ tsdf_values, u32 e) { return (e & 1u) ? WEIGHT_CLUSTER : tsdf_values[e >> 1]; }
+
+__global__ void __launch_bounds__(DAG_THREADS) cluster_probe_kernel(u64* entries, u32* first, u64 capacity, const u64* __restrict__ tsdf_values,
+                                                                    u32 n_work, const u64* __restrict__ raw, u32* __restrict__ slot_of,
+                                                                    u32* d_error) {
+    const u32 p = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (p >= n_work) return;
+    const u32 e = cluster_seq_of(p);
+    const u64 value = cluster_value(tsdf_values, e);
+    const u32 tag = (u32)(mix64(value) >> 32);
+    const u64 mask = capacity - 1;
+    u64 slot = tag & mask;
+    for (u64 probes = 0; probes < capacity; probes++) {
+        u64 ent = ld_entry(&entries[slot]);
+        if (ent == 0) {
+            const u64 mine = (u64(tag) << 32) | (REF_PENDING | e);
+            ent = atomicCAS(&entries[slot], 0ull, mine);
+            if (ent == 0) { note_first(&first[slot], e); slot_of[p] = (u32)slot; return; }
+        }
+        if ((u32)(ent >> 32) == tag) {
+            const u32 ref = (u32)ent;
+            const u64 other = (ref & REF_PENDING) ? cluster_value(tsdf_values, ref & ~REF_PENDING) : raw[ref];
+            if (other == value) {
+                if (ref & REF_PENDING) note_first(&first[slot], e);
+                slot_of[p] = (u32)slot;
+                return;
+            }
+        }
+        slot = (slot + 1) & mask;
+    }
+    atomicOr(d_error, ERRF_DEDUP_FULL);
+    slot_of[p] = 0;
+}
+
+__global__ void __launch_bounds__(DAG_THREADS) cluster_mark_kernel(const u64* __restrict__ entries, const u32* __restrict__ first,
+                                                                   const u32* __restrict__ slot_of, u32 n_work, u32* __restrict__ is_new) {
+    const u32 p = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (p >= n_work) return;
+    const u32 slot = slot_of[p];
+    const u32 ref = (u32)entries[slot];
+    is_new[p] = ((ref & REF_PENDING) && first[slot] == cluster_seq_of(p)) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(DAG_THREADS) cluster_commit_kernel(u64* entries, u32* first, const u32* __restrict__ slot_of,
+                                                                     const u32* __restrict__ is_new, const u32* __restrict__ rank, u32 n_work,
+                                                                     const u64* __restrict__ tsdf_values, u64* __restrict__ raw,
+                                                                     u32 uniques_before) {
+    const u32 p = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (p >= n_work || !is_new[p]) return;
+    const u32 slot = slot_of[p];
+    const u32 addr = uniques_before + 1 + rank[p];  // levels.hpp:125
+    raw[addr] = cluster_value(tsdf_values, cluster_seq_of(p));
+    entries[slot] = (entries[slot] & 0xFFFFFFFF00000000ull) | addr;
+    first[slot] = FIRST_IDLE;
+}
+
+// addr_out[2i] = tsdf address, addr_out[2i+1] = weight address of chunk i
+__global__ void __launch_bounds__(DAG_THREADS) cluster_resolve_kernel(const u64* __restrict__ entries, const u32* __restrict__ slot_of, u32 n_chunks,
+                                                                      u32* __restrict__ addr_out) {
+    const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (i >= n_chunks) return;
+    const u32 p = (i == 0) ? 0 : i + 1;
+    addr_out[2 * i] = (u32)entries[slot_of[p]];
+    addr_out[2 * i + 1] = (u32)entries[slot_of[1]];
+}
+
+// ------------------------------------------------------------------------------------------
+// node levels: submap.hpp:31-61, levels.hpp:57-88
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DAG_THREADS) group_heads_kernel(const u64* __restrict__ child_ids, u32 n, u32* __restrict__ head) {
+    const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (i >= n) return;
+    head[i] = (i == 0 || (child_ids[i] >> 3) != (child_ids[i - 1] >> 3)) ? 1u : 0u;
+}
+
+// One thread per parent (sitting on its first child): two candidate records, TSDF then weight, each
+// 9 words = child mask + children compacted in ascending child index, zero padded (levels.hpp:63-74).
+__global__ void __launch_bounds__(DAG_THREADS) node_candidates_kernel(const u64* __restrict__ child_ids, const u32* __restrict__ child_addr,
+                                                                      const u32* __restrict__ head, const u32* __restrict__ head_rank, u32 n,
+                                                                      u32* __restrict__ cand, u64* __restrict__ parent_ids) {
+    const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (i >= n || !head[i]) return;
+    const u32 p = head_rank[i];
+    const u64 pid = child_ids[i] >> 3;
+    u32 rt[9], rw[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) { rt[q] = 0; rw[q] = 0; }
+    u32 c = 0;
+    for (u32 j = i; j < n && (child_ids[j] >> 3) == pid; j++) {
+        const u32 bit = 1u << (u32)(child_ids[j] & 7ull);
+        rt[0] |= bit; rw[0] |= bit;
+        c++;
+        // static indexing keeps the records in registers
+#pragma unroll
+        for (int q = 1; q < 9; q++)
+            if ((u32)q == c) { rt[q] = child_addr[2 * j]; rw[q] = child_addr[2 * j + 1]; }
+    }
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+        cand[size_t(2 * p) * 9 + q] = rt[q];
+        cand[size_t(2 * p + 1) * 9 + q] = rw[q];
+    }
+    parent_ids[p] = pid;
+}
+
+__device__ __forceinline__ u32 node_tag(const u32* __restrict__ rec) {
+    u64 h = rec[0];
+#pragma unroll
+    for (int q = 1; q < 9; q++) h = mix64(h ^ (u64(rec[q]) << 8) ^ (u64(q) << 48));
+    return (u32)(mix64(h) >> 32);
+}
+
+__global__ void __launch_bounds__(DAG_THREADS) node_probe_kernel(u64* entries, u32* first, u64 capacity, const u32* __restrict__ cand, u32 n_records,
+                                                                 const u32* __restrict__ raw, u32* __restrict__ slot_of, u32* d_error) {
+    const u32 e = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (e >= n_records) return;
+    u32 rec[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) rec[q] = cand[size_t(e) * 9 + q];
+    const u32 tag = node_tag(rec);
+    const u32 nchild = __popc(rec[0]);
+    const u64 mask = capacity - 1;
+    u64 slot = tag & mask;
+    for (u64 probes = 0; probes < capacity; probes++) {
+        u64 ent = ld_entry(&entries[slot]);
+        if (ent == 0) {
+            const u64 mine = (u64(tag) << 32) | (REF_PENDING | e);
+            ent = atomicCAS(&entries[slot], 0ull, mine);
+            if (ent == 0) { note_first(&first[slot], e); slot_of[e] = (u32)slot; return; }
+        }
+        if ((u32)(ent >> 32) == tag) {
+            const u32 ref = (u32)ent;
+            // levels.hpp:27-44: same mask and the same children
+            const u32* other = (ref & REF_PENDING) ? (cand + size_t(ref & ~REF_PENDING) * 9) : (raw + ref);
+            bool eq = (other[0] & 0xFFu) == rec[0];
+            for (u32 q = 1; eq && q <= nchild; q++) eq = other[q] == rec[q];
+            if (eq) {
+                if (ref & REF_PENDING) note_first(&first[slot], e);
+                slot_of[e] = (u32)slot;
+                return;
+            }
+        }
+        slot = (slot + 1) & mask;
+    }
+    atomicOr(d_error, ERRF_DEDUP_FULL);
+    slot_of[e] = 0;
+}
+
+// packed (words << 0) | (1 << 32) for new records, 0 otherwise
+__global__ void __launch_bounds__(DAG_THREADS) node_mark_kernel(const u64* __restrict__ entries, const u32* __restrict__ first,
+                                                                const u32* __restrict__ slot_of, const u32* __restrict__ cand, u32 n_records,
+                                                                u64* __restrict__ is_new) {
+    const u32 e = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (e >= n_records) return;
+    const u32 slot = slot_of[e];
+    const u32 ref = (u32)entries[slot];
+    const bool fresh = (ref & REF_PENDING) && first[slot] == e;
+    is_new[e] = fresh ? ((1ull << 32) | (1u + (u32)__popc(cand[size_t(e) * 9]))) : 0ull;
+}
+
+__global__ void __launch_bounds__(DAG_THREADS) node_commit_kernel(u64* entries, u32* first, const u32* __restrict__ slot_of,
+                                                                  const u64* __restrict__ is_new, const u64* __restrict__ rank, u32 n_records,
+                                                                  const u32* __restrict__ cand, u32* __restrict__ raw, u32 occupied_before) {
+    const u32 e = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (e >= n_records || is_new[e] == 0) return;
+    const u32 slot = slot_of[e];
+    const u32 addr = occupied_before + (u32)rank[e];  // levels.hpp:77: address = _occupied_n before the add
+    const u32 words = (u32)is_new[e];
+    for (u32 q = 0; q < words; q++) raw[addr + q] = cand[size_t(e) * 9 + q];
+    entries[slot] = (entries[slot] & 0xFFFFFFFF00000000ull) | addr;
+    first[slot] = FIRST_IDLE;
+}
+
+__global__ void __launch_bounds__(DAG_THREADS) node_resolve_kernel(const u64* __restrict__ entries, const u32* __restrict__ slot_of, u32 n_records,
+                                                                   u32* __restrict__ addr_out) {
+    const u32 e = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (e >= n_records) return;
+    addr_out[e] = (u32)entries[slot_of[e]];
+}
+
+__global__ void __launch_bounds__(DAG_THREADS) dedup_rehash_kernel(const u64* __restrict__ from, u64 from_capacity, u64* to, u64 to_capacity) {
+    const u64 mask = to_capacity - 1;
+    for (u64 s = u64(blockIdx.x) * DAG_THREADS + threadIdx.x; s < from_capacity; s += u64(gridDim.x) * DAG_THREADS) {
+        const u64 ent = from[s];
+        if (ent == 0) continue;
+        u64 slot = (ent >> 32) & mask;
+        while (true) {  // all entries are distinct records: plain first-free insertion
+            if (atomicCAS(&to[slot], 0ull, ent) == 0ull) break;
+            slot = (slot + 1) & mask;
+        }
+    }
+}
+
+}  // namespace
+
+int launch_dedup_clear(cudaStream_t s, const DedupTable& t) {
+    cudaMemsetAsync(t.entries, 0, t.capacity * 8, s);
+    cudaMemsetAsync(t.first, 0xFF, t.capacity * 4, s);
+    return 0;
+}
+
+int launch_dedup_rehash(cudaStream_t s, const DedupTable& from, const DedupTable& to, int num_sms) {
+    launch_dedup_clear(s, to);
+    dedup_rehash_kernel<<<num_sms * 4, DAG_THREADS, 0, s>>>(from.entries, from.capacity, to.entries, to.capacity);
+    return 1;
+}
+
+int launch_cluster_build(cudaStream_t s, const void* gathered_cells, u32 n_chunks, const MapParams& mp, u64* tsdf_values) {
+    if (!n_chunks) return 0;
+    cluster_build_kernel<<<blocks_for(n_chunks), DAG_THREADS, 0, s>>>(static_cast<const uint2*>(gathered_cells), n_chunks, mp.trunc_recip, tsdf_values);
+    return 1;
+}
+
+int launch_cluster_dedup(cudaStream_t s, const DedupTable& t, const u64* tsdf_values, u32 n_chunks, u64* raw, u32 uniques_before, u32* slot_of,
+                         u32* is_new, u32* rank, void* scan_ws, u32* addr_out, u32* d_new_count, u32* d_error) {
+    if (!n_chunks) { cudaMemsetAsync(d_new_count, 0, 4, s); return 0; }
+    const u32 n_work = n_chunks + 1;
+    cluster_probe_kernel<<<blocks_for(n_work), DAG_THREADS, 0, s>>>(t.entries, t.first, t.capacity, tsdf_values, n_work, raw, slot_of, d_error);
+    cluster_mark_kernel<<<blocks_for(n_work), DAG_THREADS, 0, s>>>(t.entries, t.first, slot_of, n_work, is_new);
+    int launches = 2 + exclusive_scan<u32, u32>(s, is_new, rank, n_work, scan_ws, d_new_count);
+    cluster_commit_kernel<<<blocks_for(n_work), DAG_THREADS, 0, s>>>(t.entries, t.first, slot_of, is_new, rank, n_work, tsdf_values, raw, uniques_before);
+    cluster_resolve_kernel<<<blocks_for(n_chunks), DAG_THREADS, 0, s>>>(t.entries, slot_of, n_chunks, addr_out);
+    return launches + 2;
+}
+
+int launch_group_heads(cudaStream_t s, const u64* child_ids, u32 n_children, u32* head, u32* head_rank, void* scan_ws, u32* d_parents) {
+    if (!n_children) { cudaMemsetAsync(d_parents, 0, 4, s); return 0; }
+    group_heads_kernel<<<blocks_for(n_children), DAG_THREADS, 0, s>>>(child_ids, n_children, head);
+    return 1 + exclusive_scan<u32, u32>(s, head, head_rank, n_children, scan_ws, d_parents);
+}
+
+int launch_node_candidates(cudaStream_t s, const u64* child_ids, const u32* child_addr, const u32* head, const u32* head_rank, u32 n_children,
+                           u32* cand, u64* parent_ids) {
+    if (!n_children) return 0;
+    node_candidates_kernel<<<blocks_for(n_children), DAG_THREADS, 0, s>>>(child_ids, child_addr, head, head_rank, n_children, cand, parent_ids);
+    return 1;
+}
+
+int launch_node_dedup(cudaStream_t s, const DedupTable& t, const u32* cand, u32 n_records, u32* raw, u32 occupied_before, u32* slot_of,
+                      u64* is_new, u64* rank, void* scan_ws, u32* addr_out, u64* d_new_packed, u32* d_error) {
+    if (!n_records) { cudaMemsetAsync(d_new_packed, 0, 8, s); return 0; }
+    node_probe_kernel<<<blocks_for(n_records), DAG_THREADS, 0, s>>>(t.entries, t.first, t.capacity, cand, n_records, raw, slot_of, d_error);
+    node_mark_kernel<<<blocks_for(n_records), DAG_THREADS, 0, s>>>(t.entries, t.first, slot_of, cand, n_records, is_new);
+    int launches = 2 + exclusive_scan<u64, u64>(s, is_new, rank, n_records, scan_ws, d_new_packed);
+    node_commit_kernel<<<blocks_for(n_records), DAG_THREADS, 0, s>>>(t.entries, t.first, slot_of, is_new, rank, n_records, cand, raw, occupied_before);
+    node_resolve_kernel<<<blocks_for(n_records), DAG_THREADS, 0, s>>>(t.entries, slot_of, n_records, addr_out);
+    return launches + 2;
+}
+
+}  // namespace chadgpu

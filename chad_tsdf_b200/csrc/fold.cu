@@ -1,0 +1,237 @@
+// Ordered segmented fold of the sorted (voxel key, sd) stream into the resident leaf-chunk table.
+//
+// Replaces, per emitted voxel, Octree::insert(MortonCode) (hash probe + 21-level pointer walk,
+// /root/reference/include/chad/detail/octree.hpp:31-78) and the running average of
+// octree.hpp:161-163:   sd = (sd * float(w) + new) / float(++w)   -- three rounded fp32 operations
+// per update, applied in the reference's order (sorted point, then ray step), which the stable
+// radix sort has preserved inside every equal-key segment. One thread owns one segment, so the
+// result is deterministic and bit-identical to the sequential CPU loop.
+//
+// The resident map is an open-addressing hash table of 2x2x2-voxel leaf chunks keyed by
+// (Morton key >> 3): the octree's node layout and leaf addresses are not observable outside
+// Submap::finalize's Morton-ordered walk, and a chunk is exactly the
+// unit finalize packs into one LeafCluster (submap.hpp:74-100). weight == 0 marks an absent voxel
+// (a touched voxel always has weight >= 1).
+#include "kernels.cuh"
+#include "radix_sort.cuh"
+
+namespace chadgpu {
+
+namespace {
+
+constexpr int FOLD_THREADS = 256;
+
+__device__ __forceinline__ u64 mix64(u64 h) {
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull;
+    h ^= h >> 33;
+    return h;
+}
+
+// find or insert `chunk`; returns the slot, or ~0 when the table is full
+__device__ __forceinline__ u64 table_upsert(u64* __restrict__ keys, u64 capacity, u64 chunk, bool& inserted) {
+    const u64 mask = capacity - 1;
+    u64 h = mix64(chunk) & mask;
+    inserted = false;
+    for (u64 probes = 0; probes < capacity; probes++) {
+        u64 cur = keys[h];
+        if (cur == chunk) return h;
+        if (cur == CHUNK_EMPTY) {
+            const u64 old = atomicCAS(&keys[h], CHUNK_EMPTY, chunk);
+            if (old == CHUNK_EMPTY) { inserted = true; return h; }
+            if (old == chunk) return h;
+        }
+        h = (h + 1) & mask;
+    }
+    return ~0ull;
+}
+
+__global__ void __launch_bounds__(FOLD_THREADS) fold_kernel(const u64* __restrict__ keys_a, const u64* __restrict__ keys_b,
+                                                            const u32* __restrict__ sd_a, const u32* __restrict__ sd_b, BatchPlan* plan,
+                                                            u64* __restrict__ tkeys, uint2* __restrict__ tcells, u64 capacity, u32* tcount) {
+    const u32 n = plan->n_pairs;
+    const u32 k = plan->k;
+    const bool alt = radix_result_in_alt(plan->nbits_pairs);
+    const u64* __restrict__ keys = alt ? keys_b : keys_a;
+    const u32* __restrict__ sds = alt ? sd_b : sd_a;
+    u32 new_chunks = 0, err = 0;
+    for (u32 i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < n; i += gridDim.x * FOLD_THREADS) {
+        const u64 ckey = keys[i];
+        if (i > 0 && keys[i - 1] == ckey) continue;  // not a segment head
+        const u64 full = expand_key(ckey, k);
+        bool inserted;
+        const u64 slot = table_upsert(tkeys, capacity, full >> 3, inserted);
+        if (slot == ~0ull) { err |= ERRF_TABLE_FULL; continue; }
+        new_chunks += inserted ? 1u : 0u;
+        uint2* cell = &tcells[slot * 8 + (full & 7ull)];
+        uint2 c = *cell;  // (sd bits, weight); zero for a voxel touched for the first time (octree.hpp:68-75)
+        float acc = __uint_as_float(c.x);
+        u32 w = c.y;
+        u32 j = i;
+        do {
+            acc = fadd(fmul(acc, __uint2float_rn(w)), __uint_as_float(sds[j]));  // octree.hpp:161
+            w++;                                                                 // octree.hpp:162
+            acc = fdiv(acc, __uint2float_rn(w));                                 // octree.hpp:163
+            j++;
+        } while (j < n && keys[j] == ckey);
+        *cell = make_uint2(__float_as_uint(acc), w);
+    }
+    // block-level reduction of the counters: one atomic per block
+    __shared__ u32 s_red[2];
+    if (threadIdx.x < 2) s_red[threadIdx.x] = 0;
+    __syncthreads();
+    new_chunks = __reduce_add_sync(0xffffffffu, new_chunks);
+    err = __reduce_or_sync(0xffffffffu, err);
+    if ((threadIdx.x & 31) == 0) {
+        if (new_chunks) atomicAdd(&s_red[0], new_chunks);
+        if (err) atomicOr(&s_red[1], err);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_red[0]) { atomicAdd(&plan->n_new_chunks, s_red[0]); atomicAdd(tcount, s_red[0]); }
+        if (s_red[1]) atomicOr(&plan->error, s_red[1]);
+    }
+}
+
+// distinct voxels (segments) and distinct leaf chunks of the sorted batch: the chunk count bounds
+// what the fold can insert, so the host can size the table exactly before launching the fold
+__global__ void __launch_bounds__(FOLD_THREADS) segment_count_kernel(const u64* __restrict__ keys_a, const u64* __restrict__ keys_b, BatchPlan* plan) {
+    const u32 n = plan->n_pairs;
+    const u64* __restrict__ keys = radix_result_in_alt(plan->nbits_pairs) ? keys_b : keys_a;
+    u32 segments = 0, chunks = 0;
+    for (u32 i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < n; i += gridDim.x * FOLD_THREADS) {
+        const u64 key = keys[i];
+        const u64 prev = (i > 0) ? keys[i - 1] : ~key;
+        segments += (prev != key) ? 1u : 0u;
+        chunks += ((prev >> 3) != (key >> 3)) ? 1u : 0u;
+    }
+    __shared__ u32 s_red[2];
+    if (threadIdx.x < 2) s_red[threadIdx.x] = 0;
+    __syncthreads();
+    segments = __reduce_add_sync(0xffffffffu, segments);
+    chunks = __reduce_add_sync(0xffffffffu, chunks);
+    if ((threadIdx.x & 31) == 0) {
+        if (segments) atomicAdd(&s_red[0], segments);
+        if (chunks) atomicAdd(&s_red[1], chunks);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_red[0]) atomicAdd(&plan->n_segments, s_red[0]);
+        if (s_red[1]) atomicAdd(&plan->n_chunk_heads, s_red[1]);
+    }
+}
+
+__global__ void __launch_bounds__(FOLD_THREADS) table_rehash_kernel(const u64* __restrict__ from_keys, const uint4* __restrict__ from_cells,
+                                                                    u64 from_capacity, u64* __restrict__ to_keys, uint4* __restrict__ to_cells,
+                                                                    u64 to_capacity, u32* to_count) {
+    for (u64 s = u64(blockIdx.x) * FOLD_THREADS + threadIdx.x; s < from_capacity; s += u64(gridDim.x) * FOLD_THREADS) {
+        const u64 chunk = from_keys[s];
+        if (chunk == CHUNK_EMPTY) continue;
+        bool inserted;
+        const u64 slot = table_upsert(to_keys, to_capacity, chunk, inserted);
+        if (slot == ~0ull) continue;  // cannot happen: the target is larger
+#pragma unroll
+        for (int q = 0; q < 4; q++) to_cells[slot * 4 + q] = from_cells[s * 4 + q];
+        atomicAdd(to_count, 1u);
+    }
+}
+
+// occupied chunks -> (full chunk key, slot) in arbitrary order (the sort that follows makes the
+// result deterministic); also the max range code over all resident voxels
+__global__ void __launch_bounds__(FOLD_THREADS) table_compact_kernel(const u64* __restrict__ tkeys, u64 capacity, u64* __restrict__ out_keys,
+                                                                     u32* __restrict__ out_slots, u32* d_count, u32* d_rmax) {
+    u32 rmax = 0;
+    for (u64 s0 = u64(blockIdx.x) * FOLD_THREADS; s0 < capacity; s0 += u64(gridDim.x) * FOLD_THREADS) {
+        const u64 s = s0 + threadIdx.x;
+        const u64 chunk = (s < capacity) ? tkeys[s] : CHUNK_EMPTY;
+        const bool occ = chunk != CHUNK_EMPTY;
+        const u32 ballot = __ballot_sync(0xffffffffu, occ);
+        if (ballot == 0) continue;
+        const u32 lane = threadIdx.x & 31;
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(d_count, (u32)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (occ) {
+            const u32 dst = base + __popc(ballot & ((1u << lane) - 1u));
+            out_keys[dst] = chunk;
+            out_slots[dst] = (u32)s;
+            i32 x, y, z;
+            morton_decode(chunk << 3, x, y, z);
+            rmax = max(rmax, max(rcode(x), max(rcode(y), rcode(z))) | 1u);  // the chunk spans v and v+1 on every axis
+        }
+    }
+    rmax = __reduce_max_sync(0xffffffffu, rmax);
+    if ((threadIdx.x & 31) == 0 && rmax) atomicMax(d_rmax, rmax);
+}
+
+// chunk sort keys: compact(full voxel key) >> 3 -> 3k bits; writes k-derived nbits for the radix sort
+__global__ void __launch_bounds__(FOLD_THREADS) chunk_sortkeys_kernel(u64* __restrict__ keys, const u32* __restrict__ d_count,
+                                                                      const u32* __restrict__ d_rmax, u32* __restrict__ d_nbits) {
+    const u32 n = *d_count;
+    u32 k = 32 - __clz(*d_rmax);
+    if (k < 3) k = 3;
+    if (k > 20) k = 20;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d_nbits = 3 * k;
+    for (u32 i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < n; i += gridDim.x * FOLD_THREADS) keys[i] = compact_key(keys[i] << 3, k) >> 3;
+}
+
+// sorted slots -> contiguous (full chunk key, 8 cells) for export / cluster building
+__global__ void __launch_bounds__(FOLD_THREADS) chunk_gather_kernel(const u64* __restrict__ tkeys, const uint4* __restrict__ tcells,
+                                                                    const u32* __restrict__ sorted_slots, u32 n, u64* __restrict__ out_keys,
+                                                                    uint4* __restrict__ out_cells) {
+    const u32 i = blockIdx.x * FOLD_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const u32 s = sorted_slots[i];
+    out_keys[i] = tkeys[s];
+#pragma unroll
+    for (int q = 0; q < 4; q++) out_cells[size_t(i) * 4 + q] = tcells[size_t(s) * 4 + q];
+}
+
+}  // namespace
+
+int launch_table_clear(cudaStream_t s, const ChunkTable& t) {
+    cudaMemsetAsync(t.keys, 0xFF, t.capacity * sizeof(u64), s);
+    cudaMemsetAsync(t.cells, 0, t.capacity * 8 * sizeof(uint2), s);
+    cudaMemsetAsync(t.count, 0, 4, s);
+    return 0;
+}
+
+int launch_fold(cudaStream_t s, const u64* keys_a, const u64* keys_b, const u32* sd_a, const u32* sd_b, u32 max_pairs, BatchPlan* plan,
+                const ChunkTable& t, int num_sms) {
+    if (!max_pairs) return 0;
+    u32 want = (max_pairs + FOLD_THREADS - 1) / FOLD_THREADS;
+    u32 cap = (u32)num_sms * 16;
+    fold_kernel<<<want < cap ? want : cap, FOLD_THREADS, 0, s>>>(keys_a, keys_b, sd_a, sd_b, plan, t.keys, t.cells, t.capacity, t.count);
+    return 1;
+}
+
+int launch_segment_count(cudaStream_t s, const u64* keys_a, const u64* keys_b, u32 max_pairs, BatchPlan* plan, int num_sms) {
+    if (!max_pairs) return 0;
+    u32 want = (max_pairs + FOLD_THREADS - 1) / FOLD_THREADS;
+    u32 cap = (u32)num_sms * 16;
+    segment_count_kernel<<<want < cap ? want : cap, FOLD_THREADS, 0, s>>>(keys_a, keys_b, plan);
+    return 1;
+}
+
+int launch_table_rehash(cudaStream_t s, const ChunkTable& from, const ChunkTable& to, int num_sms) {
+    table_rehash_kernel<<<num_sms * 8, FOLD_THREADS, 0, s>>>(from.keys, reinterpret_cast<const uint4*>(from.cells), from.capacity, to.keys,
+                                                             reinterpret_cast<uint4*>(to.cells), to.capacity, to.count);
+    return 1;
+}
+
+int launch_table_compact(cudaStream_t s, const ChunkTable& t, u64* out_keys, u32* out_slots, u32* d_count, u32* d_rmax, u32* d_nbits, int num_sms) {
+    cudaMemsetAsync(d_count, 0, 4, s);
+    cudaMemsetAsync(d_rmax, 0, 4, s);
+    table_compact_kernel<<<num_sms * 8, FOLD_THREADS, 0, s>>>(t.keys, t.capacity, out_keys, out_slots, d_count, d_rmax);
+    chunk_sortkeys_kernel<<<num_sms * 4, FOLD_THREADS, 0, s>>>(out_keys, d_count, d_rmax, d_nbits);
+    return 2;
+}
+
+int launch_chunk_gather(cudaStream_t s, const ChunkTable& t, const u32* sorted_slots, u32 n, u64* out_keys, void* out_cells) {
+    if (!n) return 0;
+    chunk_gather_kernel<<<(n + FOLD_THREADS - 1) / FOLD_THREADS, FOLD_THREADS, 0, s>>>(t.keys, reinterpret_cast<const uint4*>(t.cells), sorted_slots,
+                                                                                      n, out_keys, static_cast<uint4*>(out_cells));
+    return 1;
+}
+
+}  // namespace chadgpu

@@ -1,0 +1,76 @@
+// Host-callable launchers of the hot-path kernels. Each returns the number of kernels it queued.
+#pragma once
+#include "common.cuh"
+
+namespace chadgpu {
+
+struct MapParams {
+    float res;          // sdf_res
+    float trunc;        // sdf_trunc
+    float recip;        // float(1.0 / double(res))   (morton.hpp:63, octree.hpp:82)
+    float trunc_recip;  // 1.0f / trunc               (submap.hpp:24)
+    u32 band_margin;    // voxels a band voxel can lie from its point's voxel (bounds the plan's k)
+    u32 max_ray_voxels; // per-ray capacity bound used to size the pair buffers
+};
+
+// ---- points.cu: voxelise + Morton (morton.hpp:59-80), sort keys, gather, normals (normals.hpp) ----
+int launch_plan(cudaStream_t s, const float* xyz, u32 n_points, u32 n_scans, const MapParams& mp, BatchPlan* plan);
+int launch_point_keys(cudaStream_t s, const float* xyz, u32 n_points, const BatchScans* scans, const MapParams& mp, const BatchPlan* plan,
+                      u64* sortkeys, u32* index);
+// keys_a/keys_b, idx_a/idx_b: the two radix buffers; the sorted result is picked with plan->nbits_points
+int launch_point_gather(cudaStream_t s, const float* xyz, u32 n_points, const BatchPlan* plan, const u64* keys_a, const u64* keys_b,
+                        const u32* idx_a, const u32* idx_b, u64* sorted_keys, u32* sorted_order, float* xyz_sorted);
+int launch_normals(cudaStream_t s, const float* xyz_sorted, const u64* sorted_keys, u32 n_points, const BatchScans* scans,
+                   const BatchPlan* plan, u32* seg_info, float* normals);
+// full Morton keys of the sorted points (for the stage API): expands the compact sort keys
+int launch_point_full_keys(cudaStream_t s, const u64* sorted_keys, u32 n_points, const BatchPlan* plan, u64* full_keys);
+int launch_morton_encode(cudaStream_t s, const i32* voxels, u32 n, u64* keys);
+
+// ---- band.cu: truncation-band DDA (octree.hpp:86-159) ----
+int launch_band_count(cudaStream_t s, const float* xyz_sorted, u32 n_points, const BatchScans* scans, const MapParams& mp,
+                      const BatchPlan* plan, u32* counts);
+int launch_band_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const BatchScans* scans,
+                     const MapParams& mp, BatchPlan* plan, const u32* offsets, u64* pair_keys, u32* pair_sd, u32 pair_capacity,
+                     bool full_keys);
+
+// ---- fold.cu: ordered segmented fold (octree.hpp:161-163) into the resident chunk table ----
+struct ChunkTable {
+    u64* keys;      // [capacity] chunk key = voxel key >> 3, EMPTY = ~0
+    uint2* cells;   // [capacity][8] (sd bits, weight) per voxel slot, weight 0 = absent
+    u64 capacity;   // power of two
+    u32* count;     // device counter of occupied chunks
+};
+constexpr u64 CHUNK_EMPTY = ~0ull;
+int launch_table_clear(cudaStream_t s, const ChunkTable& t);
+int launch_segment_count(cudaStream_t s, const u64* keys_a, const u64* keys_b, u32 max_pairs, BatchPlan* plan, int num_sms);
+int launch_fold(cudaStream_t s, const u64* keys_a, const u64* keys_b, const u32* sd_a, const u32* sd_b, u32 max_pairs, BatchPlan* plan,
+                const ChunkTable& t, int num_sms);
+int launch_table_rehash(cudaStream_t s, const ChunkTable& from, const ChunkTable& to, int num_sms);
+// occupied chunks -> (chunk sort key on *d_nbits bits, slot), arbitrary order; *d_count = number of chunks
+int launch_table_compact(cudaStream_t s, const ChunkTable& t, u64* out_keys, u32* out_slots, u32* d_count, u32* d_rmax, u32* d_nbits, int num_sms);
+// sorted slots -> contiguous (full chunk key, 8 x (sd bits, weight))
+int launch_chunk_gather(cudaStream_t s, const ChunkTable& t, const u32* sorted_slots, u32 n, u64* out_keys, void* out_cells);
+
+// ---- dag.cu: Submap::finalize (submap.hpp:10-106) level by level ----
+struct DedupTable {   // open addressing; entry = (hash tag << 32) | ref, 0 = empty
+    u64* entries;
+    u32* first;       // per slot: min sequence index of a pending record, 0xFFFFFFFF when idle
+    u64 capacity;     // power of two
+};
+constexpr u32 REF_PENDING = 0x80000000u;
+int launch_dedup_clear(cudaStream_t s, const DedupTable& t);
+int launch_dedup_rehash(cudaStream_t s, const DedupTable& from, const DedupTable& to, int num_sms);
+int launch_cluster_build(cudaStream_t s, const void* gathered_cells, u32 n_chunks, const MapParams& mp, u64* tsdf_values);
+// cluster level: sequence tsdf_0, W, tsdf_1, W, ...; addr_out[2i] / addr_out[2i+1] = tsdf / weight cluster address of chunk i
+int launch_cluster_dedup(cudaStream_t s, const DedupTable& t, const u64* tsdf_values, u32 n_chunks, u64* raw, u32 uniques_before, u32* slot_of,
+                         u32* is_new, u32* rank, void* scan_ws, u32* addr_out, u32* d_new_count, u32* d_error);
+// children (ids ascending) -> head flags, dense parent index on the heads, *d_parents = parent count
+int launch_group_heads(cudaStream_t s, const u64* child_ids, u32 n_children, u32* head, u32* head_rank, void* scan_ws, u32* d_parents);
+// 2 candidate records (TSDF, weight) of 9 words per parent + the parent ids
+int launch_node_candidates(cudaStream_t s, const u64* child_ids, const u32* child_addr, const u32* head, const u32* head_rank, u32 n_children,
+                           u32* cand, u64* parent_ids);
+// node level dedup over n_records = 2 * parents candidates; *d_new_packed = (new records << 32) | new words
+int launch_node_dedup(cudaStream_t s, const DedupTable& t, const u32* cand, u32 n_records, u32* raw, u32 occupied_before, u32* slot_of,
+                      u64* is_new, u64* rank, void* scan_ws, u32* addr_out, u64* d_new_packed, u32* d_error);
+
+}  // namespace chadgpu

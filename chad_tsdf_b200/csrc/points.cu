@@ -1,0 +1,297 @@
+// Point stage of TSDFMap::insert on the device:
+//   * voxelise + Morton encode      -- include/chad/detail/morton.hpp:21-28,59-80
+//   * sort keys (descending Morton per scan, ties by input index; the radix sort itself is in
+//     radix_sort.cu)                -- include/chad/detail/morton.hpp:81-102
+//   * greedy Morton neighbourhoods + FP64 plane fit + sensor-facing flip
+//                                   -- include/chad/detail/normals.hpp:10-148
+// All citations are into /root/reference.
+#include "kernels.cuh"
+#include "radix_sort.cuh"
+
+namespace chadgpu {
+
+namespace {
+
+constexpr int PT_THREADS = 256;
+
+// Coalesced float4 staging of a tile of AoS xyz points (12 B each) into shared memory.
+// `xyz` must be 16-byte aligned; tile_base (in points) must be a multiple of 4.
+__device__ __forceinline__ void load_xyz_tile(const float* __restrict__ xyz, u32 tile_base, u32 n_points, float* s_xyz) {
+    const u32 pts = min((u32)PT_THREADS, n_points - tile_base);
+    const u32 nf = pts * 3;
+    const float* src = xyz + size_t(tile_base) * 3;
+    const u32 nvec = nf >> 2;
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    float4* dst4 = reinterpret_cast<float4*>(s_xyz);
+    for (u32 v = threadIdx.x; v < nvec; v += PT_THREADS) dst4[v] = __ldg(&src4[v]);
+    for (u32 f = (nvec << 2) + threadIdx.x; f < nf; f += PT_THREADS) s_xyz[f] = __ldg(&src[f]);
+    __syncthreads();
+}
+
+// morton.hpp:71-73: v = ivec3(floor(p * recip)), fp32
+__device__ __forceinline__ bool voxel_of(float px, float py, float pz, float recip, i32& vx, i32& vy, i32& vz) {
+    const float fx = floorf(fmul(px, recip)), fy = floorf(fmul(py, recip)), fz = floorf(fmul(pz, recip));
+    const float lim = 1048576.0f;  // 2^20
+    const bool ok = (fabsf(fx) < lim) && (fabsf(fy) < lim) && (fabsf(fz) < lim);  // false for NaN / Inf too
+    vx = ok ? (i32)fx : 0;
+    vy = ok ? (i32)fy : 0;
+    vz = ok ? (i32)fz : 0;
+    return ok;
+}
+
+__global__ void __launch_bounds__(PT_THREADS) plan_reset_kernel(BatchPlan* plan, u32 n_points, u32 n_scans) {
+    plan->rmax = 0; plan->k = 0; plan->nbits_points = 0; plan->nbits_pairs = 0;
+    plan->n_points = n_points; plan->n_scans = n_scans; plan->n_pairs = 0;
+    plan->n_segments = 0; plan->n_chunk_heads = 0; plan->n_new_chunks = 0;
+    // plan->error is sticky: cleared by the host when it reports it
+}
+
+__global__ void __launch_bounds__(PT_THREADS) plan_bbox_kernel(const float* __restrict__ xyz, u32 n_points, float recip, BatchPlan* plan) {
+    __shared__ __align__(16) float s_xyz[PT_THREADS * 3];
+    const u32 tile_base = blockIdx.x * PT_THREADS;
+    load_xyz_tile(xyz, tile_base, n_points, s_xyz);
+    const u32 i = tile_base + threadIdx.x;
+    u32 r = 0;
+    u32 err = 0;
+    if (i < n_points) {
+        const float px = s_xyz[threadIdx.x * 3], py = s_xyz[threadIdx.x * 3 + 1], pz = s_xyz[threadIdx.x * 3 + 2];
+        i32 vx, vy, vz;
+        if (!voxel_of(px, py, pz, recip, vx, vy, vz)) err = (isfinite(px) && isfinite(py) && isfinite(pz)) ? ERRF_RANGE : ERRF_NUMERIC;
+        r = max(rcode(vx), max(rcode(vy), rcode(vz)));
+    }
+    r = __reduce_max_sync(0xffffffffu, r);
+    err = __reduce_or_sync(0xffffffffu, err);
+    if ((threadIdx.x & 31) == 0) {
+        if (r) atomicMax(&plan->rmax, r);
+        if (err) atomicOr(&plan->error, err);
+    }
+}
+
+__global__ void plan_finalize_kernel(BatchPlan* plan, u32 margin) {
+    const u32 reach = plan->rmax + margin;  // every band voxel of the batch has range code <= reach
+    u32 k = 32 - __clz(reach);              // smallest k with reach < 2^k
+    if (k < 3) k = 3;                       // keep at least the 4^3 neighbourhood bits below the top triple
+    if (k > 20) { k = 20; atomicOr(&plan->error, ERRF_RANGE); }
+    const u32 n_scans = plan->n_scans;
+    const u32 sbits = (n_scans > 1) ? (32 - __clz(n_scans - 1)) : 0;
+    u32 nb = 3 * k + 3 + sbits;
+    if (nb > 64) { nb = 64; atomicOr(&plan->error, ERRF_KEY_BUDGET); }
+    plan->k = k;
+    plan->nbits_pairs = 3 * k + 3;
+    plan->nbits_points = nb;
+}
+
+// sort key of a point: (scan << (3k+3)) | (~compact(morton) & mask): ascending sort == per scan
+// descending Morton (morton.hpp:85-89); the stable LSD sort breaks ties by input index (canonical).
+__global__ void __launch_bounds__(PT_THREADS) point_keys_kernel(const float* __restrict__ xyz, u32 n_points, const BatchScans* __restrict__ scans,
+                                                                float recip, const BatchPlan* __restrict__ plan, u64* __restrict__ sortkeys,
+                                                                u32* __restrict__ index) {
+    __shared__ __align__(16) float s_xyz[PT_THREADS * 3];
+    const u32 tile_base = blockIdx.x * PT_THREADS;
+    load_xyz_tile(xyz, tile_base, n_points, s_xyz);
+    const u32 i = tile_base + threadIdx.x;
+    if (i >= n_points) return;
+    const u32 k = plan->k;
+    i32 vx, vy, vz;
+    voxel_of(s_xyz[threadIdx.x * 3], s_xyz[threadIdx.x * 3 + 1], s_xyz[threadIdx.x * 3 + 2], recip, vx, vy, vz);
+    const u64 full = morton_encode(vx, vy, vz);
+    const u32 cbits = 3 * k + 3;
+    const u64 cmask = (cbits >= 64) ? ~0ull : ((1ull << cbits) - 1ull);
+    const u64 inv = ~compact_key(full, k) & cmask;
+    const u32 s = scan_of(scans, plan->n_scans, i);
+    sortkeys[i] = (cbits >= 64 ? 0ull : (u64(s) << cbits)) | inv;
+    index[i] = i;
+}
+
+__global__ void __launch_bounds__(PT_THREADS) point_gather_kernel(const float* __restrict__ xyz, u32 n_points, const BatchPlan* __restrict__ plan,
+                                                                  const u64* __restrict__ keys_a, const u64* __restrict__ keys_b,
+                                                                  const u32* __restrict__ idx_a, const u32* __restrict__ idx_b,
+                                                                  u64* __restrict__ sorted_keys, u32* __restrict__ sorted_order,
+                                                                  float* __restrict__ xyz_sorted) {
+    const u32 i = blockIdx.x * PT_THREADS + threadIdx.x;
+    if (i >= n_points) return;
+    const bool alt = radix_result_in_alt(plan->nbits_points);
+    const u64 key = alt ? keys_b[i] : keys_a[i];
+    const u32 src = alt ? idx_b[i] : idx_a[i];
+    sorted_keys[i] = key;
+    sorted_order[i] = src;
+    const float x = __ldg(&xyz[size_t(src) * 3]), y = __ldg(&xyz[size_t(src) * 3 + 1]), z = __ldg(&xyz[size_t(src) * 3 + 2]);
+    xyz_sorted[size_t(i) * 3] = x;
+    xyz_sorted[size_t(i) * 3 + 1] = y;
+    xyz_sorted[size_t(i) * 3 + 2] = z;
+}
+
+// Greedy neighbourhood segmentation (normals.hpp:86-108,137). A neighbourhood never crosses a
+// 4^3-voxel block (the depth-2 mask) nor a scan, so every (scan, key >> 6) block is segmented
+// independently by the thread sitting on its first point. seg_info[j] = neighbourhood size on the
+// first point of a neighbourhood with >= 8 points, 0 on its other members, 1 on every point of a
+// smaller neighbourhood (those take the per-point fallback normal, normals.hpp:127-134).
+__global__ void __launch_bounds__(PT_THREADS) segment_kernel(const u64* __restrict__ sorted_keys, u32 n_points, const BatchScans* __restrict__ scans,
+                                                             const BatchPlan* __restrict__ plan, u32* __restrict__ seg_info) {
+    const u32 i = blockIdx.x * PT_THREADS + threadIdx.x;
+    if (i >= n_points) return;
+    const u64 block_id = sorted_keys[i] >> 6;  // includes the scan bits
+    if (i > 0 && (sorted_keys[i - 1] >> 6) == block_id) return;
+    const u32 s = scan_of(scans, plan->n_scans, i);
+    const u32 scan_end = scans->offset[s + 1];
+    const u32 last = scan_end - 1;  // normals.hpp:100: the scan's last point is never absorbed
+    u32 it = i;
+    while (it < scan_end && (sorted_keys[it] >> 6) == block_id) {
+        const u64 key_it = sorted_keys[it];
+        u32 end = it + 1;
+#pragma unroll 1
+        for (u32 depth = 0; depth < 3; depth++) {
+            const u32 sh = depth * 3;
+            while (end != last && end < scan_end && (sorted_keys[end] >> sh) == (key_it >> sh)) end++;
+            if (end - it >= 8) break;
+        }
+        const u32 size = end - it;
+        if (size >= 8) {
+            seg_info[it] = size;
+            for (u32 j = it + 1; j < end; j++) seg_info[j] = 0;
+        } else {
+            for (u32 j = it; j < end; j++) seg_info[j] = 1;
+        }
+        it = end;
+    }
+}
+
+// normals.hpp:10-80 (plane fit, FP64, sequential accumulation order), :117-118 (flip), :127-134 (fallback)
+__global__ void __launch_bounds__(PT_THREADS) normals_kernel(const float* __restrict__ xyz_sorted, u32 n_points, const BatchScans* __restrict__ scans,
+                                                             const BatchPlan* __restrict__ plan, const u32* __restrict__ seg_info,
+                                                             float* __restrict__ normals) {
+    const u32 i = blockIdx.x * PT_THREADS + threadIdx.x;
+    if (i >= n_points) return;
+    const u32 info = seg_info[i];
+    if (info == 0) return;  // member of a neighbourhood whose first point writes the shared normal
+    const u32 s = scan_of(scans, plan->n_scans, i);
+    const float posx = scans->pose[s][0], posy = scans->pose[s][1], posz = scans->pose[s][2];
+    const float px = xyz_sorted[size_t(i) * 3], py = xyz_sorted[size_t(i) * 3 + 1], pz = xyz_sorted[size_t(i) * 3 + 2];
+    // normalize(position - point): v * (1 / sqrt(dot(v, v)))
+    const float dx = fsub(posx, px), dy = fsub(posy, py), dz = fsub(posz, pz);
+    const float invl = fdiv(1.0f, fsqrt(dot3(dx, dy, dz, dx, dy, dz)));
+    const float tx = fmul(dx, invl), ty = fmul(dy, invl), tz = fmul(dz, invl);
+    if (info < 8) {
+        normals[size_t(i) * 3] = tx;
+        normals[size_t(i) * 3 + 1] = ty;
+        normals[size_t(i) * 3 + 2] = tz;
+        return;
+    }
+    const u32 end = i + info;
+    double cx = 0.0, cy = 0.0, cz = 0.0;
+    for (u32 j = i; j < end; j++) {
+        cx = dadd(cx, (double)xyz_sorted[size_t(j) * 3]);
+        cy = dadd(cy, (double)xyz_sorted[size_t(j) * 3 + 1]);
+        cz = dadd(cz, (double)xyz_sorted[size_t(j) * 3 + 2]);
+    }
+    const double recip = ddiv(1.0, (double)info);
+    cx = dmul(cx, recip); cy = dmul(cy, recip); cz = dmul(cz, recip);
+    double xx = 0.0, xy = 0.0, xz = 0.0, yy = 0.0, yz = 0.0, zz = 0.0;
+    for (u32 j = i; j < end; j++) {
+        const double rx = dsub((double)xyz_sorted[size_t(j) * 3], cx);
+        const double ry = dsub((double)xyz_sorted[size_t(j) * 3 + 1], cy);
+        const double rz = dsub((double)xyz_sorted[size_t(j) * 3 + 2], cz);
+        xx = dadd(xx, dmul(rx, rx)); xy = dadd(xy, dmul(rx, ry)); xz = dadd(xz, dmul(rx, rz));
+        yy = dadd(yy, dmul(ry, ry)); yz = dadd(yz, dmul(ry, rz)); zz = dadd(zz, dmul(rz, rz));
+    }
+    xx = dmul(xx, recip); xy = dmul(xy, recip); xz = dmul(xz, recip);
+    yy = dmul(yy, recip); yz = dmul(yz, recip); zz = dmul(zz, recip);
+    double wx = 0.0, wy = 0.0, wz = 0.0;
+    {   // determinant x (normals.hpp:42-52)
+        const double det = dsub(dmul(yy, zz), dmul(yz, yz));
+        const double ax = det, ay = dsub(dmul(xz, yz), dmul(xy, zz)), az = dsub(dmul(xy, yz), dmul(xz, yy));
+        double w = dmul(det, det);
+        if (ddot3(wx, wy, wz, ax, ay, az) < 0.0) w = -w;
+        wx = dadd(wx, dmul(ax, w)); wy = dadd(wy, dmul(ay, w)); wz = dadd(wz, dmul(az, w));
+    }
+    {   // determinant y (normals.hpp:54-64)
+        const double det = dsub(dmul(xx, zz), dmul(xz, xz));
+        const double ax = dsub(dmul(xz, yz), dmul(xy, zz)), ay = det, az = dsub(dmul(xy, xz), dmul(yz, xx));
+        double w = dmul(det, det);
+        if (ddot3(wx, wy, wz, ax, ay, az) < 0.0) w = -w;
+        wx = dadd(wx, dmul(ax, w)); wy = dadd(wy, dmul(ay, w)); wz = dadd(wz, dmul(az, w));
+    }
+    {   // determinant z (normals.hpp:66-76)
+        const double det = dsub(dmul(xx, yy), dmul(xy, xy));
+        const double ax = dsub(dmul(xy, yz), dmul(xz, yy)), ay = dsub(dmul(xy, xz), dmul(yz, xx)), az = det;
+        double w = dmul(det, det);
+        if (ddot3(wx, wy, wz, ax, ay, az) < 0.0) w = -w;
+        wx = dadd(wx, dmul(ax, w)); wy = dadd(wy, dmul(ay, w)); wz = dadd(wz, dmul(az, w));
+    }
+    const double inv = ddiv(1.0, dsqrt(ddot3(wx, wy, wz, wx, wy, wz)));
+    float nx = (float)dmul(wx, inv), ny = (float)dmul(wy, inv), nz = (float)dmul(wz, inv);
+    if (dot3(nx, ny, nz, tx, ty, tz) < 0.0f) { nx = -nx; ny = -ny; nz = -nz; }  // normals.hpp:117-118
+    for (u32 j = i; j < end; j++) {
+        normals[size_t(j) * 3] = nx;
+        normals[size_t(j) * 3 + 1] = ny;
+        normals[size_t(j) * 3 + 2] = nz;
+    }
+}
+
+__global__ void __launch_bounds__(PT_THREADS) point_full_keys_kernel(const u64* __restrict__ sorted_keys, u32 n_points,
+                                                                     const BatchPlan* __restrict__ plan, u64* __restrict__ full_keys) {
+    const u32 i = blockIdx.x * PT_THREADS + threadIdx.x;
+    if (i >= n_points) return;
+    const u32 k = plan->k;
+    const u32 cbits = 3 * k + 3;
+    const u64 cmask = (cbits >= 64) ? ~0ull : ((1ull << cbits) - 1ull);
+    full_keys[i] = expand_key(~sorted_keys[i] & cmask, k);
+}
+
+__global__ void __launch_bounds__(PT_THREADS) morton_encode_kernel(const i32* __restrict__ voxels, u32 n, u64* __restrict__ keys) {
+    const u32 i = blockIdx.x * PT_THREADS + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = morton_encode(voxels[size_t(i) * 3], voxels[size_t(i) * 3 + 1], voxels[size_t(i) * 3 + 2]);
+}
+
+inline unsigned blocks_for(u32 n) { return (n + PT_THREADS - 1) / PT_THREADS; }
+
+}  // namespace
+
+int launch_plan(cudaStream_t s, const float* xyz, u32 n_points, u32 n_scans, const MapParams& mp, BatchPlan* plan) {
+    plan_reset_kernel<<<1, 1, 0, s>>>(plan, n_points, n_scans);
+    int launches = 1;
+    if (n_points) {
+        plan_bbox_kernel<<<blocks_for(n_points), PT_THREADS, 0, s>>>(xyz, n_points, mp.recip, plan);
+        launches++;
+    }
+    plan_finalize_kernel<<<1, 1, 0, s>>>(plan, mp.band_margin);
+    return launches + 1;
+}
+
+int launch_point_keys(cudaStream_t s, const float* xyz, u32 n_points, const BatchScans* scans, const MapParams& mp, const BatchPlan* plan,
+                      u64* sortkeys, u32* index) {
+    if (!n_points) return 0;
+    point_keys_kernel<<<blocks_for(n_points), PT_THREADS, 0, s>>>(xyz, n_points, scans, mp.recip, plan, sortkeys, index);
+    return 1;
+}
+
+int launch_point_gather(cudaStream_t s, const float* xyz, u32 n_points, const BatchPlan* plan, const u64* keys_a, const u64* keys_b,
+                        const u32* idx_a, const u32* idx_b, u64* sorted_keys, u32* sorted_order, float* xyz_sorted) {
+    if (!n_points) return 0;
+    point_gather_kernel<<<blocks_for(n_points), PT_THREADS, 0, s>>>(xyz, n_points, plan, keys_a, keys_b, idx_a, idx_b, sorted_keys, sorted_order,
+                                                                    xyz_sorted);
+    return 1;
+}
+
+int launch_normals(cudaStream_t s, const float* xyz_sorted, const u64* sorted_keys, u32 n_points, const BatchScans* scans,
+                   const BatchPlan* plan, u32* seg_info, float* normals) {
+    if (!n_points) return 0;
+    segment_kernel<<<blocks_for(n_points), PT_THREADS, 0, s>>>(sorted_keys, n_points, scans, plan, seg_info);
+    normals_kernel<<<blocks_for(n_points), PT_THREADS, 0, s>>>(xyz_sorted, n_points, scans, plan, seg_info, normals);
+    return 2;
+}
+
+int launch_point_full_keys(cudaStream_t s, const u64* sorted_keys, u32 n_points, const BatchPlan* plan, u64* full_keys) {
+    if (!n_points) return 0;
+    point_full_keys_kernel<<<blocks_for(n_points), PT_THREADS, 0, s>>>(sorted_keys, n_points, plan, full_keys);
+    return 1;
+}
+
+int launch_morton_encode(cudaStream_t s, const i32* voxels, u32 n, u64* keys) {
+    if (!n) return 0;
+    morton_encode_kernel<<<blocks_for(n), PT_THREADS, 0, s>>>(voxels, n, keys);
+    return 1;
+}
+
+}  // namespace chadgpu

@@ -1,0 +1,160 @@
+"""Python mirror of the reference's public class chad::TSDFMap
+(/root/reference/include/chad/tsdf.hpp:21-171) on top of the C ABI: same constructor arguments,
+`insert(points, position)`, and the first half of `save()` (`finalize_active`); plus the state
+exports the parity tests need. Everything computes on the GPU through libchad_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class TSDFMap:
+    def __init__(self, sdf_res: float = 0.05, sdf_trunc: float = 0.1, device: int = 0, max_batch_scans: int = 0):
+        self._lib = capi.load()
+        self._h = C.c_void_p()
+        rc = self._lib.chad_create(sdf_res, sdf_trunc, device, max_batch_scans, C.byref(self._h))
+        if rc != capi.CHAD_OK:
+            raise capi.ChadError(rc, self._lib.chad_last_error(None).decode())
+        self._sdf_res, self._sdf_trunc = float(sdf_res), float(sdf_trunc)
+        self.sdf_res, self.sdf_trunc = self._sdf_res, self._sdf_trunc
+
+    # -- lifetime --
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.chad_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc != capi.CHAD_OK:
+            raise capi.ChadError(rc, self._lib.chad_last_error(self._h).decode())
+
+    # -- the reference's API --
+    def insert(self, points, position) -> None:
+        """TSDFMap::insert(points, position): points = (n, 3) float32 (any host memory; pinned memory is DMA'd directly)."""
+        if hasattr(points, "data_ptr"):  # torch tensor (host, possibly pinned) -- no numpy round trip
+            assert points.dtype.is_floating_point and points.element_size() == 4 and points.is_contiguous() and not points.is_cuda
+            n, p = points.numel() // 3, C.c_void_p(points.data_ptr())
+        else:
+            points = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+            n, p = points.shape[0], capi.ptr(points)
+        pos = np.ascontiguousarray(position, dtype=np.float32).reshape(3)
+        self._check(self._lib.chad_insert(self._h, p, n, capi.ptr(pos)))
+
+    def insert_device(self, device_ptr: int, n: int, position) -> None:
+        pos = np.ascontiguousarray(position, dtype=np.float32).reshape(3)
+        self._check(self._lib.chad_insert_device(self._h, C.c_void_p(device_ptr), n, capi.ptr(pos)))
+
+    def flush(self) -> None:
+        self._check(self._lib.chad_flush(self._h))
+
+    def finalize_active(self) -> int:
+        """What TSDFMap::save does before meshing (tsdf.cpp:78-81). Returns the number of finalised submaps."""
+        self._check(self._lib.chad_finalize_active(self._h))
+        return len(self.roots())
+
+    # -- state export --
+    def roots(self):
+        n = C.c_uint32()
+        self._check(self._lib.chad_submap_count(self._h, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            a, b = C.c_uint32(), C.c_uint32()
+            self._check(self._lib.chad_submap_roots(self._h, i, C.byref(a), C.byref(b)))
+            out.append((a.value, b.value))
+        return out
+
+    def voxels(self):
+        """(keys u64 ascending, sd_bits u32, weights u32) of the active submap."""
+        n = C.c_size_t()
+        self._check(self._lib.chad_voxel_count(self._h, C.byref(n)))
+        keys, sd, w = np.empty(n.value, np.uint64), np.empty(n.value, np.uint32), np.empty(n.value, np.uint32)
+        got = C.c_size_t()
+        self._check(self._lib.chad_export_voxels(self._h, capi.ptr(keys), capi.ptr(sd), capi.ptr(w), n.value, C.byref(got)))
+        assert got.value == n.value
+        return keys, sd, w
+
+    def level(self, level: int):
+        n = C.c_size_t()
+        self._check(self._lib.chad_level_words(self._h, level, C.byref(n)))
+        arr = np.empty(n.value, np.uint32 if level < capi.LEVEL_CLUSTERS else np.uint64)
+        self._check(self._lib.chad_export_level(self._h, level, capi.ptr(arr), n.value))
+        u, d = C.c_uint32(), C.c_uint32()
+        self._check(self._lib.chad_level_counters(self._h, level, C.byref(u), C.byref(d)))
+        return arr, u.value, d.value
+
+    def stats(self) -> dict:
+        s = capi.Stats()
+        self._check(self._lib.chad_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self) -> None:
+        self._check(self._lib.chad_reset_stats(self._h))
+
+    # -- stage entry points (kernel-by-kernel parity) --
+    def stage_points(self, points, position):
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        pos = np.ascontiguousarray(position, dtype=np.float32).reshape(3)
+        n = pts.shape[0]
+        xyz, keys = np.empty((n, 3), np.float32), np.empty(n, np.uint64)
+        order, nrm = np.empty(n, np.uint32), np.empty((n, 3), np.float32)
+        self._check(self._lib.chad_stage_points(self._h, capi.ptr(pts), n, capi.ptr(pos), capi.ptr(xyz), capi.ptr(keys), capi.ptr(order), capi.ptr(nrm)))
+        return xyz, keys, order, nrm
+
+    def stage_pairs(self, xyz_sorted, normals, position):
+        pts = np.ascontiguousarray(xyz_sorted, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        pos = np.ascontiguousarray(position, dtype=np.float32).reshape(3)
+        n = pts.shape[0]
+        total = C.c_size_t()
+        counts = np.empty(n, np.uint32)
+        self._check(self._lib.chad_stage_pairs(self._h, capi.ptr(pts), capi.ptr(nrm), n, capi.ptr(pos), capi.ptr(counts), None, None, 0, C.byref(total)))
+        keys, sd = np.empty(total.value, np.uint64), np.empty(total.value, np.float32)
+        self._check(self._lib.chad_stage_pairs(self._h, capi.ptr(pts), capi.ptr(nrm), n, capi.ptr(pos), capi.ptr(counts), capi.ptr(keys), capi.ptr(sd),
+                                               total.value, C.byref(total)))
+        return keys, sd, counts
+
+    def stage_sort(self, keys, values, nbits: int):
+        k = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+        v = np.ascontiguousarray(values, dtype=np.uint32).copy()
+        self._check(self._lib.chad_stage_sort(self._h, capi.ptr(k), capi.ptr(v), k.shape[0], nbits))
+        return k, v
+
+    def stage_morton(self, voxels):
+        vx = np.ascontiguousarray(voxels, dtype=np.int32).reshape(-1, 3)
+        keys = np.empty(vx.shape[0], np.uint64)
+        self._check(self._lib.chad_stage_morton(self._h, capi.ptr(vx), vx.shape[0], capi.ptr(keys)))
+        return keys
+
+    # -- device helpers for benchmarks --
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.chad_device_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, p: int) -> None:
+        self._check(self._lib.chad_device_free(self._h, C.c_void_p(p)))
+
+    def upload(self, device_ptr: int, host: np.ndarray) -> None:
+        host = np.ascontiguousarray(host)
+        self._check(self._lib.chad_upload(self._h, C.c_void_p(device_ptr), capi.ptr(host), host.nbytes))
+
+    def timer_begin(self) -> None:
+        self._check(self._lib.chad_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.chad_timer_end(self._h, C.byref(ms)))
+        return ms.value

@@ -1,0 +1,126 @@
+/* chad_b200.h -- C ABI of the B200-native (sm_100a) implementation of the chad_tsdf integration
+ * hot path. This is the drop-in boundary: plain pointers and sizes, no
+ * C++/torch types. The reference has no FFI of its own; its only operator boundary is the C++
+ * class chad::TSDFMap (/root/reference/include/chad/tsdf.hpp:21-171), whose implementation
+ * (/root/reference/src/chad/tsdf.cpp:27-86) this library replaces. include/chad/tsdf.hpp in
+ * this repo is the same class re-implemented on top of these entry points.
+ *
+ * Every function returns CHAD_OK (0) or a negative error code; chad_last_error() gives the
+ * message. All host pointers are plain (pageable or pinned) memory owned by the caller unless
+ * a parameter is explicitly called a device pointer. A context is bound to one CUDA device and
+ * is not thread-safe (like the reference, SURVEY.md section 8b "Threading").
+ *
+ * There is NO CPU fallback: without a CUDA device chad_create fails with CHAD_ERR_CUDA. */
+#ifndef CHAD_B200_H
+#define CHAD_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHAD_OK 0
+#define CHAD_ERR_INVALID (-1)  /* bad argument */
+#define CHAD_ERR_CUDA (-2)     /* CUDA runtime error (no device, launch failure, out of memory) */
+#define CHAD_ERR_RANGE (-3)    /* a voxel coordinate left the 21-bit Morton range (morton.hpp:21-28) or the batch key budget */
+#define CHAD_ERR_CAPACITY (-4) /* a device table or arena could not hold the data */
+#define CHAD_ERR_NUMERIC (-5)  /* NaN/Inf input coordinates */
+
+#define CHAD_LEVEL_CLUSTERS 20 /* level index of the leaf-cluster level (levels.hpp:146-200) */
+#define CHAD_NUM_LEVELS 21
+
+typedef struct chad_ctx chad_ctx;
+
+/* Counters since creation (or the last chad_reset_stats). `updates` is U and `scan_voxels` is the
+ * sum over insert calls of V_scan; scan_voxels is only exact while
+ * max_batch_scans == 1 (with larger batches it counts distinct voxels per batch). */
+typedef struct chad_stats {
+    uint64_t scans;          /* insert calls */
+    uint64_t points;         /* sum of N */
+    uint64_t updates;        /* sum of emitted (voxel, sd) updates, U */
+    uint64_t scan_voxels;    /* sum of distinct voxels per processed batch */
+    uint64_t batches;        /* device batches processed */
+    uint64_t submaps;        /* submaps finalised */
+    uint64_t kernel_launches;/* CUDA kernels launched by this library */
+    uint64_t h2d_bytes;      /* bytes copied host -> device for inserts */
+    uint64_t resident_clusters; /* leaf chunks (2x2x2 voxels) in the active submap's table (as of last flush) */
+} chad_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* Replaces TSDFMap::TSDFMap(float sdf_res, float sdf_trunc) (tsdf.cpp:27-31). `device` is the CUDA
+ * ordinal. `max_batch_scans` >= 1: how many consecutive scans of one submap may be fused into one
+ * device batch (results are identical for every value; 0 selects the default). */
+int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans, chad_ctx** out);
+/* Replaces TSDFMap::~TSDFMap (tsdf.cpp:32-38). */
+void chad_destroy(chad_ctx* ctx);
+/* Message of the last error on `ctx` (or of the last failed chad_create when ctx == NULL). */
+const char* chad_last_error(const chad_ctx* ctx);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+/* Replaces TSDFMap::insert(const std::vector<std::array<float,3>>&, const std::array<float,3>&)
+ * (tsdf.cpp:39-75) and its raw-pointer overloads (tsdf.hpp:50-64). `xyz` = n x 3 floats (AoS) in
+ * HOST memory; it is copied before the call returns, so the caller may reuse it (same ownership
+ * rule as the reference, which copies at tsdf.hpp:53,62). The device work is queued and may still
+ * be running when the call returns; the submap switch rule (> 5 m from the submap's first pose,
+ * tsdf.cpp:51-58) is applied here. */
+int chad_insert(chad_ctx* ctx, const float* xyz, size_t n, const float position[3]);
+/* Same, but `xyz_device` already lives in this context's device memory (no host copy). */
+int chad_insert_device(chad_ctx* ctx, const float* xyz_device, size_t n, const float position[3]);
+/* Wait until every queued insert has been applied; reports deferred device errors. */
+int chad_flush(chad_ctx* ctx);
+/* Replaces the part of TSDFMap::save before meshing (tsdf.cpp:78-81): Submap::finalize of the
+ * active submap (submap.hpp:10-106) into the global DAG. A fresh active submap is started
+ * afterwards (the reference's save() is terminal). No-op if the active
+ * submap has no pose yet. */
+int chad_finalize_active(chad_ctx* ctx);
+
+/* ---- state export (parity tests, save()) ---------------------------------------------- */
+int chad_submap_count(chad_ctx* ctx, uint32_t* count);
+/* Submap::root_addr_tsdf / root_addr_weight (submap.hpp:108-109) of finalised submap i. */
+int chad_submap_roots(chad_ctx* ctx, uint32_t i, uint32_t* root_tsdf, uint32_t* root_weight);
+/* Octree leaves of the ACTIVE submap (octree.hpp:15) as parallel arrays in ascending Morton-key
+ * order. Two-call protocol: chad_voxel_count, then chad_export_voxels with capacity >= count. */
+int chad_voxel_count(chad_ctx* ctx, size_t* count);
+int chad_export_voxels(chad_ctx* ctx, uint64_t* keys, uint32_t* sd_bits, uint32_t* weights, size_t capacity, size_t* count);
+/* NodeLevel::_raw_data[0.._occupied_n) for level 0..19 (u32 words) and
+ * LeafClusterLevel::_raw_data[0.._uniques_n] for level 20 (u64 words) (levels.hpp:90-93,141-143). */
+int chad_level_words(chad_ctx* ctx, int level, size_t* words);
+int chad_level_counters(chad_ctx* ctx, int level, uint32_t* uniques, uint32_t* dupes);
+int chad_export_level(chad_ctx* ctx, int level, void* dst, size_t capacity_words);
+
+int chad_get_stats(chad_ctx* ctx, chad_stats* out);
+int chad_reset_stats(chad_ctx* ctx);
+
+/* ---- stage entry points (kernel-by-kernel parity tests; host buffers) ------------------- */
+/* calc_morton_vector + sort_morton_vector + estimate_normals (morton.hpp:59-102,
+ * normals.hpp:81-148) of one scan: sorted points, their Morton keys, `order[i]` = input index of
+ * sorted point i, normals. Any output pointer may be NULL. Does not touch the map. */
+int chad_stage_points(chad_ctx* ctx, const float* xyz, size_t n, const float position[3], float* xyz_sorted,
+                      uint64_t* keys, uint32_t* order, float* normals);
+/* Band enumeration of octree.hpp:86-159 for already sorted points + normals: per-point voxel
+ * counts and the (key, sd) stream in (point, ray step) order. `capacity` = room in keys/sd;
+ * *total receives U. keys/sd may be NULL to query U. Does not touch the map. */
+int chad_stage_pairs(chad_ctx* ctx, const float* xyz_sorted, const float* normals, size_t n, const float position[3],
+                     uint32_t* counts, uint64_t* keys, float* sd, size_t capacity, size_t* total);
+/* The onesweep radix sort on its own: stable ascending sort of (key, value) pairs on bits
+ * [0, nbits) of the key (higher bits must be equal across keys or they are ignored). In place. */
+int chad_stage_sort(chad_ctx* ctx, uint64_t* keys, uint32_t* values, size_t n, int nbits);
+/* Morton encode (morton.hpp:21-28) on the device, n voxel coordinates (x,y,z int32 AoS). */
+int chad_stage_morton(chad_ctx* ctx, const int32_t* voxels, size_t n, uint64_t* keys);
+
+/* Raw device pointer + CUDA stream used by the context, for callers that place inputs on the
+ * device themselves (bench `value` leg). */
+int chad_device_alloc(chad_ctx* ctx, size_t bytes, void** device_ptr);
+int chad_device_free(chad_ctx* ctx, void* device_ptr);
+int chad_upload(chad_ctx* ctx, void* device_dst, const void* host_src, size_t bytes);
+
+/* Device timing helpers (CUDA events on the context's stream): begin/end a timed region and get
+ * its duration; the region includes everything queued between the two calls. */
+int chad_timer_begin(chad_ctx* ctx);
+int chad_timer_end(chad_ctx* ctx, float* milliseconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHAD_B200_H */

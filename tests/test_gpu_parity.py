@@ -1,0 +1,140 @@
+"""GPU parity of the whole path (insert -> fold -> finalize) through the C ABI against the CPU oracle:
+bit-exact voxel keys, u32 weights, fp32 sd bits, every DAG level word, counters and roots."""
+import numpy as np
+import pytest
+
+from chad_tsdf_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_same_state(g, o, check_levels=True):
+    gk, gs, gw = g.voxels()
+    ok, os_, ow = o.voxels()
+    assert len(gk) == len(ok)
+    assert np.array_equal(gk, ok), "voxel key set differs"
+    assert np.array_equal(gw, ow), "weights differ"
+    assert np.array_equal(gs, os_), f"sd bits differ at {(gs != os_).sum()} voxels"
+    assert g.roots() == o.roots()
+    if check_levels:
+        for lv in range(21):
+            ga, gu, gd = g.level(lv)
+            oa, ou, od = o.level(lv)
+            assert (gu, gd) == (ou, od), f"level {lv} counters"
+            assert np.array_equal(ga, oa), f"level {lv} words"
+
+
+def _run_pair(w, scans, batch, finalize_every=None):
+    from chad_tsdf_b200 import TSDFMap
+    from oracle import bindings as ob
+    g = TSDFMap(w.sdf_res, w.sdf_trunc, max_batch_scans=batch)
+    o = ob.OracleMap(w.sdf_res, w.sdf_trunc)
+    U = V = 0
+    for s in range(scans):
+        pts, pos = w.scan(s)
+        g.insert(pts, pos)
+        o.insert(pts, pos)
+        u, v = o.last_scan_stats()
+        U += u
+        V += v
+        if finalize_every and (s + 1) % finalize_every == 0:
+            g.finalize_active()
+            o.finalize_active()
+    return g, o, U, V
+
+
+@pytest.mark.parametrize("batch", [1, 4])
+def test_single_scan_cfg0(chad_lib, oracle_lib, batch):
+    w = synth.WORKLOADS["cfg0_single_64beam"]
+    g, o, U, V = _run_pair(w, 1, batch)
+    g.flush()
+    _assert_same_state(g, o, check_levels=False)
+    st = g.stats()
+    assert st["updates"] == U and st["points"] == 131072
+    if batch == 1:
+        assert st["scan_voxels"] == V
+    g.finalize_active(); o.finalize_active()
+    _assert_same_state(g, o)
+    assert g.roots() == [(1, 10)]
+    g.close(); o.close()
+
+
+@pytest.mark.parametrize("batch", [1, 3, 16])
+def test_trajectory_with_submap_switch(chad_lib, oracle_lib, batch):
+    """cfg1 prefix: 24 scans at 0.25 m/scan => one submap switch inside insert (> 5 m from the first pose)."""
+    w = synth.WORKLOADS["cfg1_traj100_128beam"]
+    g, o, U, V = _run_pair(w, 24, batch)
+    _assert_same_state(g, o)
+    assert len(g.roots()) == 1
+    g.finalize_active(); o.finalize_active()
+    _assert_same_state(g, o)
+    assert g.stats()["updates"] == U
+    g.close(); o.close()
+
+
+def test_fine_voxels_cfg2(chad_lib, oracle_lib):
+    w = synth.WORKLOADS["cfg2_fine_indoor"]
+    g, o, _, _ = _run_pair(w, 5, 2, finalize_every=2)
+    g.finalize_active(); o.finalize_active()
+    _assert_same_state(g, o)
+    g.close(); o.close()
+
+
+def test_urban_cfg3_many_submaps(chad_lib, oracle_lib):
+    w = synth.WORKLOADS["cfg3_urban_5km"]
+    g, o, _, _ = _run_pair(w, 14, 4)  # 1 m/scan: switches at scans 6 and 12
+    assert len(g.roots()) == 2
+    g.finalize_active(); o.finalize_active()
+    _assert_same_state(g, o)
+    g.close(); o.close()
+
+
+def test_sphere_demo_shape(chad_lib, oracle_lib):
+    """The reference demo's workload shape (main.cpp:7-38): dense points on a 5 m sphere, many points per voxel."""
+    from chad_tsdf_b200 import TSDFMap
+    from oracle import bindings as ob
+    pts = synth.sphere_demo_points(200_000)
+    pos = np.zeros(3, np.float32)
+    g, o = TSDFMap(0.05, 0.1), ob.OracleMap(0.05, 0.1)
+    g.insert(pts, pos); o.insert(pts, pos)
+    g.finalize_active(); o.finalize_active()
+    _assert_same_state(g, o)
+    # analytic sanity (lvr2.cpp:81-85): decoded sd ~ +-(5 - |voxel|) within discretisation
+    g.close(); o.close()
+
+
+def test_empty_and_tiny_inputs(chad_lib, oracle_lib):
+    from chad_tsdf_b200 import TSDFMap
+    from oracle import bindings as ob
+    g, o = TSDFMap(0.05, 0.1, max_batch_scans=2), ob.OracleMap(0.05, 0.1)
+    pos = np.zeros(3, np.float32)
+    empty = np.zeros((0, 3), np.float32)
+    g.insert(empty, pos); o.insert(empty, pos)
+    g.finalize_active(); o.finalize_active()  # empty octree: root record added twice (submap.hpp:31-46)
+    _assert_same_state(g, o)
+    assert g.roots() == [(1, 1)]
+    one = np.array([[1.0, 2.0, 0.5]], np.float32)
+    g.insert(one, pos); o.insert(one, pos)
+    g.insert(empty, pos); o.insert(empty, pos)
+    g.insert(one * 1.01, pos); o.insert(one * 1.01, pos)
+    _assert_same_state(g, o)
+    g.finalize_active(); o.finalize_active()
+    _assert_same_state(g, o)
+    g.close(); o.close()
+
+
+def test_errors_are_reported(chad_lib):
+    from chad_tsdf_b200 import TSDFMap, ChadError
+    g = TSDFMap(0.05, 0.1)
+    bad = np.array([[1e9, 0, 0], [1, 1, 1]], np.float32)  # outside the 21-bit Morton range
+    g.insert(bad, np.zeros(3, np.float32))
+    with pytest.raises(ChadError):
+        g.flush()
+    g.close()
+    g = TSDFMap(0.05, 0.1)
+    g.insert(np.array([[np.nan, 0, 0]], np.float32), np.zeros(3, np.float32))
+    with pytest.raises(ChadError):
+        g.flush()
+    g.close()
+    with pytest.raises(ChadError):
+        TSDFMap(-1.0, 0.1)
