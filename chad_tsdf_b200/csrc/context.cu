@@ -307,7 +307,7 @@ u64* scalar64(chad_ctx* ctx) { return ctx->f_scalars.as<u64>() + SC_NEW64; }
 
 int ensure_finalize_capacity(chad_ctx* ctx, size_t chunks) {
     TRY(dev_ensure(ctx, ctx->f_scalars, 256));
-    if (chunks <= ctx->cap_chunks) return CHAD_OK;
+    if (chunks <= ctx->cap_chunks && ctx->cap_chunks > 0) return CHAD_OK;
     const size_t nc = chunks + chunks / 8 + 1024;
     for (int i = 0; i < 2; i++) {
         TRY(dev_ensure(ctx, ctx->f_ids[i], nc * 8));
