@@ -25,7 +25,7 @@ class ChadError(RuntimeError):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("scans", "points", "updates", "scan_voxels", "batches", "submaps", "kernel_launches",
-                                           "h2d_bytes", "resident_clusters")]
+                                           "h2d_bytes", "d2h_bytes", "key_bits_points", "key_bits_pairs", "resident_clusters")]
 
     def as_dict(self) -> dict:
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -48,6 +48,7 @@ SYMBOLS = {
     "chad_level_words": (C.c_int, [_P, C.c_int, C.POINTER(C.c_size_t)]),
     "chad_level_counters": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "chad_export_level": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
+    "chad_reset": (C.c_int, [_P]),
     "chad_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "chad_reset_stats": (C.c_int, [_P]),
     "chad_stage_points": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P, _P, _P]),
@@ -59,6 +60,9 @@ SYMBOLS = {
     "chad_upload": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "chad_timer_begin": (C.c_int, [_P]),
     "chad_timer_end": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "chad_profile_enable": (C.c_int, [_P, C.c_int]),
+    "chad_profile_classes": (C.c_int, []),
+    "chad_profile_get": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 }
 
 _LIB: C.CDLL | None = None

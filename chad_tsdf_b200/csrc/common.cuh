@@ -131,4 +131,12 @@ __device__ __forceinline__ u32 scan_of(const BatchScans* __restrict__ sc, u32 n_
     return lo;
 }
 
+
+// optional instrumentation around kernel launches (bench.py's per-kernel CUDA-event timing)
+struct LaunchHook {
+    void* user;
+    void (*begin)(void* user, int cls);
+    void (*end)(void* user);
+};
+
 }  // namespace chadgpu

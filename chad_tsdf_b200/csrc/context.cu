@@ -99,6 +99,15 @@ struct chad_ctx {
     Level levels[CHAD_NUM_LEVELS];
     chad_stats stats{};
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+
+    // optional per-kernel CUDA-event instrumentation (chad_profile_*)
+    bool profiling = false;
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    double prof_ms[PC_COUNT] = {};
+    u64 prof_launches[PC_COUNT] = {};
+    LaunchHook hook{nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -116,6 +125,40 @@ int fail(chad_ctx* ctx, int code, const std::string& msg) {
     do {                            \
         int _r = (expr);            \
         if (_r != CHAD_OK) return _r; \
+    } while (0)
+
+void prof_begin(void* user, int cls) {
+    chad_ctx* ctx = static_cast<chad_ctx*>(user);
+    if (!ctx->profiling) return;
+    chad_ctx::Span sp{cls, nullptr, nullptr};
+    for (cudaEvent_t* e : {&sp.a, &sp.b}) {
+        if (!ctx->event_pool.empty()) { *e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+        else cudaEventCreate(e);
+    }
+    cudaEventRecord(sp.a, ctx->stream);
+    ctx->spans.push_back(sp);
+}
+void prof_end(void* user) {
+    chad_ctx* ctx = static_cast<chad_ctx*>(user);
+    if (!ctx->profiling || ctx->spans.empty()) return;
+    cudaEventRecord(ctx->spans.back().b, ctx->stream);
+}
+// after a stream synchronisation: fold the recorded spans into the per-class totals
+void prof_resolve(chad_ctx* ctx) {
+    for (auto& sp : ctx->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { ctx->prof_ms[sp.cls] += ms; ctx->prof_launches[sp.cls]++; }
+        else cudaGetLastError();
+        ctx->event_pool.push_back(sp.a);
+        ctx->event_pool.push_back(sp.b);
+    }
+    ctx->spans.clear();
+}
+#define PROF(ctx, cls, expr)         \
+    do {                             \
+        prof_begin(ctx, cls);        \
+        launches += (expr);          \
+        prof_end(ctx);               \
     } while (0)
 
 int dev_ensure(chad_ctx* ctx, DevBuf& b, size_t bytes, bool preserve = false) {
@@ -221,15 +264,20 @@ int complete_pending_fold(chad_ctx* ctx) {
     const BatchPlan plan = *ctx->h_plan;
     ctx->table_count_known = *ctx->h_table_count;
     ctx->stats.updates += plan.n_pairs;
+    ctx->stats.key_bits_points = plan.nbits_points;
+    ctx->stats.key_bits_pairs = plan.nbits_pairs;
     ctx->stats.scan_voxels += plan.n_segments;
     if (plan.error) {
         CUDA_TRY(ctx, cudaMemsetAsync(plan_field<u32>(ctx, offsetof(BatchPlan, error)), 0, 4, ctx->stream));
         return error_from_flags(ctx, plan.error);
     }
     TRY(table_reserve(ctx, ctx->table_count_known + plan.n_chunk_heads));
-    ctx->stats.kernel_launches += launch_fold(ctx->stream, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(),
-                                              ctx->pending_max_pairs, ctx->d_plan.as<BatchPlan>(), ctx->table, ctx->num_sms);
+    u64 launches = 0;
+    PROF(ctx, PC_FOLD, launch_fold(ctx->stream, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(),
+                                   ctx->pending_max_pairs, ctx->d_plan.as<BatchPlan>(), ctx->table, ctx->num_sms));
+    ctx->stats.kernel_launches += launches;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_table_count, ctx->table.count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += 4;
     CUDA_TRY(ctx, cudaGetLastError());
     return CHAD_OK;
 }
@@ -252,26 +300,29 @@ int process_front(chad_ctx* ctx) {
     const BatchScans* scans = ctx->d_scans.as<BatchScans>();
     const float* xyz = ctx->d_xyz[b].as<float>();
     u64 launches = 0;
-    launches += launch_plan(s, xyz, n, ns, ctx->mp, plan);
-    launches += launch_point_keys(s, xyz, n, scans, ctx->mp, plan, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>());
+    const LaunchHook* hook = ctx->profiling ? &ctx->hook : nullptr;
+    PROF(ctx, PC_PLAN, launch_plan(s, xyz, n, ns, ctx->mp, plan));
+    PROF(ctx, PC_POINT_KEYS, launch_point_keys(s, xyz, n, scans, ctx->mp, plan, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>()));
     launches += radix_sort_pairs(s, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), ctx->keys_b.as<u64>(), ctx->vals_b.as<u32>(),
                                  plan_field<u32>(ctx, offsetof(BatchPlan, n_points)), plan_field<u32>(ctx, offsetof(BatchPlan, nbits_points)), n,
-                                 RS_MAX_PASSES, ctx->rws, ctx->num_sms);
-    launches += launch_point_gather(s, xyz, n, plan, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(),
-                                    ctx->sorted_keys.as<u64>(), ctx->sorted_order.as<u32>(), ctx->xyz_sorted.as<float>());
-    launches += launch_normals(s, ctx->xyz_sorted.as<float>(), ctx->sorted_keys.as<u64>(), n, scans, plan, ctx->seg_info.as<u32>(),
-                               ctx->normals.as<float>());
-    launches += launch_band_count(s, ctx->xyz_sorted.as<float>(), n, scans, ctx->mp, plan, ctx->counts.as<u32>());
-    launches += exclusive_scan<u32, u32>(s, ctx->counts.as<u32>(), ctx->offsets.as<u32>(), n, ctx->scan_ws.p, (u32*)nullptr,
-                                         plan_field<u32>(ctx, offsetof(BatchPlan, n_pairs)));
+                                 RS_MAX_PASSES, ctx->rws, ctx->num_sms, hook, PC_POINT_SORT_HIST);
+    PROF(ctx, PC_POINT_GATHER, launch_point_gather(s, xyz, n, plan, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(),
+                                                   ctx->vals_b.as<u32>(), ctx->sorted_keys.as<u64>(), ctx->sorted_order.as<u32>(),
+                                                   ctx->xyz_sorted.as<float>()));
+    PROF(ctx, PC_NORMALS, launch_normals(s, ctx->xyz_sorted.as<float>(), ctx->sorted_keys.as<u64>(), n, scans, plan, ctx->seg_info.as<u32>(),
+                                         ctx->normals.as<float>()));
+    PROF(ctx, PC_BAND_COUNT, launch_band_count(s, ctx->xyz_sorted.as<float>(), n, scans, ctx->mp, plan, ctx->counts.as<u32>()));
+    PROF(ctx, PC_BAND_SCAN, (exclusive_scan<u32, u32>(s, ctx->counts.as<u32>(), ctx->offsets.as<u32>(), n, ctx->scan_ws.p, (u32*)nullptr,
+                                                      plan_field<u32>(ctx, offsetof(BatchPlan, n_pairs)))));
     const size_t max_pairs = size_t(n) * ctx->mp.max_ray_voxels;
-    launches += launch_band_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan, ctx->offsets.as<u32>(),
-                                 ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), (u32)ctx->cap_pairs, false);
+    PROF(ctx, PC_BAND_EMIT, launch_band_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan,
+                                             ctx->offsets.as<u32>(), ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), (u32)ctx->cap_pairs, false));
     launches += radix_sort_pairs(s, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), ctx->keys_b.as<u64>(), ctx->vals_b.as<u32>(),
                                  plan_field<u32>(ctx, offsetof(BatchPlan, n_pairs)), plan_field<u32>(ctx, offsetof(BatchPlan, nbits_pairs)), max_pairs,
-                                 RS_MAX_PASSES, ctx->rws, ctx->num_sms);
-    launches += launch_segment_count(s, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), (u32)max_pairs, plan, ctx->num_sms);
+                                 RS_MAX_PASSES, ctx->rws, ctx->num_sms, hook, PC_PAIR_SORT_HIST);
+    PROF(ctx, PC_SEGMENT_COUNT, launch_segment_count(s, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), (u32)max_pairs, plan, ctx->num_sms));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_plan, plan, sizeof(BatchPlan), cudaMemcpyDeviceToHost, s));
+    ctx->stats.d2h_bytes += sizeof(BatchPlan);
     CUDA_TRY(ctx, cudaEventRecord(ctx->front_done, s));
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->stats.kernel_launches += launches;
@@ -288,6 +339,7 @@ int drain(chad_ctx* ctx) {
     TRY(process_front(ctx));
     TRY(complete_pending_fold(ctx));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    prof_resolve(ctx);
     ctx->table_count_known = *ctx->h_table_count;
     ctx->stats.resident_clusters = ctx->table_count_known;
     // deferred flags raised by the fold
@@ -381,7 +433,7 @@ int sorted_chunks(chad_ctx* ctx, u32* n_chunks) {
     return CHAD_OK;
 }
 
-int finalize_submap(chad_ctx* ctx) {
+int finalize_submap_impl(chad_ctx* ctx) {
     u32 C = 0;
     TRY(sorted_chunks(ctx, &C));
     cudaStream_t s = ctx->stream;
@@ -402,6 +454,7 @@ int finalize_submap(chad_ctx* ctx) {
                                          scalar32(ctx, SC_ERR));
         launches += launch_group_heads(s, ids, n_children, ctx->f_head.as<u32>(), ctx->f_head_rank.as<u32>(), ctx->f_scan_ws.p, scalar32(ctx, SC_PARENTS));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->f_scalars.p, 64, cudaMemcpyDeviceToHost, s));
+        ctx->stats.d2h_bytes += 64;
         CUDA_TRY(ctx, cudaStreamSynchronize(s));
         const u32* hs = reinterpret_cast<const u32*>(ctx->h_scalars);
         if (hs[SC_ERR]) return error_from_flags(ctx, hs[SC_ERR]);
@@ -430,6 +483,7 @@ int finalize_submap(chad_ctx* ctx) {
         n_children = parents;
         if (d > 0 && C) launches += launch_group_heads(s, ids, n_children, ctx->f_head.as<u32>(), ctx->f_head_rank.as<u32>(), ctx->f_scan_ws.p, scalar32(ctx, SC_PARENTS));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->f_scalars.p, 64, cudaMemcpyDeviceToHost, s));
+        ctx->stats.d2h_bytes += 64;
         CUDA_TRY(ctx, cudaStreamSynchronize(s));
         const u32* hs = reinterpret_cast<const u32*>(ctx->h_scalars);
         if (hs[SC_ERR]) return error_from_flags(ctx, hs[SC_ERR]);
@@ -452,6 +506,24 @@ int finalize_submap(chad_ctx* ctx) {
     ctx->stats.resident_clusters = 0;
     CUDA_TRY(ctx, cudaGetLastError());
     return CHAD_OK;
+}
+
+int finalize_submap(chad_ctx* ctx) {
+    TRY(drain(ctx));
+    if (!ctx->profiling) return finalize_submap_impl(ctx);
+    // dedicated events: the nested drain() resolves (and recycles) the generic span list
+    cudaEvent_t a, b;
+    CUDA_TRY(ctx, cudaEventCreate(&a));
+    CUDA_TRY(ctx, cudaEventCreate(&b));
+    cudaEventRecord(a, ctx->stream);
+    const int r = finalize_submap_impl(ctx);
+    cudaEventRecord(b, ctx->stream);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) { ctx->prof_ms[PC_FINALIZE] += ms; ctx->prof_launches[PC_FINALIZE]++; }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return r;
 }
 
 int begin_scan(chad_ctx* ctx, size_t n, const float position[3], bool* skip) {
@@ -520,6 +592,7 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     if (device < 0 || device >= count) return fail(nullptr, CHAD_ERR_INVALID, "device ordinal out of range");
     chad_ctx* ctx = new chad_ctx();
     ctx->device = device;
+    ctx->hook = LaunchHook{ctx, prof_begin, prof_end};
     auto bail = [&](int code) { g_create_error = ctx->error; chad_destroy(ctx); return code; };
 #define CREATE_TRY(expr)                                                                                               \
     do {                                                                                                               \
@@ -596,6 +669,8 @@ void chad_destroy(chad_ctx* ctx) {
         if (ctx->stage_copied[b]) cudaEventDestroy(ctx->stage_copied[b]);
         if (ctx->copy_done[b]) cudaEventDestroy(ctx->copy_done[b]);
     }
+    for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->h_plan) cudaFreeHost(ctx->h_plan);
     if (ctx->h_table_count) cudaFreeHost(ctx->h_table_count);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
@@ -739,6 +814,66 @@ int chad_export_level(chad_ctx* ctx, int level, void* dst, size_t capacity_words
     if (capacity_words < words) return fail(ctx, CHAD_ERR_INVALID, "export capacity too small");
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaMemcpy(dst, ctx->levels[level].raw.p, words * (level == CHAD_LEVEL_CLUSTERS ? 8 : 4), cudaMemcpyDeviceToHost));
+    return CHAD_OK;
+}
+
+int chad_reset(chad_ctx* ctx) {
+    if (!ctx) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->sticky_error = CHAD_OK;
+    ctx->batch_points = 0;
+    ctx->batch_scans = 0;
+    ctx->fold_pending = false;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_plan.p, 0, sizeof(BatchPlan), ctx->stream));
+    launch_table_clear(ctx->stream, ctx->table);
+    for (int d = 0; d < CHAD_NUM_LEVELS; d++) {
+        Level& L = ctx->levels[d];
+        L.uniques = 0; L.dupes = 0; L.occupied = (d == CHAD_LEVEL_CLUSTERS) ? 0 : 1;
+        launch_dedup_clear(ctx->stream, L.table);
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *ctx->h_table_count = 0;
+    ctx->table_count_known = 0;
+    ctx->has_pose = false;
+    ctx->roots.clear();
+    ctx->stats.resident_clusters = 0;
+    return CHAD_OK;
+}
+
+int chad_profile_enable(chad_ctx* ctx, int on) {
+    if (!ctx) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(drain(ctx));
+    ctx->profiling = on != 0;
+    for (int c = 0; c < PC_COUNT; c++) { ctx->prof_ms[c] = 0.0; ctx->prof_launches[c] = 0; }
+    return CHAD_OK;
+}
+
+int chad_profile_classes(void) { return PC_COUNT; }
+
+int chad_profile_get(chad_ctx* ctx, int cls, const char** name, double* milliseconds, uint64_t* launches) {
+    if (!ctx || cls < 0 || cls >= PC_COUNT) return CHAD_ERR_INVALID;
+    static const char* base[] = {"plan_kernels", "point_keys_kernel"};
+    static char names[PC_COUNT][48];
+    const char* nm;
+    if (cls < 2) nm = base[cls];
+    else if (cls == PC_POINT_SORT_HIST) nm = "radix_histogram_kernel[points]";
+    else if (cls >= PC_POINT_SORT_PASS0 && cls < PC_POINT_GATHER) { std::snprintf(names[cls], 48, "radix_onesweep_kernel[points,pass%d]", cls - PC_POINT_SORT_PASS0); nm = names[cls]; }
+    else if (cls == PC_POINT_GATHER) nm = "point_gather_kernel";
+    else if (cls == PC_NORMALS) nm = "segment_kernel+normals_kernel";
+    else if (cls == PC_BAND_COUNT) nm = "band_count_kernel";
+    else if (cls == PC_BAND_SCAN) nm = "scan_kernels[band offsets]";
+    else if (cls == PC_BAND_EMIT) nm = "band_emit_kernel";
+    else if (cls == PC_PAIR_SORT_HIST) nm = "radix_histogram_kernel[pairs]";
+    else if (cls >= PC_PAIR_SORT_PASS0 && cls < PC_SEGMENT_COUNT) { std::snprintf(names[cls], 48, "radix_onesweep_kernel[pairs,pass%d]", cls - PC_PAIR_SORT_PASS0); nm = names[cls]; }
+    else if (cls == PC_SEGMENT_COUNT) nm = "segment_count_kernel";
+    else if (cls == PC_FOLD) nm = "fold_kernel";
+    else nm = "finalize_submap[all kernels + host syncs]";
+    if (name) *name = nm;
+    if (milliseconds) *milliseconds = ctx->prof_ms[cls];
+    if (launches) *launches = ctx->prof_launches[cls];
     return CHAD_OK;
 }
 

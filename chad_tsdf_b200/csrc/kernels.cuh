@@ -13,6 +13,12 @@ struct MapParams {
     u32 max_ray_voxels; // per-ray capacity bound used to size the pair buffers
 };
 
+// instrumentation classes (chad_profile_*): one per kernel (group); radix passes are numbered
+enum ProfClass {
+    PC_PLAN = 0, PC_POINT_KEYS, PC_POINT_SORT_HIST, PC_POINT_SORT_PASS0, PC_POINT_GATHER = PC_POINT_SORT_PASS0 + 8, PC_NORMALS, PC_BAND_COUNT,
+    PC_BAND_SCAN, PC_BAND_EMIT, PC_PAIR_SORT_HIST, PC_PAIR_SORT_PASS0, PC_SEGMENT_COUNT = PC_PAIR_SORT_PASS0 + 8, PC_FOLD, PC_FINALIZE, PC_COUNT
+};
+
 // ---- points.cu: voxelise + Morton (morton.hpp:59-80), sort keys, gather, normals (normals.hpp) ----
 int launch_plan(cudaStream_t s, const float* xyz, u32 n_points, u32 n_scans, const MapParams& mp, BatchPlan* plan);
 int launch_point_keys(cudaStream_t s, const float* xyz, u32 n_points, const BatchScans* scans, const MapParams& mp, const BatchPlan* plan,

@@ -197,20 +197,24 @@ cudaError_t radix_sort_init() {
 }
 
 int radix_sort_pairs(cudaStream_t stream, u64* keys, u32* vals, u64* keys_alt, u32* vals_alt, const u32* d_n, const u32* d_nbits,
-                     size_t max_n, int max_passes, const RadixWorkspace& ws, int num_sms) {
+                     size_t max_n, int max_passes, const RadixWorkspace& ws, int num_sms, const LaunchHook* hook, int cls_base) {
     if (max_n == 0) return 0;
     if (max_passes > RS_MAX_PASSES) max_passes = RS_MAX_PASSES;
     size_t max_tiles = (max_n + RS_TILE - 1) / RS_TILE;
     int launches = 0;
     cudaMemsetAsync(ws.hist, 0, (size_t(RS_MAX_PASSES) * 256 + 64) * 4, stream);
     int hist_grid = (int)(max_tiles < size_t(num_sms) * 4 ? max_tiles : size_t(num_sms) * 4);
+    if (hook) hook->begin(hook->user, cls_base);
     radix_histogram_kernel<<<hist_grid, RS_THREADS, 0, stream>>>(keys, d_n, d_nbits, ws.hist, ws.lookback[0]);
+    if (hook) hook->end(hook->user);
     launches++;
     int grid = (int)(max_tiles < size_t(num_sms) * 2 ? max_tiles : size_t(num_sms) * 2);
     u64* kin = keys; u32* vin = vals; u64* kout = keys_alt; u32* vout = vals_alt;
     for (int p = 0; p < max_passes; p++) {
+        if (hook) hook->begin(hook->user, cls_base + 1 + p);
         radix_onesweep_kernel<<<grid, RS_THREADS, RS_SMEM_BYTES, stream>>>(kin, vin, kout, vout, d_n, d_nbits, (u32)p, ws.hist,
                                                                             ws.tile_counter, ws.lookback[p & 1], ws.lookback[(p + 1) & 1]);
+        if (hook) hook->end(hook->user);
         launches++;
         u64* tk = kin; kin = kout; kout = tk;
         u32* tv = vin; vin = vout; vout = tv;

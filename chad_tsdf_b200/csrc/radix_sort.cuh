@@ -65,8 +65,10 @@ __host__ __device__ __forceinline__ bool radix_result_in_alt(u32 nbits) { return
 // Queue the sort on `stream`. keys/vals: primary buffers (input); keys_alt/vals_alt: same size.
 // d_n / d_nbits: device pointers. max_n: host upper bound of *d_n (sizes the grids / workspace).
 // max_passes: host upper bound on ceil(nbits/8) (<= 8). Returns the number of kernels launched.
+// hook/cls_base: optional instrumentation; class cls_base = histogram, cls_base + 1 + p = pass p.
 int radix_sort_pairs(cudaStream_t stream, u64* keys, u32* vals, u64* keys_alt, u32* vals_alt, const u32* d_n,
-                     const u32* d_nbits, size_t max_n, int max_passes, const RadixWorkspace& ws, int num_sms);
+                     const u32* d_nbits, size_t max_n, int max_passes, const RadixWorkspace& ws, int num_sms,
+                     const LaunchHook* hook = nullptr, int cls_base = 0);
 cudaError_t radix_sort_init();  // opt in to > 48 KB dynamic shared memory
 
 }  // namespace chadgpu

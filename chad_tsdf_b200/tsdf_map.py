@@ -100,6 +100,23 @@ class TSDFMap:
         self._check(self._lib.chad_get_stats(self._h, C.byref(s)))
         return s.as_dict()
 
+    def reset(self) -> None:
+        """Forget the whole map but keep the device buffers (== a freshly constructed map)."""
+        self._check(self._lib.chad_reset(self._h))
+
+    def profile_enable(self, on: bool) -> None:
+        self._check(self._lib.chad_profile_enable(self._h, 1 if on else 0))
+
+    def profile(self) -> dict:
+        """{kernel class name: (milliseconds, launches)} accumulated since profile_enable(True)."""
+        out = {}
+        for c in range(self._lib.chad_profile_classes()):
+            name, ms, n = C.c_char_p(), C.c_double(), C.c_uint64()
+            self._check(self._lib.chad_profile_get(self._h, c, C.byref(name), C.byref(ms), C.byref(n)))
+            if n.value:
+                out[name.value.decode()] = (ms.value, int(n.value))
+        return out
+
     def reset_stats(self) -> None:
         self._check(self._lib.chad_reset_stats(self._h))
 

@@ -44,6 +44,9 @@ typedef struct chad_stats {
     uint64_t submaps;        /* submaps finalised */
     uint64_t kernel_launches;/* CUDA kernels launched by this library */
     uint64_t h2d_bytes;      /* bytes copied host -> device for inserts */
+    uint64_t d2h_bytes;      /* bytes copied device -> host on the insert path (batch plans, counters, finalize scalars) */
+    uint64_t key_bits_points;/* sort-key width of the last batch's point sort (ceil(/8) = active radix passes) */
+    uint64_t key_bits_pairs; /* sort-key width of the last batch's voxel-update sort */
     uint64_t resident_clusters; /* leaf chunks (2x2x2 voxels) in the active submap's table (as of last flush) */
 } chad_stats;
 
@@ -89,6 +92,10 @@ int chad_level_words(chad_ctx* ctx, int level, size_t* words);
 int chad_level_counters(chad_ctx* ctx, int level, uint32_t* uniques, uint32_t* dupes);
 int chad_export_level(chad_ctx* ctx, int level, void* dst, size_t capacity_words);
 
+/* Forget everything (active submap, all DAG levels, submap roots, sticky errors) but keep the device
+ * buffers: equivalent to destroying the map and constructing a new one with the same parameters. */
+int chad_reset(chad_ctx* ctx);
+
 int chad_get_stats(chad_ctx* ctx, chad_stats* out);
 int chad_reset_stats(chad_ctx* ctx);
 
@@ -119,6 +126,14 @@ int chad_upload(chad_ctx* ctx, void* device_dst, const void* host_src, size_t by
  * its duration; the region includes everything queued between the two calls. */
 int chad_timer_begin(chad_ctx* ctx);
 int chad_timer_end(chad_ctx* ctx, float* milliseconds);
+
+/* ---- instrumentation (bench.py roofline leg) ------------------------------------------------ */
+/* When enabled, every kernel (group) launch on the insert path is bracketed by CUDA events on the
+ * context's stream; the per-class totals are available after the next chad_flush. Enabling or
+ * disabling flushes and zeroes the totals. Costs a few percent; leave it off in timed regions. */
+int chad_profile_enable(chad_ctx* ctx, int on);
+int chad_profile_classes(void);
+int chad_profile_get(chad_ctx* ctx, int cls, const char** name, double* milliseconds, uint64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,20 @@
+"""Profiling target for ncu: one submap of the bench workload (21 scans of cfg1, batches of 16 + 5) followed
+by Submap::finalize, run twice in-process (first run = warm-up). Usage: python profiles/prof_target.py [scans]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from chad_tsdf_b200 import TSDFMap, synth  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 21
+w = synth.WORKLOADS["cfg1_traj100_128beam"]
+scans = [w.scan(s) for s in range(n)]
+m = TSDFMap(w.sdf_res, w.sdf_trunc, max_batch_scans=16)
+for rep in range(2):
+    m.reset()
+    m.reset_stats()
+    for pts, pos in scans:
+        m.insert(pts, pos)
+    m.finalize_active()
+    print(rep, m.stats())
+m.close()
