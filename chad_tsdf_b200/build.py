@@ -13,11 +13,11 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libchad_b200.so")
-SOURCES = ["radix_sort.cu", "points.cu", "band.cu", "fold.cu", "dag.cu", "context.cu"]
+SOURCES = ["radix_sort.cu", "points.cu", "band.cu", "fold.cu", "dag.cu", "context.cu", "tsdf_host.cpp"]
 HEADERS = ["common.cuh", "kernels.cuh", "radix_sort.cuh", "scan.cuh"]
 # -fmad=false / -ffp-contract=off: the reference's strict-IEEE configuration (cmake/options_compiler.cmake:39);
 # the kernels additionally use explicit *_rn intrinsics wherever a result is observable.
-NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+NVCC_FLAGS = ["-std=c++20", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared", "-cudart", "static"]
 
 
@@ -25,8 +25,19 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "chad_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "chad_b200.h"), os.path.join(ROOT, "include", "chad", "tsdf.hpp")]
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_facade_demo(verbose: bool = False) -> str:
+    """tests/cpp/facade_demo.cpp against include/chad/tsdf.hpp + libchad_b200.so (the drop-in check)."""
+    out = os.path.join(ROOT, "tests", "cpp", "facade_demo")
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++20", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "facade_demo.cpp"),
+           "-o", out, "-L", PKG, "-lchad_b200", f"-Wl,-rpath,{PKG}"]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return out
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

@@ -60,6 +60,10 @@ SYMBOLS = {
     "chad_upload": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "chad_timer_begin": (C.c_int, [_P]),
     "chad_timer_end": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "chad_morton_encode": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32]),
+    "chad_morton_decode": (None, [C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "chad_key_compact": (C.c_uint64, [C.c_uint64, C.c_uint]),
+    "chad_key_expand": (C.c_uint64, [C.c_uint64, C.c_uint]),
     "chad_profile_enable": (C.c_int, [_P, C.c_int]),
     "chad_profile_classes": (C.c_int, []),
     "chad_profile_get": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -1019,6 +1019,11 @@ int chad_stage_morton(chad_ctx* ctx, const int32_t* voxels, size_t n, uint64_t* 
     return CHAD_OK;
 }
 
+uint64_t chad_morton_encode(int32_t x, int32_t y, int32_t z) { return morton_encode(x, y, z); }
+void chad_morton_decode(uint64_t key, int32_t* x, int32_t* y, int32_t* z) { morton_decode(key, *x, *y, *z); }
+uint64_t chad_key_compact(uint64_t key, unsigned k) { return compact_key(key, k); }
+uint64_t chad_key_expand(uint64_t compact, unsigned k) { return expand_key(compact, k); }
+
 int chad_device_alloc(chad_ctx* ctx, size_t bytes, void** device_ptr) {
     if (!ctx || !device_ptr) return CHAD_ERR_INVALID;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));

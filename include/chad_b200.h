@@ -127,6 +127,15 @@ int chad_upload(chad_ctx* ctx, void* device_dst, const void* host_src, size_t by
 int chad_timer_begin(chad_ctx* ctx);
 int chad_timer_end(chad_ctx* ctx, float* milliseconds);
 
+/* ---- host-only helpers (pure CPU bit arithmetic; usable without a GPU) ------------------------ */
+/* MortonCode::encode / decode (morton.hpp:21-37): 21 bits per axis, bias 2^20, x -> bit 0. */
+uint64_t chad_morton_encode(int32_t x, int32_t y, int32_t z);
+void chad_morton_decode(uint64_t key, int32_t* x, int32_t* y, int32_t* z);
+/* The order-preserving compact sort key used by the device radix sorts: for voxel coordinates in
+ * [-2^k, 2^k) the 63-bit Morton key is reduced to its low 3k bits plus the top (sign) triple. */
+uint64_t chad_key_compact(uint64_t key, unsigned k);
+uint64_t chad_key_expand(uint64_t compact, unsigned k);
+
 /* ---- instrumentation (bench.py roofline leg) ------------------------------------------------ */
 /* When enabled, every kernel (group) launch on the insert path is bracketed by CUDA events on the
  * context's stream; the per-class totals are available after the next chad_flush. Enabling or

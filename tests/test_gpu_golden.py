@@ -1,0 +1,25 @@
+"""GPU parity against the committed golden pins of the REFERENCE (tests/golden/golden.json), through the C ABI."""
+import json
+import os
+
+import pytest
+
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+
+
+@pytest.mark.parametrize("batch", [1, 8])
+@pytest.mark.parametrize("name", cases.ALL_CASES)
+def test_gpu_matches_reference_golden(chad_lib, name, batch):
+    from chad_tsdf_b200 import TSDFMap
+    m, d = cases.run_case(lambda r, t: TSDFMap(r, t, max_batch_scans=batch), name)
+    g = GOLDEN[name]
+    for k, v in g["verbatim"]["before_finalize"].items():  # tier A: the reference exactly as written
+        assert d["before_finalize"][k] == v, f"tier A {k}"
+    assert d["before_finalize"] == g["stable"]["before_finalize"]  # tier B: bit-exact floats too
+    assert d["final"]["roots"] == g["stable"]["final"]["roots"]
+    for lv, (a, b) in enumerate(zip(d["final"]["levels"], g["stable"]["final"]["levels"])):
+        assert a == b, f"DAG level {lv}"
+    m.close()

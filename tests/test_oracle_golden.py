@@ -1,0 +1,32 @@
+"""CPU: the oracle restatement (oracle/chad_oracle.c) against the golden pins generated from the REFERENCE
+build (tests/golden/golden.json, made by tests/golden/make_golden.py from oracle/_ref)."""
+import json
+import os
+
+import pytest
+
+from tests.golden import cases
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+
+
+@pytest.mark.parametrize("name", cases.ALL_CASES)
+def test_synthetic_inputs_are_reproducible(name):
+    scans, _, _ = cases.case_scans(name)
+    assert cases.input_digest(scans) == GOLDEN[name]["input_sha256"], "the synthetic generator is not bit-reproducible on this machine"
+    assert sum(len(p) for p, _ in scans) == GOLDEN[name]["points"]
+
+
+@pytest.mark.parametrize("name", cases.ALL_CASES)
+def test_oracle_matches_reference_golden(oracle_lib, name):
+    m, d = cases.run_case(lambda r, t: oracle_lib.OracleMap(r, t), name)
+    g = GOLDEN[name]
+    # Tier A (reference exactly as written): tie-order independent integers
+    for k, v in g["verbatim"]["before_finalize"].items():
+        assert d["before_finalize"][k] == v, f"tier A {k}"
+    # Tier B (reference + canonical tie-break): everything, bit for bit
+    assert d["before_finalize"] == g["stable"]["before_finalize"]
+    assert d["final"]["roots"] == g["stable"]["final"]["roots"]
+    for lv, (a, b) in enumerate(zip(d["final"]["levels"], g["stable"]["final"]["levels"])):
+        assert a == b, f"DAG level {lv}"
+    m.close()
