@@ -48,15 +48,24 @@ __device__ __forceinline__ void ray_setup(Ray& r, float px, float py, float pz, 
         r.cur[a] = vs; r.vf[a] = vf; r.step[a] = st;
     }
 }
-// one iteration of the while(true) loop of octree.hpp:125-152; returns false on `break`
-__device__ __forceinline__ bool ray_advance(Ray& r) {
+// one iteration of the while(true) loop of octree.hpp:125-152; returns false on `break`; `axis` = the axis stepped
+__device__ __forceinline__ bool ray_advance(Ray& r, int& axis) {
     int a;
     if (r.tmax[0] < r.tmax[1]) a = (r.tmax[0] < r.tmax[2]) ? 0 : 2;
     else a = (r.tmax[1] < r.tmax[2]) ? 1 : 2;
+    axis = a;
     // select without dynamic register indexing
     if (a == 0) { r.cur[0] += r.step[0]; r.tmax[0] = fadd(r.tmax[0], r.delta[0]); return r.cur[0] != r.vf[0] + r.step[0]; }
     if (a == 1) { r.cur[1] += r.step[1]; r.tmax[1] = fadd(r.tmax[1], r.delta[1]); return r.cur[1] != r.vf[1] + r.step[1]; }
     r.cur[2] += r.step[2]; r.tmax[2] = fadd(r.tmax[2], r.delta[2]); return r.cur[2] != r.vf[2] + r.step[2];
+}
+__device__ __forceinline__ bool ray_advance(Ray& r) { int a; return ray_advance(r, a); }
+// Morton key of the neighbour one voxel along `axis` (dir = +1 / -1 / 0): add or subtract 1 inside the axis' bit lane
+__device__ __forceinline__ u64 morton_step(u64 key, int axis, i32 dir) {
+    const u64 lane = 0x1249249249249249ull << axis;
+    if (dir > 0) return (((key | ~lane) + 1ull) & lane) | (key & ~lane);
+    if (dir < 0) return (((key & lane) - 1ull) & lane) | (key & ~lane);
+    return key;
 }
 
 __global__ void __launch_bounds__(BAND_THREADS) band_count_kernel(const float* __restrict__ xyz_sorted, u32 n_points,
@@ -90,21 +99,25 @@ __global__ void __launch_bounds__(BAND_THREADS) band_emit_kernel(const float* __
     u32 out = offsets[i];
     u32 c = 0;
     u32 err = 0;
+    u64 full = morton_encode(r.cur[0], r.cur[1], r.cur[2]);
     while (true) {
         if (out >= pair_capacity) { err |= ERRF_PAIR_CAPACITY; break; }
         const i32 vx = r.cur[0], vy = r.cur[1], vz = r.cur[2];
-        if (max(rcode(vx), max(rcode(vy), rcode(vz))) >= (1u << k)) err |= ERRF_RANGE;  // outside the batch plan
-        const u64 full = morton_encode(vx, vy, vz);
-        // octree.hpp:157-159: the voxel's LOWER CORNER, decoded from the stored code, projected on the normal
-        i32 dx, dy, dz;
-        morton_decode(full, dx, dy, dz);
-        float sd = dot3(nx, ny, nz, fsub(fmul((float)dx, res), r.px), fsub(fmul((float)dy, res), r.py), fsub(fmul((float)dz, res), r.pz));
+        // inside the plan's range (hence inside the 21-bit Morton range) the stored code decodes back to (vx, vy, vz)
+        // exactly, so the reference's decode (octree.hpp:157) is the identity and need not be recomputed
+        if (max(rcode(vx), max(rcode(vy), rcode(vz))) >= (1u << k)) err |= ERRF_RANGE;
+        // octree.hpp:157-159: the voxel's LOWER CORNER projected on the normal, clamped to +-trunc
+        float sd = dot3(nx, ny, nz, fsub(fmul((float)vx, res), r.px), fsub(fmul((float)vy, res), r.py), fsub(fmul((float)vz, res), r.pz));
         sd = fclamp(sd, -trunc, trunc);
         pair_keys[out] = FULL_KEYS ? full : compact_key(full, k);
         pair_sd[out] = __float_as_uint(sd);
         out++;
         c++;
-        if (c >= max_ray_voxels || !ray_advance(r)) break;
+        if (c >= max_ray_voxels) break;
+        int axis;
+        const bool more = ray_advance(r, axis);
+        if (!more) break;
+        full = morton_step(full, axis, axis == 0 ? r.step[0] : (axis == 1 ? r.step[1] : r.step[2]));
     }
     if (err) atomicOr(&plan->error, err);
 }

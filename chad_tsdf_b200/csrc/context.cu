@@ -76,19 +76,40 @@ struct chad_ctx {
     BatchScans* h_scans_pinned[2] = {nullptr, nullptr};
     DevBuf d_scans, d_plan;
     BatchPlan* h_plan = nullptr;  // pinned
-    u32* h_table_count = nullptr; // pinned
+    u32* h_table_count = nullptr; // pinned: chunk count of `table` after its last fold
+    u32* h_table_count2 = nullptr; // pinned: same for `table2`
     cudaEvent_t front_done = nullptr;
     bool fold_pending = false;
+    bool close_pending = false;   // the batch whose fold is pending is the last one of its submap: finalize starts right after that fold
     u32 pending_max_pairs = 0;
 
     // batch work buffers
     DevBuf keys_a, keys_b, vals_a, vals_b, sorted_keys, sorted_order, xyz_sorted, normals, seg_info, counts, offsets, radix_ws, scan_ws;
     RadixWorkspace rws{};
 
-    // resident chunk table of the active submap
+    // resident chunk tables: `table` belongs to the active submap; the other one is being finalised / is spare
     DevBuf t_keys, t_cells, t_count;
     ChunkTable table{nullptr, nullptr, 0, nullptr};
+    DevBuf t2_keys, t2_cells, t2_count;
+    ChunkTable table2{nullptr, nullptr, 0, nullptr};
     u64 table_count_known = 0;
+
+    // asynchronous Submap::finalize (see finalize_begin): part 1 and part 2 run on fin_stream
+    cudaStream_t fin_stream = nullptr;
+    enum FinState { FIN_IDLE = 0, FIN_PART1 = 1, FIN_PART2 = 2 };
+    int fin_state = FIN_IDLE;
+    u32 fin_max_chunks = 0;       // host upper bound of the chunk count of the submap being finalised
+    u32 fin_chunks = 0;           // exact count (known after part 1)
+    u32 fin_level_nodes[20] = {}; // exact node count per level (known after part 1)
+    cudaEvent_t submap_closed = nullptr, fin_p1_done = nullptr, fin_done = nullptr;
+    cudaEvent_t fin_t0 = nullptr, fin_t1 = nullptr, fin_t2 = nullptr, fin_t3 = nullptr;  // profiling: part 1 = t0..t1, part 2 = t2..t3
+    struct FinHost {              // pinned read-back area
+        u32 scalars[16];
+        u32 level_nodes[20];
+        u64 level_new[20];        // per level: (new records << 32) | new words
+        u32 root[2];
+    }* h_fin = nullptr;
+    DevBuf f_level_new;           // device u64[20]
 
     // finalize work buffers
     size_t cap_chunks = 0;
@@ -256,6 +277,8 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
     return CHAD_OK;
 }
 
+int finalize_begin(chad_ctx* ctx, u32 max_chunks);
+
 // launch the fold of the batch whose front has been queued (see the file comment)
 int complete_pending_fold(chad_ctx* ctx) {
     if (!ctx->fold_pending) return CHAD_OK;
@@ -268,6 +291,7 @@ int complete_pending_fold(chad_ctx* ctx) {
     ctx->stats.key_bits_pairs = plan.nbits_pairs;
     ctx->stats.scan_voxels += plan.n_segments;
     if (plan.error) {
+        ctx->close_pending = false;
         CUDA_TRY(ctx, cudaMemsetAsync(plan_field<u32>(ctx, offsetof(BatchPlan, error)), 0, 4, ctx->stream));
         return error_from_flags(ctx, plan.error);
     }
@@ -279,6 +303,13 @@ int complete_pending_fold(chad_ctx* ctx) {
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_table_count, ctx->table.count, 4, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.d2h_bytes += 4;
     CUDA_TRY(ctx, cudaGetLastError());
+    if (ctx->close_pending) {  // that was the submap's last batch: swap tables and start its asynchronous finalize
+        ctx->close_pending = false;
+        const u64 bound = ctx->table_count_known + plan.n_chunk_heads;
+        if (bound >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
+        TRY(finalize_begin(ctx, (u32)bound));
+        ctx->stats.resident_clusters = 0;
+    }
     return CHAD_OK;
 }
 
@@ -335,9 +366,15 @@ int process_front(chad_ctx* ctx) {
     return CHAD_OK;
 }
 
+int finalize_part2(chad_ctx* ctx);
+
 int drain(chad_ctx* ctx) {
     TRY(process_front(ctx));
     TRY(complete_pending_fold(ctx));
+    if (ctx->fin_state == chad_ctx::FIN_PART1) {  // let part 2 of an in-flight finalize overlap the tail of the compute stream
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->fin_p1_done));
+        TRY(finalize_part2(ctx));
+    }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     prof_resolve(ctx);
     ctx->table_count_known = *ctx->h_table_count;
@@ -352,14 +389,31 @@ int drain(chad_ctx* ctx) {
     return CHAD_OK;
 }
 
+int finalize_wait(chad_ctx* ctx);
+int finalize_poll(chad_ctx* ctx);
+// everything queued has been applied AND any asynchronous Submap::finalize has completed
+int settle(chad_ctx* ctx) {
+    TRY(drain(ctx));
+    return finalize_wait(ctx);
+}
+
 // ---- finalize -----------------------------------------------------------------------------
-enum { SC_COUNT = 0, SC_RMAX = 1, SC_NBITS = 2, SC_PARENTS = 3, SC_NEW32 = 4, SC_ERR = 5, SC_NEW64 = 6 /* u64 slot 6 = words 12,13 */ };
+// Submap::finalize runs asynchronously on its own stream, in two parts, so that neither the device nor the host
+// waits for it and the next submap's inserts overlap it:
+//   begin  (at the submap switch): the active chunk table is swapped with the spare one; fin_stream waits for the
+//          compute stream's last fold into the old table.
+//   part 1 (queued at begin): compact + sort + gather the old table, build and dedup the leaf clusters, count the
+//          nodes every level will receive, copy those 20 counts to pinned host memory.
+//   part 2 (queued by the next API call that finds part 1 complete -- every insert polls): with the exact counts the
+//          host sizes every level (no worst-case allocation) and queues the 20 node levels back to back; per-level
+//          results accumulate in device memory and come back in one copy; the old table is cleared.
+//   finish (next API call that finds part 2 complete, or any call that needs the DAG): host mirrors are updated.
+enum { SC_COUNT = 0, SC_RMAX = 1, SC_NBITS = 2, SC_PARENTS = 3, SC_NEW32 = 4, SC_ERR = 5, SC_LEVELS = 16 /* u32[20] */ };
 u32* scalar32(chad_ctx* ctx, int i) { return ctx->f_scalars.as<u32>() + i; }
-u64* scalar64(chad_ctx* ctx) { return ctx->f_scalars.as<u64>() + SC_NEW64; }
 
 int ensure_finalize_capacity(chad_ctx* ctx, size_t chunks) {
-    TRY(dev_ensure(ctx, ctx->f_scalars, 256));
     if (chunks <= ctx->cap_chunks && ctx->cap_chunks > 0) return CHAD_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fin_stream));
     const size_t nc = chunks + chunks / 8 + 1024;
     for (int i = 0; i < 2; i++) {
         TRY(dev_ensure(ctx, ctx->f_ids[i], nc * 8));
@@ -381,154 +435,230 @@ int ensure_finalize_capacity(chad_ctx* ctx, size_t chunks) {
     return CHAD_OK;
 }
 
+// only called while the finalize stream is idle or between its kernels from the host's point of view: growth
+// synchronises fin_stream, the only stream that touches the DAG levels
 int level_reserve(chad_ctx* ctx, Level& L, bool cluster, size_t new_records) {
+    cudaStream_t s = ctx->fin_stream;
     const size_t word = cluster ? 8 : 4;
     const size_t need_words = cluster ? (size_t(L.uniques) + new_records + 2) : (size_t(L.occupied) + 9 * new_records + 9);
     if (need_words >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "DAG level exceeds 2^31 words");
     if (need_words > L.raw_cap) {
         const size_t cap = next_pow2(need_words * 2);
-        TRY(dev_ensure(ctx, L.raw, cap * word, true));
+        void* np = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&np, cap * word));
+        if (L.raw.p) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(np, L.raw.p, L.raw.bytes, cudaMemcpyDeviceToDevice, s));
+            CUDA_TRY(ctx, cudaStreamSynchronize(s));
+            CUDA_TRY(ctx, cudaFree(L.raw.p));
+        }
+        L.raw.p = np;
+        L.raw.bytes = cap * word;
         L.raw_cap = cap;
     }
     const size_t need_slots = (size_t(L.uniques) + new_records) * 2;
     if (need_slots > L.table.capacity) {
         const u64 cap = next_pow2(need_slots * 2);
-        DevBuf ne, nf;
-        TRY(dev_ensure(ctx, ne, cap * 8));
-        TRY(dev_ensure(ctx, nf, cap * 4));
-        DedupTable nt{ne.as<u64>(), nf.as<u32>(), cap};
+        void *ne = nullptr, *nf = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&ne, cap * 8));
+        CUDA_TRY(ctx, cudaMalloc(&nf, cap * 4));
+        DedupTable nt{static_cast<u64*>(ne), static_cast<u32*>(nf), cap};
         if (L.table.capacity) {
-            ctx->stats.kernel_launches += launch_dedup_rehash(ctx->stream, L.table, nt, ctx->num_sms);
-            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->stats.kernel_launches += launch_dedup_rehash(s, L.table, nt, ctx->num_sms);
+            CUDA_TRY(ctx, cudaStreamSynchronize(s));
         } else {
-            launch_dedup_clear(ctx->stream, nt);
+            launch_dedup_clear(s, nt);
         }
         dev_free(L.entries); dev_free(L.first);
-        L.entries = ne; L.first = nf; L.table = nt;
+        L.entries.p = ne; L.entries.bytes = cap * 8;
+        L.first.p = nf; L.first.bytes = cap * 4;
+        L.table = nt;
     }
     return CHAD_OK;
 }
 
-// compact + sort + gather the resident chunks: f_ids[0] = full chunk keys ascending, f_cells = their cells
-int sorted_chunks(chad_ctx* ctx, u32* n_chunks) {
-    TRY(drain(ctx));
-    const size_t C = ctx->table_count_known;
-    *n_chunks = (u32)C;
-    TRY(ensure_finalize_capacity(ctx, C));
-    if (C == 0) return CHAD_OK;
-    cudaStream_t s = ctx->stream;
+// compact + sort + gather the chunks of table `t` on stream `s`: f_ids[0] = full chunk keys ascending, f_cells = their
+// cells; the exact count stays in device memory (SC_COUNT). max_chunks = host upper bound.
+int queue_sorted_chunks(chad_ctx* ctx, cudaStream_t s, const ChunkTable& t, u32 max_chunks) {
     u64 launches = 0;
-    launches += launch_table_compact(s, ctx->table, ctx->f_ids[0].as<u64>(), ctx->f_slots[0].as<u32>(), scalar32(ctx, SC_COUNT), scalar32(ctx, SC_RMAX),
+    launches += launch_table_compact(s, t, ctx->f_ids[0].as<u64>(), ctx->f_slots[0].as<u32>(), scalar32(ctx, SC_COUNT), scalar32(ctx, SC_RMAX),
                                      scalar32(ctx, SC_NBITS), ctx->num_sms);
     launches += radix_sort_pairs(s, ctx->f_ids[0].as<u64>(), ctx->f_slots[0].as<u32>(), ctx->f_ids[1].as<u64>(), ctx->f_slots[1].as<u32>(),
-                                 scalar32(ctx, SC_COUNT), scalar32(ctx, SC_NBITS), C, RS_MAX_PASSES, ctx->f_rws, ctx->num_sms);
-    u32 nbits = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars, scalar32(ctx, SC_NBITS), 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    nbits = (u32)ctx->h_scalars[0];
-    const u32* sorted_slots = radix_result_in_alt(nbits) ? ctx->f_slots[1].as<u32>() : ctx->f_slots[0].as<u32>();
-    launches += launch_chunk_gather(s, ctx->table, sorted_slots, (u32)C, ctx->f_ids[0].as<u64>(), ctx->f_cells.p);
+                                 scalar32(ctx, SC_COUNT), scalar32(ctx, SC_NBITS), max_chunks, RS_MAX_PASSES, ctx->f_rws, ctx->num_sms);
+    launches += launch_chunk_gather(s, t, ctx->f_slots[0].as<u32>(), ctx->f_slots[1].as<u32>(), scalar32(ctx, SC_COUNT), scalar32(ctx, SC_NBITS),
+                                    max_chunks, ctx->f_ids[0].as<u64>(), ctx->f_cells.p);
     ctx->stats.kernel_launches += launches;
     CUDA_TRY(ctx, cudaGetLastError());
     return CHAD_OK;
 }
 
-int finalize_submap_impl(chad_ctx* ctx) {
-    u32 C = 0;
-    TRY(sorted_chunks(ctx, &C));
-    cudaStream_t s = ctx->stream;
+int finalize_part2(chad_ctx* ctx);
+int finalize_finish(chad_ctx* ctx);
+
+// non-blocking progress of an in-flight finalize (called from every API entry)
+int finalize_poll(chad_ctx* ctx) {
+    if (ctx->fin_state == chad_ctx::FIN_PART1 && cudaEventQuery(ctx->fin_p1_done) == cudaSuccess) TRY(finalize_part2(ctx));
+    if (ctx->fin_state == chad_ctx::FIN_PART2 && cudaEventQuery(ctx->fin_done) == cudaSuccess) TRY(finalize_finish(ctx));
+    cudaGetLastError();  // cudaErrorNotReady is not an error
+    return CHAD_OK;
+}
+// blocking completion
+int finalize_wait(chad_ctx* ctx) {
+    if (ctx->fin_state == chad_ctx::FIN_PART1) {
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->fin_p1_done));
+        TRY(finalize_part2(ctx));
+    }
+    if (ctx->fin_state == chad_ctx::FIN_PART2) {
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->fin_done));
+        TRY(finalize_finish(ctx));
+    }
+    return CHAD_OK;
+}
+
+// Close the active submap: everything of it must already be queued on the compute stream (process_front +
+// complete_pending_fold). `max_chunks` = upper bound of its chunk count.
+int finalize_begin(chad_ctx* ctx, u32 max_chunks) {
+    TRY(finalize_wait(ctx));  // one finalize in flight at a time (they are ~2 ms apart at the very least)
+    cudaStream_t fs = ctx->fin_stream;
+    TRY(ensure_finalize_capacity(ctx, max_chunks));
+    Level& LC = ctx->levels[CHAD_LEVEL_CLUSTERS];
+    TRY(level_reserve(ctx, LC, true, size_t(max_chunks) + 1));
+    // swap tables: the spare one was cleared at the end of the previous finalize (complete: see finalize_wait above)
+    CUDA_TRY(ctx, cudaEventRecord(ctx->submap_closed, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(fs, ctx->submap_closed, 0));
+    std::swap(ctx->table, ctx->table2);
+    std::swap(ctx->t_keys, ctx->t2_keys);
+    std::swap(ctx->t_cells, ctx->t2_cells);
+    std::swap(ctx->t_count, ctx->t2_count);
+    std::swap(ctx->h_table_count, ctx->h_table_count2);  // no copy into the new active slot is in flight (its table was idle)
+    *ctx->h_table_count = 0;
+    ctx->table_count_known = 0;
+    ctx->fin_max_chunks = max_chunks;
+    if (ctx->profiling) cudaEventRecord(ctx->fin_t0, fs);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->f_scalars.p, 0, 256, fs));
+    if (max_chunks) {
+        u64 launches = 0;
+        TRY(queue_sorted_chunks(ctx, fs, ctx->table2, max_chunks));
+        launches += launch_cluster_build(fs, ctx->f_cells.p, scalar32(ctx, SC_COUNT), max_chunks, ctx->mp, ctx->f_tsdf.as<u64>());
+        launches += launch_cluster_dedup(fs, LC.table, ctx->f_tsdf.as<u64>(), scalar32(ctx, SC_COUNT), max_chunks, LC.raw.as<u64>(), LC.uniques,
+                                         ctx->f_slot_of.as<u32>(), ctx->f_is_new.as<u32>(), ctx->f_rank.as<u32>(), ctx->f_scan_ws.p,
+                                         ctx->f_addr[0].as<u32>(), scalar32(ctx, SC_NEW32), scalar32(ctx, SC_ERR));
+        launches += launch_level_counts(fs, ctx->f_ids[0].as<u64>(), scalar32(ctx, SC_COUNT), max_chunks, scalar32(ctx, SC_LEVELS), ctx->num_sms);
+        ctx->stats.kernel_launches += launches;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->scalars, ctx->f_scalars.p, 16 * 4 + 20 * 4, cudaMemcpyDeviceToHost, fs));
+    ctx->stats.d2h_bytes += 16 * 4 + 20 * 4;
+    if (ctx->profiling) cudaEventRecord(ctx->fin_t1, fs);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->fin_p1_done, fs));
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->fin_state = chad_ctx::FIN_PART1;
+    return CHAD_OK;
+}
+
+int finalize_part2(chad_ctx* ctx) {
+    cudaStream_t fs = ctx->fin_stream;
+    const u32* hs = ctx->h_fin->scalars;
+    if (hs[SC_ERR]) { ctx->fin_state = chad_ctx::FIN_IDLE; return error_from_flags(ctx, hs[SC_ERR]); }
+    const u32 C = hs[SC_COUNT];
+    ctx->fin_chunks = C;
+    Level& LC = ctx->levels[CHAD_LEVEL_CLUSTERS];
+    if (C) {
+        const u32 fresh = hs[SC_NEW32];
+        LC.uniques += fresh;
+        LC.dupes += 2 * C - fresh;  // levels.hpp:135-138
+    }
+    for (int d = 0; d < 20; d++) ctx->fin_level_nodes[d] = C ? ctx->h_fin->level_nodes[d] : 0;
+    if (ctx->profiling) cudaEventRecord(ctx->fin_t2, fs);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->f_level_new.p, 0, 20 * 8, fs));
     u64 launches = 0;
-    CUDA_TRY(ctx, cudaMemsetAsync(scalar32(ctx, SC_ERR), 0, 4, s));
     u64* ids = ctx->f_ids[0].as<u64>();
     u64* ids_next = ctx->f_ids[1].as<u64>();
     u32* addr = ctx->f_addr[0].as<u32>();
     u32* addr_next = ctx->f_addr[1].as<u32>();
     u32 n_children = C;
-    u32 parents = 0;
-    if (C) {
-        Level& L = ctx->levels[CHAD_LEVEL_CLUSTERS];
-        launches += launch_cluster_build(s, ctx->f_cells.p, C, ctx->mp, ctx->f_tsdf.as<u64>());
-        TRY(level_reserve(ctx, L, true, size_t(C) + 1));
-        launches += launch_cluster_dedup(s, L.table, ctx->f_tsdf.as<u64>(), C, L.raw.as<u64>(), L.uniques, ctx->f_slot_of.as<u32>(),
-                                         ctx->f_is_new.as<u32>(), ctx->f_rank.as<u32>(), ctx->f_scan_ws.p, addr, scalar32(ctx, SC_NEW32),
-                                         scalar32(ctx, SC_ERR));
-        launches += launch_group_heads(s, ids, n_children, ctx->f_head.as<u32>(), ctx->f_head_rank.as<u32>(), ctx->f_scan_ws.p, scalar32(ctx, SC_PARENTS));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->f_scalars.p, 64, cudaMemcpyDeviceToHost, s));
-        ctx->stats.d2h_bytes += 64;
-        CUDA_TRY(ctx, cudaStreamSynchronize(s));
-        const u32* hs = reinterpret_cast<const u32*>(ctx->h_scalars);
-        if (hs[SC_ERR]) return error_from_flags(ctx, hs[SC_ERR]);
-        const u32 fresh = hs[SC_NEW32];
-        L.uniques += fresh;
-        L.dupes += 2 * C - fresh;  // levels.hpp:135-138
-        parents = hs[SC_PARENTS];
-    }
     for (int d = 19; d >= 0; d--) {
         Level& L = ctx->levels[d];
         u32 n_records;
         if (C == 0) {
             if (d > 0) continue;  // empty octree: only the root is added, twice (submap.hpp:31-46)
-            CUDA_TRY(ctx, cudaMemsetAsync(ctx->f_cand.p, 0, 2 * 9 * 4, s));
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->f_cand.p, 0, 2 * 9 * 4, fs));
             n_records = 2;
-            parents = 1;
         } else {
-            launches += launch_node_candidates(s, ids, addr, ctx->f_head.as<u32>(), ctx->f_head_rank.as<u32>(), n_children, ctx->f_cand.as<u32>(), ids_next);
+            const u32 parents = ctx->fin_level_nodes[d];
+            launches += launch_group_heads(fs, ids, n_children, ctx->f_head.as<u32>(), ctx->f_head_rank.as<u32>(), ctx->f_scan_ws.p, scalar32(ctx, SC_PARENTS));
+            launches += launch_node_candidates(fs, ids, addr, ctx->f_head.as<u32>(), ctx->f_head_rank.as<u32>(), n_children, ctx->f_cand.as<u32>(), ids_next);
             n_records = 2 * parents;
+            n_children = parents;
         }
         TRY(level_reserve(ctx, L, false, n_records));
-        launches += launch_node_dedup(s, L.table, ctx->f_cand.as<u32>(), n_records, L.raw.as<u32>(), L.occupied, ctx->f_slot_of.as<u32>(),
-                                      ctx->f_is_new.as<u64>(), ctx->f_rank.as<u64>(), ctx->f_scan_ws.p, addr_next, scalar64(ctx), scalar32(ctx, SC_ERR));
+        // occupied_before must be exact: it is, because the previous finalize has finished (finalize_begin waits)
+        launches += launch_node_dedup(fs, L.table, ctx->f_cand.as<u32>(), n_records, L.raw.as<u32>(), L.occupied, ctx->f_slot_of.as<u32>(),
+                                      ctx->f_is_new.as<u64>(), ctx->f_rank.as<u64>(), ctx->f_scan_ws.p, addr_next, ctx->f_level_new.as<u64>() + d,
+                                      scalar32(ctx, SC_ERR));
         std::swap(ids, ids_next);
         std::swap(addr, addr_next);
-        n_children = parents;
-        if (d > 0 && C) launches += launch_group_heads(s, ids, n_children, ctx->f_head.as<u32>(), ctx->f_head_rank.as<u32>(), ctx->f_scan_ws.p, scalar32(ctx, SC_PARENTS));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->f_scalars.p, 64, cudaMemcpyDeviceToHost, s));
-        ctx->stats.d2h_bytes += 64;
-        CUDA_TRY(ctx, cudaStreamSynchronize(s));
-        const u32* hs = reinterpret_cast<const u32*>(ctx->h_scalars);
-        if (hs[SC_ERR]) return error_from_flags(ctx, hs[SC_ERR]);
-        const u64 packed = ctx->h_scalars[SC_NEW64];
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->level_new, ctx->f_level_new.p, 20 * 8, cudaMemcpyDeviceToHost, fs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->root, addr, 8, cudaMemcpyDeviceToHost, fs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->scalars, ctx->f_scalars.p, 16 * 4, cudaMemcpyDeviceToHost, fs));
+    ctx->stats.d2h_bytes += 20 * 8 + 8 + 64;
+    launch_table_clear(fs, ctx->table2);  // octree.clear(), tsdf.cpp:57
+    if (ctx->profiling) cudaEventRecord(ctx->fin_t3, fs);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->fin_done, fs));
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += launches;
+    ctx->fin_state = chad_ctx::FIN_PART2;
+    return CHAD_OK;
+}
+
+int finalize_finish(chad_ctx* ctx) {
+    ctx->fin_state = chad_ctx::FIN_IDLE;
+    if (ctx->h_fin->scalars[SC_ERR]) return error_from_flags(ctx, ctx->h_fin->scalars[SC_ERR]);
+    const u32 C = ctx->fin_chunks;
+    for (int d = 19; d >= 0; d--) {
+        if (C == 0 && d > 0) continue;
+        Level& L = ctx->levels[d];
+        const u32 n_records = C ? 2 * ctx->fin_level_nodes[d] : 2;
+        const u64 packed = ctx->h_fin->level_new[d];
         const u32 fresh = (u32)(packed >> 32), words = (u32)packed;
         L.uniques += fresh;
         L.dupes += n_records - fresh;   // levels.hpp:83-86
         L.occupied += words;            // levels.hpp:79-81
-        parents = hs[SC_PARENTS];
     }
-    u32 root[2] = {0, 0};
-    CUDA_TRY(ctx, cudaMemcpy(root, addr, 8, cudaMemcpyDeviceToHost));
-    ctx->roots.push_back({root[0], root[1]});
-    launch_table_clear(s, ctx->table);  // octree.clear(), tsdf.cpp:57
-    CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    *ctx->h_table_count = 0;
-    ctx->table_count_known = 0;
-    ctx->stats.kernel_launches += launches;
+    ctx->roots.push_back({ctx->h_fin->root[0], ctx->h_fin->root[1]});
     ctx->stats.submaps++;
-    ctx->stats.resident_clusters = 0;
-    CUDA_TRY(ctx, cudaGetLastError());
+    if (ctx->profiling) {
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, ctx->fin_t0, ctx->fin_t1) == cudaSuccess && cudaEventElapsedTime(&b, ctx->fin_t2, ctx->fin_t3) == cudaSuccess) {
+            ctx->prof_ms[PC_FINALIZE] += a + b;
+            ctx->prof_launches[PC_FINALIZE]++;
+        } else cudaGetLastError();
+    }
     return CHAD_OK;
 }
 
-int finalize_submap(chad_ctx* ctx) {
-    TRY(drain(ctx));
-    if (!ctx->profiling) return finalize_submap_impl(ctx);
-    // dedicated events: the nested drain() resolves (and recycles) the generic span list
-    cudaEvent_t a, b;
-    CUDA_TRY(ctx, cudaEventCreate(&a));
-    CUDA_TRY(ctx, cudaEventCreate(&b));
-    cudaEventRecord(a, ctx->stream);
-    const int r = finalize_submap_impl(ctx);
-    cudaEventRecord(b, ctx->stream);
-    cudaEventSynchronize(b);
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) { ctx->prof_ms[PC_FINALIZE] += ms; ctx->prof_launches[PC_FINALIZE]++; }
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
-    return r;
+// Close the active submap. lazy = true (submap switch inside insert): if a batch of the submap is still in flight, only
+// mark it; its fold and the finalize are queued by the next process_front / drain, so the host never waits for the
+// device here. lazy = false (chad_finalize_active): queue everything now.
+int finalize_submap(chad_ctx* ctx, bool lazy) {
+    TRY(process_front(ctx));
+    if (ctx->fold_pending) {
+        ctx->close_pending = true;
+        if (lazy) return CHAD_OK;
+        return complete_pending_fold(ctx);  // waits for the front of the last batch, queues its fold, begins the finalize
+    }
+    // no batch in flight: the exact count of the last fold may not have been read yet
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->table_count_known = *ctx->h_table_count;
+    if (ctx->table_count_known >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
+    TRY(finalize_begin(ctx, (u32)ctx->table_count_known));
+    ctx->stats.resident_clusters = 0;
+    return CHAD_OK;
 }
 
 int begin_scan(chad_ctx* ctx, size_t n, const float position[3], bool* skip) {
     *skip = false;
     if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
+    TRY(finalize_poll(ctx));
     // tsdf.cpp:46-61: a pose more than 5 m (strictly) from the submap's FIRST pose finalises the submap;
     // the triggering scan goes entirely into the new one
     if (!ctx->has_pose) {
@@ -540,7 +670,7 @@ int begin_scan(chad_ctx* ctx, size_t n, const float position[3], bool* skip) {
         volatile float sum = tx + ty;  // glm::distance = sqrt((x*x + y*y) + z*z), no contraction
         sum = sum + tz;
         if (std::sqrt((float)sum) > 5.0f) {
-            TRY(finalize_submap(ctx));
+            TRY(finalize_submap(ctx, true));
             std::memcpy(ctx->first_pose, position, 12);
         }
     }
@@ -605,6 +735,13 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     ctx->num_sms = prop.multiProcessorCount;
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->fin_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreateWithFlags(&ctx->submap_closed, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&ctx->fin_p1_done, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&ctx->fin_done, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&ctx->fin_t0, &ctx->fin_t1, &ctx->fin_t2, &ctx->fin_t3}) CREATE_TRY(cudaEventCreate(e));
+    CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_fin), sizeof(chad_ctx::FinHost)));
+    std::memset(ctx->h_fin, 0, sizeof(chad_ctx::FinHost));
     for (int b = 0; b < 2; b++) {
         CREATE_TRY(cudaEventCreateWithFlags(&ctx->stage_copied[b], cudaEventDisableTiming));
         CREATE_TRY(cudaEventCreateWithFlags(&ctx->copy_done[b], cudaEventDisableTiming));
@@ -615,6 +752,8 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     CREATE_TRY(cudaEventCreate(&ctx->t1));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_plan), sizeof(BatchPlan)));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_table_count), 64));
+    CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_table_count2), 64));
+    *ctx->h_table_count2 = 0;
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_scalars), 64));
     *ctx->h_table_count = 0;
     CREATE_TRY(radix_sort_init());
@@ -632,9 +771,11 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     int r = dev_ensure(ctx, ctx->d_scans, sizeof(BatchScans));
     if (r == CHAD_OK) r = dev_ensure(ctx, ctx->d_plan, sizeof(BatchPlan));
     if (r == CHAD_OK) r = dev_ensure(ctx, ctx->f_scalars, 256);
+    if (r == CHAD_OK) r = dev_ensure(ctx, ctx->f_level_new, 256);
     if (r != CHAD_OK) return bail(r);
     CREATE_TRY(cudaMemsetAsync(ctx->d_plan.p, 0, sizeof(BatchPlan), ctx->stream));
     r = table_alloc(ctx, ctx->table, ctx->t_keys, ctx->t_cells, ctx->t_count, 1ull << 20);
+    if (r == CHAD_OK) r = table_alloc(ctx, ctx->table2, ctx->t2_keys, ctx->t2_cells, ctx->t2_count, 1ull << 20);
     if (r != CHAD_OK) return bail(r);
     // NodeLevel / LeafClusterLevel constructors reserve index 0 (levels.hpp:52-54,119-120)
     for (int d = 0; d < CHAD_NUM_LEVELS; d++) {
@@ -646,6 +787,7 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
         CREATE_TRY(cudaMemsetAsync(L.raw.p, 0, 64, ctx->stream));
     }
     CREATE_TRY(cudaStreamSynchronize(ctx->stream));
+    CREATE_TRY(cudaStreamSynchronize(ctx->fin_stream));
 #undef CREATE_TRY
     *out = ctx;
     return CHAD_OK;
@@ -656,7 +798,8 @@ void chad_destroy(chad_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-    DevBuf* bufs[] = {&ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
+    if (ctx->fin_stream) cudaStreamSynchronize(ctx->fin_stream);
+    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->f_level_new, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
                       &ctx->sorted_keys, &ctx->sorted_order, &ctx->xyz_sorted, &ctx->normals, &ctx->seg_info, &ctx->counts, &ctx->offsets,
                       &ctx->radix_ws, &ctx->scan_ws, &ctx->t_keys, &ctx->t_cells, &ctx->t_count, &ctx->f_ids[0], &ctx->f_ids[1], &ctx->f_slots[0],
                       &ctx->f_slots[1], &ctx->f_cells, &ctx->f_tsdf, &ctx->f_addr[0], &ctx->f_addr[1], &ctx->f_head, &ctx->f_head_rank, &ctx->f_cand,
@@ -673,6 +816,10 @@ void chad_destroy(chad_ctx* ctx) {
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->h_plan) cudaFreeHost(ctx->h_plan);
     if (ctx->h_table_count) cudaFreeHost(ctx->h_table_count);
+    if (ctx->h_table_count2) cudaFreeHost(ctx->h_table_count2);
+    if (ctx->h_fin) cudaFreeHost(ctx->h_fin);
+    for (cudaEvent_t e : {ctx->submap_closed, ctx->fin_p1_done, ctx->fin_done, ctx->fin_t0, ctx->fin_t1, ctx->fin_t2, ctx->fin_t3}) if (e) cudaEventDestroy(e);
+    if (ctx->fin_stream) cudaStreamDestroy(ctx->fin_stream);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->front_done) cudaEventDestroy(ctx->front_done);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
@@ -725,27 +872,31 @@ int chad_flush(chad_ctx* ctx) {
     if (!ctx) return CHAD_ERR_INVALID;
     if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    return drain(ctx);
+    return settle(ctx);
 }
 
 int chad_finalize_active(chad_ctx* ctx) {
     if (!ctx) return CHAD_ERR_INVALID;
     if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (!ctx->has_pose) return drain(ctx);
-    TRY(finalize_submap(ctx));
+    if (!ctx->has_pose) return settle(ctx);
+    TRY(finalize_submap(ctx, false));
     ctx->has_pose = false;
     return CHAD_OK;
 }
 
 int chad_submap_count(chad_ctx* ctx, uint32_t* count) {
     if (!ctx || !count) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(settle(ctx));
     *count = (uint32_t)ctx->roots.size();
     return CHAD_OK;
 }
 
 int chad_submap_roots(chad_ctx* ctx, uint32_t i, uint32_t* root_tsdf, uint32_t* root_weight) {
     if (!ctx || !root_tsdf || !root_weight) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(settle(ctx));
     if (i >= ctx->roots.size()) return fail(ctx, CHAD_ERR_INVALID, "submap index out of range");
     *root_tsdf = ctx->roots[i][0];
     *root_weight = ctx->roots[i][1];
@@ -754,8 +905,10 @@ int chad_submap_roots(chad_ctx* ctx, uint32_t i, uint32_t* root_tsdf, uint32_t* 
 
 // voxel export: sorted chunks are copied to the host and expanded there (parity / debugging path)
 static int export_voxels_impl(chad_ctx* ctx, uint64_t* keys, uint32_t* sd_bits, uint32_t* weights, size_t capacity, size_t* count) {
-    u32 C = 0;
-    TRY(sorted_chunks(ctx, &C));
+    TRY(settle(ctx));
+    const u32 C = (u32)ctx->table_count_known;
+    TRY(ensure_finalize_capacity(ctx, C));
+    if (C) TRY(queue_sorted_chunks(ctx, ctx->stream, ctx->table, C));
     std::vector<u64> ck(C);
     std::vector<uint2> cells(size_t(C) * 8);
     if (C) {
@@ -794,6 +947,8 @@ int chad_export_voxels(chad_ctx* ctx, uint64_t* keys, uint32_t* sd_bits, uint32_
 
 int chad_level_words(chad_ctx* ctx, int level, size_t* words) {
     if (!ctx || !words || level < 0 || level >= CHAD_NUM_LEVELS) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(settle(ctx));
     const Level& L = ctx->levels[level];
     *words = (level == CHAD_LEVEL_CLUSTERS) ? size_t(L.uniques) + 1 : size_t(L.occupied);
     return CHAD_OK;
@@ -801,6 +956,8 @@ int chad_level_words(chad_ctx* ctx, int level, size_t* words) {
 
 int chad_level_counters(chad_ctx* ctx, int level, uint32_t* uniques, uint32_t* dupes) {
     if (!ctx || !uniques || !dupes || level < 0 || level >= CHAD_NUM_LEVELS) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(settle(ctx));
     *uniques = ctx->levels[level].uniques;
     *dupes = ctx->levels[level].dupes;
     return CHAD_OK;
@@ -812,7 +969,7 @@ int chad_export_level(chad_ctx* ctx, int level, void* dst, size_t capacity_words
     size_t words;
     chad_level_words(ctx, level, &words);
     if (capacity_words < words) return fail(ctx, CHAD_ERR_INVALID, "export capacity too small");
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fin_stream));
     CUDA_TRY(ctx, cudaMemcpy(dst, ctx->levels[level].raw.p, words * (level == CHAD_LEVEL_CLUSTERS ? 8 : 4), cudaMemcpyDeviceToHost));
     return CHAD_OK;
 }
@@ -824,10 +981,15 @@ int chad_reset(chad_ctx* ctx) {
     ctx->batch_points = 0;
     ctx->batch_scans = 0;
     ctx->fold_pending = false;
+    ctx->close_pending = false;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fin_stream));
+    ctx->fin_state = chad_ctx::FIN_IDLE;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_plan.p, 0, sizeof(BatchPlan), ctx->stream));
     launch_table_clear(ctx->stream, ctx->table);
+    launch_table_clear(ctx->stream, ctx->table2);
+    *ctx->h_table_count2 = 0;
     for (int d = 0; d < CHAD_NUM_LEVELS; d++) {
         Level& L = ctx->levels[d];
         L.uniques = 0; L.dupes = 0; L.occupied = (d == CHAD_LEVEL_CLUSTERS) ? 0 : 1;
@@ -845,7 +1007,7 @@ int chad_reset(chad_ctx* ctx) {
 int chad_profile_enable(chad_ctx* ctx, int on) {
     if (!ctx) return CHAD_ERR_INVALID;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    TRY(drain(ctx));
+    TRY(settle(ctx));
     ctx->profiling = on != 0;
     for (int c = 0; c < PC_COUNT; c++) { ctx->prof_ms[c] = 0.0; ctx->prof_launches[c] = 0; }
     return CHAD_OK;
@@ -870,7 +1032,7 @@ int chad_profile_get(chad_ctx* ctx, int cls, const char** name, double* millisec
     else if (cls >= PC_PAIR_SORT_PASS0 && cls < PC_SEGMENT_COUNT) { std::snprintf(names[cls], 48, "radix_onesweep_kernel[pairs,pass%d]", cls - PC_PAIR_SORT_PASS0); nm = names[cls]; }
     else if (cls == PC_SEGMENT_COUNT) nm = "segment_count_kernel";
     else if (cls == PC_FOLD) nm = "fold_kernel";
-    else nm = "finalize_submap[all kernels + host syncs]";
+    else nm = "finalize_submap[part 1 + part 2 on the finalize stream, overlapped with inserts]";
     if (name) *name = nm;
     if (milliseconds) *milliseconds = ctx->prof_ms[cls];
     if (launches) *launches = ctx->prof_launches[cls];
@@ -893,7 +1055,7 @@ int chad_reset_stats(chad_ctx* ctx) {
 
 // ---- stage entry points ---------------------------------------------------------------------
 static int stage_prepare(chad_ctx* ctx, size_t n) {
-    TRY(drain(ctx));
+    TRY(settle(ctx));
     if (n > ctx->cap_points || ctx->cap_points == 0) TRY(ensure_batch_capacity(ctx, n ? n : 1));
     return CHAD_OK;
 }

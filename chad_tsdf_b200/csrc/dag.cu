@@ -51,10 +51,10 @@ inline unsigned blocks_for(u32 n) { return (n + DAG_THREADS - 1) / DAG_THREADS; 
 // ------------------------------------------------------------------------------------------
 // leaf clusters: cluster.hpp:13-32 (TSDFs::set / set_empty), submap.hpp:83-100
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DAG_THREADS) cluster_build_kernel(const uint2* __restrict__ cells, u32 n_chunks, float trunc_recip,
+__global__ void __launch_bounds__(DAG_THREADS) cluster_build_kernel(const uint2* __restrict__ cells, const u32* __restrict__ d_chunks, float trunc_recip,
                                                                     u64* __restrict__ tsdf_values) {
     const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
-    if (i >= n_chunks) return;
+    if (i >= *d_chunks) return;
     u64 v = 0;
 #pragma unroll
     for (int s = 0; s < 8; s++) {
@@ -77,11 +77,13 @@ __global__ void __launch_bounds__(DAG_THREADS) cluster_build_kernel(const uint2*
 __device__ __forceinline__ u32 cluster_seq_of(u32 p) { return p < 2 ? p : 2 * (p - 1); }
 __device__ __forceinline__ u64 cluster_value(const u64* __restrict__ tsdf_values, u32 e) { return (e & 1u) ? WEIGHT_CLUSTER : tsdf_values[e >> 1]; }
 
+__device__ __forceinline__ u32 cluster_work(const u32* __restrict__ d_chunks) { const u32 c = *d_chunks; return c ? c + 1 : 0; }
+
 __global__ void __launch_bounds__(DAG_THREADS) cluster_probe_kernel(u64* entries, u32* first, u64 capacity, const u64* __restrict__ tsdf_values,
-                                                                    u32 n_work, const u64* __restrict__ raw, u32* __restrict__ slot_of,
-                                                                    u32* d_error) {
+                                                                    const u32* __restrict__ d_chunks, const u64* __restrict__ raw,
+                                                                    u32* __restrict__ slot_of, u32* d_error) {
     const u32 p = blockIdx.x * DAG_THREADS + threadIdx.x;
-    if (p >= n_work) return;
+    if (p >= cluster_work(d_chunks)) return;
     const u32 e = cluster_seq_of(p);
     const u64 value = cluster_value(tsdf_values, e);
     const u32 tag = (u32)(mix64(value) >> 32);
@@ -109,21 +111,24 @@ __global__ void __launch_bounds__(DAG_THREADS) cluster_probe_kernel(u64* entries
     slot_of[p] = 0;
 }
 
+// is_new is written for all max_work positions (zero beyond the actual count): the prefix sum runs over max_work
 __global__ void __launch_bounds__(DAG_THREADS) cluster_mark_kernel(const u64* __restrict__ entries, const u32* __restrict__ first,
-                                                                   const u32* __restrict__ slot_of, u32 n_work, u32* __restrict__ is_new) {
+                                                                   const u32* __restrict__ slot_of, const u32* __restrict__ d_chunks, u32 max_work,
+                                                                   u32* __restrict__ is_new) {
     const u32 p = blockIdx.x * DAG_THREADS + threadIdx.x;
-    if (p >= n_work) return;
+    if (p >= max_work) return;
+    if (p >= cluster_work(d_chunks)) { is_new[p] = 0; return; }
     const u32 slot = slot_of[p];
     const u32 ref = (u32)entries[slot];
     is_new[p] = ((ref & REF_PENDING) && first[slot] == cluster_seq_of(p)) ? 1u : 0u;
 }
 
 __global__ void __launch_bounds__(DAG_THREADS) cluster_commit_kernel(u64* entries, u32* first, const u32* __restrict__ slot_of,
-                                                                     const u32* __restrict__ is_new, const u32* __restrict__ rank, u32 n_work,
-                                                                     const u64* __restrict__ tsdf_values, u64* __restrict__ raw,
-                                                                     u32 uniques_before) {
+                                                                     const u32* __restrict__ is_new, const u32* __restrict__ rank,
+                                                                     const u32* __restrict__ d_chunks, const u64* __restrict__ tsdf_values,
+                                                                     u64* __restrict__ raw, u32 uniques_before) {
     const u32 p = blockIdx.x * DAG_THREADS + threadIdx.x;
-    if (p >= n_work || !is_new[p]) return;
+    if (p >= cluster_work(d_chunks) || !is_new[p]) return;
     const u32 slot = slot_of[p];
     const u32 addr = uniques_before + 1 + rank[p];  // levels.hpp:125
     raw[addr] = cluster_value(tsdf_values, cluster_seq_of(p));
@@ -132,10 +137,10 @@ __global__ void __launch_bounds__(DAG_THREADS) cluster_commit_kernel(u64* entrie
 }
 
 // addr_out[2i] = tsdf address, addr_out[2i+1] = weight address of chunk i
-__global__ void __launch_bounds__(DAG_THREADS) cluster_resolve_kernel(const u64* __restrict__ entries, const u32* __restrict__ slot_of, u32 n_chunks,
-                                                                      u32* __restrict__ addr_out) {
+__global__ void __launch_bounds__(DAG_THREADS) cluster_resolve_kernel(const u64* __restrict__ entries, const u32* __restrict__ slot_of,
+                                                                      const u32* __restrict__ d_chunks, u32* __restrict__ addr_out) {
     const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
-    if (i >= n_chunks) return;
+    if (i >= *d_chunks) return;
     const u32 p = (i == 0) ? 0 : i + 1;
     addr_out[2 * i] = (u32)entries[slot_of[p]];
     addr_out[2 * i + 1] = (u32)entries[slot_of[1]];
@@ -144,6 +149,34 @@ __global__ void __launch_bounds__(DAG_THREADS) cluster_resolve_kernel(const u64*
 // ------------------------------------------------------------------------------------------
 // node levels: submap.hpp:31-61, levels.hpp:57-88
 // ------------------------------------------------------------------------------------------
+// Number of nodes every level will receive, from the sorted chunk ids alone: chunk i starts a new level-d node iff
+// (id >> 3(20-d)) differs from its predecessor's, i.e. iff the highest differing bit of the two ids is >= 3(20-d).
+// counts[d] = nodes at level d (d = 0..19), so the host can size every level exactly with ONE read-back.
+__global__ void __launch_bounds__(DAG_THREADS) level_counts_kernel(const u64* __restrict__ chunk_ids, const u32* __restrict__ d_chunks,
+                                                                   u32* __restrict__ counts /*[20]*/) {
+    __shared__ u32 s_cnt[20];
+    if (threadIdx.x < 20) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 n = *d_chunks;
+    for (u32 i = blockIdx.x * DAG_THREADS + threadIdx.x; i < n; i += gridDim.x * DAG_THREADS) {
+        u32 levels;  // number of levels (counted from level 19 upwards) at which chunk i opens a new node
+        if (i == 0) levels = 20;
+        else {
+            const u64 x = chunk_ids[i] ^ chunk_ids[i - 1];
+            const u32 hb = 63 - __clzll(x);      // highest differing bit (ids are distinct)
+            levels = min(20u, hb / 3);           // opens level d iff hb >= 3(20-d)  <=>  20-d <= hb/3
+        }
+        // warp-aggregate: lanes opening at least j levels
+        for (u32 j = 1; j <= 20; j++) {
+            const u32 m = __ballot_sync(__activemask(), levels >= j);
+            if (m == 0) break;
+            if ((threadIdx.x & 31) == (u32)(__ffs(m) - 1)) atomicAdd(&s_cnt[20 - j], (u32)__popc(m));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 20 && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
 __global__ void __launch_bounds__(DAG_THREADS) group_heads_kernel(const u64* __restrict__ child_ids, u32 n, u32* __restrict__ head) {
     const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
     if (i >= n) return;
@@ -282,22 +315,30 @@ int launch_dedup_rehash(cudaStream_t s, const DedupTable& from, const DedupTable
     return 1;
 }
 
-int launch_cluster_build(cudaStream_t s, const void* gathered_cells, u32 n_chunks, const MapParams& mp, u64* tsdf_values) {
-    if (!n_chunks) return 0;
-    cluster_build_kernel<<<blocks_for(n_chunks), DAG_THREADS, 0, s>>>(static_cast<const uint2*>(gathered_cells), n_chunks, mp.trunc_recip, tsdf_values);
+int launch_cluster_build(cudaStream_t s, const void* gathered_cells, const u32* d_chunks, u32 max_chunks, const MapParams& mp, u64* tsdf_values) {
+    if (!max_chunks) return 0;
+    cluster_build_kernel<<<blocks_for(max_chunks), DAG_THREADS, 0, s>>>(static_cast<const uint2*>(gathered_cells), d_chunks, mp.trunc_recip, tsdf_values);
     return 1;
 }
 
-int launch_cluster_dedup(cudaStream_t s, const DedupTable& t, const u64* tsdf_values, u32 n_chunks, u64* raw, u32 uniques_before, u32* slot_of,
-                         u32* is_new, u32* rank, void* scan_ws, u32* addr_out, u32* d_new_count, u32* d_error) {
-    if (!n_chunks) { cudaMemsetAsync(d_new_count, 0, 4, s); return 0; }
-    const u32 n_work = n_chunks + 1;
-    cluster_probe_kernel<<<blocks_for(n_work), DAG_THREADS, 0, s>>>(t.entries, t.first, t.capacity, tsdf_values, n_work, raw, slot_of, d_error);
-    cluster_mark_kernel<<<blocks_for(n_work), DAG_THREADS, 0, s>>>(t.entries, t.first, slot_of, n_work, is_new);
-    int launches = 2 + exclusive_scan<u32, u32>(s, is_new, rank, n_work, scan_ws, d_new_count);
-    cluster_commit_kernel<<<blocks_for(n_work), DAG_THREADS, 0, s>>>(t.entries, t.first, slot_of, is_new, rank, n_work, tsdf_values, raw, uniques_before);
-    cluster_resolve_kernel<<<blocks_for(n_chunks), DAG_THREADS, 0, s>>>(t.entries, slot_of, n_chunks, addr_out);
+int launch_cluster_dedup(cudaStream_t s, const DedupTable& t, const u64* tsdf_values, const u32* d_chunks, u32 max_chunks, u64* raw, u32 uniques_before,
+                         u32* slot_of, u32* is_new, u32* rank, void* scan_ws, u32* addr_out, u32* d_new_count, u32* d_error) {
+    if (!max_chunks) { cudaMemsetAsync(d_new_count, 0, 4, s); return 0; }
+    const u32 max_work = max_chunks + 1;
+    cluster_probe_kernel<<<blocks_for(max_work), DAG_THREADS, 0, s>>>(t.entries, t.first, t.capacity, tsdf_values, d_chunks, raw, slot_of, d_error);
+    cluster_mark_kernel<<<blocks_for(max_work), DAG_THREADS, 0, s>>>(t.entries, t.first, slot_of, d_chunks, max_work, is_new);
+    int launches = 2 + exclusive_scan<u32, u32>(s, is_new, rank, max_work, scan_ws, d_new_count);
+    cluster_commit_kernel<<<blocks_for(max_work), DAG_THREADS, 0, s>>>(t.entries, t.first, slot_of, is_new, rank, d_chunks, tsdf_values, raw, uniques_before);
+    cluster_resolve_kernel<<<blocks_for(max_chunks), DAG_THREADS, 0, s>>>(t.entries, slot_of, d_chunks, addr_out);
     return launches + 2;
+}
+
+int launch_level_counts(cudaStream_t s, const u64* chunk_ids, const u32* d_chunks, u32 max_chunks, u32* counts20, int num_sms) {
+    cudaMemsetAsync(counts20, 0, 20 * 4, s);
+    if (!max_chunks) return 0;
+    const u32 want = blocks_for(max_chunks), cap = (u32)num_sms * 4;
+    level_counts_kernel<<<want < cap ? want : cap, DAG_THREADS, 0, s>>>(chunk_ids, d_chunks, counts20);
+    return 1;
 }
 
 int launch_group_heads(cudaStream_t s, const u64* child_ids, u32 n_children, u32* head, u32* head_rank, void* scan_ws, u32* d_parents) {

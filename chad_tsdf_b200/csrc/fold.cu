@@ -46,35 +46,79 @@ __device__ __forceinline__ u64 table_upsert(u64* __restrict__ keys, u64 capacity
     return ~0ull;
 }
 
+// Work distribution: every warp takes chunks of FOLD_CHUNK consecutive sorted updates, stages them in shared memory
+// (coalesced), lists the segment heads of the chunk, and hands the heads out round-robin to its lanes -- ONE LANE PER
+// SEGMENT, so all 32 lanes run the dependent (mul, add, div) chain of their own voxel instead of idling next to a
+// head lane (ncu r01: 650 M warp instructions with one lane per update). A segment that runs past the chunk end is
+// finished from global memory by the lane that owns its head.
+constexpr int FOLD_CHUNK = 256;            // updates per warp iteration
+constexpr int FOLD_WARPS = FOLD_THREADS / 32;
+
 __global__ void __launch_bounds__(FOLD_THREADS) fold_kernel(const u64* __restrict__ keys_a, const u64* __restrict__ keys_b,
                                                             const u32* __restrict__ sd_a, const u32* __restrict__ sd_b, BatchPlan* plan,
                                                             u64* __restrict__ tkeys, uint2* __restrict__ tcells, u64 capacity, u32* tcount) {
+    __shared__ u64 s_keys[FOLD_WARPS][FOLD_CHUNK];
+    __shared__ u32 s_sd[FOLD_WARPS][FOLD_CHUNK];
+    __shared__ unsigned short s_heads[FOLD_WARPS][FOLD_CHUNK];
     const u32 n = plan->n_pairs;
     const u32 k = plan->k;
     const bool alt = radix_result_in_alt(plan->nbits_pairs);
     const u64* __restrict__ keys = alt ? keys_b : keys_a;
     const u32* __restrict__ sds = alt ? sd_b : sd_a;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lanemask_lt = (1u << lane) - 1u;
+    const u32 num_chunks = (n + FOLD_CHUNK - 1) / FOLD_CHUNK;
     u32 new_chunks = 0, err = 0;
-    for (u32 i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < n; i += gridDim.x * FOLD_THREADS) {
-        const u64 ckey = keys[i];
-        if (i > 0 && keys[i - 1] == ckey) continue;  // not a segment head
-        const u64 full = expand_key(ckey, k);
-        bool inserted;
-        const u64 slot = table_upsert(tkeys, capacity, full >> 3, inserted);
-        if (slot == ~0ull) { err |= ERRF_TABLE_FULL; continue; }
-        new_chunks += inserted ? 1u : 0u;
-        uint2* cell = &tcells[slot * 8 + (full & 7ull)];
-        uint2 c = *cell;  // (sd bits, weight); zero for a voxel touched for the first time (octree.hpp:68-75)
-        float acc = __uint_as_float(c.x);
-        u32 w = c.y;
-        u32 j = i;
-        do {
-            acc = fadd(fmul(acc, __uint2float_rn(w)), __uint_as_float(sds[j]));  // octree.hpp:161
-            w++;                                                                 // octree.hpp:162
-            acc = fdiv(acc, __uint2float_rn(w));                                 // octree.hpp:163
-            j++;
-        } while (j < n && keys[j] == ckey);
-        *cell = make_uint2(__float_as_uint(acc), w);
+    for (u32 chunk = blockIdx.x * FOLD_WARPS + warp; chunk < num_chunks; chunk += gridDim.x * FOLD_WARPS) {
+        const u32 base = chunk * FOLD_CHUNK;
+        const u32 cn = min((u32)FOLD_CHUNK, n - base);
+        // ---- stage the chunk and list its segment heads ----
+        u64 prev_last = (base > 0) ? keys[base - 1] : 0ull;  // key just before the chunk (only used when base > 0)
+        u32 n_heads = 0;
+#pragma unroll
+        for (int r = 0; r < FOLD_CHUNK / 32; r++) {
+            const u32 e = r * 32 + lane;
+            const bool valid = e < cn;
+            const u64 key = valid ? keys[base + e] : 0ull;
+            if (valid) { s_keys[warp][e] = key; s_sd[warp][e] = sds[base + e]; }
+            u64 before = __shfl_up_sync(0xffffffffu, key, 1);
+            if (lane == 0) before = prev_last;
+            const bool head = valid && ((base + e == 0) || before != key);
+            const u32 m = __ballot_sync(0xffffffffu, head);
+            if (head) s_heads[warp][n_heads + __popc(m & lanemask_lt)] = (unsigned short)e;
+            n_heads += __popc(m);
+            prev_last = __shfl_sync(0xffffffffu, key, 31);
+        }
+        __syncwarp();
+        // ---- one lane per segment ----
+        for (u32 h = lane; h < n_heads; h += 32) {
+            const u32 e0 = s_heads[warp][h];
+            const u32 e1 = (h + 1 < n_heads) ? (u32)s_heads[warp][h + 1] : cn;  // end inside the chunk
+            const u64 ckey = s_keys[warp][e0];
+            const u64 full = expand_key(ckey, k);
+            bool inserted;
+            const u64 slot = table_upsert(tkeys, capacity, full >> 3, inserted);
+            if (slot == ~0ull) { err |= ERRF_TABLE_FULL; continue; }
+            new_chunks += inserted ? 1u : 0u;
+            uint2* cell = &tcells[slot * 8 + (full & 7ull)];
+            uint2 c = *cell;  // (sd bits, weight); zero for a voxel touched for the first time (octree.hpp:68-75)
+            float acc = __uint_as_float(c.x);
+            u32 w = c.y;
+            for (u32 e = e0; e < e1; e++) {
+                acc = fadd(fmul(acc, __uint2float_rn(w)), __uint_as_float(s_sd[warp][e]));  // octree.hpp:161
+                w++;                                                                          // octree.hpp:162
+                acc = fdiv(acc, __uint2float_rn(w));                                          // octree.hpp:163
+            }
+            if (h + 1 == n_heads) {  // the chunk's last segment may continue in the following chunks
+                for (u32 j = base + cn; j < n && keys[j] == ckey; j++) {
+                    acc = fadd(fmul(acc, __uint2float_rn(w)), __uint_as_float(sds[j]));
+                    w++;
+                    acc = fdiv(acc, __uint2float_rn(w));
+                }
+            }
+            *cell = make_uint2(__float_as_uint(acc), w);
+        }
+        __syncwarp();
     }
     // block-level reduction of the counters: one atomic per block
     __shared__ u32 s_red[2];
@@ -175,13 +219,15 @@ __global__ void __launch_bounds__(FOLD_THREADS) chunk_sortkeys_kernel(u64* __res
     for (u32 i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < n; i += gridDim.x * FOLD_THREADS) keys[i] = compact_key(keys[i] << 3, k) >> 3;
 }
 
-// sorted slots -> contiguous (full chunk key, 8 cells) for export / cluster building
+// sorted slots -> contiguous (full chunk key, 8 cells) for export / cluster building. The count and the buffer the
+// radix sort left its result in are read from device memory, so the host needs only an upper bound of the count.
 __global__ void __launch_bounds__(FOLD_THREADS) chunk_gather_kernel(const u64* __restrict__ tkeys, const uint4* __restrict__ tcells,
-                                                                    const u32* __restrict__ sorted_slots, u32 n, u64* __restrict__ out_keys,
-                                                                    uint4* __restrict__ out_cells) {
+                                                                    const u32* __restrict__ slots_a, const u32* __restrict__ slots_b,
+                                                                    const u32* __restrict__ d_count, const u32* __restrict__ d_nbits,
+                                                                    u64* __restrict__ out_keys, uint4* __restrict__ out_cells) {
     const u32 i = blockIdx.x * FOLD_THREADS + threadIdx.x;
-    if (i >= n) return;
-    const u32 s = sorted_slots[i];
+    if (i >= *d_count) return;
+    const u32 s = radix_result_in_alt(*d_nbits) ? slots_b[i] : slots_a[i];
     out_keys[i] = tkeys[s];
 #pragma unroll
     for (int q = 0; q < 4; q++) out_cells[size_t(i) * 4 + q] = tcells[size_t(s) * 4 + q];
@@ -199,8 +245,8 @@ int launch_table_clear(cudaStream_t s, const ChunkTable& t) {
 int launch_fold(cudaStream_t s, const u64* keys_a, const u64* keys_b, const u32* sd_a, const u32* sd_b, u32 max_pairs, BatchPlan* plan,
                 const ChunkTable& t, int num_sms) {
     if (!max_pairs) return 0;
-    u32 want = (max_pairs + FOLD_THREADS - 1) / FOLD_THREADS;
-    u32 cap = (u32)num_sms * 16;
+    u32 want = (max_pairs + FOLD_CHUNK * FOLD_WARPS - 1) / (FOLD_CHUNK * FOLD_WARPS);
+    u32 cap = (u32)num_sms * 8;
     fold_kernel<<<want < cap ? want : cap, FOLD_THREADS, 0, s>>>(keys_a, keys_b, sd_a, sd_b, plan, t.keys, t.cells, t.capacity, t.count);
     return 1;
 }
@@ -227,10 +273,11 @@ int launch_table_compact(cudaStream_t s, const ChunkTable& t, u64* out_keys, u32
     return 2;
 }
 
-int launch_chunk_gather(cudaStream_t s, const ChunkTable& t, const u32* sorted_slots, u32 n, u64* out_keys, void* out_cells) {
-    if (!n) return 0;
-    chunk_gather_kernel<<<(n + FOLD_THREADS - 1) / FOLD_THREADS, FOLD_THREADS, 0, s>>>(t.keys, reinterpret_cast<const uint4*>(t.cells), sorted_slots,
-                                                                                      n, out_keys, static_cast<uint4*>(out_cells));
+int launch_chunk_gather(cudaStream_t s, const ChunkTable& t, const u32* slots_a, const u32* slots_b, const u32* d_count, const u32* d_nbits,
+                        u32 max_n, u64* out_keys, void* out_cells) {
+    if (!max_n) return 0;
+    chunk_gather_kernel<<<(max_n + FOLD_THREADS - 1) / FOLD_THREADS, FOLD_THREADS, 0, s>>>(t.keys, reinterpret_cast<const uint4*>(t.cells), slots_a, slots_b,
+                                                                                          d_count, d_nbits, out_keys, static_cast<uint4*>(out_cells));
     return 1;
 }
 

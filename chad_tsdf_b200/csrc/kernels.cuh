@@ -54,8 +54,9 @@ int launch_fold(cudaStream_t s, const u64* keys_a, const u64* keys_b, const u32*
 int launch_table_rehash(cudaStream_t s, const ChunkTable& from, const ChunkTable& to, int num_sms);
 // occupied chunks -> (chunk sort key on *d_nbits bits, slot), arbitrary order; *d_count = number of chunks
 int launch_table_compact(cudaStream_t s, const ChunkTable& t, u64* out_keys, u32* out_slots, u32* d_count, u32* d_rmax, u32* d_nbits, int num_sms);
-// sorted slots -> contiguous (full chunk key, 8 x (sd bits, weight))
-int launch_chunk_gather(cudaStream_t s, const ChunkTable& t, const u32* sorted_slots, u32 n, u64* out_keys, void* out_cells);
+// sorted slots -> contiguous (full chunk key, 8 x (sd bits, weight)); count and result buffer selected on the device
+int launch_chunk_gather(cudaStream_t s, const ChunkTable& t, const u32* slots_a, const u32* slots_b, const u32* d_count, const u32* d_nbits,
+                        u32 max_n, u64* out_keys, void* out_cells);
 
 // ---- dag.cu: Submap::finalize (submap.hpp:10-106) level by level ----
 struct DedupTable {   // open addressing; entry = (hash tag << 32) | ref, 0 = empty
@@ -66,10 +67,13 @@ struct DedupTable {   // open addressing; entry = (hash tag << 32) | ref, 0 = em
 constexpr u32 REF_PENDING = 0x80000000u;
 int launch_dedup_clear(cudaStream_t s, const DedupTable& t);
 int launch_dedup_rehash(cudaStream_t s, const DedupTable& from, const DedupTable& to, int num_sms);
-int launch_cluster_build(cudaStream_t s, const void* gathered_cells, u32 n_chunks, const MapParams& mp, u64* tsdf_values);
+// the chunk count is read from device memory (*d_chunks <= max_chunks): finalize part 1 runs without a host round trip
+int launch_cluster_build(cudaStream_t s, const void* gathered_cells, const u32* d_chunks, u32 max_chunks, const MapParams& mp, u64* tsdf_values);
 // cluster level: sequence tsdf_0, W, tsdf_1, W, ...; addr_out[2i] / addr_out[2i+1] = tsdf / weight cluster address of chunk i
-int launch_cluster_dedup(cudaStream_t s, const DedupTable& t, const u64* tsdf_values, u32 n_chunks, u64* raw, u32 uniques_before, u32* slot_of,
-                         u32* is_new, u32* rank, void* scan_ws, u32* addr_out, u32* d_new_count, u32* d_error);
+int launch_cluster_dedup(cudaStream_t s, const DedupTable& t, const u64* tsdf_values, const u32* d_chunks, u32 max_chunks, u64* raw, u32 uniques_before,
+                         u32* slot_of, u32* is_new, u32* rank, void* scan_ws, u32* addr_out, u32* d_new_count, u32* d_error);
+// counts20[d] = number of level-d nodes the sorted chunk ids will produce
+int launch_level_counts(cudaStream_t s, const u64* chunk_ids, const u32* d_chunks, u32 max_chunks, u32* counts20, int num_sms);
 // children (ids ascending) -> head flags, dense parent index on the heads, *d_parents = parent count
 int launch_group_heads(cudaStream_t s, const u64* child_ids, u32 n_children, u32* head, u32* head_rank, void* scan_ws, u32* d_parents);
 // 2 candidate records (TSDF, weight) of 9 words per parent + the parent ids

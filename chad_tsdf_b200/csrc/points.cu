@@ -61,9 +61,16 @@ __global__ void __launch_bounds__(PT_THREADS) plan_bbox_kernel(const float* __re
     }
     r = __reduce_max_sync(0xffffffffu, r);
     err = __reduce_or_sync(0xffffffffu, err);
-    if ((threadIdx.x & 31) == 0) {
-        if (r) atomicMax(&plan->rmax, r);
-        if (err) atomicOr(&plan->error, err);
+    // one global atomic per block, and only when it would raise the maximum (the first blocks settle it)
+    __shared__ u32 s_r[PT_THREADS / 32], s_e[PT_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) { s_r[threadIdx.x >> 5] = r; s_e[threadIdx.x >> 5] = err; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 br = 0, be = 0;
+#pragma unroll
+        for (int w = 0; w < PT_THREADS / 32; w++) { br = max(br, s_r[w]); be |= s_e[w]; }
+        if (br > *(volatile u32*)&plan->rmax) atomicMax(&plan->rmax, br);
+        if (be) atomicOr(&plan->error, be);
     }
 }
 

@@ -10,7 +10,7 @@
 //   * radix_histogram: every CTA accumulates 256-bin histograms for all active digits in shared
 //     memory (warp-aggregated with match.any, because Morton-coherent inputs make whole warps hit
 //     one bin) and adds them to the global histograms.
-//   * radix_onesweep_pass: persistent CTAs take tiles of 4096 keys in order from an atomic ticket,
+//   * radix_onesweep_pass: persistent CTAs take tiles of 2048 keys in order from an atomic ticket,
 //     rank keys inside the tile with warp-level match.any multi-split (stable), publish the tile's
 //     digit counts in a status word per (tile, digit) and resolve their global prefix by decoupled
 //     look-back over earlier tiles, stage the tile in shared memory in sorted order and write
@@ -26,8 +26,9 @@ namespace chadgpu {
 constexpr int RS_RADIX_BITS = 8;
 constexpr int RS_RADIX = 256;
 constexpr int RS_THREADS = 256;  // == RS_RADIX: thread t owns digit t in scans and look-back
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per tile
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 keys per tile
+constexpr int RS_CTAS_PER_SM = 4;             // occupancy target: the ranking loop is latency bound (ncu r01: 20 % issue active at 2 CTAs/SM)
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_MAX_PASSES = 8;
 constexpr u32 RS_FLAG_AGG = 1u << 30;
