@@ -112,7 +112,7 @@ struct BatchPlan {
     u32 n_segments;    // distinct voxels in the batch (written by the segment count)
     u32 n_chunk_heads; // distinct leaf chunks in the batch (upper bound of the chunks the fold can insert)
     u32 n_new_chunks;  // chunks inserted by the fold
-    u32 pad[1];
+    u32 fold_ticket;   // dynamic work counter of the fold kernel
 };
 
 constexpr int MAX_BATCH_SCANS = 64;

@@ -74,8 +74,10 @@ struct chad_ctx {
     u32 batch_points = 0, batch_scans = 0;
     BatchScans h_scans{};
     BatchScans* h_scans_pinned[2] = {nullptr, nullptr};
-    DevBuf d_scans, d_plan;
-    BatchPlan* h_plan = nullptr;  // pinned
+    DevBuf d_scans, d_plan;       // d_plan = BatchPlan[2]: the batch being queued and the batch whose fold is pending
+    BatchPlan* h_plan = nullptr;  // pinned BatchPlan[2]
+    int plan_slot = 0;            // slot of the batch being assembled
+    int pending_slot = 0;         // slot of the batch whose fold is pending
     u32* h_table_count = nullptr; // pinned: chunk count of `table` after its last fold
     u32* h_table_count2 = nullptr; // pinned: same for `table2`
     cudaEvent_t front_done = nullptr;
@@ -84,6 +86,8 @@ struct chad_ctx {
     u32 pending_max_pairs = 0;
 
     // batch work buffers
+    DevBuf pk_a, pk_b, pv_a, pv_b;  // point-sort ping-pong (N-sized): separate from the pair buffers so that the next batch's point
+                                    // stage can be queued while the previous batch's pairs still wait for their fold
     DevBuf keys_a, keys_b, vals_a, vals_b, sorted_keys, sorted_order, xyz_sorted, normals, seg_info, counts, offsets, radix_ws, scan_ws;
     RadixWorkspace rws{};
 
@@ -201,7 +205,8 @@ void dev_free(DevBuf& b) {
     b.p = nullptr;
     b.bytes = 0;
 }
-template <typename T> T* plan_field(chad_ctx* ctx, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ctx->d_plan.p) + off); }
+BatchPlan* plan_ptr(chad_ctx* ctx, int slot) { return ctx->d_plan.as<BatchPlan>() + slot; }
+template <typename T> T* plan_field(chad_ctx* ctx, int slot, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<char*>(plan_ptr(ctx, slot)) + off); }
 
 int error_from_flags(chad_ctx* ctx, u32 flags) {
     if (!flags) return CHAD_OK;
@@ -258,6 +263,10 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
         ctx->stage_busy[b] = false;
         TRY(dev_ensure(ctx, ctx->d_xyz[b], np * 12, true));
     }
+    TRY(dev_ensure(ctx, ctx->pk_a, np * 8));
+    TRY(dev_ensure(ctx, ctx->pk_b, np * 8));
+    TRY(dev_ensure(ctx, ctx->pv_a, np * 4));
+    TRY(dev_ensure(ctx, ctx->pv_b, np * 4));
     TRY(dev_ensure(ctx, ctx->keys_a, pairs * 8));
     TRY(dev_ensure(ctx, ctx->keys_b, pairs * 8));
     TRY(dev_ensure(ctx, ctx->vals_a, pairs * 4));
@@ -283,8 +292,9 @@ int finalize_begin(chad_ctx* ctx, u32 max_chunks);
 int complete_pending_fold(chad_ctx* ctx) {
     if (!ctx->fold_pending) return CHAD_OK;
     ctx->fold_pending = false;
+    const int slot = ctx->pending_slot;
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->front_done));
-    const BatchPlan plan = *ctx->h_plan;
+    const BatchPlan plan = ctx->h_plan[slot];
     ctx->table_count_known = *ctx->h_table_count;
     ctx->stats.updates += plan.n_pairs;
     ctx->stats.key_bits_points = plan.nbits_points;
@@ -292,13 +302,13 @@ int complete_pending_fold(chad_ctx* ctx) {
     ctx->stats.scan_voxels += plan.n_segments;
     if (plan.error) {
         ctx->close_pending = false;
-        CUDA_TRY(ctx, cudaMemsetAsync(plan_field<u32>(ctx, offsetof(BatchPlan, error)), 0, 4, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(plan_field<u32>(ctx, slot, offsetof(BatchPlan, error)), 0, 4, ctx->stream));
         return error_from_flags(ctx, plan.error);
     }
     TRY(table_reserve(ctx, ctx->table_count_known + plan.n_chunk_heads));
     u64 launches = 0;
     PROF(ctx, PC_FOLD, launch_fold(ctx->stream, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(),
-                                   ctx->pending_max_pairs, ctx->d_plan.as<BatchPlan>(), ctx->table, ctx->num_sms));
+                                   ctx->pending_max_pairs, plan_ptr(ctx, slot), ctx->table, ctx->num_sms));
     ctx->stats.kernel_launches += launches;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_table_count, ctx->table.count, 4, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.d2h_bytes += 4;
@@ -313,11 +323,14 @@ int complete_pending_fold(chad_ctx* ctx) {
     return CHAD_OK;
 }
 
-// queue everything of the assembled batch up to (not including) the fold
+// Queue everything of the assembled batch up to (not including) the fold. The point stage (which does not touch the
+// pair buffers) is queued FIRST, before the host waits for the previous batch's counts and queues its fold: the
+// device always has that much work in hand while the host synchronises and launches (the pipeline was launch-bound
+// otherwise: ~50 launches per batch against ~2 ms of kernels).
 int process_front(chad_ctx* ctx) {
     if (ctx->batch_scans == 0) return CHAD_OK;
-    TRY(complete_pending_fold(ctx));  // the previous batch's pairs live in the buffers we are about to reuse
     const int b = ctx->cur;
+    const int slot = ctx->plan_slot;
     const u32 n = ctx->batch_points, ns = ctx->batch_scans;
     cudaStream_t s = ctx->stream;
     ctx->h_scans.offset[ns] = n;
@@ -327,38 +340,46 @@ int process_front(chad_ctx* ctx) {
     CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->copy_done[b], 0));
     if (ctx->stage_busy[b]) CUDA_TRY(ctx, cudaEventRecord(ctx->stage_copied[b], ctx->copy_stream));
 
-    BatchPlan* plan = ctx->d_plan.as<BatchPlan>();
+    BatchPlan* plan = plan_ptr(ctx, slot);
     const BatchScans* scans = ctx->d_scans.as<BatchScans>();
     const float* xyz = ctx->d_xyz[b].as<float>();
     u64 launches = 0;
     const LaunchHook* hook = ctx->profiling ? &ctx->hook : nullptr;
+    // ---- point stage ----
     PROF(ctx, PC_PLAN, launch_plan(s, xyz, n, ns, ctx->mp, plan));
-    PROF(ctx, PC_POINT_KEYS, launch_point_keys(s, xyz, n, scans, ctx->mp, plan, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>()));
-    launches += radix_sort_pairs(s, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), ctx->keys_b.as<u64>(), ctx->vals_b.as<u32>(),
-                                 plan_field<u32>(ctx, offsetof(BatchPlan, n_points)), plan_field<u32>(ctx, offsetof(BatchPlan, nbits_points)), n,
+    PROF(ctx, PC_POINT_KEYS, launch_point_keys(s, xyz, n, scans, ctx->mp, plan, ctx->pk_a.as<u64>(), ctx->pv_a.as<u32>()));
+    launches += radix_sort_pairs(s, ctx->pk_a.as<u64>(), ctx->pv_a.as<u32>(), ctx->pk_b.as<u64>(), ctx->pv_b.as<u32>(),
+                                 plan_field<u32>(ctx, slot, offsetof(BatchPlan, n_points)), plan_field<u32>(ctx, slot, offsetof(BatchPlan, nbits_points)), n,
                                  RS_MAX_PASSES, ctx->rws, ctx->num_sms, hook, PC_POINT_SORT_HIST);
-    PROF(ctx, PC_POINT_GATHER, launch_point_gather(s, xyz, n, plan, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(),
-                                                   ctx->vals_b.as<u32>(), ctx->sorted_keys.as<u64>(), ctx->sorted_order.as<u32>(),
+    PROF(ctx, PC_POINT_GATHER, launch_point_gather(s, xyz, n, plan, ctx->pk_a.as<u64>(), ctx->pk_b.as<u64>(), ctx->pv_a.as<u32>(),
+                                                   ctx->pv_b.as<u32>(), ctx->sorted_keys.as<u64>(), ctx->sorted_order.as<u32>(),
                                                    ctx->xyz_sorted.as<float>()));
     PROF(ctx, PC_NORMALS, launch_normals(s, ctx->xyz_sorted.as<float>(), ctx->sorted_keys.as<u64>(), n, scans, plan, ctx->seg_info.as<u32>(),
                                          ctx->normals.as<float>()));
     PROF(ctx, PC_BAND_COUNT, launch_band_count(s, ctx->xyz_sorted.as<float>(), n, scans, ctx->mp, plan, ctx->counts.as<u32>()));
     PROF(ctx, PC_BAND_SCAN, (exclusive_scan<u32, u32>(s, ctx->counts.as<u32>(), ctx->offsets.as<u32>(), n, ctx->scan_ws.p, (u32*)nullptr,
-                                                      plan_field<u32>(ctx, offsetof(BatchPlan, n_pairs)))));
+                                                      plan_field<u32>(ctx, slot, offsetof(BatchPlan, n_pairs)))));
+    ctx->stats.kernel_launches += launches;
+    launches = 0;
+    // ---- the previous batch's fold: its pairs live in the buffers the pair stage is about to reuse ----
+    TRY(complete_pending_fold(ctx));
+    // ---- pair stage ----
     const size_t max_pairs = size_t(n) * ctx->mp.max_ray_voxels;
     PROF(ctx, PC_BAND_EMIT, launch_band_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan,
                                              ctx->offsets.as<u32>(), ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), (u32)ctx->cap_pairs, false));
     launches += radix_sort_pairs(s, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), ctx->keys_b.as<u64>(), ctx->vals_b.as<u32>(),
-                                 plan_field<u32>(ctx, offsetof(BatchPlan, n_pairs)), plan_field<u32>(ctx, offsetof(BatchPlan, nbits_pairs)), max_pairs,
-                                 RS_MAX_PASSES, ctx->rws, ctx->num_sms, hook, PC_PAIR_SORT_HIST);
+                                 plan_field<u32>(ctx, slot, offsetof(BatchPlan, n_pairs)), plan_field<u32>(ctx, slot, offsetof(BatchPlan, nbits_pairs)),
+                                 max_pairs, RS_MAX_PASSES, ctx->rws, ctx->num_sms, hook, PC_PAIR_SORT_HIST);
     PROF(ctx, PC_SEGMENT_COUNT, launch_segment_count(s, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), (u32)max_pairs, plan, ctx->num_sms));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_plan, plan, sizeof(BatchPlan), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->h_plan[slot], plan, sizeof(BatchPlan), cudaMemcpyDeviceToHost, s));
     ctx->stats.d2h_bytes += sizeof(BatchPlan);
     CUDA_TRY(ctx, cudaEventRecord(ctx->front_done, s));
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->stats.kernel_launches += launches;
     ctx->stats.batches++;
     ctx->fold_pending = true;
+    ctx->pending_slot = slot;
+    ctx->plan_slot ^= 1;
     ctx->pending_max_pairs = (u32)max_pairs;
     ctx->cur ^= 1;
     ctx->batch_points = 0;
@@ -379,13 +400,15 @@ int drain(chad_ctx* ctx) {
     prof_resolve(ctx);
     ctx->table_count_known = *ctx->h_table_count;
     ctx->stats.resident_clusters = ctx->table_count_known;
-    // deferred flags raised by the fold
+    // deferred flags raised by the fold (either plan slot)
     u32 flags = 0;
-    CUDA_TRY(ctx, cudaMemcpy(&flags, plan_field<u32>(ctx, offsetof(BatchPlan, error)), 4, cudaMemcpyDeviceToHost));
-    if (flags) {
-        CUDA_TRY(ctx, cudaMemset(plan_field<u32>(ctx, offsetof(BatchPlan, error)), 0, 4));
-        return error_from_flags(ctx, flags);
+    for (int slot = 0; slot < 2; slot++) {
+        u32 f = 0;
+        CUDA_TRY(ctx, cudaMemcpy(&f, plan_field<u32>(ctx, slot, offsetof(BatchPlan, error)), 4, cudaMemcpyDeviceToHost));
+        if (f) CUDA_TRY(ctx, cudaMemset(plan_field<u32>(ctx, slot, offsetof(BatchPlan, error)), 0, 4));
+        flags |= f;
     }
+    if (flags) return error_from_flags(ctx, flags);
     return CHAD_OK;
 }
 
@@ -735,7 +758,12 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     ctx->num_sms = prop.multiProcessorCount;
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->fin_stream, cudaStreamNonBlocking));
+    {   // the finalize stream gets the highest priority: its ~300 tiny dependent kernels then take the first SM slot that frees up
+        // instead of queueing behind the thousands of CTAs of an insert kernel
+        int prio_lo = 0, prio_hi = 0;
+        CREATE_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CREATE_TRY(cudaStreamCreateWithPriority(&ctx->fin_stream, cudaStreamNonBlocking, prio_hi));
+    }
     CREATE_TRY(cudaEventCreateWithFlags(&ctx->submap_closed, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&ctx->fin_p1_done, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&ctx->fin_done, cudaEventDisableTiming));
@@ -750,7 +778,7 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     CREATE_TRY(cudaEventCreateWithFlags(&ctx->front_done, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreate(&ctx->t0));
     CREATE_TRY(cudaEventCreate(&ctx->t1));
-    CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_plan), sizeof(BatchPlan)));
+    CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_plan), 2 * sizeof(BatchPlan)));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_table_count), 64));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_table_count2), 64));
     *ctx->h_table_count2 = 0;
@@ -769,11 +797,11 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     ctx->max_batch = max_batch_scans == 0 ? 16 : max_batch_scans;
 
     int r = dev_ensure(ctx, ctx->d_scans, sizeof(BatchScans));
-    if (r == CHAD_OK) r = dev_ensure(ctx, ctx->d_plan, sizeof(BatchPlan));
+    if (r == CHAD_OK) r = dev_ensure(ctx, ctx->d_plan, 2 * sizeof(BatchPlan));
     if (r == CHAD_OK) r = dev_ensure(ctx, ctx->f_scalars, 256);
     if (r == CHAD_OK) r = dev_ensure(ctx, ctx->f_level_new, 256);
     if (r != CHAD_OK) return bail(r);
-    CREATE_TRY(cudaMemsetAsync(ctx->d_plan.p, 0, sizeof(BatchPlan), ctx->stream));
+    CREATE_TRY(cudaMemsetAsync(ctx->d_plan.p, 0, 2 * sizeof(BatchPlan), ctx->stream));
     r = table_alloc(ctx, ctx->table, ctx->t_keys, ctx->t_cells, ctx->t_count, 1ull << 20);
     if (r == CHAD_OK) r = table_alloc(ctx, ctx->table2, ctx->t2_keys, ctx->t2_cells, ctx->t2_count, 1ull << 20);
     if (r != CHAD_OK) return bail(r);
@@ -799,7 +827,7 @@ void chad_destroy(chad_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->fin_stream) cudaStreamSynchronize(ctx->fin_stream);
-    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->f_level_new, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
+    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->f_level_new, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
                       &ctx->sorted_keys, &ctx->sorted_order, &ctx->xyz_sorted, &ctx->normals, &ctx->seg_info, &ctx->counts, &ctx->offsets,
                       &ctx->radix_ws, &ctx->scan_ws, &ctx->t_keys, &ctx->t_cells, &ctx->t_count, &ctx->f_ids[0], &ctx->f_ids[1], &ctx->f_slots[0],
                       &ctx->f_slots[1], &ctx->f_cells, &ctx->f_tsdf, &ctx->f_addr[0], &ctx->f_addr[1], &ctx->f_head, &ctx->f_head_rank, &ctx->f_cand,
@@ -986,7 +1014,7 @@ int chad_reset(chad_ctx* ctx) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fin_stream));
     ctx->fin_state = chad_ctx::FIN_IDLE;
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_plan.p, 0, sizeof(BatchPlan), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_plan.p, 0, 2 * sizeof(BatchPlan), ctx->stream));
     launch_table_clear(ctx->stream, ctx->table);
     launch_table_clear(ctx->stream, ctx->table2);
     *ctx->h_table_count2 = 0;
@@ -1070,9 +1098,9 @@ static int stage_check(chad_ctx* ctx) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaGetLastError());
     u32 flags = 0;
-    CUDA_TRY(ctx, cudaMemcpy(&flags, plan_field<u32>(ctx, offsetof(BatchPlan, error)), 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(ctx, cudaMemcpy(&flags, plan_field<u32>(ctx, 0, offsetof(BatchPlan, error)), 4, cudaMemcpyDeviceToHost));
     if (flags) {
-        CUDA_TRY(ctx, cudaMemset(plan_field<u32>(ctx, offsetof(BatchPlan, error)), 0, 4));
+        CUDA_TRY(ctx, cudaMemset(plan_field<u32>(ctx, 0, offsetof(BatchPlan, error)), 0, 4));
         int code = error_from_flags(ctx, flags);
         ctx->sticky_error = CHAD_OK;  // stage calls do not poison the map
         return code;
@@ -1096,7 +1124,7 @@ int chad_stage_points(chad_ctx* ctx, const float* xyz, size_t n, const float pos
     launches += launch_plan(s, dxyz, (u32)n, 1, ctx->mp, plan);
     launches += launch_point_keys(s, dxyz, (u32)n, scans, ctx->mp, plan, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>());
     launches += radix_sort_pairs(s, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), ctx->keys_b.as<u64>(), ctx->vals_b.as<u32>(),
-                                 plan_field<u32>(ctx, offsetof(BatchPlan, n_points)), plan_field<u32>(ctx, offsetof(BatchPlan, nbits_points)), n,
+                                 plan_field<u32>(ctx, 0, offsetof(BatchPlan, n_points)), plan_field<u32>(ctx, 0, offsetof(BatchPlan, nbits_points)), n,
                                  RS_MAX_PASSES, ctx->rws, ctx->num_sms);
     launches += launch_point_gather(s, dxyz, (u32)n, plan, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(),
                                     ctx->sorted_keys.as<u64>(), ctx->sorted_order.as<u32>(), ctx->xyz_sorted.as<float>());
@@ -1129,13 +1157,13 @@ int chad_stage_pairs(chad_ctx* ctx, const float* xyz_sorted, const float* normal
     launches += launch_plan(s, ctx->xyz_sorted.as<float>(), (u32)n, 1, ctx->mp, plan);
     launches += launch_band_count(s, ctx->xyz_sorted.as<float>(), (u32)n, scans, ctx->mp, plan, ctx->counts.as<u32>());
     launches += exclusive_scan<u32, u32>(s, ctx->counts.as<u32>(), ctx->offsets.as<u32>(), n, ctx->scan_ws.p, (u32*)nullptr,
-                                         plan_field<u32>(ctx, offsetof(BatchPlan, n_pairs)));
+                                         plan_field<u32>(ctx, 0, offsetof(BatchPlan, n_pairs)));
     launches += launch_band_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), (u32)n, scans, ctx->mp, plan, ctx->offsets.as<u32>(),
                                  ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), (u32)ctx->cap_pairs, true);
     ctx->stats.kernel_launches += launches;
     TRY(stage_check(ctx));
     u32 U = 0;
-    CUDA_TRY(ctx, cudaMemcpy(&U, plan_field<u32>(ctx, offsetof(BatchPlan, n_pairs)), 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(ctx, cudaMemcpy(&U, plan_field<u32>(ctx, 0, offsetof(BatchPlan, n_pairs)), 4, cudaMemcpyDeviceToHost));
     *total = U;
     if (counts) CUDA_TRY(ctx, cudaMemcpy(counts, ctx->counts.p, n * 4, cudaMemcpyDeviceToHost));
     if (keys || sd) {

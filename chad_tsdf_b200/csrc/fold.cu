@@ -46,20 +46,29 @@ __device__ __forceinline__ u64 table_upsert(u64* __restrict__ keys, u64 capacity
     return ~0ull;
 }
 
-// Work distribution: every warp takes chunks of FOLD_CHUNK consecutive sorted updates, stages them in shared memory
-// (coalesced), lists the segment heads of the chunk, and hands the heads out round-robin to its lanes -- ONE LANE PER
-// SEGMENT, so all 32 lanes run the dependent (mul, add, div) chain of their own voxel instead of idling next to a
-// head lane (ncu r01: 650 M warp instructions with one lane per update). A segment that runs past the chunk end is
-// finished from global memory by the lane that owns its head.
+// Work distribution (ncu r01b: with one lane per segment the variance of segment lengths -- voxels near the sensor
+// are hit by every scan of the batch -- left 6.8 of 32 lanes active). Every warp takes chunks of FOLD_CHUNK consecutive
+// sorted updates and runs three phases:
+//   0. stage keys + sd in shared memory (coalesced) and list the segment heads of the chunk;
+//   1. lane-parallel over heads: probe / insert the leaf chunk, read the voxel's (sd, weight) seed;
+//   2. the dependent (mul, add, div) chains with DYNAMIC lane scheduling: a lane that finishes its segment takes the
+//      next unprocessed head of the chunk in the same iteration, so the lanes stay packed whatever the lengths are;
+//   3. lane-parallel write-back of the folded cells.
+// The chunk's last segment usually runs past the chunk end (ncu r01b: 1.7 M single-lane iterations, each behind a
+// dependent global load, were the kernel's critical path): FOLD_LOOK further updates are staged so that it is folded
+// in phase 2 like every other segment; only a segment longer than that is finished from global memory, by the whole
+// warp with coalesced loads. Chunks are handed out dynamically (one ticket per warp) to even out the warps.
 constexpr int FOLD_CHUNK = 256;            // updates per warp iteration
+constexpr int FOLD_LOOK = 64;              // look-ahead past the chunk end
 constexpr int FOLD_WARPS = FOLD_THREADS / 32;
 
 __global__ void __launch_bounds__(FOLD_THREADS) fold_kernel(const u64* __restrict__ keys_a, const u64* __restrict__ keys_b,
                                                             const u32* __restrict__ sd_a, const u32* __restrict__ sd_b, BatchPlan* plan,
                                                             u64* __restrict__ tkeys, uint2* __restrict__ tcells, u64 capacity, u32* tcount) {
-    __shared__ u64 s_keys[FOLD_WARPS][FOLD_CHUNK];
-    __shared__ u32 s_sd[FOLD_WARPS][FOLD_CHUNK];
-    __shared__ unsigned short s_heads[FOLD_WARPS][FOLD_CHUNK];
+    __shared__ u64 s_keys[FOLD_WARPS][FOLD_CHUNK];   // phase 0/1: keys; afterwards slot h = (acc bits, weight) of head h
+    __shared__ u64 s_cell[FOLD_WARPS][FOLD_CHUNK];   // cell index of head h in the table
+    __shared__ u32 s_sd[FOLD_WARPS][FOLD_CHUNK + FOLD_LOOK];
+    __shared__ unsigned short s_heads[FOLD_WARPS][FOLD_CHUNK + 1];
     const u32 n = plan->n_pairs;
     const u32 k = plan->k;
     const bool alt = radix_result_in_alt(plan->nbits_pairs);
@@ -69,10 +78,14 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_kernel(const u64* __restric
     const u32 lanemask_lt = (1u << lane) - 1u;
     const u32 num_chunks = (n + FOLD_CHUNK - 1) / FOLD_CHUNK;
     u32 new_chunks = 0, err = 0;
-    for (u32 chunk = blockIdx.x * FOLD_WARPS + warp; chunk < num_chunks; chunk += gridDim.x * FOLD_WARPS) {
+    while (true) {
+        u32 chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&plan->fold_ticket, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= num_chunks) break;
         const u32 base = chunk * FOLD_CHUNK;
         const u32 cn = min((u32)FOLD_CHUNK, n - base);
-        // ---- stage the chunk and list its segment heads ----
+        // ---- phase 0: stage the chunk and list its segment heads ----
         u64 prev_last = (base > 0) ? keys[base - 1] : 0ull;  // key just before the chunk (only used when base > 0)
         u32 n_heads = 0;
 #pragma unroll
@@ -89,34 +102,116 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_kernel(const u64* __restric
             n_heads += __popc(m);
             prev_last = __shfl_sync(0xffffffffu, key, 31);
         }
+        // look-ahead: how far does the chunk's last segment (key prev_last) extend past the chunk?
+        u32 ext = 0;
+        bool ext_open = (cn == FOLD_CHUNK);  // more updates may follow
+#pragma unroll
+        for (int r = 0; r < FOLD_LOOK / 32; r++) {
+            const u32 idx = base + FOLD_CHUNK + r * 32 + lane;
+            const bool valid = ext_open && idx < n;
+            const u64 key = valid ? keys[idx] : ~prev_last;
+            if (valid) s_sd[warp][FOLD_CHUNK + r * 32 + lane] = sds[idx];
+            const u32 same = __ballot_sync(0xffffffffu, valid && key == prev_last);
+            const u32 run = (same == 0xffffffffu) ? 32u : (u32)(__ffs(~same) - 1);
+            if (ext_open) ext += run;
+            if (run < 32) ext_open = false;
+        }
+        // ext_open still true: the segment is longer than the look-ahead; the rest is folded after phase 2
+        if (lane == 0) s_heads[warp][n_heads] = (unsigned short)(cn + ext);  // sentinel: end of the chunk's last segment in shared memory
         __syncwarp();
-        // ---- one lane per segment ----
-        for (u32 h = lane; h < n_heads; h += 32) {
-            const u32 e0 = s_heads[warp][h];
-            const u32 e1 = (h + 1 < n_heads) ? (u32)s_heads[warp][h + 1] : cn;  // end inside the chunk
-            const u64 ckey = s_keys[warp][e0];
-            const u64 full = expand_key(ckey, k);
-            bool inserted;
-            const u64 slot = table_upsert(tkeys, capacity, full >> 3, inserted);
-            if (slot == ~0ull) { err |= ERRF_TABLE_FULL; continue; }
-            new_chunks += inserted ? 1u : 0u;
-            uint2* cell = &tcells[slot * 8 + (full & 7ull)];
-            uint2 c = *cell;  // (sd bits, weight); zero for a voxel touched for the first time (octree.hpp:68-75)
-            float acc = __uint_as_float(c.x);
-            u32 w = c.y;
-            for (u32 e = e0; e < e1; e++) {
+        // ---- phase 1: seeds (rounds of 32 heads; round r only overwrites s_keys[32r .. 32r+31], whose keys belong to
+        //      heads of rounds <= r because a head's position is >= its index) ----
+        u64 last_key = 0ull;  // key of the chunk's last head (its segment may continue past the chunk)
+        for (u32 h0 = 0; h0 < n_heads; h0 += 32) {
+            const u32 h = h0 + lane;
+            const bool has = h < n_heads;
+            const u64 ckey = has ? s_keys[warp][s_heads[warp][h]] : 0ull;
+            __syncwarp();
+            if (has) {
+                const u64 full = expand_key(ckey, k);
+                bool inserted;
+                const u64 slot = table_upsert(tkeys, capacity, full >> 3, inserted);
+                if (slot == ~0ull) {
+                    err |= ERRF_TABLE_FULL;
+                    s_cell[warp][h] = ~0ull;
+                    s_keys[warp][h] = 0ull;
+                } else {
+                    new_chunks += inserted ? 1u : 0u;
+                    const u64 ci = slot * 8 + (full & 7ull);
+                    const uint2 c = tcells[ci];  // (sd bits, weight); zero for a voxel touched for the first time (octree.hpp:68-75)
+                    s_cell[warp][h] = ci;
+                    s_keys[warp][h] = (u64(c.y) << 32) | c.x;
+                }
+                if (h + 1 == n_heads) last_key = ckey;
+            }
+            __syncwarp();
+        }
+        last_key = __shfl_sync(0xffffffffu, last_key, (n_heads - 1) & 31);
+        // every head but the last ends where the next one starts; fix the ends: head h ends at min(next head, cn), the
+        // last one at the sentinel (cn + ext)
+        // ---- phase 2: dependent chains, dynamically packed ----
+        u32 next = 0;            // next unassigned head (warp-uniform)
+        u32 my_h = 0xFFFFFFFFu;  // head this lane is folding
+        u32 e = 0, e_end = 0, w = 0;
+        float acc = 0.0f;
+        while (true) {
+            const bool need = my_h == 0xFFFFFFFFu;
+            const u32 m = __ballot_sync(0xffffffffu, need);
+            if (need) {
+                const u32 cand = next + __popc(m & lanemask_lt);
+                if (cand < n_heads) {
+                    my_h = cand;
+                    e = s_heads[warp][cand];
+                    e_end = s_heads[warp][cand + 1];
+                    const u64 seed = s_keys[warp][cand];
+                    acc = __uint_as_float((u32)seed);
+                    w = (u32)(seed >> 32);
+                }
+            }
+            next += __popc(m);
+            if (__ballot_sync(0xffffffffu, my_h != 0xFFFFFFFFu) == 0) break;
+            if (my_h != 0xFFFFFFFFu) {
                 acc = fadd(fmul(acc, __uint2float_rn(w)), __uint_as_float(s_sd[warp][e]));  // octree.hpp:161
                 w++;                                                                          // octree.hpp:162
                 acc = fdiv(acc, __uint2float_rn(w));                                          // octree.hpp:163
-            }
-            if (h + 1 == n_heads) {  // the chunk's last segment may continue in the following chunks
-                for (u32 j = base + cn; j < n && keys[j] == ckey; j++) {
-                    acc = fadd(fmul(acc, __uint2float_rn(w)), __uint_as_float(sds[j]));
-                    w++;
-                    acc = fdiv(acc, __uint2float_rn(w));
+                e++;
+                if (e == e_end) {
+                    s_keys[warp][my_h] = (u64(w) << 32) | __float_as_uint(acc);
+                    my_h = 0xFFFFFFFFu;
                 }
             }
-            *cell = make_uint2(__float_as_uint(acc), w);
+        }
+        __syncwarp();
+        if (ext_open && n_heads > 0) {
+            // rare: the last segment is longer than the look-ahead. The whole warp walks it with coalesced loads; every lane
+            // runs the same chain (uniform), lane 0 stores it.
+            const u64 seed = s_keys[warp][n_heads - 1];
+            float tacc = __uint_as_float((u32)seed);
+            u32 tw = (u32)(seed >> 32);
+            for (u32 j0 = base + FOLD_CHUNK + FOLD_LOOK; j0 < n; j0 += 32) {
+                const u32 idx = j0 + lane;
+                const bool valid = idx < n;
+                const u64 key = valid ? keys[idx] : ~last_key;
+                const u32 sdv = valid ? sds[idx] : 0u;
+                const u32 same = __ballot_sync(0xffffffffu, valid && key == last_key);
+                const u32 run = (same == 0xffffffffu) ? 32u : (u32)(__ffs(~same) - 1);
+                for (u32 t = 0; t < run; t++) {
+                    tacc = fadd(fmul(tacc, __uint2float_rn(tw)), __uint_as_float(__shfl_sync(0xffffffffu, sdv, t)));
+                    tw++;
+                    tacc = fdiv(tacc, __uint2float_rn(tw));
+                }
+                if (run < 32) break;
+            }
+            if (lane == 0) s_keys[warp][n_heads - 1] = (u64(tw) << 32) | __float_as_uint(tacc);
+            __syncwarp();
+        }
+        // ---- phase 3: write the folded cells back ----
+        for (u32 h = lane; h < n_heads; h += 32) {
+            const u64 ci = s_cell[warp][h];
+            if (ci != ~0ull) {
+                const u64 v = s_keys[warp][h];
+                tcells[ci] = make_uint2((u32)v, (u32)(v >> 32));
+            }
         }
         __syncwarp();
     }
@@ -246,7 +341,7 @@ int launch_fold(cudaStream_t s, const u64* keys_a, const u64* keys_b, const u32*
                 const ChunkTable& t, int num_sms) {
     if (!max_pairs) return 0;
     u32 want = (max_pairs + FOLD_CHUNK * FOLD_WARPS - 1) / (FOLD_CHUNK * FOLD_WARPS);
-    u32 cap = (u32)num_sms * 8;
+    u32 cap = (u32)num_sms * 4;  // persistent: chunks are handed out by ticket
     fold_kernel<<<want < cap ? want : cap, FOLD_THREADS, 0, s>>>(keys_a, keys_b, sd_a, sd_b, plan, t.keys, t.cells, t.capacity, t.count);
     return 1;
 }
