@@ -98,6 +98,7 @@ enum : u32 {
     ERRF_TABLE_FULL = 8u,    // resident chunk table over capacity
     ERRF_NUMERIC = 16u,      // NaN / Inf coordinate
     ERRF_DEDUP_FULL = 32u,   // DAG dedup table over capacity
+    ERRF_BLOCKS_FULL = 64u,  // block table of the block-binned pair path over capacity (or > 8192 updates of ONE voxel in a batch)
 };
 
 struct BatchPlan {
@@ -113,6 +114,9 @@ struct BatchPlan {
     u32 n_chunk_heads; // distinct leaf chunks in the batch (upper bound of the chunks the fold can insert)
     u32 n_new_chunks;  // chunks inserted by the fold
     u32 fold_ticket;   // dynamic work counter of the fold kernel
+    u32 n_blocks;      // non-empty 8^3-voxel blocks of the batch (block-binned pair path)
+    u32 sort_ticket;   // dynamic work counter of the per-block sort
+    u32 pad[2];
 };
 
 constexpr int MAX_BATCH_SCANS = 64;

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -86,6 +87,9 @@ struct chad_ctx {
     u32 pending_max_pairs = 0;
 
     // batch work buffers
+    DevBuf bt_mem;                  // block table of the block-binned pair path
+    BlockTable bt{};
+    int pair_path = 0;              // 0 = block-binned (default), 1 = global radix sort
     DevBuf pk_a, pk_b, pv_a, pv_b;  // point-sort ping-pong (N-sized): separate from the pair buffers so that the next batch's point
                                     // stage can be queued while the previous batch's pairs still wait for their fold
     DevBuf keys_a, keys_b, vals_a, vals_b, sorted_keys, sorted_order, xyz_sorted, normals, seg_info, counts, offsets, radix_ws, scan_ws;
@@ -218,6 +222,7 @@ int error_from_flags(chad_ctx* ctx, u32 flags) {
     if (flags & ERRF_PAIR_CAPACITY) { msg += " band voxel buffer overflow;"; code = CHAD_ERR_CAPACITY; }
     if (flags & ERRF_TABLE_FULL) { msg += " resident chunk table full;"; code = CHAD_ERR_CAPACITY; }
     if (flags & ERRF_DEDUP_FULL) { msg += " DAG dedup table full;"; code = CHAD_ERR_CAPACITY; }
+    if (flags & ERRF_BLOCKS_FULL) { msg += " block table of the block-binned pair path full (chad_set_pair_path(ctx, 1) selects the global sort);"; code = CHAD_ERR_CAPACITY; }
     ctx->sticky_error = code;
     return fail(ctx, code, msg);
 }
@@ -279,7 +284,12 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
     TRY(dev_ensure(ctx, ctx->counts, np * 4));
     TRY(dev_ensure(ctx, ctx->offsets, np * 4));
     TRY(dev_ensure(ctx, ctx->radix_ws, radix_workspace_bytes(pairs)));
-    TRY(dev_ensure(ctx, ctx->scan_ws, scan_workspace_bytes(np)));
+    size_t bcap = next_pow2(np / 4);
+    if (bcap < (1u << 16)) bcap = 1u << 16;
+    if (bcap > (1u << 22)) bcap = 1u << 22;
+    TRY(dev_ensure(ctx, ctx->bt_mem, blocks_table_bytes((u32)bcap)));
+    ctx->bt = blocks_table_carve(ctx->bt_mem.p, (u32)bcap);
+    TRY(dev_ensure(ctx, ctx->scan_ws, scan_workspace_bytes(np > bcap ? np : bcap)));
     ctx->rws = radix_workspace_carve(ctx->radix_ws.p, pairs);
     ctx->cap_points = np;
     ctx->cap_pairs = pairs;
@@ -356,21 +366,30 @@ int process_front(chad_ctx* ctx) {
                                                    ctx->xyz_sorted.as<float>()));
     PROF(ctx, PC_NORMALS, launch_normals(s, ctx->xyz_sorted.as<float>(), ctx->sorted_keys.as<u64>(), n, scans, plan, ctx->seg_info.as<u32>(),
                                          ctx->normals.as<float>()));
-    PROF(ctx, PC_BAND_COUNT, launch_band_count(s, ctx->xyz_sorted.as<float>(), n, scans, ctx->mp, plan, ctx->counts.as<u32>()));
-    PROF(ctx, PC_BAND_SCAN, (exclusive_scan<u32, u32>(s, ctx->counts.as<u32>(), ctx->offsets.as<u32>(), n, ctx->scan_ws.p, (u32*)nullptr,
-                                                      plan_field<u32>(ctx, slot, offsetof(BatchPlan, n_pairs)))));
+    const bool use_blocks = ctx->pair_path == 0 && n <= blocks_max_batch_points();
+    if (!use_blocks) {
+        PROF(ctx, PC_BAND_COUNT, launch_band_count(s, ctx->xyz_sorted.as<float>(), n, scans, ctx->mp, plan, ctx->counts.as<u32>()));
+        PROF(ctx, PC_BAND_SCAN, (exclusive_scan<u32, u32>(s, ctx->counts.as<u32>(), ctx->offsets.as<u32>(), n, ctx->scan_ws.p, (u32*)nullptr,
+                                                          plan_field<u32>(ctx, slot, offsetof(BatchPlan, n_pairs)))));
+    }
     ctx->stats.kernel_launches += launches;
     launches = 0;
     // ---- the previous batch's fold: its pairs live in the buffers the pair stage is about to reuse ----
     TRY(complete_pending_fold(ctx));
     // ---- pair stage ----
     const size_t max_pairs = size_t(n) * ctx->mp.max_ray_voxels;
-    PROF(ctx, PC_BAND_EMIT, launch_band_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan,
-                                             ctx->offsets.as<u32>(), ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), (u32)ctx->cap_pairs, false));
-    launches += radix_sort_pairs(s, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), ctx->keys_b.as<u64>(), ctx->vals_b.as<u32>(),
-                                 plan_field<u32>(ctx, slot, offsetof(BatchPlan, n_pairs)), plan_field<u32>(ctx, slot, offsetof(BatchPlan, nbits_pairs)),
-                                 max_pairs, RS_MAX_PASSES, ctx->rws, ctx->num_sms, hook, PC_PAIR_SORT_HIST);
-    PROF(ctx, PC_SEGMENT_COUNT, launch_segment_count(s, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), (u32)max_pairs, plan, ctx->num_sms));
+    if (use_blocks) {
+        launches += launch_blocks_pairs(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan, ctx->bt, ctx->scan_ws.p,
+                                        ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(), (u32)ctx->cap_pairs,
+                                        ctx->num_sms, hook, PC_BLOCKS_COUNT, PC_BLOCKS_SCAN, PC_BLOCKS_EMIT, PC_BLOCKS_SORT);
+    } else {
+        PROF(ctx, PC_BAND_EMIT, launch_band_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan,
+                                                 ctx->offsets.as<u32>(), ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), (u32)ctx->cap_pairs, false));
+        launches += radix_sort_pairs(s, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), ctx->keys_b.as<u64>(), ctx->vals_b.as<u32>(),
+                                     plan_field<u32>(ctx, slot, offsetof(BatchPlan, n_pairs)), plan_field<u32>(ctx, slot, offsetof(BatchPlan, nbits_pairs)),
+                                     max_pairs, RS_MAX_PASSES, ctx->rws, ctx->num_sms, hook, PC_PAIR_SORT_HIST);
+        PROF(ctx, PC_SEGMENT_COUNT, launch_segment_count(s, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), (u32)max_pairs, plan, ctx->num_sms));
+    }
     CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->h_plan[slot], plan, sizeof(BatchPlan), cudaMemcpyDeviceToHost, s));
     ctx->stats.d2h_bytes += sizeof(BatchPlan);
     CUDA_TRY(ctx, cudaEventRecord(ctx->front_done, s));
@@ -785,6 +804,8 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_scalars), 64));
     *ctx->h_table_count = 0;
     CREATE_TRY(radix_sort_init());
+    CREATE_TRY(blocks_init());
+    if (const char* env = std::getenv("CHAD_PAIR_PATH")) ctx->pair_path = std::atoi(env) ? 1 : 0;
 
     ctx->mp.res = sdf_res;
     ctx->mp.trunc = sdf_trunc;
@@ -827,7 +848,7 @@ void chad_destroy(chad_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->fin_stream) cudaStreamSynchronize(ctx->fin_stream);
-    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->f_level_new, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
+    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->f_level_new, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->bt_mem, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
                       &ctx->sorted_keys, &ctx->sorted_order, &ctx->xyz_sorted, &ctx->normals, &ctx->seg_info, &ctx->counts, &ctx->offsets,
                       &ctx->radix_ws, &ctx->scan_ws, &ctx->t_keys, &ctx->t_cells, &ctx->t_count, &ctx->f_ids[0], &ctx->f_ids[1], &ctx->f_slots[0],
                       &ctx->f_slots[1], &ctx->f_cells, &ctx->f_tsdf, &ctx->f_addr[0], &ctx->f_addr[1], &ctx->f_head, &ctx->f_head_rank, &ctx->f_cand,
@@ -1032,6 +1053,14 @@ int chad_reset(chad_ctx* ctx) {
     return CHAD_OK;
 }
 
+int chad_set_pair_path(chad_ctx* ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 1) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(settle(ctx));
+    ctx->pair_path = mode;
+    return CHAD_OK;
+}
+
 int chad_profile_enable(chad_ctx* ctx, int on) {
     if (!ctx) return CHAD_ERR_INVALID;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1060,6 +1089,10 @@ int chad_profile_get(chad_ctx* ctx, int cls, const char** name, double* millisec
     else if (cls >= PC_PAIR_SORT_PASS0 && cls < PC_SEGMENT_COUNT) { std::snprintf(names[cls], 48, "radix_onesweep_kernel[pairs,pass%d]", cls - PC_PAIR_SORT_PASS0); nm = names[cls]; }
     else if (cls == PC_SEGMENT_COUNT) nm = "segment_count_kernel";
     else if (cls == PC_FOLD) nm = "fold_kernel";
+    else if (cls == PC_BLOCKS_COUNT) nm = "blocks_count_kernel";
+    else if (cls == PC_BLOCKS_SCAN) nm = "scan_kernels+blocks_compact_kernel";
+    else if (cls == PC_BLOCKS_EMIT) nm = "blocks_emit_kernel";
+    else if (cls == PC_BLOCKS_SORT) nm = "blocks_sort_kernel";
     else nm = "finalize_submap[part 1 + part 2 on the finalize stream, overlapped with inserts]";
     if (name) *name = nm;
     if (milliseconds) *milliseconds = ctx->prof_ms[cls];

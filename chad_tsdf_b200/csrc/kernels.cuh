@@ -16,7 +16,8 @@ struct MapParams {
 // instrumentation classes (chad_profile_*): one per kernel (group); radix passes are numbered
 enum ProfClass {
     PC_PLAN = 0, PC_POINT_KEYS, PC_POINT_SORT_HIST, PC_POINT_SORT_PASS0, PC_POINT_GATHER = PC_POINT_SORT_PASS0 + 8, PC_NORMALS, PC_BAND_COUNT,
-    PC_BAND_SCAN, PC_BAND_EMIT, PC_PAIR_SORT_HIST, PC_PAIR_SORT_PASS0, PC_SEGMENT_COUNT = PC_PAIR_SORT_PASS0 + 8, PC_FOLD, PC_FINALIZE, PC_COUNT
+    PC_BAND_SCAN, PC_BAND_EMIT, PC_PAIR_SORT_HIST, PC_PAIR_SORT_PASS0, PC_SEGMENT_COUNT = PC_PAIR_SORT_PASS0 + 8, PC_FOLD, PC_FINALIZE,
+    PC_BLOCKS_COUNT, PC_BLOCKS_SCAN, PC_BLOCKS_EMIT, PC_BLOCKS_SORT, PC_COUNT
 };
 
 // ---- points.cu: voxelise + Morton (morton.hpp:59-80), sort keys, gather, normals (normals.hpp) ----
@@ -38,6 +39,23 @@ int launch_band_count(cudaStream_t s, const float* xyz_sorted, u32 n_points, con
 int launch_band_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const BatchScans* scans,
                      const MapParams& mp, BatchPlan* plan, const u32* offsets, u64* pair_keys, u32* pair_sd, u32 pair_capacity,
                      bool full_keys);
+
+// ---- blocks.cu: block-binned grouping of the band-voxel updates (default pair path) ----
+struct BlockTable {   // open addressing over 8^3-voxel block ids (Morton key >> 9), rebuilt per batch
+    u64* keys;        // [capacity], ~0 = empty
+    u32* count;       // updates per block
+    u32* cursor;      // emit cursor
+    u32* offset;      // exclusive prefix sum of count
+    u32* list;        // slots of the non-empty blocks
+    u32 capacity;     // power of two
+};
+size_t blocks_table_bytes(u32 capacity);
+BlockTable blocks_table_carve(void* mem, u32 capacity);
+cudaError_t blocks_init();
+u32 blocks_max_batch_points();
+int launch_blocks_pairs(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const BatchScans* scans, const MapParams& mp,
+                        BatchPlan* plan, const BlockTable& bt, void* scan_ws, u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, u32 pair_capacity,
+                        int num_sms, const LaunchHook* hook, int cls_count, int cls_scan, int cls_emit, int cls_sort);
 
 // ---- fold.cu: ordered segmented fold (octree.hpp:161-163) into the resident chunk table ----
 struct ChunkTable {

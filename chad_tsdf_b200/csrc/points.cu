@@ -42,7 +42,7 @@ __device__ __forceinline__ bool voxel_of(float px, float py, float pz, float rec
 __global__ void __launch_bounds__(PT_THREADS) plan_reset_kernel(BatchPlan* plan, u32 n_points, u32 n_scans) {
     plan->rmax = 0; plan->k = 0; plan->nbits_points = 0; plan->nbits_pairs = 0;
     plan->n_points = n_points; plan->n_scans = n_scans; plan->n_pairs = 0;
-    plan->n_segments = 0; plan->n_chunk_heads = 0; plan->n_new_chunks = 0; plan->fold_ticket = 0;
+    plan->n_segments = 0; plan->n_chunk_heads = 0; plan->n_new_chunks = 0; plan->fold_ticket = 0; plan->n_blocks = 0; plan->sort_ticket = 0;
     // plan->error is sticky: cleared by the host when it reports it
 }
 

@@ -13,7 +13,7 @@ from . import capi
 
 
 class TSDFMap:
-    def __init__(self, sdf_res: float = 0.05, sdf_trunc: float = 0.1, device: int = 0, max_batch_scans: int = 0):
+    def __init__(self, sdf_res: float = 0.05, sdf_trunc: float = 0.1, device: int = 0, max_batch_scans: int = 0, pair_path: int | None = None):
         self._lib = capi.load()
         self._h = C.c_void_p()
         rc = self._lib.chad_create(sdf_res, sdf_trunc, device, max_batch_scans, C.byref(self._h))
@@ -21,6 +21,8 @@ class TSDFMap:
             raise capi.ChadError(rc, self._lib.chad_last_error(None).decode())
         self._sdf_res, self._sdf_trunc = float(sdf_res), float(sdf_trunc)
         self.sdf_res, self.sdf_trunc = self._sdf_res, self._sdf_trunc
+        if pair_path is not None:
+            self.set_pair_path(pair_path)
 
     # -- lifetime --
     def close(self) -> None:
@@ -99,6 +101,10 @@ class TSDFMap:
         s = capi.Stats()
         self._check(self._lib.chad_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def set_pair_path(self, mode: int) -> None:
+        """0 = block-binned grouping of the voxel updates (default), 1 = global radix sort. Identical results."""
+        self._check(self._lib.chad_set_pair_path(self._h, mode))
 
     def reset(self) -> None:
         """Forget the whole map but keep the device buffers (== a freshly constructed map)."""

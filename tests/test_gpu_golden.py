@@ -10,11 +10,11 @@ pytestmark = pytest.mark.gpu
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
 
 
-@pytest.mark.parametrize("batch", [1, 8])
+@pytest.mark.parametrize("batch,path", [(1, 0), (8, 0), (8, 1)])
 @pytest.mark.parametrize("name", cases.ALL_CASES)
-def test_gpu_matches_reference_golden(chad_lib, name, batch):
+def test_gpu_matches_reference_golden(chad_lib, name, batch, path):
     from chad_tsdf_b200 import TSDFMap
-    m, d = cases.run_case(lambda r, t: TSDFMap(r, t, max_batch_scans=batch), name)
+    m, d = cases.run_case(lambda r, t: TSDFMap(r, t, max_batch_scans=batch, pair_path=path), name)
     g = GOLDEN[name]
     for k, v in g["verbatim"]["before_finalize"].items():  # tier A: the reference exactly as written
         assert d["before_finalize"][k] == v, f"tier A {k}"

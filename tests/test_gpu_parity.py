@@ -24,10 +24,10 @@ def _assert_same_state(g, o, check_levels=True):
             assert np.array_equal(ga, oa), f"level {lv} words"
 
 
-def _run_pair(w, scans, batch, finalize_every=None):
+def _run_pair(w, scans, batch, finalize_every=None, path=0):
     from chad_tsdf_b200 import TSDFMap
     from oracle import bindings as ob
-    g = TSDFMap(w.sdf_res, w.sdf_trunc, max_batch_scans=batch)
+    g = TSDFMap(w.sdf_res, w.sdf_trunc, max_batch_scans=batch, pair_path=path)
     o = ob.OracleMap(w.sdf_res, w.sdf_trunc)
     U = V = 0
     for s in range(scans):
@@ -43,10 +43,11 @@ def _run_pair(w, scans, batch, finalize_every=None):
     return g, o, U, V
 
 
+@pytest.mark.parametrize("path", [0, 1])
 @pytest.mark.parametrize("batch", [1, 4])
-def test_single_scan_cfg0(chad_lib, oracle_lib, batch):
+def test_single_scan_cfg0(chad_lib, oracle_lib, batch, path):
     w = synth.WORKLOADS["cfg0_single_64beam"]
-    g, o, U, V = _run_pair(w, 1, batch)
+    g, o, U, V = _run_pair(w, 1, batch, path=path)
     g.flush()
     _assert_same_state(g, o, check_levels=False)
     st = g.stats()
@@ -59,11 +60,12 @@ def test_single_scan_cfg0(chad_lib, oracle_lib, batch):
     g.close(); o.close()
 
 
+@pytest.mark.parametrize("path", [0, 1])
 @pytest.mark.parametrize("batch", [1, 3, 16])
-def test_trajectory_with_submap_switch(chad_lib, oracle_lib, batch):
+def test_trajectory_with_submap_switch(chad_lib, oracle_lib, batch, path):
     """cfg1 prefix: 24 scans at 0.25 m/scan => one submap switch inside insert (> 5 m from the first pose)."""
     w = synth.WORKLOADS["cfg1_traj100_128beam"]
-    g, o, U, V = _run_pair(w, 24, batch)
+    g, o, U, V = _run_pair(w, 24, batch, path=path)
     _assert_same_state(g, o)
     assert len(g.roots()) == 1
     g.finalize_active(); o.finalize_active()
@@ -72,30 +74,33 @@ def test_trajectory_with_submap_switch(chad_lib, oracle_lib, batch):
     g.close(); o.close()
 
 
-def test_fine_voxels_cfg2(chad_lib, oracle_lib):
+@pytest.mark.parametrize("path", [0, 1])
+def test_fine_voxels_cfg2(chad_lib, oracle_lib, path):
     w = synth.WORKLOADS["cfg2_fine_indoor"]
-    g, o, _, _ = _run_pair(w, 5, 2, finalize_every=2)
+    g, o, _, _ = _run_pair(w, 5, 2, finalize_every=2, path=path)
     g.finalize_active(); o.finalize_active()
     _assert_same_state(g, o)
     g.close(); o.close()
 
 
-def test_urban_cfg3_many_submaps(chad_lib, oracle_lib):
+@pytest.mark.parametrize("path", [0, 1])
+def test_urban_cfg3_many_submaps(chad_lib, oracle_lib, path):
     w = synth.WORKLOADS["cfg3_urban_5km"]
-    g, o, _, _ = _run_pair(w, 14, 4)  # 1 m/scan: switches at scans 6 and 12
+    g, o, _, _ = _run_pair(w, 14, 4, path=path)  # 1 m/scan: switches at scans 6 and 12
     assert len(g.roots()) == 2
     g.finalize_active(); o.finalize_active()
     _assert_same_state(g, o)
     g.close(); o.close()
 
 
-def test_sphere_demo_shape(chad_lib, oracle_lib):
+@pytest.mark.parametrize("path", [0, 1])
+def test_sphere_demo_shape(chad_lib, oracle_lib, path):
     """The reference demo's workload shape (main.cpp:7-38): dense points on a 5 m sphere, many points per voxel."""
     from chad_tsdf_b200 import TSDFMap
     from oracle import bindings as ob
     pts = synth.sphere_demo_points(200_000)
     pos = np.zeros(3, np.float32)
-    g, o = TSDFMap(0.05, 0.1), ob.OracleMap(0.05, 0.1)
+    g, o = TSDFMap(0.05, 0.1, pair_path=path), ob.OracleMap(0.05, 0.1)
     g.insert(pts, pos); o.insert(pts, pos)
     g.finalize_active(); o.finalize_active()
     _assert_same_state(g, o)
@@ -103,10 +108,11 @@ def test_sphere_demo_shape(chad_lib, oracle_lib):
     g.close(); o.close()
 
 
-def test_empty_and_tiny_inputs(chad_lib, oracle_lib):
+@pytest.mark.parametrize("path", [0, 1])
+def test_empty_and_tiny_inputs(chad_lib, oracle_lib, path):
     from chad_tsdf_b200 import TSDFMap
     from oracle import bindings as ob
-    g, o = TSDFMap(0.05, 0.1, max_batch_scans=2), ob.OracleMap(0.05, 0.1)
+    g, o = TSDFMap(0.05, 0.1, max_batch_scans=2, pair_path=path), ob.OracleMap(0.05, 0.1)
     pos = np.zeros(3, np.float32)
     empty = np.zeros((0, 3), np.float32)
     g.insert(empty, pos); o.insert(empty, pos)
@@ -138,3 +144,20 @@ def test_errors_are_reported(chad_lib):
     g.close()
     with pytest.raises(ChadError):
         TSDFMap(-1.0, 0.1)
+
+
+def test_dense_voxels_many_updates_per_voxel(chad_lib, oracle_lib):
+    """Thousands of points in a handful of voxels: long per-voxel segments (multi-pass block sort, fold look-ahead tail)."""
+    from chad_tsdf_b200 import TSDFMap
+    from oracle import bindings as ob
+    rng = np.random.default_rng(11)
+    pos = np.array([0.0, 0.0, 0.0], np.float32)
+    for path in (0, 1):
+        g, o = TSDFMap(0.05, 0.1, max_batch_scans=4, pair_path=path), ob.OracleMap(0.05, 0.1)
+        for s in range(4):
+            pts = (rng.random((12000, 3)) * np.array([0.12, 0.12, 0.02]) + np.array([2.0, 1.0, 0.5])).astype(np.float32)
+            g.insert(pts, pos); o.insert(pts, pos)
+        _assert_same_state(g, o, check_levels=False)
+        g.finalize_active(); o.finalize_active()
+        _assert_same_state(g, o)
+        g.close(); o.close()
