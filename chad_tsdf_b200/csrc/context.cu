@@ -118,6 +118,11 @@ struct chad_ctx {
         u32 root[2];
     }* h_fin = nullptr;
     DevBuf f_level_new;           // device u64[20]
+    bool fin_external = false;    // the finalize in flight consumes a caller-provided chunk stream (sharded mode): clear `table`, not `table2`
+
+    // Morton-range sharding (multi-GPU, driven from the host language binding)
+    DevBuf sh_tuples, sh_scalars; // send buffer (16-byte tuples grouped by destination); u64 splitters[8] | u32 counts[8] | offsets[8] | cursors[8]
+    bool sh_have_splitters = false;
 
     // finalize work buffers
     size_t cap_chunks = 0;
@@ -296,7 +301,7 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
     return CHAD_OK;
 }
 
-int finalize_begin(chad_ctx* ctx, u32 max_chunks);
+int finalize_begin(chad_ctx* ctx, u32 max_chunks, bool external = false);
 
 // launch the fold of the batch whose front has been queued (see the file comment)
 int complete_pending_fold(chad_ctx* ctx) {
@@ -333,6 +338,27 @@ int complete_pending_fold(chad_ctx* ctx) {
     return CHAD_OK;
 }
 
+// plan -> point sort keys -> sort -> gather -> normals of the batch in d_xyz[b] (n points, ns scans; d_scans uploaded)
+void queue_point_stage(chad_ctx* ctx, int slot, int b, u32 n, u32 ns) {
+    cudaStream_t s = ctx->stream;
+    BatchPlan* plan = plan_ptr(ctx, slot);
+    const BatchScans* scans = ctx->d_scans.as<BatchScans>();
+    const float* xyz = ctx->d_xyz[b].as<float>();
+    u64 launches = 0;
+    const LaunchHook* hook = ctx->profiling ? &ctx->hook : nullptr;
+    PROF(ctx, PC_PLAN, launch_plan(s, xyz, n, ns, ctx->mp, plan));
+    PROF(ctx, PC_POINT_KEYS, launch_point_keys(s, xyz, n, scans, ctx->mp, plan, ctx->pk_a.as<u64>(), ctx->pv_a.as<u32>()));
+    launches += radix_sort_pairs(s, ctx->pk_a.as<u64>(), ctx->pv_a.as<u32>(), ctx->pk_b.as<u64>(), ctx->pv_b.as<u32>(),
+                                 plan_field<u32>(ctx, slot, offsetof(BatchPlan, n_points)), plan_field<u32>(ctx, slot, offsetof(BatchPlan, nbits_points)), n,
+                                 RS_MAX_PASSES, ctx->rws, ctx->num_sms, hook, PC_POINT_SORT_HIST);
+    PROF(ctx, PC_POINT_GATHER, launch_point_gather(s, xyz, n, plan, ctx->pk_a.as<u64>(), ctx->pk_b.as<u64>(), ctx->pv_a.as<u32>(),
+                                                   ctx->pv_b.as<u32>(), ctx->sorted_keys.as<u64>(), ctx->sorted_order.as<u32>(),
+                                                   ctx->xyz_sorted.as<float>()));
+    PROF(ctx, PC_NORMALS, launch_normals(s, ctx->xyz_sorted.as<float>(), ctx->sorted_keys.as<u64>(), n, scans, plan, ctx->seg_info.as<u32>(),
+                                         ctx->normals.as<float>()));
+    ctx->stats.kernel_launches += launches;
+}
+
 // Queue everything of the assembled batch up to (not including) the fold. The point stage (which does not touch the
 // pair buffers) is queued FIRST, before the host waits for the previous batch's counts and queues its fold: the
 // device always has that much work in hand while the host synchronises and launches (the pipeline was launch-bound
@@ -352,20 +378,9 @@ int process_front(chad_ctx* ctx) {
 
     BatchPlan* plan = plan_ptr(ctx, slot);
     const BatchScans* scans = ctx->d_scans.as<BatchScans>();
-    const float* xyz = ctx->d_xyz[b].as<float>();
     u64 launches = 0;
     const LaunchHook* hook = ctx->profiling ? &ctx->hook : nullptr;
-    // ---- point stage ----
-    PROF(ctx, PC_PLAN, launch_plan(s, xyz, n, ns, ctx->mp, plan));
-    PROF(ctx, PC_POINT_KEYS, launch_point_keys(s, xyz, n, scans, ctx->mp, plan, ctx->pk_a.as<u64>(), ctx->pv_a.as<u32>()));
-    launches += radix_sort_pairs(s, ctx->pk_a.as<u64>(), ctx->pv_a.as<u32>(), ctx->pk_b.as<u64>(), ctx->pv_b.as<u32>(),
-                                 plan_field<u32>(ctx, slot, offsetof(BatchPlan, n_points)), plan_field<u32>(ctx, slot, offsetof(BatchPlan, nbits_points)), n,
-                                 RS_MAX_PASSES, ctx->rws, ctx->num_sms, hook, PC_POINT_SORT_HIST);
-    PROF(ctx, PC_POINT_GATHER, launch_point_gather(s, xyz, n, plan, ctx->pk_a.as<u64>(), ctx->pk_b.as<u64>(), ctx->pv_a.as<u32>(),
-                                                   ctx->pv_b.as<u32>(), ctx->sorted_keys.as<u64>(), ctx->sorted_order.as<u32>(),
-                                                   ctx->xyz_sorted.as<float>()));
-    PROF(ctx, PC_NORMALS, launch_normals(s, ctx->xyz_sorted.as<float>(), ctx->sorted_keys.as<u64>(), n, scans, plan, ctx->seg_info.as<u32>(),
-                                         ctx->normals.as<float>()));
+    queue_point_stage(ctx, slot, b, n, ns);
     const bool use_blocks = ctx->pair_path == 0 && n <= blocks_max_batch_points();
     if (!use_blocks) {
         PROF(ctx, PC_BAND_COUNT, launch_band_count(s, ctx->xyz_sorted.as<float>(), n, scans, ctx->mp, plan, ctx->counts.as<u32>()));
@@ -558,28 +573,34 @@ int finalize_wait(chad_ctx* ctx) {
 
 // Close the active submap: everything of it must already be queued on the compute stream (process_front +
 // complete_pending_fold). `max_chunks` = upper bound of its chunk count.
-int finalize_begin(chad_ctx* ctx, u32 max_chunks) {
+int finalize_begin(chad_ctx* ctx, u32 max_chunks, bool external) {
     TRY(finalize_wait(ctx));  // one finalize in flight at a time (they are ~2 ms apart at the very least)
     cudaStream_t fs = ctx->fin_stream;
     TRY(ensure_finalize_capacity(ctx, max_chunks));
     Level& LC = ctx->levels[CHAD_LEVEL_CLUSTERS];
     TRY(level_reserve(ctx, LC, true, size_t(max_chunks) + 1));
-    // swap tables: the spare one was cleared at the end of the previous finalize (complete: see finalize_wait above)
     CUDA_TRY(ctx, cudaEventRecord(ctx->submap_closed, ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(fs, ctx->submap_closed, 0));
-    std::swap(ctx->table, ctx->table2);
-    std::swap(ctx->t_keys, ctx->t2_keys);
-    std::swap(ctx->t_cells, ctx->t2_cells);
-    std::swap(ctx->t_count, ctx->t2_count);
-    std::swap(ctx->h_table_count, ctx->h_table_count2);  // no copy into the new active slot is in flight (its table was idle)
-    *ctx->h_table_count = 0;
-    ctx->table_count_known = 0;
+    ctx->fin_external = external;
+    if (!external) {
+        // swap tables: the spare one was cleared at the end of the previous finalize (complete: see finalize_wait above)
+        std::swap(ctx->table, ctx->table2);
+        std::swap(ctx->t_keys, ctx->t2_keys);
+        std::swap(ctx->t_cells, ctx->t2_cells);
+        std::swap(ctx->t_count, ctx->t2_count);
+        std::swap(ctx->h_table_count, ctx->h_table_count2);  // no copy into the new active slot is in flight (its table was idle)
+        *ctx->h_table_count = 0;
+        ctx->table_count_known = 0;
+    }
     ctx->fin_max_chunks = max_chunks;
     if (ctx->profiling) cudaEventRecord(ctx->fin_t0, fs);
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->f_scalars.p, 0, 256, fs));
+    if (external) {  // f_ids[0] / f_cells already hold the globally sorted chunk stream: only the count is needed
+        CUDA_TRY(ctx, cudaMemcpyAsync(scalar32(ctx, SC_COUNT), &ctx->fin_max_chunks, 4, cudaMemcpyHostToDevice, fs));
+    }
     if (max_chunks) {
         u64 launches = 0;
-        TRY(queue_sorted_chunks(ctx, fs, ctx->table2, max_chunks));
+        if (!external) TRY(queue_sorted_chunks(ctx, fs, ctx->table2, max_chunks));
         launches += launch_cluster_build(fs, ctx->f_cells.p, scalar32(ctx, SC_COUNT), max_chunks, ctx->mp, ctx->f_tsdf.as<u64>());
         launches += launch_cluster_dedup(fs, LC.table, ctx->f_tsdf.as<u64>(), scalar32(ctx, SC_COUNT), max_chunks, LC.raw.as<u64>(), LC.uniques,
                                          ctx->f_slot_of.as<u32>(), ctx->f_is_new.as<u32>(), ctx->f_rank.as<u32>(), ctx->f_scan_ws.p,
@@ -643,7 +664,7 @@ int finalize_part2(chad_ctx* ctx) {
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->root, addr, 8, cudaMemcpyDeviceToHost, fs));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->scalars, ctx->f_scalars.p, 16 * 4, cudaMemcpyDeviceToHost, fs));
     ctx->stats.d2h_bytes += 20 * 8 + 8 + 64;
-    launch_table_clear(fs, ctx->table2);  // octree.clear(), tsdf.cpp:57
+    launch_table_clear(fs, ctx->fin_external ? ctx->table : ctx->table2);  // octree.clear(), tsdf.cpp:57
     if (ctx->profiling) cudaEventRecord(ctx->fin_t3, fs);
     CUDA_TRY(ctx, cudaEventRecord(ctx->fin_done, fs));
     CUDA_TRY(ctx, cudaGetLastError());
@@ -668,6 +689,7 @@ int finalize_finish(chad_ctx* ctx) {
     }
     ctx->roots.push_back({ctx->h_fin->root[0], ctx->h_fin->root[1]});
     ctx->stats.submaps++;
+    if (ctx->fin_external) { *ctx->h_table_count = 0; ctx->table_count_known = 0; ctx->fin_external = false; }
     if (ctx->profiling) {
         float a = 0.f, b = 0.f;
         if (cudaEventElapsedTime(&a, ctx->fin_t0, ctx->fin_t1) == cudaSuccess && cudaEventElapsedTime(&b, ctx->fin_t2, ctx->fin_t3) == cudaSuccess) {
@@ -848,7 +870,7 @@ void chad_destroy(chad_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->fin_stream) cudaStreamSynchronize(ctx->fin_stream);
-    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->f_level_new, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->bt_mem, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
+    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->f_level_new, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->sh_tuples, &ctx->sh_scalars, &ctx->bt_mem, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
                       &ctx->sorted_keys, &ctx->sorted_order, &ctx->xyz_sorted, &ctx->normals, &ctx->seg_info, &ctx->counts, &ctx->offsets,
                       &ctx->radix_ws, &ctx->scan_ws, &ctx->t_keys, &ctx->t_cells, &ctx->t_count, &ctx->f_ids[0], &ctx->f_ids[1], &ctx->f_slots[0],
                       &ctx->f_slots[1], &ctx->f_cells, &ctx->f_tsdf, &ctx->f_addr[0], &ctx->f_addr[1], &ctx->f_head, &ctx->f_head_rank, &ctx->f_cand,
@@ -1031,6 +1053,7 @@ int chad_reset(chad_ctx* ctx) {
     ctx->batch_scans = 0;
     ctx->fold_pending = false;
     ctx->close_pending = false;
+    ctx->sh_have_splitters = false;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fin_stream));
@@ -1246,6 +1269,130 @@ uint64_t chad_morton_encode(int32_t x, int32_t y, int32_t z) { return morton_enc
 void chad_morton_decode(uint64_t key, int32_t* x, int32_t* y, int32_t* z) { morton_decode(key, *x, *y, *z); }
 uint64_t chad_key_compact(uint64_t key, unsigned k) { return compact_key(key, k); }
 uint64_t chad_key_expand(uint64_t compact, unsigned k) { return expand_key(compact, k); }
+
+// ---- Morton-range sharding across GPUs -----------------------------------------------
+// Synchronous building blocks; the exchange itself (NCCL all-to-all / all-gather over NVLink) is done by the caller
+// between them (chad_tsdf_b200/sharded.py uses torch.distributed). All ranks must call them with the same batch.
+int chad_shard_front(chad_ctx* ctx, const float* xyz, const uint32_t* scan_offsets, const float* poses, int n_scans, int rank, int world,
+                     int new_submap, uint64_t* send_counts) {
+    if (!ctx || !scan_offsets || !poses || !send_counts || n_scans < 1 || n_scans > MAX_BATCH_SCANS || world < 1 || world > SHARD_WORLD_MAX ||
+        rank < 0 || rank >= world)
+        return fail(ctx, CHAD_ERR_INVALID, "chad_shard_front: bad argument");
+    if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(settle(ctx));
+    const size_t n = scan_offsets[n_scans];
+    for (int d = 0; d < world; d++) send_counts[d] = 0;
+    if (n == 0) return CHAD_OK;
+    if (!xyz) return fail(ctx, CHAD_ERR_INVALID, "chad_shard_front: xyz is NULL");
+    if (n > blocks_max_batch_points()) return fail(ctx, CHAD_ERR_CAPACITY, "sharded batch exceeds 2^23 points");
+    if (n > ctx->cap_points || ctx->cap_points == 0) TRY(ensure_batch_capacity(ctx, n));
+    TRY(dev_ensure(ctx, ctx->sh_scalars, 512));
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_xyz[0].p, xyz, n * 12, cudaMemcpyHostToDevice, s));
+    for (int i = 0; i <= n_scans; i++) ctx->h_scans.offset[i] = scan_offsets[i];
+    std::memcpy(ctx->h_scans.pose, poses, size_t(n_scans) * 12);
+    *ctx->h_scans_pinned[0] = ctx->h_scans;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scans.p, ctx->h_scans_pinned[0], sizeof(BatchScans), cudaMemcpyHostToDevice, s));
+    queue_point_stage(ctx, 0, 0, (u32)n, (u32)n_scans);
+    BatchPlan* plan = plan_ptr(ctx, 0);
+    const BatchScans* scans = ctx->d_scans.as<BatchScans>();
+    u64* splitters = ctx->sh_scalars.as<u64>();
+    u32* dest = reinterpret_cast<u32*>(splitters + 8);  // counts[8] | offsets[8] | cursors[8]
+    u64 launches = 0;
+    if (new_submap || !ctx->sh_have_splitters) {
+        // every rank sorts the same points, so every rank derives the same splitters: no communication
+        launches += launch_shard_splitters(s, ctx->sorted_keys.as<u64>(), scan_offsets[1], plan, (u32)world, splitters);
+        ctx->sh_have_splitters = true;
+    }
+    const u32 i_begin = (u32)(size_t(rank) * n / world), i_end = (u32)(size_t(rank + 1) * n / world);
+    launches += launch_shard_count(s, ctx->xyz_sorted.as<float>(), i_begin, i_end, scans, ctx->mp, plan, splitters, (u32)world, dest);
+    u32 counts[8] = {0};
+    CUDA_TRY(ctx, cudaMemcpyAsync(counts, dest, 32, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    u32 offsets[8];
+    size_t total = 0;
+    for (int d = 0; d < 8; d++) { offsets[d] = (u32)total; total += counts[d]; }
+    if (total >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "sharded batch emits more than 2^31 updates");
+    TRY(dev_ensure(ctx, ctx->sh_tuples, (total + 1) * 16));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dest + 8, offsets, 32, cudaMemcpyHostToDevice, s));
+    launches += launch_shard_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), i_begin, i_end, scans, ctx->mp, plan, splitters, (u32)world,
+                                  dest + 8, dest + 16, ctx->sh_tuples.p, (u32)total);
+    ctx->stats.kernel_launches += launches;
+    TRY(stage_check(ctx));
+    for (int d = 0; d < world; d++) send_counts[d] = counts[d];
+    ctx->stats.scans += (u64)n_scans;
+    ctx->stats.points += n;
+    ctx->stats.h2d_bytes += n * 12;
+    ctx->stats.batches++;
+    return CHAD_OK;
+}
+
+int chad_shard_send_buffer(chad_ctx* ctx, void** tuples_device) {
+    if (!ctx || !tuples_device) return CHAD_ERR_INVALID;
+    *tuples_device = ctx->sh_tuples.p;
+    return CHAD_OK;
+}
+
+int chad_shard_ingest(chad_ctx* ctx, const void* tuples_device, size_t n_tuples) {
+    if (!ctx || (n_tuples && !tuples_device)) return CHAD_ERR_INVALID;
+    if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->cap_points == 0) TRY(ensure_batch_capacity(ctx, 1));
+    if (n_tuples > ctx->cap_pairs) return fail(ctx, CHAD_ERR_CAPACITY, "chad_shard_ingest: more updates than the pair buffers hold");
+    cudaStream_t s = ctx->stream;
+    BatchPlan* plan = plan_ptr(ctx, 0);
+    u64 launches = 0;
+    launches += launch_blocks_from_tuples(s, tuples_device, (u32)n_tuples, plan, ctx->bt, ctx->scan_ws.p, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(),
+                                          ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(), (u32)ctx->cap_pairs, ctx->num_sms);
+    CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->h_plan[0], plan, sizeof(BatchPlan), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    const BatchPlan hp = ctx->h_plan[0];
+    if (hp.error) {
+        CUDA_TRY(ctx, cudaMemset(plan_field<u32>(ctx, 0, offsetof(BatchPlan, error)), 0, 4));
+        return error_from_flags(ctx, hp.error);
+    }
+    ctx->stats.updates += hp.n_pairs;
+    ctx->stats.scan_voxels += hp.n_segments;
+    TRY(table_reserve(ctx, ctx->table_count_known + hp.n_chunk_heads));
+    launches += launch_fold(s, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(), (u32)n_tuples, plan, ctx->table,
+                            ctx->num_sms);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_table_count, ctx->table.count, 4, cudaMemcpyDeviceToHost, s));
+    ctx->stats.kernel_launches += launches;
+    return drain(ctx);
+}
+
+int chad_shard_export_chunks(chad_ctx* ctx, size_t* n_chunks, void** keys_device, void** cells_device) {
+    if (!ctx || !n_chunks || !keys_device || !cells_device) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(settle(ctx));
+    const u32 C = (u32)ctx->table_count_known;
+    TRY(ensure_finalize_capacity(ctx, C));
+    if (C) TRY(queue_sorted_chunks(ctx, ctx->stream, ctx->table, C));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_chunks = C;
+    *keys_device = ctx->f_ids[0].p;
+    *cells_device = ctx->f_cells.p;
+    return CHAD_OK;
+}
+
+int chad_shard_finalize_from(chad_ctx* ctx, const uint64_t* keys_device, const void* cells_device, size_t n_chunks) {
+    if (!ctx || (n_chunks && (!keys_device || !cells_device))) return CHAD_ERR_INVALID;
+    if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n_chunks >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
+    TRY(settle(ctx));
+    TRY(ensure_finalize_capacity(ctx, n_chunks));
+    if (n_chunks) {
+        if (keys_device != ctx->f_ids[0].p) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_ids[0].p, keys_device, n_chunks * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (cells_device != ctx->f_cells.p) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_cells.p, cells_device, n_chunks * 64, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    TRY(finalize_begin(ctx, (u32)n_chunks, true));
+    TRY(finalize_wait(ctx));
+    ctx->has_pose = false;
+    ctx->stats.resident_clusters = 0;
+    return CHAD_OK;
+}
 
 int chad_device_alloc(chad_ctx* ctx, size_t bytes, void** device_ptr) {
     if (!ctx || !device_ptr) return CHAD_ERR_INVALID;

@@ -57,6 +57,18 @@ int launch_blocks_pairs(cudaStream_t s, const float* xyz_sorted, const float* no
                         BatchPlan* plan, const BlockTable& bt, void* scan_ws, u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, u32 pair_capacity,
                         int num_sms, const LaunchHook* hook, int cls_count, int cls_scan, int cls_emit, int cls_sort);
 
+// Morton-range sharding (multi-GPU): sender side (ray slice -> 16-byte tuples grouped by destination) and receiver side
+constexpr int SHARD_WORLD_MAX = 8;
+int launch_shard_splitters(cudaStream_t s, const u64* sorted_keys, u32 n_first_scan, const BatchPlan* plan, u32 world, u64* splitters);
+// dest_count = u32[3][8] (counts | offsets | cursors), zeroed here
+int launch_shard_count(cudaStream_t s, const float* xyz_sorted, u32 i_begin, u32 i_end, const BatchScans* scans, const MapParams& mp,
+                       const BatchPlan* plan, const u64* splitters, u32 world, u32* dest_count);
+int launch_shard_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 i_begin, u32 i_end, const BatchScans* scans,
+                      const MapParams& mp, BatchPlan* plan, const u64* splitters, u32 world, const u32* dest_offset, u32* dest_cursor, void* tuples,
+                      u32 tuple_capacity);
+int launch_blocks_from_tuples(cudaStream_t s, const void* tuples, u32 n, BatchPlan* plan, const BlockTable& bt, void* scan_ws, u64* keys_a, u64* keys_b,
+                              u32* vals_a, u32* vals_b, u32 pair_capacity, int num_sms);
+
 // ---- fold.cu: ordered segmented fold (octree.hpp:161-163) into the resident chunk table ----
 struct ChunkTable {
     u64* keys;      // [capacity] chunk key = voxel key >> 3, EMPTY = ~0

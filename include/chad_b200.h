@@ -131,6 +131,27 @@ int chad_upload(chad_ctx* ctx, void* device_dst, const void* host_src, size_t by
 int chad_timer_begin(chad_ctx* ctx);
 int chad_timer_end(chad_ctx* ctx, float* milliseconds);
 
+/* ---- Morton-range sharding across GPUs ----------------------------------
+ * One context per rank / GPU; the map is cut into `world` contiguous Morton ranges of 8x8x8-voxel blocks. Every rank
+ * calls these with the SAME batch; between the calls the caller exchanges device buffers (NCCL all-to-all / all-gather;
+ * chad_tsdf_b200/sharded.py does it with torch.distributed). An update travels as a 16-byte tuple
+ * {u64 Morton key, u32 sorted-point rank, u32 sd bits}; the rank restores the reference's fold order on the receiver.
+ *   chad_shard_front        host points of <= 64 scans (scan_offsets[n_scans+1], poses[n_scans][3]) -> point stage on the
+ *                           whole batch, band enumeration of this rank's slice of the sorted rays, tuples grouped by
+ *                           destination in the send buffer; send_counts[world] = tuples per destination. new_submap != 0
+ *                           recomputes the range splitters (identically on every rank, from the batch's sorted points).
+ *   chad_shard_send_buffer  device pointer of the send buffer
+ *   chad_shard_ingest       received tuples (device memory, any order) -> bin, sort, fold into this rank's shard
+ *   chad_shard_export_chunks  this rank's leaf chunks, ascending: device pointers to n x u64 chunk keys and n x 64 B cells
+ *   chad_shard_finalize_from  Submap::finalize from the concatenation (rank order = Morton order) of all ranks' chunks;
+ *                           every rank ends up with the identical DAG; the local shard is cleared */
+int chad_shard_front(chad_ctx* ctx, const float* xyz, const uint32_t* scan_offsets, const float* poses, int n_scans, int rank, int world,
+                     int new_submap, uint64_t* send_counts);
+int chad_shard_send_buffer(chad_ctx* ctx, void** tuples_device);
+int chad_shard_ingest(chad_ctx* ctx, const void* tuples_device, size_t n_tuples);
+int chad_shard_export_chunks(chad_ctx* ctx, size_t* n_chunks, void** keys_device, void** cells_device);
+int chad_shard_finalize_from(chad_ctx* ctx, const uint64_t* keys_device, const void* cells_device, size_t n_chunks);
+
 /* ---- host-only helpers (pure CPU bit arithmetic; usable without a GPU) ------------------------ */
 /* MortonCode::encode / decode (morton.hpp:21-37): 21 bits per axis, bias 2^20, x -> bit 0. */
 uint64_t chad_morton_encode(int32_t x, int32_t y, int32_t z);
