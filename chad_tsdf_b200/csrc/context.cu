@@ -1319,7 +1319,7 @@ int chad_shard_front(chad_ctx* ctx, const float* xyz, const uint32_t* scan_offse
     launches += launch_shard_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), i_begin, i_end, scans, ctx->mp, plan, splitters, (u32)world,
                                   dest + 8, dest + 16, ctx->sh_tuples.p, (u32)total);
     ctx->stats.kernel_launches += launches;
-    TRY(stage_check(ctx));
+    { const int rc = stage_check(ctx); if (rc != CHAD_OK) { ctx->error += " [chad_shard_front]"; return rc; } }
     for (int d = 0; d < world; d++) send_counts[d] = counts[d];
     ctx->stats.scans += (u64)n_scans;
     ctx->stats.points += n;
@@ -1350,7 +1350,9 @@ int chad_shard_ingest(chad_ctx* ctx, const void* tuples_device, size_t n_tuples)
     const BatchPlan hp = ctx->h_plan[0];
     if (hp.error) {
         CUDA_TRY(ctx, cudaMemset(plan_field<u32>(ctx, 0, offsetof(BatchPlan, error)), 0, 4));
-        return error_from_flags(ctx, hp.error);
+        const int rc = error_from_flags(ctx, hp.error);
+        ctx->error += " [chad_shard_ingest: " + std::to_string(n_tuples) + " tuples, " + std::to_string(hp.n_pairs) + " binned, " + std::to_string(hp.n_blocks) + " blocks, table " + std::to_string(ctx->bt.capacity) + "]";
+        return rc;
     }
     ctx->stats.updates += hp.n_pairs;
     ctx->stats.scan_voxels += hp.n_segments;

@@ -13,6 +13,7 @@ plug in a numpy/oracle engine to exercise this file's host logic (submap rule, b
 from __future__ import annotations
 
 import ctypes as C
+import time
 
 import numpy as np
 import torch
@@ -76,6 +77,10 @@ class CudaShardEngine:
     def empty(self, shape, dtype=torch.int64) -> torch.Tensor:
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    def sync(self) -> None:
+        """The collectives run on torch's stream, the engine on its own: order them."""
+        torch.cuda.current_stream(self.device).synchronize()
+
     # state export: this rank's shard / the (replicated) DAG
     def voxels(self):
         return self.map.voxels()
@@ -103,9 +108,13 @@ class ShardedTSDFMap:
         self.world = dist.get_world_size(group)
         self.max_batch = max(1, min(int(max_batch_scans), 64))
         self._scans: list[tuple[np.ndarray, np.ndarray]] = []
+        self._stage: np.ndarray | None = None   # page-locked batch buffer (the engine DMA's straight out of it)
+        self._stage_keep = None
+        self._stage_points = 0
         self._first_pose: np.ndarray | None = None
         self._new_submap = True
         self.exchanged_tuples = 0
+        self.phase_s = {"stage": 0.0, "front": 0.0, "exchange": 0.0, "ingest": 0.0, "close": 0.0}  # host wall clock per phase
 
     # -- the reference's API --
     def insert(self, points, position) -> None:
@@ -121,7 +130,9 @@ class ShardedTSDFMap:
                 self._close_submap()
                 self._first_pose = pos.copy()
         if len(pts):
-            self._scans.append((pts, pos))
+            t0 = time.perf_counter()
+            self._append(pts, pos)
+            self.phase_s["stage"] += time.perf_counter() - t0
         if len(self._scans) >= self.max_batch:
             self._process_batch()
 
@@ -135,14 +146,33 @@ class ShardedTSDFMap:
             self._first_pose = None
 
     # -- internals --
+    def _append(self, pts: np.ndarray, pos: np.ndarray) -> None:
+        need = self._stage_points + len(pts)
+        if self._stage is None or need > len(self._stage):
+            cap = max(need, len(pts) * self.max_batch)
+            try:
+                keep = torch.empty((cap, 3), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+            except RuntimeError:
+                keep = torch.empty((cap, 3), dtype=torch.float32)
+            new = keep.numpy()
+            if self._stage is not None:
+                new[: self._stage_points] = self._stage[: self._stage_points]
+            self._stage, self._stage_keep = new, keep
+        self._stage[self._stage_points: need] = pts
+        self._scans.append((self._stage[self._stage_points: need], pos))
+        self._stage_points = need
+
     def _process_batch(self) -> None:
         if not self._scans:
             return
-        xyz = np.concatenate([p for p, _ in self._scans])
+        xyz = self._stage[: self._stage_points]
         offsets = np.concatenate([[0], np.cumsum([len(p) for p, _ in self._scans])]).astype(np.uint32)
         poses = np.stack([q for _, q in self._scans]).astype(np.float32)
         self._scans = []
+        self._stage_points = 0
+        t0 = time.perf_counter()
         counts, send = self.engine.front(xyz, offsets, poses, self.rank, self.world, self._new_submap)
+        t1 = time.perf_counter()
         self._new_submap = False
         send_counts = self.engine.empty((self.world,))
         send_counts.copy_(torch.tensor(counts, dtype=torch.int64))
@@ -152,10 +182,17 @@ class ShardedTSDFMap:
         recv = self.engine.empty((sum(recv_list), TUPLE_WORDS))
         dist.all_to_all_single(recv, send, output_split_sizes=recv_list, input_split_sizes=counts, group=self.group)
         self.exchanged_tuples += sum(c for r, c in enumerate(counts) if r != self.rank)
+        self.engine.sync()
+        t2 = time.perf_counter()
         self.engine.ingest(recv)
+        t3 = time.perf_counter()
+        self.phase_s["front"] += t1 - t0
+        self.phase_s["exchange"] += t2 - t1
+        self.phase_s["ingest"] += t3 - t2
 
     def _close_submap(self) -> None:
         self._process_batch()
+        t0 = time.perf_counter()
         keys, cells = self.engine.export_chunks()
         n = self.engine.empty((1,))
         n.fill_(keys.shape[0])
@@ -174,5 +211,7 @@ class ShardedTSDFMap:
         # rank order == ascending Morton order (contiguous ranges)
         gk = torch.cat([all_k[r * pad: r * pad + c] for r, c in enumerate(counts)])
         gc = torch.cat([all_c[r * pad: r * pad + c] for r, c in enumerate(counts)])
+        self.engine.sync()
         self.engine.finalize_from(gk, gc)
         self._new_submap = True
+        self.phase_s["close"] += time.perf_counter() - t0

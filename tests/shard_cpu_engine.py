@@ -17,6 +17,9 @@ class NumpyShardEngine:
     def empty(self, shape, dtype=torch.int64):
         return torch.empty(shape, dtype=dtype)
 
+    def sync(self):
+        pass
+
     def front(self, xyz, offsets, poses, rank, world, new_submap):
         pts_sorted, keys_sorted, normals, scan_of = [], [], [], []
         for s in range(len(offsets) - 1):
