@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libchad_b200.so")
-SOURCES = ["radix_sort.cu", "points.cu", "band.cu", "blocks.cu", "fold.cu", "dag.cu", "context.cu", "tsdf_host.cpp"]
+SOURCES = ["radix_sort.cu", "points.cu", "band.cu", "blocks.cu", "runs.cu", "fold.cu", "dag.cu", "context.cu", "tsdf_host.cpp"]
 HEADERS = ["common.cuh", "kernels.cuh", "radix_sort.cuh", "scan.cuh", "ray.cuh"]
 # -fmad=false / -ffp-contract=off: the reference's strict-IEEE configuration (cmake/options_compiler.cmake:39);
 # the kernels additionally use explicit *_rn intrinsics wherever a result is observable.

@@ -116,7 +116,12 @@ struct BatchPlan {
     u32 fold_ticket;   // dynamic work counter of the fold kernel
     u32 n_blocks;      // non-empty 8^3-voxel blocks of the batch (block-binned pair path)
     u32 sort_ticket;   // dynamic work counter of the per-block sort
-    u32 pad[2];
+    u32 n_runs;        // (tile, block) runs of the batch (tile-run pair path)
+    u32 nbits_blocks;  // 3k - 6 + tile_bits: width of a run descriptor's sort key (compact 8^3-block id, tile)
+    u32 tile_bits;     // bits of a 256-ray tile index inside the batch
+    u32 n_big_blocks;  // tile-run path: blocks listed from the front of the work list (many updates) ...
+    u32 n_small_blocks;//                ... and from its back
+    u32 pad[1];
 };
 
 constexpr int MAX_BATCH_SCANS = 64;

@@ -89,7 +89,12 @@ struct chad_ctx {
     // batch work buffers
     DevBuf bt_mem;                  // block table of the block-binned pair path
     BlockTable bt{};
-    int pair_path = 0;              // 0 = block-binned (default), 1 = global radix sort
+    int pair_path = 2;              // 2 = tile runs + fused block sort/fold (default), 0 = block-binned, 1 = global radix sort
+    DevBuf run_mem;                 // run descriptors of the tile-run path
+    RunBuffers rb{};
+    bool pending_runs = false;      // the batch whose fold is pending went through the tile-run path
+    BatchPlan* h_plan_fold = nullptr;  // pinned BatchPlan[2]: the plan as the fused fold left it (distinct voxels, deferred errors)
+    bool fold_stats_pending[2] = {false, false};
     DevBuf pk_a, pk_b, pv_a, pv_b;  // point-sort ping-pong (N-sized): separate from the pair buffers so that the next batch's point
                                     // stage can be queued while the previous batch's pairs still wait for their fold
     DevBuf keys_a, keys_b, vals_a, vals_b, sorted_keys, sorted_order, xyz_sorted, normals, seg_info, counts, offsets, radix_ws, scan_ws;
@@ -295,6 +300,11 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
     TRY(dev_ensure(ctx, ctx->bt_mem, blocks_table_bytes((u32)bcap)));
     ctx->bt = blocks_table_carve(ctx->bt_mem.p, (u32)bcap);
     TRY(dev_ensure(ctx, ctx->scan_ws, scan_workspace_bytes(np > bcap ? np : bcap)));
+    if (ctx->mp.max_ray_runs <= runs_max_ray_runs() && ctx->mp.max_ray_voxels <= runs_max_ray_voxels()) {
+        const size_t dcap = np * ctx->mp.max_ray_runs;
+        TRY(dev_ensure(ctx, ctx->run_mem, runs_desc_bytes(dcap)));
+        ctx->rb = runs_carve(ctx->run_mem.p, dcap);
+    }
     ctx->rws = radix_workspace_carve(ctx->radix_ws.p, pairs);
     ctx->cap_points = np;
     ctx->cap_pairs = pairs;
@@ -303,18 +313,38 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
 
 int finalize_begin(chad_ctx* ctx, u32 max_chunks, bool external = false);
 
+// the fused fold of the tile-run path reports the batch's distinct voxels after the fact: collect what has arrived.
+// Only called when the stream has passed the copies (after an event / stream synchronisation that follows them).
+void account_fold_stats(chad_ctx* ctx) {
+    for (int slot = 0; slot < 2; slot++) {
+        if (!ctx->fold_stats_pending[slot]) continue;
+        ctx->fold_stats_pending[slot] = false;
+        ctx->stats.scan_voxels += ctx->h_plan_fold[slot].n_segments;
+    }
+}
+
 // launch the fold of the batch whose front has been queued (see the file comment)
 int complete_pending_fold(chad_ctx* ctx) {
     if (!ctx->fold_pending) return CHAD_OK;
     ctx->fold_pending = false;
     const int slot = ctx->pending_slot;
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->front_done));
-    const BatchPlan plan = ctx->h_plan[slot];
+    account_fold_stats(ctx);  // every earlier fold precedes front_done in stream order
+    BatchPlan plan = ctx->h_plan[slot];
+    const bool runs = ctx->pending_runs;
     ctx->table_count_known = *ctx->h_table_count;
     ctx->stats.updates += plan.n_pairs;
     ctx->stats.key_bits_points = plan.nbits_points;
     ctx->stats.key_bits_pairs = plan.nbits_pairs;
-    ctx->stats.scan_voxels += plan.n_segments;
+    if (runs) {
+        // the fused fold counts the distinct voxels / chunks itself; before it runs only a bound is known:
+        // a block holds 64 leaf chunks and every new chunk needs at least one update
+        const u64 bound = std::min<u64>(u64(plan.n_blocks) * 64, plan.n_pairs);
+        if (bound >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "batch touches more than 2^31 leaf chunks");
+        plan.n_chunk_heads = (u32)bound;
+    } else {
+        ctx->stats.scan_voxels += plan.n_segments;
+    }
     if (plan.error) {
         ctx->close_pending = false;
         CUDA_TRY(ctx, cudaMemsetAsync(plan_field<u32>(ctx, slot, offsetof(BatchPlan, error)), 0, 4, ctx->stream));
@@ -322,8 +352,15 @@ int complete_pending_fold(chad_ctx* ctx) {
     }
     TRY(table_reserve(ctx, ctx->table_count_known + plan.n_chunk_heads));
     u64 launches = 0;
-    PROF(ctx, PC_FOLD, launch_fold(ctx->stream, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(),
-                                   ctx->pending_max_pairs, plan_ptr(ctx, slot), ctx->table, ctx->num_sms));
+    if (runs) {
+        if (plan.n_pairs) PROF(ctx, PC_RUNS_FOLD, launch_runs_fold(ctx->stream, ctx->keys_a.as<u64>(), ctx->rb, plan_ptr(ctx, slot), ctx->table, ctx->num_sms));
+        CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->h_plan_fold[slot], plan_ptr(ctx, slot), sizeof(BatchPlan), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += sizeof(BatchPlan);
+        ctx->fold_stats_pending[slot] = true;
+    } else {
+        PROF(ctx, PC_FOLD, launch_fold(ctx->stream, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(),
+                                       ctx->pending_max_pairs, plan_ptr(ctx, slot), ctx->table, ctx->num_sms));
+    }
     ctx->stats.kernel_launches += launches;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_table_count, ctx->table.count, 4, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.d2h_bytes += 4;
@@ -381,8 +418,9 @@ int process_front(chad_ctx* ctx) {
     u64 launches = 0;
     const LaunchHook* hook = ctx->profiling ? &ctx->hook : nullptr;
     queue_point_stage(ctx, slot, b, n, ns);
-    const bool use_blocks = ctx->pair_path == 0 && n <= blocks_max_batch_points();
-    if (!use_blocks) {
+    const bool use_runs = ctx->pair_path == 2 && n <= runs_max_batch_points() && ctx->rb.capacity != 0;
+    const bool use_blocks = !use_runs && ctx->pair_path != 1 && n <= blocks_max_batch_points();
+    if (!use_blocks && !use_runs) {
         PROF(ctx, PC_BAND_COUNT, launch_band_count(s, ctx->xyz_sorted.as<float>(), n, scans, ctx->mp, plan, ctx->counts.as<u32>()));
         PROF(ctx, PC_BAND_SCAN, (exclusive_scan<u32, u32>(s, ctx->counts.as<u32>(), ctx->offsets.as<u32>(), n, ctx->scan_ws.p, (u32*)nullptr,
                                                           plan_field<u32>(ctx, slot, offsetof(BatchPlan, n_pairs)))));
@@ -393,7 +431,10 @@ int process_front(chad_ctx* ctx) {
     TRY(complete_pending_fold(ctx));
     // ---- pair stage ----
     const size_t max_pairs = size_t(n) * ctx->mp.max_ray_voxels;
-    if (use_blocks) {
+    if (use_runs) {
+        launches += launch_runs_front(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan, ctx->rb, ctx->keys_a.as<u64>(),
+                                      (u32)ctx->cap_pairs, ctx->rws, ctx->num_sms, hook, PC_RUNS_EMIT, PC_RUNS_SORT);
+    } else if (use_blocks) {
         launches += launch_blocks_pairs(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan, ctx->bt, ctx->scan_ws.p,
                                         ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(), (u32)ctx->cap_pairs,
                                         ctx->num_sms, hook, PC_BLOCKS_COUNT, PC_BLOCKS_SCAN, PC_BLOCKS_EMIT, PC_BLOCKS_SORT);
@@ -412,6 +453,7 @@ int process_front(chad_ctx* ctx) {
     ctx->stats.kernel_launches += launches;
     ctx->stats.batches++;
     ctx->fold_pending = true;
+    ctx->pending_runs = use_runs;
     ctx->pending_slot = slot;
     ctx->plan_slot ^= 1;
     ctx->pending_max_pairs = (u32)max_pairs;
@@ -431,6 +473,7 @@ int drain(chad_ctx* ctx) {
         TRY(finalize_part2(ctx));
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    account_fold_stats(ctx);
     prof_resolve(ctx);
     ctx->table_count_known = *ctx->h_table_count;
     ctx->stats.resident_clusters = ctx->table_count_known;
@@ -820,6 +863,7 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     CREATE_TRY(cudaEventCreate(&ctx->t0));
     CREATE_TRY(cudaEventCreate(&ctx->t1));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_plan), 2 * sizeof(BatchPlan)));
+    CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_plan_fold), 2 * sizeof(BatchPlan)));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_table_count), 64));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_table_count2), 64));
     *ctx->h_table_count2 = 0;
@@ -827,7 +871,8 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     *ctx->h_table_count = 0;
     CREATE_TRY(radix_sort_init());
     CREATE_TRY(blocks_init());
-    if (const char* env = std::getenv("CHAD_PAIR_PATH")) ctx->pair_path = std::atoi(env) ? 1 : 0;
+    CREATE_TRY(runs_init());
+    if (const char* env = std::getenv("CHAD_PAIR_PATH")) { const int m = std::atoi(env); if (m >= 0 && m <= 2) ctx->pair_path = m; }
 
     ctx->mp.res = sdf_res;
     ctx->mp.trunc = sdf_trunc;
@@ -837,6 +882,10 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     // a ray crosses at most 1 + sum_a(|dv_a|) voxels with |dv_a| <= 2*ratio*|dir_a| + 1 (octree.hpp:94-97,121-152)
     ctx->mp.max_ray_voxels = (u32)std::ceil(4.0 + 2.0 * std::sqrt(3.0) * ratio) + 2;
     ctx->mp.band_margin = (u32)std::ceil(ratio) + 3;
+    {   // a ray takes at most L = ceil(2 ratio) + 1 steps along one axis, i.e. crosses at most ceil(L / 8) block faces per axis
+        const u32 L = (u32)std::ceil(2.0 * ratio) + 1;
+        ctx->mp.max_ray_runs = 1 + 3 * ((L + 7) / 8);
+    }
     ctx->max_batch = max_batch_scans == 0 ? 16 : max_batch_scans;
 
     int r = dev_ensure(ctx, ctx->d_scans, sizeof(BatchScans));
@@ -870,7 +919,7 @@ void chad_destroy(chad_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->fin_stream) cudaStreamSynchronize(ctx->fin_stream);
-    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->f_level_new, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->sh_tuples, &ctx->sh_scalars, &ctx->bt_mem, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
+    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->f_level_new, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->sh_tuples, &ctx->sh_scalars, &ctx->bt_mem, &ctx->run_mem, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
                       &ctx->sorted_keys, &ctx->sorted_order, &ctx->xyz_sorted, &ctx->normals, &ctx->seg_info, &ctx->counts, &ctx->offsets,
                       &ctx->radix_ws, &ctx->scan_ws, &ctx->t_keys, &ctx->t_cells, &ctx->t_count, &ctx->f_ids[0], &ctx->f_ids[1], &ctx->f_slots[0],
                       &ctx->f_slots[1], &ctx->f_cells, &ctx->f_tsdf, &ctx->f_addr[0], &ctx->f_addr[1], &ctx->f_head, &ctx->f_head_rank, &ctx->f_cand,
@@ -886,6 +935,7 @@ void chad_destroy(chad_ctx* ctx) {
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->h_plan) cudaFreeHost(ctx->h_plan);
+    if (ctx->h_plan_fold) cudaFreeHost(ctx->h_plan_fold);
     if (ctx->h_table_count) cudaFreeHost(ctx->h_table_count);
     if (ctx->h_table_count2) cudaFreeHost(ctx->h_table_count2);
     if (ctx->h_fin) cudaFreeHost(ctx->h_fin);
@@ -1053,6 +1103,7 @@ int chad_reset(chad_ctx* ctx) {
     ctx->batch_scans = 0;
     ctx->fold_pending = false;
     ctx->close_pending = false;
+    ctx->fold_stats_pending[0] = ctx->fold_stats_pending[1] = false;
     ctx->sh_have_splitters = false;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1077,7 +1128,7 @@ int chad_reset(chad_ctx* ctx) {
 }
 
 int chad_set_pair_path(chad_ctx* ctx, int mode) {
-    if (!ctx || mode < 0 || mode > 1) return CHAD_ERR_INVALID;
+    if (!ctx || mode < 0 || mode > 2) return CHAD_ERR_INVALID;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     TRY(settle(ctx));
     ctx->pair_path = mode;
@@ -1116,6 +1167,9 @@ int chad_profile_get(chad_ctx* ctx, int cls, const char** name, double* millisec
     else if (cls == PC_BLOCKS_SCAN) nm = "scan_kernels+blocks_compact_kernel";
     else if (cls == PC_BLOCKS_EMIT) nm = "blocks_emit_kernel";
     else if (cls == PC_BLOCKS_SORT) nm = "blocks_sort_kernel";
+    else if (cls == PC_RUNS_EMIT) nm = "runs_emit_kernel";
+    else if (cls == PC_RUNS_SORT) nm = "run descriptor sort + runs_group_kernel";
+    else if (cls == PC_RUNS_FOLD) nm = "runs_fold_kernel";
     else nm = "finalize_submap[part 1 + part 2 on the finalize stream, overlapped with inserts]";
     if (name) *name = nm;
     if (milliseconds) *milliseconds = ctx->prof_ms[cls];

@@ -11,13 +11,14 @@ struct MapParams {
     float trunc_recip;  // 1.0f / trunc               (submap.hpp:24)
     u32 band_margin;    // voxels a band voxel can lie from its point's voxel (bounds the plan's k)
     u32 max_ray_voxels; // per-ray capacity bound used to size the pair buffers
+    u32 max_ray_runs;   // 8^3-voxel blocks one ray can touch
 };
 
 // instrumentation classes (chad_profile_*): one per kernel (group); radix passes are numbered
 enum ProfClass {
     PC_PLAN = 0, PC_POINT_KEYS, PC_POINT_SORT_HIST, PC_POINT_SORT_PASS0, PC_POINT_GATHER = PC_POINT_SORT_PASS0 + 8, PC_NORMALS, PC_BAND_COUNT,
     PC_BAND_SCAN, PC_BAND_EMIT, PC_PAIR_SORT_HIST, PC_PAIR_SORT_PASS0, PC_SEGMENT_COUNT = PC_PAIR_SORT_PASS0 + 8, PC_FOLD, PC_FINALIZE,
-    PC_BLOCKS_COUNT, PC_BLOCKS_SCAN, PC_BLOCKS_EMIT, PC_BLOCKS_SORT, PC_COUNT
+    PC_BLOCKS_COUNT, PC_BLOCKS_SCAN, PC_BLOCKS_EMIT, PC_BLOCKS_SORT, PC_RUNS_EMIT, PC_RUNS_SORT, PC_RUNS_FOLD, PC_COUNT
 };
 
 // ---- points.cu: voxelise + Morton (morton.hpp:59-80), sort keys, gather, normals (normals.hpp) ----
@@ -68,6 +69,28 @@ int launch_shard_emit(cudaStream_t s, const float* xyz_sorted, const float* norm
                       u32 tuple_capacity);
 int launch_blocks_from_tuples(cudaStream_t s, const void* tuples, u32 n, BatchPlan* plan, const BlockTable& bt, void* scan_ws, u64* keys_a, u64* keys_b,
                               u32* vals_a, u32* vals_b, u32 pair_capacity, int num_sms);
+
+// ---- runs.cu: tile-run grouping with the fold fused into the per-block sort (default pair path) ----
+struct RadixWorkspace;
+struct RunBuffers {   // run descriptors of a batch: sort ping-pong (block id, descriptor index), descriptor = (first record, records)
+    u64 *key_a, *key_b;
+    u32 *val_a, *val_b;
+    uint2* desc;
+    uint2* sdesc;     // descriptors in sorted (block id) order
+    uint2* work;      // (first sorted descriptor, descriptors) of every block
+    u32 capacity;
+};
+cudaError_t runs_init();
+u32 runs_max_batch_points();
+u32 runs_max_ray_voxels();
+u32 runs_max_ray_runs();
+size_t runs_desc_bytes(size_t capacity);
+RunBuffers runs_carve(void* mem, size_t capacity);
+struct ChunkTable;
+int launch_runs_front(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const BatchScans* scans, const MapParams& mp,
+                      BatchPlan* plan, const RunBuffers& rb, u64* records, u32 rec_capacity, const RadixWorkspace& rws, int num_sms,
+                      const LaunchHook* hook, int cls_emit, int cls_sort);
+int launch_runs_fold(cudaStream_t s, const u64* records, const RunBuffers& rb, BatchPlan* plan, const ChunkTable& t, int num_sms);
 
 // ---- fold.cu: ordered segmented fold (octree.hpp:161-163) into the resident chunk table ----
 struct ChunkTable {

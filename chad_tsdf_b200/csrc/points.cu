@@ -42,7 +42,7 @@ __device__ __forceinline__ bool voxel_of(float px, float py, float pz, float rec
 __global__ void __launch_bounds__(PT_THREADS) plan_reset_kernel(BatchPlan* plan, u32 n_points, u32 n_scans) {
     plan->rmax = 0; plan->k = 0; plan->nbits_points = 0; plan->nbits_pairs = 0;
     plan->n_points = n_points; plan->n_scans = n_scans; plan->n_pairs = 0;
-    plan->n_segments = 0; plan->n_chunk_heads = 0; plan->n_new_chunks = 0; plan->fold_ticket = 0; plan->n_blocks = 0; plan->sort_ticket = 0;
+    plan->n_segments = 0; plan->n_chunk_heads = 0; plan->n_new_chunks = 0; plan->fold_ticket = 0; plan->n_blocks = 0; plan->sort_ticket = 0; plan->n_runs = 0; plan->nbits_blocks = 0; plan->tile_bits = 0; plan->n_big_blocks = 0; plan->n_small_blocks = 0;
     // plan->error is sticky: cleared by the host when it reports it
 }
 
@@ -85,6 +85,13 @@ __global__ void plan_finalize_kernel(BatchPlan* plan, u32 margin) {
     if (nb > 64) { nb = 64; atomicOr(&plan->error, ERRF_KEY_BUDGET); }
     plan->k = k;
     plan->nbits_pairs = 3 * k + 3;
+    {   // run descriptors of the tile-run pair path sort by (compact block id, tile)
+        const u32 tiles = (plan->n_points + 255u) / 256u;
+        const u32 tbits = (tiles > 1) ? (32 - __clz(tiles - 1)) : 0;
+        plan->tile_bits = tbits;
+        plan->nbits_blocks = 3 * k - 6 + tbits;
+        if (3 * k - 6 + tbits > 64) plan->nbits_blocks = 0xFFFFFFFFu;  // the tile-run path reports ERRF_KEY_BUDGET; paths 0 / 1 do not use it
+    }
     plan->nbits_points = nb;
 }
 

@@ -1,0 +1,584 @@
+// Tile-run grouping of the band-voxel updates with the fold fused into the per-block sort: the default replacement
+// for the octree's per-voxel grouping and running average (/root/reference/include/chad/detail/octree.hpp:31-78,
+// 86-164). Successor of blocks.cu (which stays as pair path 0): ncu r01b showed the count / emit / sort / fold chain
+// issue bound (1360 warp instructions per warp in the count walk alone, DRAM below 17 % everywhere), so this path
+//   * walks every ray ONCE (no counting pass): a CTA takes a tile of 256 consecutive sorted rays, keeps the tile's
+//     updates in shared memory, groups them by 8x8x8-voxel block with a shared-memory hash, reserves one contiguous
+//     span of the record buffer with ONE global atomic and writes one "run" per (tile, block) plus a 16-byte run
+//     descriptor -- no global hash table, no per-ray global atomics;
+//   * sorts the run descriptors by block id (a few hundred thousand keys: the existing onesweep sort);
+//   * gives every block to one CTA that reads the block's runs, sorts its records by (voxel, sorted-point rank) in
+//     shared memory and folds them IN PLACE into the resident leaf-chunk table: one hash probe per 2x2x2 chunk instead
+//     of one per voxel, and the sorted (key, sd) stream never goes back to HBM.
+// The reference's update order inside a voxel (sorted point rank, then ray step; a ray touches a voxel at most once)
+// is restored exactly by the rank sort, so results are bit-identical to paths 0 / 1 and to the CPU reference.
+#include "kernels.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+#include <algorithm>
+
+namespace chadgpu {
+
+namespace {
+
+constexpr int RUN_THREADS = 256;
+constexpr u32 RUN_HASH = 1024;             // shared-memory slots for the distinct blocks of a tile (>= 256 rays x 4 runs)
+constexpr u32 RUN_BLK_SHIFT = 9;           // 8^3 voxels per block
+constexpr u32 RUN_RANK_BITS = 23;          // sorted-point rank inside the batch
+constexpr u64 RUN_EMPTY = ~0ull;
+constexpr u32 RUN_BIG_BLOCK = 2048;        // updates from which a block is scheduled ahead of the others
+
+constexpr int RF_THREADS = 128;             // fold: four independent warps per CTA, one block per warp at a time
+constexpr u32 RF_VOXELS = 512;
+constexpr int RF_DEPTH = 4;                // 32-update chunks a fold warp keeps in flight
+
+// ---- lean ray walk: octree.hpp:92-152 with the state in scalars and a branch-free step ------------------------
+struct RayL {
+    float px, py, pz;
+    i32 cx, cy, cz;   // current voxel
+    i32 ex, ey, ez;   // vf + step: the walk ends when the stepped axis reaches it (octree.hpp:131,138,145)
+    i32 sx, sy, sz;
+    float tx, ty, tz; // tMax
+    float dx, dy, dz; // tDelta
+};
+__device__ __forceinline__ void axis_setup(float p, float d, float invl, float res, float trunc, float recip, i32& c, i32& e, i32& st, float& tmax,
+                                           float& delta, u32& rmax) {
+    const float dir = fmul(d, invl);
+    const float dir_recip = fdiv(1.0f, dir);                  // :93
+    const float start = fsub(p, fmul(dir, trunc));            // :94
+    const float fin = fadd(p, fmul(dir, trunc));              // :95
+    const float sv = fmul(start, recip);
+    const float fl = floorf(sv);
+    const i32 vs = (i32)fl;                                   // :96
+    const i32 vf = (i32)floorf(fmul(fin, recip));             // :97
+    const i32 dv = vf - vs;
+    st = (0 < dv) - (dv < 0);                                 // :100
+    delta = fabsf(fmul(res, dir_recip));                      // :102
+    float m;                                                  // :104-116
+    if (st < 0) m = fmul(res, fl);
+    else if (st > 0) m = fmul(res, ceilf(sv));
+    else m = 3.402823466e+38f;
+    m = fsub(m, start);                                       // :117
+    tmax = fabsf(fmul(m, dir_recip));                         // :118
+    c = vs;
+    e = vf + st;
+    rmax = max(rmax, max(rcode(vs), rcode(vf)));              // the walk is monotone: its extremes are vs and vf
+}
+__device__ __forceinline__ u32 rayl_setup(RayL& r, float px, float py, float pz, float ox, float oy, float oz, float res, float trunc, float recip) {
+    r.px = px; r.py = py; r.pz = pz;
+    const float dx = fsub(px, ox), dy = fsub(py, oy), dz = fsub(pz, oz);
+    const float invl = fdiv(1.0f, fsqrt(dot3(dx, dy, dz, dx, dy, dz)));  // normalize, :92
+    u32 rmax = 0;
+    axis_setup(px, dx, invl, res, trunc, recip, r.cx, r.ex, r.sx, r.tx, r.dx, rmax);
+    axis_setup(py, dy, invl, res, trunc, recip, r.cy, r.ey, r.sy, r.ty, r.dy, rmax);
+    axis_setup(pz, dz, invl, res, trunc, recip, r.cz, r.ez, r.sz, r.tz, r.dz, rmax);
+    return rmax;
+}
+// one iteration of octree.hpp:125-152; returns false on `break`; crossed = the step left the current 8^3 block
+__device__ __forceinline__ bool rayl_advance(RayL& r, bool& crossed) {
+    const bool xy = r.tx < r.ty, xz = r.tx < r.tz, yz = r.ty < r.tz;
+    const bool ax = xy && xz, ay = !xy && yz;  // else z  (:126-150: x if tx<ty && tx<tz; y if !(tx<ty) && ty<tz; else z)
+    const bool az = !ax && !ay;
+    const i32 ox = r.cx, oy = r.cy, oz = r.cz;
+    r.cx += ax ? r.sx : 0;
+    r.cy += ay ? r.sy : 0;
+    r.cz += az ? r.sz : 0;
+    r.tx = ax ? fadd(r.tx, r.dx) : r.tx;
+    r.ty = ay ? fadd(r.ty, r.dy) : r.ty;
+    r.tz = az ? fadd(r.tz, r.dz) : r.tz;
+    crossed = (((ox ^ r.cx) | (oy ^ r.cy) | (oz ^ r.cz)) >> 3) != 0;
+    return ax ? (r.cx != r.ex) : (ay ? (r.cy != r.ey) : (r.cz != r.ez));
+}
+// low three bits of a coordinate spread to bits 0, 3, 6
+__device__ __forceinline__ u32 spread_low3(i32 c) {
+    const u32 l = (u32)c & 7u;
+    return (l | (l << 2) | (l << 4)) & 0x49u;
+}
+__device__ __forceinline__ u32 local_voxel(i32 x, i32 y, i32 z) { return spread_low3(x) | (spread_low3(y) << 1) | (spread_low3(z) << 2); }
+
+// shared-memory hash of the tile's distinct blocks, keyed by the packed block coordinates (cheap to form per crossing;
+// the Morton block id is only computed once per distinct block, when the descriptors are written)
+__device__ __forceinline__ u64 pack_block(i32 x, i32 y, i32 z) {
+    return (u64)(u32)((x >> 3) + (1 << 17)) | ((u64)(u32)((y >> 3) + (1 << 17)) << 18) | ((u64)(u32)((z >> 3) + (1 << 17)) << 36);
+}
+__device__ __forceinline__ u64 packed_block_to_morton(u64 pb) {  // (Morton key of the block's first voxel) >> 9
+    const u32 mask = (1u << 18) - 1u;
+    return (spread3((u32)pb & mask) | (spread3((u32)(pb >> 18) & mask) << 1) | (spread3((u32)(pb >> 36) & mask) << 2));
+}
+__device__ __forceinline__ u32 tile_hash_insert(u64* s_hkey, u64 pb) {
+    u32 h = ((u32)pb * 0x9E3779B1u + (u32)(pb >> 32) * 0x85EBCA77u) >> 22;  // RUN_HASH = 2^10
+    for (u32 probes = 0; probes < RUN_HASH; probes++) {
+        const u64 cur = s_hkey[h];
+        if (cur == pb) return h;
+        if (cur == RUN_EMPTY) {
+            const u64 old = atomicCAS(&s_hkey[h], RUN_EMPTY, pb);
+            if (old == RUN_EMPTY || old == pb) return h;
+        }
+        h = (h + 1) & (RUN_HASH - 1);
+    }
+    return 0xFFFFFFFFu;  // cannot happen: a tile has at most 256 x max_ray_runs <= 1024 distinct blocks
+}
+
+// ---- 1. walk + emit ---------------------------------------------------------------------------------
+// record = (sd bits << 32) | (local voxel << 23) | sorted-point rank. Inside a run the records are written in RANK
+// order (ray by ray), and the descriptors sort by (block, tile): the concatenation of a block's runs is its update
+// stream in the reference's order, which the fold then consumes sequentially without sorting anything.
+constexpr u32 RUN_WARPS = RUN_THREADS / 32;
+__global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __restrict__ xyz_sorted, const float* __restrict__ normals, u32 n_points,
+                                                                const BatchScans* __restrict__ scans, float res, float trunc, float recip, u32 mrv,
+                                                                BatchPlan* plan, u64* __restrict__ records, u32 rec_capacity,
+                                                                u64* __restrict__ desc_key, u32* __restrict__ desc_val, uint2* __restrict__ desc,
+                                                                u32 desc_capacity) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    uint2* s_rec = reinterpret_cast<uint2*>(s_dyn);  // [RUN_THREADS][stride]: x = (slot << 9) | local voxel, y = sd bits
+    __shared__ u64 s_hkey[RUN_HASH];
+    __shared__ u32 s_wcnt[RUN_WARPS / 2][RUN_HASH];  // records per (warp, slot), two warps per word; later: per-warp cursors inside the slot
+    __shared__ u32 s_hbase[RUN_HASH];                // first record of the slot's run inside the tile's span
+    __shared__ u32 s_warp[RUN_THREADS / 32];
+    __shared__ u32 s_gbase, s_dbase;
+    __shared__ u32 s_scan[2];  // scans of the tile's first and last point
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 stride = mrv | 1u;  // odd: the ray-major reads of the write-out and the step-major writes of the walk both spread over the banks
+#pragma unroll
+    for (u32 q = 0; q < RUN_HASH / RUN_THREADS; q++) {
+        s_hkey[tid + q * RUN_THREADS] = RUN_EMPTY;
+#pragma unroll
+        for (u32 w = 0; w < RUN_WARPS / 2; w++) s_wcnt[w][tid + q * RUN_THREADS] = 0;
+    }
+    const u32 tile0 = blockIdx.x * RUN_THREADS;
+    if (tid < 2) s_scan[tid] = scan_of(scans, plan->n_scans, tid == 0 ? tile0 : min(tile0 + RUN_THREADS, n_points) - 1);
+    __syncthreads();
+    const u32 i = tile0 + tid;
+    u32 cnt = 0, err = 0;
+    RayL r;
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    bool alive = false;
+    u32 slot = 0, run = 0;
+    const u32 wsh = (warp & 1u) * 16u;
+    if (i < n_points) {
+        u32 s = s_scan[0];
+        const u32 s_last = s_scan[1];
+        while (s < s_last && scans->offset[s + 1] <= i) s++;  // a tile rarely straddles scans
+        nx = normals[size_t(i) * 3]; ny = normals[size_t(i) * 3 + 1]; nz = normals[size_t(i) * 3 + 2];
+        const u32 rmax = rayl_setup(r, xyz_sorted[size_t(i) * 3], xyz_sorted[size_t(i) * 3 + 1], xyz_sorted[size_t(i) * 3 + 2], scans->pose[s][0],
+                                    scans->pose[s][1], scans->pose[s][2], res, trunc, recip);
+        if (rmax >= (1u << 20)) err |= ERRF_RANGE;
+        else {
+            alive = true;
+            slot = tile_hash_insert(s_hkey, pack_block(r.cx, r.cy, r.cz));
+        }
+    }
+    // warp-uniform walk: every lane iterates until the warp's longest ray is done, so the lanes stay converged
+    while (__any_sync(0xffffffffu, alive)) {
+        if (alive) {
+            // octree.hpp:157-159: the voxel's LOWER CORNER projected on the normal, clamped to +-trunc
+            float sd = dot3(nx, ny, nz, fsub(fmul((float)r.cx, res), r.px), fsub(fmul((float)r.cy, res), r.py), fsub(fmul((float)r.cz, res), r.pz));
+            sd = fclamp(sd, -trunc, trunc);
+            s_rec[tid * stride + cnt] = make_uint2((slot << 9) | local_voxel(r.cx, r.cy, r.cz), __float_as_uint(sd));
+            cnt++;
+            run++;
+            bool crossed = false;
+            const bool more = (cnt < mrv) && rayl_advance(r, crossed);
+            if (!more || crossed) {
+                if (slot != 0xFFFFFFFFu) atomicAdd(&s_wcnt[warp >> 1][slot], run << wsh); else err |= ERRF_BLOCKS_FULL;
+                run = 0;
+                if (more) slot = tile_hash_insert(s_hkey, pack_block(r.cx, r.cy, r.cz));
+                alive = more;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- one span of the record buffer per tile, one run per distinct block; inside a run the warps follow each other ----
+    u32 c[RUN_HASH / RUN_THREADS];
+    u32 packed = 0;  // (non-empty slots << 16) | records   (a tile holds <= 256 * 32 = 8192 records)
+#pragma unroll
+    for (u32 q = 0; q < RUN_HASH / RUN_THREADS; q++) {
+        const u32 hs = tid * (RUN_HASH / RUN_THREADS) + q;
+        u32 sum = 0;
+#pragma unroll
+        for (u32 w = 0; w < RUN_WARPS / 2; w++) {
+            const u32 word = s_wcnt[w][hs];
+            const u32 lo = word & 0xFFFFu, hi = word >> 16;
+            s_wcnt[w][hs] = sum | ((sum + lo) << 16);  // exclusive prefix over the warps = each warp's cursor inside the run
+            sum += lo + hi;
+        }
+        c[q] = sum;
+        packed += sum + (sum ? (1u << 16) : 0u);
+    }
+    u32 total;
+    u32 ex = block_exclusive_scan<u32>(packed, s_warp, total);
+    if (tid == 0) {
+        const u32 nrec = total & 0xFFFFu, nd = total >> 16;
+        u32 gb = 0, db = 0;
+        if (nrec) { gb = atomicAdd(&plan->n_pairs, nrec); db = atomicAdd(&plan->n_runs, nd); }
+        u32 e = 0;
+        if (gb + nrec > rec_capacity || gb + nrec < gb) e |= ERRF_PAIR_CAPACITY;
+        if (db + nd > desc_capacity) e |= ERRF_BLOCKS_FULL;
+        if (plan->nbits_blocks > 64) e |= ERRF_KEY_BUDGET;
+        if (e) { atomicOr(&plan->error, e); gb = 0xFFFFFFFFu; }
+        s_gbase = gb;
+        s_dbase = db;
+    }
+    __syncthreads();
+    const u32 gbase = s_gbase;
+    if (gbase != 0xFFFFFFFFu && packed) {
+        const u32 k = plan->k, tbits = plan->tile_bits;
+#pragma unroll
+        for (u32 q = 0; q < RUN_HASH / RUN_THREADS; q++) {
+            const u32 hs = tid * (RUN_HASH / RUN_THREADS) + q;
+            const u32 base = ex & 0xFFFFu;
+            if (c[q]) {
+                const u32 d = s_dbase + (ex >> 16);
+                const u64 cid = compact_key(packed_block_to_morton(s_hkey[hs]) << RUN_BLK_SHIFT, k) >> RUN_BLK_SHIFT;
+                desc_key[d] = (cid << tbits) | (u64)blockIdx.x;
+                desc_val[d] = d;
+                desc[d] = make_uint2(gbase + base, c[q]);
+                s_hbase[hs] = base;
+            }
+            ex += c[q] + (c[q] ? (1u << 16) : 0u);
+        }
+    }
+    __syncthreads();
+    if (gbase != 0xFFFFFFFFu) {
+        // ray-major write-out: one ray per warp iteration, one lane per step, so that the positions handed out inside a
+        // (warp, slot) follow the rays' order (records of ONE ray never share a voxel: their mutual order is free)
+        const u32 wmax = __reduce_max_sync(0xffffffffu, cnt);
+        if (wmax) {
+            const u32 rec_base = warp * 32 * stride + lane;
+            u32* wc = s_wcnt[warp >> 1];
+            for (u32 ray = 0; ray < 32; ray++) {
+                const u32 rcnt = __shfl_sync(0xffffffffu, cnt, ray);
+                if (lane < rcnt) {
+                    const uint2 rc = s_rec[rec_base + ray * stride];
+                    const u32 hs = rc.x >> 9;
+                    if (hs < RUN_HASH) {
+                        const u32 old = atomicAdd(&wc[hs], 1u << wsh);
+                        const u32 pos = gbase + s_hbase[hs] + ((old >> wsh) & 0xFFFFu);
+                        records[pos] = (u64(rc.y) << 32) | (u64)(((rc.x & 511u) << RUN_RANK_BITS) | (tile0 + warp * 32 + ray));
+                    }
+                }
+            }
+        }
+    }
+    if (err) atomicOr(&plan->error, err);
+}
+
+// ---- 2. after the descriptor sort: gather the descriptors in sorted order and list the blocks ------------------
+// work[w] = (first sorted descriptor, descriptors) of block w (blocks in arbitrary order: every block is independent)
+__global__ void __launch_bounds__(RUN_THREADS) runs_group_kernel(const u64* __restrict__ dkeys_a, const u64* __restrict__ dkeys_b,
+                                                                 const u32* __restrict__ dvals_a, const u32* __restrict__ dvals_b,
+                                                                 const uint2* __restrict__ desc, uint2* __restrict__ sdesc, BatchPlan* plan,
+                                                                 uint2* __restrict__ work, u32 work_capacity) {
+    const u32 n = plan->n_runs;
+    if (plan->nbits_blocks > 64) return;
+    const bool alt = radix_result_in_alt(plan->nbits_blocks);
+    const u64* __restrict__ keys = alt ? dkeys_b : dkeys_a;
+    const u32* __restrict__ vals = alt ? dvals_b : dvals_a;
+    const u32 tbits = plan->tile_bits;
+    const u32 lane = threadIdx.x & 31;
+    for (u32 q0 = blockIdx.x * RUN_THREADS; q0 < n; q0 += gridDim.x * RUN_THREADS) {  // uniform per CTA
+        const u32 p = q0 + threadIdx.x;
+        u64 cid = 0;
+        bool head = false;
+        if (p < n) {
+            cid = keys[p] >> tbits;
+            sdesc[p] = desc[vals[p]];
+            head = (p == 0) || (keys[p - 1] >> tbits) != cid;
+        }
+        u32 len = 0, recs = 0;
+        if (head) {
+            u32 q = p;
+            while (q < n && (keys[q] >> tbits) == cid) { recs += desc[vals[q]].y; q++; }
+            len = q - p;
+        }
+        // blocks with many updates go to the front of the list (a block is folded by ONE warp: start the long ones first),
+        // the others are listed from the back
+        const bool big = head && recs >= RUN_BIG_BLOCK;
+        const bool small = head && !big;
+        const u32 bb = __ballot_sync(0xffffffffu, big), bs = __ballot_sync(0xffffffffu, small);
+        u32 base_b = 0, base_s = 0;
+        if (lane == 0) {
+            if (bb) base_b = atomicAdd(&plan->n_big_blocks, (u32)__popc(bb));
+            if (bs) base_s = atomicAdd(&plan->n_small_blocks, (u32)__popc(bs));
+            if (bb | bs) atomicAdd(&plan->n_blocks, (u32)__popc(bb | bs));
+        }
+        base_b = __shfl_sync(0xffffffffu, base_b, 0);
+        base_s = __shfl_sync(0xffffffffu, base_s, 0);
+        const u32 ltm = (1u << lane) - 1u;
+        if (big) work[base_b + __popc(bb & ltm)] = make_uint2(p, len);
+        if (small) work[work_capacity - 1 - (base_s + __popc(bs & ltm))] = make_uint2(p, len);
+    }
+}
+
+// ---- 3. fold: one WARP per block streams the block's updates in order into the resident table ----------------
+__device__ __forceinline__ u64 mix64(u64 h) {
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull;
+    h ^= h >> 33;
+    return h;
+}
+__device__ __forceinline__ u64 table_find(const u64* __restrict__ keys, u64 capacity, u64 chunk) {
+    const u64 mask = capacity - 1;
+    u64 h = mix64(chunk) & mask;
+    for (u64 probes = 0; probes < capacity; probes++) {
+        const u64 cur = keys[h];
+        if (cur == chunk) return h;
+        if (cur == CHUNK_EMPTY) return ~0ull;
+        h = (h + 1) & mask;
+    }
+    return ~0ull;
+}
+__device__ __forceinline__ u64 table_insert(u64* __restrict__ keys, u64 capacity, u64 chunk) {  // the chunk is not in the table
+    const u64 mask = capacity - 1;
+    u64 h = mix64(chunk) & mask;
+    for (u64 probes = 0; probes < capacity; probes++) {
+        if (keys[h] == CHUNK_EMPTY && atomicCAS(&keys[h], CHUNK_EMPTY, chunk) == CHUNK_EMPTY) return h;
+        h = (h + 1) & mask;
+    }
+    return ~0ull;
+}
+
+struct FoldWarp {
+    uint2 cell[RF_VOXELS];   // (sd bits, weight) of the block's 512 voxels: the table's cell layout, chunk c = cells 8c .. 8c+7
+    u32 touched[RF_VOXELS / 32];
+};
+
+__global__ void __launch_bounds__(RF_THREADS) runs_fold_kernel(const u64* __restrict__ records, const u64* __restrict__ dkeys_a,
+                                                               const u64* __restrict__ dkeys_b, const uint2* __restrict__ sdesc,
+                                                               const uint2* __restrict__ work, u32 work_capacity, BatchPlan* plan,
+                                                               u64* __restrict__ tkeys, uint2* tcells, u64 capacity, u32* tcount) {
+    __shared__ __align__(16) FoldWarp s_w[RF_THREADS / 32];
+    __shared__ u32 s_red[4];
+    const u32 tid = threadIdx.x, lane = tid & 31;
+    FoldWarp& S = s_w[tid >> 5];
+    if (tid < 4) s_red[tid] = 0;
+    __syncthreads();
+    const u32 pe = plan->error;
+    const u32 nbits = plan->nbits_blocks;
+    const bool bad = (pe & (ERRF_BLOCKS_FULL | ERRF_PAIR_CAPACITY | ERRF_RANGE | ERRF_KEY_BUDGET)) != 0 || nbits > 64;
+    const u64* __restrict__ dkeys = radix_result_in_alt(nbits) ? dkeys_b : dkeys_a;
+    const u32 n_big = plan->n_big_blocks;
+    const u32 n_blocks = bad ? 0u : (n_big + plan->n_small_blocks), k = plan->k, tbits = plan->tile_bits;
+    auto work_item = [&](u32 t) { return work[t < n_big ? t : work_capacity - 1 - (t - n_big)]; };
+    const u32 lt = (1u << lane) - 1u;
+    u32 st_segments = 0, st_chunks = 0, st_new = 0, err = 0;
+    // ticket + work item of the first block
+    u32 t = 0;
+    uint2 wk = make_uint2(0, 0);
+    if (lane == 0) { t = atomicAdd(&plan->fold_ticket, 1u); if (t < n_blocks) wk = work_item(t); }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    wk.x = __shfl_sync(0xffffffffu, wk.x, 0);
+    wk.y = __shfl_sync(0xffffffffu, wk.y, 0);
+    while (t < n_blocks) {
+        const u32 p0 = wk.x, nruns = wk.y;
+        // lane 0 fetches the NEXT ticket and work item now; they are only waited for at the end of this block
+        u32 t_next = 0;
+        uint2 w_next = make_uint2(0, 0);
+        if (lane == 0) { t_next = atomicAdd(&plan->fold_ticket, 1u); if (t_next < n_blocks) w_next = work_item(t_next); }
+        const u64 blk = expand_key((dkeys[p0] >> tbits) << RUN_BLK_SHIFT, k) >> RUN_BLK_SHIFT;
+        // ---- seeds: the block's 64 leaf chunks that are already resident (lane l owns chunks l and l + 32) ----
+        u64 slot0 = table_find(tkeys, capacity, (blk << 6) | (u64)lane);
+        u64 slot1 = table_find(tkeys, capacity, (blk << 6) | (u64)(lane + 32));
+        {
+            uint4* dst0 = reinterpret_cast<uint4*>(&S.cell[8 * lane]);
+            uint4* dst1 = reinterpret_cast<uint4*>(&S.cell[8 * (lane + 32)]);
+            const uint4 z = make_uint4(0, 0, 0, 0);  // a voxel touched for the first time starts from (0, 0) (octree.hpp:68-75)
+            const uint4* src0 = reinterpret_cast<const uint4*>(tcells + slot0 * 8);
+            const uint4* src1 = reinterpret_cast<const uint4*>(tcells + slot1 * 8);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                dst0[q] = (slot0 != ~0ull) ? src0[q] : z;
+                dst1[q] = (slot1 != ~0ull) ? src1[q] : z;
+            }
+            if (lane < RF_VOXELS / 32) S.touched[lane] = 0;
+        }
+        __syncwarp();
+        // ---- stream the runs in (tile, ray, step) order: 32 updates per iteration, the next RF_DEPTH x 32 already in flight
+        //      (one warp walks its block alone: without the look-ahead every iteration would wait one DRAM round trip) ----
+        uint2 dlane = (lane < nruns) ? sdesc[p0 + lane] : make_uint2(0, 0);  // descriptors r0 .. r0 + 31, one per lane
+        u32 r0 = 0;
+        u32 lr = 0, loff = 0;          // load cursor: run, offset inside it
+        uint2 ld = make_uint2(__shfl_sync(0xffffffffu, dlane.x, 0), __shfl_sync(0xffffffffu, dlane.y, 0));
+        u64 buf[RF_DEPTH];
+        u32 vbits = 0;                 // bit q: buf[q] holds an update for this lane
+#pragma unroll
+        for (int q = 0; q < RF_DEPTH; q++) {
+            const bool valid = (lr < nruns) && (loff + lane < ld.y);
+            buf[q] = valid ? records[ld.x + loff + lane] : ~0ull;
+            vbits |= valid ? (1u << q) : 0u;
+            if (lr < nruns) {
+                loff += 32;
+                if (loff >= ld.y) {
+                    lr++; loff = 0;
+                    if (lr < nruns) {
+                        if (lr - r0 >= 32) { r0 = lr; dlane = (r0 + lane < nruns) ? sdesc[p0 + r0 + lane] : make_uint2(0, 0); }
+                        ld.x = __shfl_sync(0xffffffffu, dlane.x, lr - r0);
+                        ld.y = __shfl_sync(0xffffffffu, dlane.y, lr - r0);
+                    }
+                }
+            }
+        }
+        bool more = true;
+        while (more) {
+            const u64 cur = buf[0];
+            const bool cur_valid = (vbits & 1u) != 0;
+            // shift the look-ahead window and refill its tail
+#pragma unroll
+            for (int q = 0; q + 1 < RF_DEPTH; q++) buf[q] = buf[q + 1];
+            vbits >>= 1;
+            {
+                const bool valid = (lr < nruns) && (loff + lane < ld.y);
+                buf[RF_DEPTH - 1] = valid ? records[ld.x + loff + lane] : ~0ull;
+                vbits |= valid ? (1u << (RF_DEPTH - 1)) : 0u;
+                if (lr < nruns) {
+                    loff += 32;
+                    if (loff >= ld.y) {
+                        lr++; loff = 0;
+                        if (lr < nruns) {
+                            if (lr - r0 >= 32) { r0 = lr; dlane = (r0 + lane < nruns) ? sdesc[p0 + r0 + lane] : make_uint2(0, 0); }
+                            ld.x = __shfl_sync(0xffffffffu, dlane.x, lr - r0);
+                            ld.y = __shfl_sync(0xffffffffu, dlane.y, lr - r0);
+                        }
+                    }
+                }
+            }
+            // ---- apply the 32 updates: lanes that share a voxel go one after the other in lane (= rank) order ----
+            const u32 key = (u32)cur;
+            const u32 v = cur_valid ? (key >> RUN_RANK_BITS) : (0x80000000u | lane);
+            const u32 m = __match_any_sync(0xffffffffu, v);
+            const u32 ord = (u32)__popc(m & lt);
+            const u32 rounds = __reduce_max_sync(0xffffffffu, cur_valid ? (u32)__popc(m) : 0u);
+            const float sd = __uint_as_float((u32)(cur >> 32));
+            for (u32 q = 0; q < rounds; q++) {
+                if (cur_valid && ord == q) {
+                    const uint2 c = S.cell[v];
+                    float acc = fadd(fmul(__uint_as_float(c.x), __uint2float_rn(c.y)), sd);  // octree.hpp:161
+                    const u32 w = c.y + 1;                                                     // :162
+                    acc = fdiv(acc, __uint2float_rn(w));                                       // :163
+                    S.cell[v] = make_uint2(__float_as_uint(acc), w);
+                    if (q == 0) atomicOr(&S.touched[v >> 5], 1u << (v & 31u));
+                }
+                __syncwarp();
+            }
+            // a chunk always holds lane 0's update: the stream ends when the window's head is empty for lane 0
+            more = __shfl_sync(0xffffffffu, vbits & 1u, 0) != 0;
+        }
+        __syncwarp();
+        // ---- write the touched chunks back (chunk c = byte c of the touched bitmap) ----
+        {
+            const u32 word0 = S.touched[lane >> 2], word1 = S.touched[(lane + 32) >> 2];
+            const u32 b0 = (word0 >> ((lane & 3u) * 8u)) & 0xFFu, b1 = (word1 >> ((lane & 3u) * 8u)) & 0xFFu;
+            st_segments += (u32)__popc(b0) + (u32)__popc(b1);
+            if (b0) {
+                st_chunks++;
+                if (slot0 == ~0ull) { slot0 = table_insert(tkeys, capacity, (blk << 6) | (u64)lane); st_new++; }
+                if (slot0 == ~0ull) err |= ERRF_TABLE_FULL;
+                else {
+                    uint4* dst = reinterpret_cast<uint4*>(tcells + slot0 * 8);
+                    const uint4* src = reinterpret_cast<const uint4*>(&S.cell[8 * lane]);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) dst[q] = src[q];
+                }
+            }
+            if (b1) {
+                st_chunks++;
+                if (slot1 == ~0ull) { slot1 = table_insert(tkeys, capacity, (blk << 6) | (u64)(lane + 32)); st_new++; }
+                if (slot1 == ~0ull) err |= ERRF_TABLE_FULL;
+                else {
+                    uint4* dst = reinterpret_cast<uint4*>(tcells + slot1 * 8);
+                    const uint4* src = reinterpret_cast<const uint4*>(&S.cell[8 * (lane + 32)]);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) dst[q] = src[q];
+                }
+            }
+        }
+        __syncwarp();
+        t = __shfl_sync(0xffffffffu, t_next, 0);
+        wk.x = __shfl_sync(0xffffffffu, w_next.x, 0);
+        wk.y = __shfl_sync(0xffffffffu, w_next.y, 0);
+    }
+    // ---- counters: one atomic per CTA ----
+    st_segments = __reduce_add_sync(0xffffffffu, st_segments);
+    st_chunks = __reduce_add_sync(0xffffffffu, st_chunks);
+    st_new = __reduce_add_sync(0xffffffffu, st_new);
+    err = __reduce_or_sync(0xffffffffu, err);
+    if (lane == 0) {
+        if (st_segments) atomicAdd(&s_red[0], st_segments);
+        if (st_chunks) atomicAdd(&s_red[1], st_chunks);
+        if (st_new) atomicAdd(&s_red[2], st_new);
+        if (err) atomicOr(&s_red[3], err);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_red[0]) atomicAdd(&plan->n_segments, s_red[0]);
+        if (s_red[1]) atomicAdd(&plan->n_chunk_heads, s_red[1]);
+        if (s_red[2]) { atomicAdd(&plan->n_new_chunks, s_red[2]); atomicAdd(tcount, s_red[2]); }
+        if (s_red[3]) atomicOr(&plan->error, s_red[3]);
+    }
+}
+
+inline unsigned blocks_for(u32 n) { return (n + RUN_THREADS - 1) / RUN_THREADS; }
+
+}  // namespace
+
+static int g_fold_ctas_per_sm = 4;
+
+cudaError_t runs_init() {
+    cudaError_t e = cudaFuncSetAttribute(runs_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RUN_THREADS * 33 * sizeof(uint2)));
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;  // the fold is persistent (blocks are handed out by ticket): launch exactly what is resident
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, runs_fold_kernel, RF_THREADS, 0);
+    if (e != cudaSuccess) return e;
+    g_fold_ctas_per_sm = per_sm > 0 ? per_sm : 1;
+    return cudaSuccess;
+}
+
+u32 runs_max_batch_points() { return 1u << RUN_RANK_BITS; }
+u32 runs_max_ray_voxels() { return 32; }
+u32 runs_max_ray_runs() { return RUN_HASH / RUN_THREADS; }
+
+size_t runs_desc_bytes(size_t capacity) { return capacity * (8 + 8 + 8 + 8 + 8 + 4 + 4) + 1024; }
+
+RunBuffers runs_carve(void* mem, size_t capacity) {
+    RunBuffers b;
+    unsigned char* p = static_cast<unsigned char*>(mem);
+    b.key_a = reinterpret_cast<u64*>(p); p += capacity * 8;
+    b.key_b = reinterpret_cast<u64*>(p); p += capacity * 8;
+    b.desc = reinterpret_cast<uint2*>(p); p += capacity * 8;
+    b.sdesc = reinterpret_cast<uint2*>(p); p += capacity * 8;
+    b.work = reinterpret_cast<uint2*>(p); p += capacity * 8;
+    b.val_a = reinterpret_cast<u32*>(p); p += capacity * 4;
+    b.val_b = reinterpret_cast<u32*>(p);
+    b.capacity = (u32)capacity;
+    return b;
+}
+
+// Everything between the point stage and the fold: walk + emit, descriptor sort, block list. Returns the kernels queued.
+int launch_runs_front(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const BatchScans* scans, const MapParams& mp,
+                      BatchPlan* plan, const RunBuffers& rb, u64* records, u32 rec_capacity, const RadixWorkspace& rws, int num_sms,
+                      const LaunchHook* hook, int cls_emit, int cls_sort) {
+    if (!n_points) return 0;
+    int launches = 0;
+    if (hook) hook->begin(hook->user, cls_emit);
+    runs_emit_kernel<<<blocks_for(n_points), RUN_THREADS, size_t(RUN_THREADS) * (mp.max_ray_voxels | 1u) * sizeof(uint2), s>>>(
+        xyz_sorted, normals, n_points, scans, mp.res, mp.trunc, mp.recip, mp.max_ray_voxels, plan, records, rec_capacity, rb.key_a, rb.val_a, rb.desc,
+        rb.capacity);
+    if (hook) hook->end(hook->user);
+    launches++;
+    if (hook) hook->begin(hook->user, cls_sort);
+    const size_t max_runs = std::min<size_t>(rb.capacity, size_t(blocks_for(n_points)) * RUN_HASH);
+    launches += radix_sort_pairs(s, rb.key_a, rb.val_a, rb.key_b, rb.val_b, &plan->n_runs, &plan->nbits_blocks, max_runs, RS_MAX_PASSES, rws, num_sms);
+    runs_group_kernel<<<(unsigned)std::min<size_t>(blocks_for((u32)max_runs), size_t(num_sms) * 8), RUN_THREADS, 0, s>>>(rb.key_a, rb.key_b, rb.val_a, rb.val_b, rb.desc, rb.sdesc, plan, rb.work, rb.capacity);
+    if (hook) hook->end(hook->user);
+    launches++;
+    return launches;
+}
+
+int launch_runs_fold(cudaStream_t s, const u64* records, const RunBuffers& rb, BatchPlan* plan, const ChunkTable& t, int num_sms) {
+    runs_fold_kernel<<<num_sms * g_fold_ctas_per_sm, RF_THREADS, 0, s>>>(records, rb.key_a, rb.key_b, rb.sdesc, rb.work, rb.capacity, plan, t.keys, t.cells,
+                                                                              t.capacity, t.count);
+    return 1;
+}
+
+}  // namespace chadgpu

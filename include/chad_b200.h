@@ -92,8 +92,8 @@ int chad_level_words(chad_ctx* ctx, int level, size_t* words);
 int chad_level_counters(chad_ctx* ctx, int level, uint32_t* uniques, uint32_t* dupes);
 int chad_export_level(chad_ctx* ctx, int level, void* dst, size_t capacity_words);
 
-/* How the band-voxel updates of a batch are grouped per voxel before the fold: 0 = block-binned (default: hashed
- * 8x8x8-voxel blocks + shared-memory sort), 1 = global onesweep radix sort. Both give bit-identical results. */
+/* How the band-voxel updates of a batch are grouped per voxel before the fold: 2 = tile runs + fused per-block sort and fold (default: runs.cu), 0 = block-binned (hashed
+ * 8x8x8-voxel blocks + shared-memory sort), 1 = global onesweep radix sort. All give bit-identical results. */
 int chad_set_pair_path(chad_ctx* ctx, int mode);
 
 /* Forget everything (active submap, all DAG levels, submap roots, sticky errors) but keep the device

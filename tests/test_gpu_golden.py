@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
 
 
-@pytest.mark.parametrize("batch,path", [(1, 0), (8, 0), (8, 1)])
+@pytest.mark.parametrize("batch,path", [(1, 2), (8, 2), (8, 0), (8, 1)])
 @pytest.mark.parametrize("name", cases.ALL_CASES)
 def test_gpu_matches_reference_golden(chad_lib, name, batch, path):
     from chad_tsdf_b200 import TSDFMap

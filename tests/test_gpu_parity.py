@@ -43,7 +43,7 @@ def _run_pair(w, scans, batch, finalize_every=None, path=0):
     return g, o, U, V
 
 
-@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("path", [2, 0, 1])
 @pytest.mark.parametrize("batch", [1, 4])
 def test_single_scan_cfg0(chad_lib, oracle_lib, batch, path):
     w = synth.WORKLOADS["cfg0_single_64beam"]
@@ -60,7 +60,7 @@ def test_single_scan_cfg0(chad_lib, oracle_lib, batch, path):
     g.close(); o.close()
 
 
-@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("path", [2, 0, 1])
 @pytest.mark.parametrize("batch", [1, 3, 16])
 def test_trajectory_with_submap_switch(chad_lib, oracle_lib, batch, path):
     """cfg1 prefix: 24 scans at 0.25 m/scan => one submap switch inside insert (> 5 m from the first pose)."""
@@ -74,7 +74,7 @@ def test_trajectory_with_submap_switch(chad_lib, oracle_lib, batch, path):
     g.close(); o.close()
 
 
-@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("path", [2, 0, 1])
 def test_fine_voxels_cfg2(chad_lib, oracle_lib, path):
     w = synth.WORKLOADS["cfg2_fine_indoor"]
     g, o, _, _ = _run_pair(w, 5, 2, finalize_every=2, path=path)
@@ -83,7 +83,7 @@ def test_fine_voxels_cfg2(chad_lib, oracle_lib, path):
     g.close(); o.close()
 
 
-@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("path", [2, 0, 1])
 def test_urban_cfg3_many_submaps(chad_lib, oracle_lib, path):
     w = synth.WORKLOADS["cfg3_urban_5km"]
     g, o, _, _ = _run_pair(w, 14, 4, path=path)  # 1 m/scan: switches at scans 6 and 12
@@ -93,7 +93,7 @@ def test_urban_cfg3_many_submaps(chad_lib, oracle_lib, path):
     g.close(); o.close()
 
 
-@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("path", [2, 0, 1])
 def test_sphere_demo_shape(chad_lib, oracle_lib, path):
     """The reference demo's workload shape (main.cpp:7-38): dense points on a 5 m sphere, many points per voxel."""
     from chad_tsdf_b200 import TSDFMap
@@ -108,7 +108,7 @@ def test_sphere_demo_shape(chad_lib, oracle_lib, path):
     g.close(); o.close()
 
 
-@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("path", [2, 0, 1])
 def test_empty_and_tiny_inputs(chad_lib, oracle_lib, path):
     from chad_tsdf_b200 import TSDFMap
     from oracle import bindings as ob
@@ -152,7 +152,7 @@ def test_dense_voxels_many_updates_per_voxel(chad_lib, oracle_lib):
     from oracle import bindings as ob
     rng = np.random.default_rng(11)
     pos = np.array([0.0, 0.0, 0.0], np.float32)
-    for path in (0, 1):
+    for path in (2, 0, 1):
         g, o = TSDFMap(0.05, 0.1, max_batch_scans=4, pair_path=path), ob.OracleMap(0.05, 0.1)
         for s in range(4):
             pts = (rng.random((12000, 3)) * np.array([0.12, 0.12, 0.02]) + np.array([2.0, 1.0, 0.5])).astype(np.float32)
