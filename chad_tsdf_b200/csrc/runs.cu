@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
     __shared__ u32 s_warp[RUN_THREADS / 32];
     __shared__ u32 s_gbase, s_dbase;
     __shared__ u32 s_scan[2];  // scans of the tile's first and last point
+    __shared__ u32 s_prefix[RUN_WARPS][33];  // per warp: records of the lower lanes' rays (write-out)
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 stride = mrv | 1u;  // odd: the ray-major reads of the write-out and the step-major writes of the walk both spread over the banks
 #pragma unroll
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
     }
     const u32 tile0 = blockIdx.x * RUN_THREADS;
     if (tid < 2) s_scan[tid] = scan_of(scans, plan->n_scans, tid == 0 ? tile0 : min(tile0 + RUN_THREADS, n_points) - 1);
+    if (lane == 0) s_prefix[warp][32] = 0xFFFFFFFFu;  // sentinel of the write-out's binary search
     __syncthreads();
     const u32 i = tile0 + tid;
     u32 cnt = 0, err = 0;
@@ -241,23 +243,34 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
     }
     __syncthreads();
     if (gbase != 0xFFFFFFFFu) {
-        // ray-major write-out: one ray per warp iteration, one lane per step, so that the positions handed out inside a
-        // (warp, slot) follow the rays' order (records of ONE ray never share a voxel: their mutual order is free)
-        const u32 wmax = __reduce_max_sync(0xffffffffu, cnt);
-        if (wmax) {
-            const u32 rec_base = warp * 32 * stride + lane;
-            u32* wc = s_wcnt[warp >> 1];
-            for (u32 ray = 0; ray < 32; ray++) {
-                const u32 rcnt = __shfl_sync(0xffffffffu, cnt, ray);
-                if (lane < rcnt) {
-                    const uint2 rc = s_rec[rec_base + ray * stride];
-                    const u32 hs = rc.x >> 9;
-                    if (hs < RUN_HASH) {
-                        const u32 old = atomicAdd(&wc[hs], 1u << wsh);
-                        const u32 pos = gbase + s_hbase[hs] + ((old >> wsh) & 0xFFFFu);
-                        records[pos] = (u64(rc.y) << 32) | (u64)(((rc.x & 511u) << RUN_RANK_BITS) | (tile0 + warp * 32 + ray));
-                    }
-                }
+        // ray-major write-out: the warp's records, ordered (ray, step), are taken 32 at a time (lane f of the flat sequence finds
+        // its ray by binary search over the rays' prefix sums), so that the positions handed out inside a (warp, slot) follow
+        // the rays' order; lanes of one iteration that share a slot are ordered by lane
+        u32 P = cnt;  // inclusive scan over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, P, o); if (lane >= (u32)o) P += up; }
+        const u32 T = __shfl_sync(0xffffffffu, P, 31);
+        u32* sp = s_prefix[warp];
+        sp[lane] = P - cnt;
+        __syncwarp();
+        u32* wc = s_wcnt[warp >> 1];
+        for (u32 f = lane; f - lane < T; f += 32) {
+            const bool has = f < T;
+            u32 ray = 0;
+#pragma unroll
+            for (u32 st = 16; st > 0; st >>= 1)
+                if (sp[ray + st] <= f) ray += st;  // largest ray with prefix <= f (rays without records share their successor's prefix)
+            uint2 rc = make_uint2(0xFFFFFFFFu, 0);
+            if (has) rc = s_rec[(warp * 32 + ray) * stride + (f - sp[ray])];
+            const u32 hs = (has && (rc.x >> 9) < RUN_HASH) ? (rc.x >> 9) : (0x80000000u | lane);  // unique for idle lanes
+            const u32 m = __match_any_sync(0xffffffffu, hs);
+            if (hs < RUN_HASH) {
+                const u32 leader = (u32)(__ffs(m) - 1);
+                u32 old = 0;
+                if (lane == leader) old = atomicAdd(&wc[hs], (u32)__popc(m) << wsh);
+                old = __shfl_sync(m, old, leader);
+                const u32 pos = gbase + s_hbase[hs] + ((old >> wsh) & 0xFFFFu) + (u32)__popc(m & ((1u << lane) - 1u));
+                records[pos] = (u64(rc.y) << 32) | (u64)(((rc.x & 511u) << RUN_RANK_BITS) | (tile0 + warp * 32 + ray));
             }
         }
     }
@@ -342,6 +355,9 @@ __device__ __forceinline__ u64 table_insert(u64* __restrict__ keys, u64 capacity
 struct FoldWarp {
     uint2 cell[RF_VOXELS];   // (sd bits, weight) of the block's 512 voxels: the table's cell layout, chunk c = cells 8c .. 8c+7
     u32 touched[RF_VOXELS / 32];
+    u32 rprefix[33];         // the 32 runs being streamed: records before each run ([32] = sentinel) ...
+    u32 rstart[32];          // ... and (first record - prefix)
+    u32 pad[15];
 };
 
 __global__ void __launch_bounds__(RF_THREADS) runs_fold_kernel(const u64* __restrict__ records, const u64* __restrict__ dkeys_a,
@@ -353,6 +369,7 @@ __global__ void __launch_bounds__(RF_THREADS) runs_fold_kernel(const u64* __rest
     const u32 tid = threadIdx.x, lane = tid & 31;
     FoldWarp& S = s_w[tid >> 5];
     if (tid < 4) s_red[tid] = 0;
+    if (lane == 0) S.rprefix[32] = 0xFFFFFFFFu;
     __syncthreads();
     const u32 pe = plan->error;
     const u32 nbits = plan->nbits_blocks;
@@ -394,75 +411,55 @@ __global__ void __launch_bounds__(RF_THREADS) runs_fold_kernel(const u64* __rest
             if (lane < RF_VOXELS / 32) S.touched[lane] = 0;
         }
         __syncwarp();
-        // ---- stream the runs in (tile, ray, step) order: 32 updates per iteration, the next RF_DEPTH x 32 already in flight
-        //      (one warp walks its block alone: without the look-ahead every iteration would wait one DRAM round trip) ----
-        uint2 dlane = (lane < nruns) ? sdesc[p0 + lane] : make_uint2(0, 0);  // descriptors r0 .. r0 + 31, one per lane
-        u32 r0 = 0;
-        u32 lr = 0, loff = 0;          // load cursor: run, offset inside it
-        uint2 ld = make_uint2(__shfl_sync(0xffffffffu, dlane.x, 0), __shfl_sync(0xffffffffu, dlane.y, 0));
-        u64 buf[RF_DEPTH];
-        u32 vbits = 0;                 // bit q: buf[q] holds an update for this lane
+        // ---- stream the runs in (tile, ray, step) order. The runs are taken 32 at a time (one descriptor per lane); their
+        //      records form one flat sequence that is consumed 32 updates per iteration (lane f finds its run by binary search
+        //      over the runs' prefix sums), with the next RF_DEPTH x 32 updates already in flight: one warp walks its block
+        //      alone, so without the look-ahead every iteration would wait one DRAM round trip ----
+        for (u32 r0 = 0; r0 < nruns; r0 += 32) {
+            const uint2 dl = (r0 + lane < nruns) ? sdesc[p0 + r0 + lane] : make_uint2(0, 0);
+            u32 P = dl.y;  // inclusive scan of the run lengths
 #pragma unroll
-        for (int q = 0; q < RF_DEPTH; q++) {
-            const bool valid = (lr < nruns) && (loff + lane < ld.y);
-            buf[q] = valid ? records[ld.x + loff + lane] : ~0ull;
-            vbits |= valid ? (1u << q) : 0u;
-            if (lr < nruns) {
-                loff += 32;
-                if (loff >= ld.y) {
-                    lr++; loff = 0;
-                    if (lr < nruns) {
-                        if (lr - r0 >= 32) { r0 = lr; dlane = (r0 + lane < nruns) ? sdesc[p0 + r0 + lane] : make_uint2(0, 0); }
-                        ld.x = __shfl_sync(0xffffffffu, dlane.x, lr - r0);
-                        ld.y = __shfl_sync(0xffffffffu, dlane.y, lr - r0);
-                    }
-                }
-            }
-        }
-        bool more = true;
-        while (more) {
-            const u64 cur = buf[0];
-            const bool cur_valid = (vbits & 1u) != 0;
-            // shift the look-ahead window and refill its tail
+            for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, P, o); if (lane >= (u32)o) P += up; }
+            const u32 T = __shfl_sync(0xffffffffu, P, 31);
+            __syncwarp();
+            S.rprefix[lane] = P - dl.y;
+            S.rstart[lane] = dl.x - (P - dl.y);  // record f of the flat sequence lives at rstart[run] + f
+            __syncwarp();
+            auto fetch = [&](u32 f) -> u64 {
+                if (f >= T) return ~0ull;
+                u32 run = 0;
 #pragma unroll
-            for (int q = 0; q + 1 < RF_DEPTH; q++) buf[q] = buf[q + 1];
-            vbits >>= 1;
-            {
-                const bool valid = (lr < nruns) && (loff + lane < ld.y);
-                buf[RF_DEPTH - 1] = valid ? records[ld.x + loff + lane] : ~0ull;
-                vbits |= valid ? (1u << (RF_DEPTH - 1)) : 0u;
-                if (lr < nruns) {
-                    loff += 32;
-                    if (loff >= ld.y) {
-                        lr++; loff = 0;
-                        if (lr < nruns) {
-                            if (lr - r0 >= 32) { r0 = lr; dlane = (r0 + lane < nruns) ? sdesc[p0 + r0 + lane] : make_uint2(0, 0); }
-                            ld.x = __shfl_sync(0xffffffffu, dlane.x, lr - r0);
-                            ld.y = __shfl_sync(0xffffffffu, dlane.y, lr - r0);
-                        }
+                for (u32 st = 16; st > 0; st >>= 1)
+                    if (S.rprefix[run + st] <= f) run += st;
+                return records[S.rstart[run] + f];
+            };
+            u64 buf[RF_DEPTH];
+#pragma unroll
+            for (int q = 0; q < RF_DEPTH; q++) buf[q] = fetch(q * 32 + lane);
+            for (u32 f = lane; f - lane < T; f += 32) {
+                const u64 cur = buf[0];
+                const bool cur_valid = f < T;
+#pragma unroll
+                for (int q = 0; q + 1 < RF_DEPTH; q++) buf[q] = buf[q + 1];
+                buf[RF_DEPTH - 1] = fetch(f + RF_DEPTH * 32);
+                // ---- apply the 32 updates: lanes that share a voxel go one after the other in lane (= rank) order ----
+                const u32 v = cur_valid ? ((u32)cur >> RUN_RANK_BITS) : (0x80000000u | lane);
+                const u32 m = __match_any_sync(0xffffffffu, v);
+                const u32 ord = (u32)__popc(m & lt);
+                const u32 rounds = __reduce_max_sync(0xffffffffu, cur_valid ? (u32)__popc(m) : 0u);
+                const float sd = __uint_as_float((u32)(cur >> 32));
+                if (cur_valid && ord == 0) atomicOr(&S.touched[v >> 5], 1u << (v & 31u));
+                for (u32 q = 0; q < rounds; q++) {
+                    if (cur_valid && ord == q) {
+                        const uint2 c = S.cell[v];
+                        float acc = fadd(fmul(__uint_as_float(c.x), __uint2float_rn(c.y)), sd);  // octree.hpp:161
+                        const u32 w = c.y + 1;                                                     // :162
+                        acc = fdiv(acc, __uint2float_rn(w));                                       // :163
+                        S.cell[v] = make_uint2(__float_as_uint(acc), w);
                     }
+                    __syncwarp();
                 }
             }
-            // ---- apply the 32 updates: lanes that share a voxel go one after the other in lane (= rank) order ----
-            const u32 key = (u32)cur;
-            const u32 v = cur_valid ? (key >> RUN_RANK_BITS) : (0x80000000u | lane);
-            const u32 m = __match_any_sync(0xffffffffu, v);
-            const u32 ord = (u32)__popc(m & lt);
-            const u32 rounds = __reduce_max_sync(0xffffffffu, cur_valid ? (u32)__popc(m) : 0u);
-            const float sd = __uint_as_float((u32)(cur >> 32));
-            for (u32 q = 0; q < rounds; q++) {
-                if (cur_valid && ord == q) {
-                    const uint2 c = S.cell[v];
-                    float acc = fadd(fmul(__uint_as_float(c.x), __uint2float_rn(c.y)), sd);  // octree.hpp:161
-                    const u32 w = c.y + 1;                                                     // :162
-                    acc = fdiv(acc, __uint2float_rn(w));                                       // :163
-                    S.cell[v] = make_uint2(__float_as_uint(acc), w);
-                    if (q == 0) atomicOr(&S.touched[v >> 5], 1u << (v & 31u));
-                }
-                __syncwarp();
-            }
-            // a chunk always holds lane 0's update: the stream ends when the window's head is empty for lane 0
-            more = __shfl_sync(0xffffffffu, vbits & 1u, 0) != 0;
         }
         __syncwarp();
         // ---- write the touched chunks back (chunk c = byte c of the touched bitmap) ----
