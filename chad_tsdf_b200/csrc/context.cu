@@ -90,8 +90,15 @@ struct chad_ctx {
     DevBuf bt_mem;                  // block table of the block-binned pair path
     BlockTable bt{};
     int pair_path = 2;              // 2 = tile runs + fused block sort/fold (default), 0 = block-binned, 1 = global radix sort
-    DevBuf run_mem;                 // run descriptors of the tile-run path
-    RunBuffers rb{};
+    DevBuf run_mem[2];              // run descriptors of the tile-run path, one set per plan slot: the fold of batch i runs on
+    RunBuffers rb[2]{};             // fold_stream while the front of batch i + 1 runs on `stream` (records: keys_a / keys_b by slot)
+    cudaStream_t fold_stream = nullptr;
+    cudaEvent_t fold_done[2] = {nullptr, nullptr};   // the fold that read slot b's records / descriptors / plan has finished
+    bool fold_done_valid[2] = {false, false};
+    bool fold_in_flight = false;    // a fold has been queued on fold_stream since the last synchronisation
+    cudaEvent_t submap_closed2 = nullptr;
+    u64 prev_fold_bound = 0;        // chunk bound of the previous fold of the active submap if its exact count may not have arrived yet
+    cudaStream_t prof_stream = nullptr;  // stream the instrumentation events are recorded on
     bool pending_runs = false;      // the batch whose fold is pending went through the tile-run path
     BatchPlan* h_plan_fold = nullptr;  // pinned BatchPlan[2]: the plan as the fused fold left it (distinct voxels, deferred errors)
     bool fold_stats_pending[2] = {false, false};
@@ -101,15 +108,16 @@ struct chad_ctx {
     RadixWorkspace rws{};
 
     // resident chunk tables: `table` belongs to the active submap; the other one is being finalised / is spare
-    DevBuf t_keys, t_cells, t_count;
-    ChunkTable table{nullptr, nullptr, 0, nullptr};
-    DevBuf t2_keys, t2_cells, t2_count;
-    ChunkTable table2{nullptr, nullptr, 0, nullptr};
+    DevBuf t_keys, t_cells, t_count, t_list;
+    ChunkTable table{nullptr, nullptr, 0, nullptr, nullptr};
+    DevBuf t2_keys, t2_cells, t2_count, t2_list;
+    ChunkTable table2{nullptr, nullptr, 0, nullptr, nullptr};
     u64 table_count_known = 0;
 
     // asynchronous Submap::finalize (see finalize_begin): part 1 and part 2 run on fin_stream
     cudaStream_t fin_stream = nullptr;
-    enum FinState { FIN_IDLE = 0, FIN_PART1 = 1, FIN_PART2 = 2 };
+    enum FinState { FIN_IDLE = 0, FIN_PART1 = 1 /* tables swapped, waiting for the closed submap's exact chunk count */,
+                    FIN_PART2 = 2 /* everything queued on fin_stream */ };
     int fin_state = FIN_IDLE;
     u32 fin_max_chunks = 0;       // host upper bound of the chunk count of the submap being finalised
     u32 fin_chunks = 0;           // exact count (known after part 1)
@@ -121,7 +129,9 @@ struct chad_ctx {
         u32 level_nodes[20];
         u64 level_new[20];        // per level: (new records << 32) | new words
         u32 root[2];
+        LevelCounters counters[CHAD_NUM_LEVELS];
     }* h_fin = nullptr;
+    DevBuf f_counters, f_partial;  // device LevelCounters[21]; partial sums of the persistent levels kernel
     DevBuf f_level_new;           // device u64[20]
     bool fin_external = false;    // the finalize in flight consumes a caller-provided chunk stream (sharded mode): clear `table`, not `table2`
 
@@ -131,6 +141,7 @@ struct chad_ctx {
 
     // finalize work buffers
     size_t cap_chunks = 0;
+    DevBuf f_sorted;  // full chunk keys in ascending order (gather output)
     DevBuf f_ids[2], f_slots[2], f_cells, f_tsdf, f_addr[2], f_head, f_head_rank, f_cand, f_slot_of, f_is_new, f_rank, f_radix_ws, f_scan_ws, f_scalars;
     RadixWorkspace f_rws{};
     u64* h_scalars = nullptr;  // pinned, 8 x u64
@@ -174,13 +185,13 @@ void prof_begin(void* user, int cls) {
         if (!ctx->event_pool.empty()) { *e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
         else cudaEventCreate(e);
     }
-    cudaEventRecord(sp.a, ctx->stream);
+    cudaEventRecord(sp.a, ctx->prof_stream ? ctx->prof_stream : ctx->stream);
     ctx->spans.push_back(sp);
 }
 void prof_end(void* user) {
     chad_ctx* ctx = static_cast<chad_ctx*>(user);
     if (!ctx->profiling || ctx->spans.empty()) return;
-    cudaEventRecord(ctx->spans.back().b, ctx->stream);
+    cudaEventRecord(ctx->spans.back().b, ctx->prof_stream ? ctx->prof_stream : ctx->stream);
 }
 // after a stream synchronisation: fold the recorded spans into the per-class totals
 void prof_resolve(chad_ctx* ctx) {
@@ -238,10 +249,12 @@ int error_from_flags(chad_ctx* ctx, u32 flags) {
 }
 
 // ---- resident chunk table ---------------------------------------------------------------
-int table_alloc(chad_ctx* ctx, ChunkTable& t, DevBuf& keys, DevBuf& cells, DevBuf& count, u64 capacity) {
+int table_alloc(chad_ctx* ctx, ChunkTable& t, DevBuf& keys, DevBuf& cells, DevBuf& count, DevBuf& list, u64 capacity) {
     TRY(dev_ensure(ctx, keys, capacity * 8));
     TRY(dev_ensure(ctx, cells, capacity * 64));
     TRY(dev_ensure(ctx, count, 256));
+    TRY(dev_ensure(ctx, list, capacity * 4 + 256));
+    t.list = list.as<u64>();
     t.keys = keys.as<u64>();
     t.cells = cells.as<uint2>();
     t.capacity = capacity;
@@ -251,14 +264,16 @@ int table_alloc(chad_ctx* ctx, ChunkTable& t, DevBuf& keys, DevBuf& cells, DevBu
 }
 int table_reserve(chad_ctx* ctx, u64 need_chunks) {
     if (need_chunks * 2 <= ctx->table.capacity) return CHAD_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));  // a fold may still be writing the table
+    ctx->fold_in_flight = false;
     const u64 new_cap = next_pow2(need_chunks * 4);
-    DevBuf nk, nc, ncount;
-    ChunkTable nt{nullptr, nullptr, 0, nullptr};
-    TRY(table_alloc(ctx, nt, nk, nc, ncount, new_cap));
+    DevBuf nk, nc, ncount, nlist;
+    ChunkTable nt{nullptr, nullptr, 0, nullptr, nullptr};
+    TRY(table_alloc(ctx, nt, nk, nc, ncount, nlist, new_cap));
     ctx->stats.kernel_launches += launch_table_rehash(ctx->stream, ctx->table, nt, ctx->num_sms);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx->t_keys); dev_free(ctx->t_cells); dev_free(ctx->t_count);
-    ctx->t_keys = nk; ctx->t_cells = nc; ctx->t_count = ncount;
+    dev_free(ctx->t_keys); dev_free(ctx->t_cells); dev_free(ctx->t_count); dev_free(ctx->t_list);
+    ctx->t_keys = nk; ctx->t_cells = nc; ctx->t_count = ncount; ctx->t_list = nlist;
     ctx->table = nt;
     return CHAD_OK;
 }
@@ -269,6 +284,7 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
     // only called while no batch is in flight
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
     const size_t np = points + points / 8 + 1024;
     const size_t pairs = np * ctx->mp.max_ray_voxels;
     if (pairs >= (1ull << 30)) return fail(ctx, CHAD_ERR_CAPACITY, "batch too large: more than 2^30 band voxels; lower max_batch_scans");
@@ -302,8 +318,11 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
     TRY(dev_ensure(ctx, ctx->scan_ws, scan_workspace_bytes(np > bcap ? np : bcap)));
     if (ctx->mp.max_ray_runs <= runs_max_ray_runs() && ctx->mp.max_ray_voxels <= runs_max_ray_voxels()) {
         const size_t dcap = np * ctx->mp.max_ray_runs;
-        TRY(dev_ensure(ctx, ctx->run_mem, runs_desc_bytes(dcap)));
-        ctx->rb = runs_carve(ctx->run_mem.p, dcap);
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
+        for (int b = 0; b < 2; b++) {
+            TRY(dev_ensure(ctx, ctx->run_mem[b], runs_desc_bytes(dcap)));
+            ctx->rb[b] = runs_carve(ctx->run_mem[b].p, dcap);
+        }
     }
     ctx->rws = radix_workspace_carve(ctx->radix_ws.p, pairs);
     ctx->cap_points = np;
@@ -311,13 +330,21 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
     return CHAD_OK;
 }
 
-int finalize_begin(chad_ctx* ctx, u32 max_chunks, bool external = false);
+int finalize_begin(chad_ctx* ctx, u32 max_chunks, bool external, cudaStream_t count_stream);
+
+// device mirror of the node levels' counters: NodeLevel's constructor reserves index 0 (levels.hpp:52-54)
+int level_counters_reset(chad_ctx* ctx) {
+    LevelCounters init[CHAD_NUM_LEVELS];
+    for (int d = 0; d < CHAD_NUM_LEVELS; d++) init[d] = LevelCounters{d == CHAD_LEVEL_CLUSTERS ? 0u : 1u, 0u, 0u, 0u};
+    CUDA_TRY(ctx, cudaMemcpy(ctx->f_counters.p, init, sizeof(init), cudaMemcpyHostToDevice));
+    return CHAD_OK;
+}
 
 // the fused fold of the tile-run path reports the batch's distinct voxels after the fact: collect what has arrived.
 // Only called when the stream has passed the copies (after an event / stream synchronisation that follows them).
-void account_fold_stats(chad_ctx* ctx) {
+void account_fold_stats(chad_ctx* ctx, int only_slot = -1) {
     for (int slot = 0; slot < 2; slot++) {
-        if (!ctx->fold_stats_pending[slot]) continue;
+        if (!ctx->fold_stats_pending[slot] || (only_slot >= 0 && slot != only_slot)) continue;
         ctx->fold_stats_pending[slot] = false;
         ctx->stats.scan_voxels += ctx->h_plan_fold[slot].n_segments;
     }
@@ -329,7 +356,7 @@ int complete_pending_fold(chad_ctx* ctx) {
     ctx->fold_pending = false;
     const int slot = ctx->pending_slot;
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->front_done));
-    account_fold_stats(ctx);  // every earlier fold precedes front_done in stream order
+    account_fold_stats(ctx, slot);  // the pair stage of this batch waited for the fold that used this slot before
     BatchPlan plan = ctx->h_plan[slot];
     const bool runs = ctx->pending_runs;
     ctx->table_count_known = *ctx->h_table_count;
@@ -350,26 +377,44 @@ int complete_pending_fold(chad_ctx* ctx) {
         CUDA_TRY(ctx, cudaMemsetAsync(plan_field<u32>(ctx, slot, offsetof(BatchPlan, error)), 0, 4, ctx->stream));
         return error_from_flags(ctx, plan.error);
     }
-    TRY(table_reserve(ctx, ctx->table_count_known + plan.n_chunk_heads));
+    // *h_table_count is exact as of the last fold whose copy has arrived; the previous fold may still be running on
+    // fold_stream, so its bound is added: an upper bound of the chunk count after this fold either way
+    const u64 count_bound = ctx->table_count_known + ctx->prev_fold_bound + plan.n_chunk_heads;
+    TRY(table_reserve(ctx, count_bound));
     u64 launches = 0;
+    cudaStream_t fold_on = ctx->stream;
     if (runs) {
-        if (plan.n_pairs) PROF(ctx, PC_RUNS_FOLD, launch_runs_fold(ctx->stream, ctx->keys_a.as<u64>(), ctx->rb, plan_ptr(ctx, slot), ctx->table, ctx->num_sms));
-        CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->h_plan_fold[slot], plan_ptr(ctx, slot), sizeof(BatchPlan), cudaMemcpyDeviceToHost, ctx->stream));
+        // the fused fold runs on its own stream, concurrently with the next batch's front (point stage, ray walk, descriptor sort)
+        cudaStream_t fs = ctx->fold_stream;
+        fold_on = fs;
+        CUDA_TRY(ctx, cudaStreamWaitEvent(fs, ctx->front_done, 0));
+        ctx->prof_stream = fs;
+        if (plan.n_pairs) PROF(ctx, PC_RUNS_FOLD, launch_runs_fold(fs, (slot ? ctx->keys_b : ctx->keys_a).as<u64>(), ctx->rb[slot], plan_ptr(ctx, slot), ctx->table, ctx->num_sms));
+        ctx->prof_stream = nullptr;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->h_plan_fold[slot], plan_ptr(ctx, slot), sizeof(BatchPlan), cudaMemcpyDeviceToHost, fs));
         ctx->stats.d2h_bytes += sizeof(BatchPlan);
         ctx->fold_stats_pending[slot] = true;
+        ctx->prev_fold_bound = plan.n_chunk_heads;
+        ctx->fold_in_flight = true;
     } else {
+        ctx->prev_fold_bound = 0;
         PROF(ctx, PC_FOLD, launch_fold(ctx->stream, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(),
                                        ctx->pending_max_pairs, plan_ptr(ctx, slot), ctx->table, ctx->num_sms));
     }
     ctx->stats.kernel_launches += launches;
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_table_count, ctx->table.count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_table_count, ctx->table.count, 4, cudaMemcpyDeviceToHost, fold_on));
     ctx->stats.d2h_bytes += 4;
+    if (runs) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->fold_done[slot], ctx->fold_stream));
+        ctx->fold_done_valid[slot] = true;
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     if (ctx->close_pending) {  // that was the submap's last batch: swap tables and start its asynchronous finalize
         ctx->close_pending = false;
-        const u64 bound = ctx->table_count_known + plan.n_chunk_heads;
+        const u64 bound = count_bound;
         if (bound >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
-        TRY(finalize_begin(ctx, (u32)bound));
+        (void)bound;
+        TRY(finalize_begin(ctx, 0, false, fold_on));
         ctx->stats.resident_clusters = 0;
     }
     return CHAD_OK;
@@ -417,8 +462,10 @@ int process_front(chad_ctx* ctx) {
     const BatchScans* scans = ctx->d_scans.as<BatchScans>();
     u64 launches = 0;
     const LaunchHook* hook = ctx->profiling ? &ctx->hook : nullptr;
+    // this slot's plan / records / descriptors were last used by the fold of two batches ago (on fold_stream)
+    if (ctx->fold_done_valid[slot]) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->fold_done[slot], 0));
     queue_point_stage(ctx, slot, b, n, ns);
-    const bool use_runs = ctx->pair_path == 2 && n <= runs_max_batch_points() && ctx->rb.capacity != 0;
+    const bool use_runs = ctx->pair_path == 2 && n <= runs_max_batch_points() && ctx->rb[0].capacity != 0;
     const bool use_blocks = !use_runs && ctx->pair_path != 1 && n <= blocks_max_batch_points();
     if (!use_blocks && !use_runs) {
         PROF(ctx, PC_BAND_COUNT, launch_band_count(s, ctx->xyz_sorted.as<float>(), n, scans, ctx->mp, plan, ctx->counts.as<u32>()));
@@ -432,8 +479,15 @@ int process_front(chad_ctx* ctx) {
     // ---- pair stage ----
     const size_t max_pairs = size_t(n) * ctx->mp.max_ray_voxels;
     if (use_runs) {
-        launches += launch_runs_front(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan, ctx->rb, ctx->keys_a.as<u64>(),
-                                      (u32)ctx->cap_pairs, ctx->rws, ctx->num_sms, hook, PC_RUNS_EMIT, PC_RUNS_SORT);
+        launches += launch_runs_front(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan, ctx->rb[slot],
+                                      (slot ? ctx->keys_b : ctx->keys_a).as<u64>(), (u32)ctx->cap_pairs, ctx->rws, ctx->num_sms, hook, PC_RUNS_EMIT,
+                                      PC_RUNS_SORT);
+    } else if (ctx->fold_in_flight) {
+        // the other pair paths use both pair buffers and fold on this stream: order them after the folds still in flight
+        for (int b = 0; b < 2; b++)
+            if (ctx->fold_done_valid[b]) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->fold_done[b], 0));
+    }
+    if (use_runs) {
     } else if (use_blocks) {
         launches += launch_blocks_pairs(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan, ctx->bt, ctx->scan_ws.p,
                                         ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(), (u32)ctx->cap_pairs,
@@ -473,6 +527,9 @@ int drain(chad_ctx* ctx) {
         TRY(finalize_part2(ctx));
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
+    ctx->fold_in_flight = false;
+    ctx->prev_fold_bound = 0;
     account_fold_stats(ctx);
     prof_resolve(ctx);
     ctx->table_count_known = *ctx->h_table_count;
@@ -508,7 +565,7 @@ int settle(chad_ctx* ctx) {
 //          host sizes every level (no worst-case allocation) and queues the 20 node levels back to back; per-level
 //          results accumulate in device memory and come back in one copy; the old table is cleared.
 //   finish (next API call that finds part 2 complete, or any call that needs the DAG): host mirrors are updated.
-enum { SC_COUNT = 0, SC_RMAX = 1, SC_NBITS = 2, SC_PARENTS = 3, SC_NEW32 = 4, SC_ERR = 5, SC_LEVELS = 16 /* u32[20] */ };
+enum { SC_COUNT = 0, SC_RMAX = 1, SC_NBITS = 2, SC_PARENTS = 3, SC_NEW32 = 4, SC_ERR = 5, SC_BAR = 6, SC_ROOT = 8 /* u32[2] */, SC_LEVELS = 16 /* u32[20] */ };
 u32* scalar32(chad_ctx* ctx, int i) { return ctx->f_scalars.as<u32>() + i; }
 
 int ensure_finalize_capacity(chad_ctx* ctx, size_t chunks) {
@@ -517,6 +574,7 @@ int ensure_finalize_capacity(chad_ctx* ctx, size_t chunks) {
     const size_t nc = chunks + chunks / 8 + 1024;
     for (int i = 0; i < 2; i++) {
         TRY(dev_ensure(ctx, ctx->f_ids[i], nc * 8));
+        if (i == 0) TRY(dev_ensure(ctx, ctx->f_sorted, nc * 8));
         TRY(dev_ensure(ctx, ctx->f_slots[i], nc * 4));
         TRY(dev_ensure(ctx, ctx->f_addr[i], nc * 2 * 4));
     }
@@ -543,7 +601,7 @@ int level_reserve(chad_ctx* ctx, Level& L, bool cluster, size_t new_records) {
     const size_t need_words = cluster ? (size_t(L.uniques) + new_records + 2) : (size_t(L.occupied) + 9 * new_records + 9);
     if (need_words >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "DAG level exceeds 2^31 words");
     if (need_words > L.raw_cap) {
-        const size_t cap = next_pow2(need_words * 2);
+        const size_t cap = next_pow2(need_words);  // (the callers' record counts are generous upper bounds already)
         void* np = nullptr;
         CUDA_TRY(ctx, cudaMalloc(&np, cap * word));
         if (L.raw.p) {
@@ -557,7 +615,7 @@ int level_reserve(chad_ctx* ctx, Level& L, bool cluster, size_t new_records) {
     }
     const size_t need_slots = (size_t(L.uniques) + new_records) * 2;
     if (need_slots > L.table.capacity) {
-        const u64 cap = next_pow2(need_slots * 2);
+        const u64 cap = next_pow2(need_slots);
         void *ne = nullptr, *nf = nullptr;
         CUDA_TRY(ctx, cudaMalloc(&ne, cap * 8));
         CUDA_TRY(ctx, cudaMalloc(&nf, cap * 4));
@@ -580,12 +638,14 @@ int level_reserve(chad_ctx* ctx, Level& L, bool cluster, size_t new_records) {
 // cells; the exact count stays in device memory (SC_COUNT). max_chunks = host upper bound.
 int queue_sorted_chunks(chad_ctx* ctx, cudaStream_t s, const ChunkTable& t, u32 max_chunks) {
     u64 launches = 0;
-    launches += launch_table_compact(s, t, ctx->f_ids[0].as<u64>(), ctx->f_slots[0].as<u32>(), scalar32(ctx, SC_COUNT), scalar32(ctx, SC_RMAX),
+    launches += launch_table_compact(s, t, max_chunks, ctx->f_ids[0].as<u64>(), ctx->f_slots[0].as<u32>(), scalar32(ctx, SC_COUNT), scalar32(ctx, SC_RMAX),
                                      scalar32(ctx, SC_NBITS), ctx->num_sms);
     launches += radix_sort_pairs(s, ctx->f_ids[0].as<u64>(), ctx->f_slots[0].as<u32>(), ctx->f_ids[1].as<u64>(), ctx->f_slots[1].as<u32>(),
                                  scalar32(ctx, SC_COUNT), scalar32(ctx, SC_NBITS), max_chunks, RS_MAX_PASSES, ctx->f_rws, ctx->num_sms);
-    launches += launch_chunk_gather(s, t, ctx->f_slots[0].as<u32>(), ctx->f_slots[1].as<u32>(), scalar32(ctx, SC_COUNT), scalar32(ctx, SC_NBITS),
-                                    max_chunks, ctx->f_ids[0].as<u64>(), ctx->f_cells.p);
+    // the gather writes f_ids[0]: when the sort left its result there, it reads it from a copy
+    launches += launch_chunk_gather(s, t, ctx->f_ids[0].as<u64>(), ctx->f_ids[1].as<u64>(), scalar32(ctx, SC_COUNT), scalar32(ctx, SC_RMAX),
+                                    scalar32(ctx, SC_NBITS), max_chunks, ctx->f_sorted.as<u64>(), ctx->f_cells.p);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_ids[0].p, ctx->f_sorted.p, size_t(max_chunks) * 8, cudaMemcpyDeviceToDevice, s));
     ctx->stats.kernel_launches += launches;
     CUDA_TRY(ctx, cudaGetLastError());
     return CHAD_OK;
@@ -614,99 +674,87 @@ int finalize_wait(chad_ctx* ctx) {
     return CHAD_OK;
 }
 
-// Close the active submap: everything of it must already be queued on the compute stream (process_front +
-// complete_pending_fold). `max_chunks` = upper bound of its chunk count.
-int finalize_begin(chad_ctx* ctx, u32 max_chunks, bool external) {
-    TRY(finalize_wait(ctx));  // one finalize in flight at a time (they are ~2 ms apart at the very least)
+// Close the active submap: everything of it must already be queued (process_front + complete_pending_fold).
+// The tables are swapped right away, so the next submap's inserts go on; the finalize itself is queued as soon as the
+// closed submap's exact chunk count has arrived on the host (count_stream: the stream its last fold and the copy of the
+// table counter were queued on) -- by the next API call that finds it there, or by whoever needs the DAG.
+// external = true (sharded mode): f_ids[0] / f_cells already hold `max_chunks` globally sorted chunks.
+int finalize_begin(chad_ctx* ctx, u32 max_chunks, bool external, cudaStream_t count_stream) {
+    TRY(finalize_wait(ctx));  // one finalize in flight at a time
     cudaStream_t fs = ctx->fin_stream;
-    TRY(ensure_finalize_capacity(ctx, max_chunks));
-    Level& LC = ctx->levels[CHAD_LEVEL_CLUSTERS];
-    TRY(level_reserve(ctx, LC, true, size_t(max_chunks) + 1));
     CUDA_TRY(ctx, cudaEventRecord(ctx->submap_closed, ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(fs, ctx->submap_closed, 0));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->submap_closed2, ctx->fold_stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(fs, ctx->submap_closed2, 0));
     ctx->fin_external = external;
-    if (!external) {
-        // swap tables: the spare one was cleared at the end of the previous finalize (complete: see finalize_wait above)
-        std::swap(ctx->table, ctx->table2);
-        std::swap(ctx->t_keys, ctx->t2_keys);
-        std::swap(ctx->t_cells, ctx->t2_cells);
-        std::swap(ctx->t_count, ctx->t2_count);
-        std::swap(ctx->h_table_count, ctx->h_table_count2);  // no copy into the new active slot is in flight (its table was idle)
-        *ctx->h_table_count = 0;
-        ctx->table_count_known = 0;
-    }
     ctx->fin_max_chunks = max_chunks;
-    if (ctx->profiling) cudaEventRecord(ctx->fin_t0, fs);
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->f_scalars.p, 0, 256, fs));
-    if (external) {  // f_ids[0] / f_cells already hold the globally sorted chunk stream: only the count is needed
-        CUDA_TRY(ctx, cudaMemcpyAsync(scalar32(ctx, SC_COUNT), &ctx->fin_max_chunks, 4, cudaMemcpyHostToDevice, fs));
+    if (external) {
+        ctx->fin_state = chad_ctx::FIN_PART1;
+        return finalize_part2(ctx);
     }
-    if (max_chunks) {
-        u64 launches = 0;
-        if (!external) TRY(queue_sorted_chunks(ctx, fs, ctx->table2, max_chunks));
-        launches += launch_cluster_build(fs, ctx->f_cells.p, scalar32(ctx, SC_COUNT), max_chunks, ctx->mp, ctx->f_tsdf.as<u64>());
-        launches += launch_cluster_dedup(fs, LC.table, ctx->f_tsdf.as<u64>(), scalar32(ctx, SC_COUNT), max_chunks, LC.raw.as<u64>(), LC.uniques,
-                                         ctx->f_slot_of.as<u32>(), ctx->f_is_new.as<u32>(), ctx->f_rank.as<u32>(), ctx->f_scan_ws.p,
-                                         ctx->f_addr[0].as<u32>(), scalar32(ctx, SC_NEW32), scalar32(ctx, SC_ERR));
-        launches += launch_level_counts(fs, ctx->f_ids[0].as<u64>(), scalar32(ctx, SC_COUNT), max_chunks, scalar32(ctx, SC_LEVELS), ctx->num_sms);
-        ctx->stats.kernel_launches += launches;
-    }
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->scalars, ctx->f_scalars.p, 16 * 4 + 20 * 4, cudaMemcpyDeviceToHost, fs));
-    ctx->stats.d2h_bytes += 16 * 4 + 20 * 4;
-    if (ctx->profiling) cudaEventRecord(ctx->fin_t1, fs);
-    CUDA_TRY(ctx, cudaEventRecord(ctx->fin_p1_done, fs));
-    CUDA_TRY(ctx, cudaGetLastError());
+    // swap tables: the spare one was cleared at the end of the previous finalize (complete: see finalize_wait above)
+    std::swap(ctx->table, ctx->table2);
+    std::swap(ctx->t_keys, ctx->t2_keys);
+    std::swap(ctx->t_cells, ctx->t2_cells);
+    std::swap(ctx->t_count, ctx->t2_count);
+    std::swap(ctx->t_list, ctx->t2_list);
+    std::swap(ctx->h_table_count, ctx->h_table_count2);  // the closed table's last count copy lands in h_table_count2
+    *ctx->h_table_count = 0;
+    ctx->table_count_known = 0;
+    ctx->prev_fold_bound = 0;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->fin_p1_done, count_stream));
     ctx->fin_state = chad_ctx::FIN_PART1;
     return CHAD_OK;
 }
 
+// the exact chunk count is on the host: size everything and queue the whole finalize on fin_stream
 int finalize_part2(chad_ctx* ctx) {
     cudaStream_t fs = ctx->fin_stream;
-    const u32* hs = ctx->h_fin->scalars;
-    if (hs[SC_ERR]) { ctx->fin_state = chad_ctx::FIN_IDLE; return error_from_flags(ctx, hs[SC_ERR]); }
-    const u32 C = hs[SC_COUNT];
+    const u32 C = ctx->fin_external ? ctx->fin_max_chunks : *ctx->h_table_count2;
     ctx->fin_chunks = C;
+    ctx->fin_state = chad_ctx::FIN_IDLE;  // (until everything is queued: the reserves below may synchronise fin_stream)
+    if (C >= (1u << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
+    TRY(ensure_finalize_capacity(ctx, C));
     Level& LC = ctx->levels[CHAD_LEVEL_CLUSTERS];
-    if (C) {
-        const u32 fresh = hs[SC_NEW32];
-        LC.uniques += fresh;
-        LC.dupes += 2 * C - fresh;  // levels.hpp:135-138
+    TRY(level_reserve(ctx, LC, true, size_t(C) + 1));
+    for (int d = 0; d < 20; d++) {
+        // level d holds at most 8^d nodes and at most one node per leaf cluster; two records (TSDF, weight) per node
+        const u64 nodes = std::max<u64>(1, (d < 10) ? std::min<u64>(C, 1ull << (3 * d)) : C);
+        TRY(level_reserve(ctx, ctx->levels[d], false, size_t(2 * nodes)));
     }
-    for (int d = 0; d < 20; d++) ctx->fin_level_nodes[d] = C ? ctx->h_fin->level_nodes[d] : 0;
-    if (ctx->profiling) cudaEventRecord(ctx->fin_t2, fs);
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->f_level_new.p, 0, 20 * 8, fs));
+    if (ctx->profiling) cudaEventRecord(ctx->fin_t0, fs);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->f_scalars.p, 0, 256, fs));
     u64 launches = 0;
-    u64* ids = ctx->f_ids[0].as<u64>();
-    u64* ids_next = ctx->f_ids[1].as<u64>();
-    u32* addr = ctx->f_addr[0].as<u32>();
-    u32* addr_next = ctx->f_addr[1].as<u32>();
-    u32 n_children = C;
-    for (int d = 19; d >= 0; d--) {
-        Level& L = ctx->levels[d];
-        u32 n_records;
-        if (C == 0) {
-            if (d > 0) continue;  // empty octree: only the root is added, twice (submap.hpp:31-46)
-            CUDA_TRY(ctx, cudaMemsetAsync(ctx->f_cand.p, 0, 2 * 9 * 4, fs));
-            n_records = 2;
-        } else {
-            const u32 parents = ctx->fin_level_nodes[d];
-            launches += launch_group_heads(fs, ids, n_children, ctx->f_head.as<u32>(), ctx->f_head_rank.as<u32>(), ctx->f_scan_ws.p, scalar32(ctx, SC_PARENTS));
-            launches += launch_node_candidates(fs, ids, addr, ctx->f_head.as<u32>(), ctx->f_head_rank.as<u32>(), n_children, ctx->f_cand.as<u32>(), ids_next);
-            n_records = 2 * parents;
-            n_children = parents;
-        }
-        TRY(level_reserve(ctx, L, false, n_records));
-        // occupied_before must be exact: it is, because the previous finalize has finished (finalize_begin waits)
-        launches += launch_node_dedup(fs, L.table, ctx->f_cand.as<u32>(), n_records, L.raw.as<u32>(), L.occupied, ctx->f_slot_of.as<u32>(),
-                                      ctx->f_is_new.as<u64>(), ctx->f_rank.as<u64>(), ctx->f_scan_ws.p, addr_next, ctx->f_level_new.as<u64>() + d,
-                                      scalar32(ctx, SC_ERR));
-        std::swap(ids, ids_next);
-        std::swap(addr, addr_next);
+    if (ctx->fin_external) CUDA_TRY(ctx, cudaMemcpyAsync(scalar32(ctx, SC_COUNT), &ctx->fin_chunks, 4, cudaMemcpyHostToDevice, fs));
+    if (C) {
+        if (!ctx->fin_external) TRY(queue_sorted_chunks(ctx, fs, ctx->table2, C));
+        launches += launch_cluster_build(fs, ctx->f_cells.p, scalar32(ctx, SC_COUNT), C, ctx->mp, ctx->f_tsdf.as<u64>());
+        launches += launch_cluster_dedup(fs, LC.table, ctx->f_tsdf.as<u64>(), scalar32(ctx, SC_COUNT), C, LC.raw.as<u64>(), LC.uniques,
+                                         ctx->f_slot_of.as<u32>(), ctx->f_is_new.as<u32>(), ctx->f_rank.as<u32>(), ctx->f_scan_ws.p,
+                                         ctx->f_addr[0].as<u32>(), scalar32(ctx, SC_NEW32), scalar32(ctx, SC_ERR));
     }
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->level_new, ctx->f_level_new.p, 20 * 8, cudaMemcpyDeviceToHost, fs));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->root, addr, 8, cudaMemcpyDeviceToHost, fs));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->scalars, ctx->f_scalars.p, 16 * 4, cudaMemcpyDeviceToHost, fs));
-    ctx->stats.d2h_bytes += 20 * 8 + 8 + 64;
+    LevelsArgs la{};
+    for (int d = 0; d < 20; d++) {
+        Level& L = ctx->levels[d];
+        la.lv[d] = LevelDev{L.table.entries, L.table.first, L.table.capacity, L.raw.as<u32>()};
+    }
+    la.counters = ctx->f_counters.as<LevelCounters>();
+    la.d_chunks = scalar32(ctx, SC_COUNT);
+    la.ids[0] = ctx->f_ids[0].as<u64>(); la.ids[1] = ctx->f_ids[1].as<u64>();
+    la.addr[0] = ctx->f_addr[0].as<u32>(); la.addr[1] = ctx->f_addr[1].as<u32>();
+    la.head_rank = ctx->f_head_rank.as<u32>();
+    la.cand = ctx->f_cand.as<u32>();
+    la.slot_of = ctx->f_slot_of.as<u32>();
+    la.rank = ctx->f_rank.as<u64>();
+    la.partial = ctx->f_partial.as<u64>();
+    la.bar = scalar32(ctx, SC_BAR);
+    la.d_error = scalar32(ctx, SC_ERR);
+    la.root_out = scalar32(ctx, SC_ROOT);
+    la.level_nodes = scalar32(ctx, SC_LEVELS);
+    launches += launch_dag_levels(fs, la, ctx->num_sms);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->scalars, ctx->f_scalars.p, 16 * 4 + 20 * 4, cudaMemcpyDeviceToHost, fs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->counters, ctx->f_counters.p, sizeof(LevelCounters) * 20, cudaMemcpyDeviceToHost, fs));
+    ctx->stats.d2h_bytes += 16 * 4 + 20 * 4 + sizeof(LevelCounters) * 20;
     launch_table_clear(fs, ctx->fin_external ? ctx->table : ctx->table2);  // octree.clear(), tsdf.cpp:57
     if (ctx->profiling) cudaEventRecord(ctx->fin_t3, fs);
     CUDA_TRY(ctx, cudaEventRecord(ctx->fin_done, fs));
@@ -718,25 +766,29 @@ int finalize_part2(chad_ctx* ctx) {
 
 int finalize_finish(chad_ctx* ctx) {
     ctx->fin_state = chad_ctx::FIN_IDLE;
-    if (ctx->h_fin->scalars[SC_ERR]) return error_from_flags(ctx, ctx->h_fin->scalars[SC_ERR]);
+    const u32* hs = ctx->h_fin->scalars;
+    if (hs[SC_ERR]) return error_from_flags(ctx, hs[SC_ERR]);
     const u32 C = ctx->fin_chunks;
-    for (int d = 19; d >= 0; d--) {
-        if (C == 0 && d > 0) continue;
-        Level& L = ctx->levels[d];
-        const u32 n_records = C ? 2 * ctx->fin_level_nodes[d] : 2;
-        const u64 packed = ctx->h_fin->level_new[d];
-        const u32 fresh = (u32)(packed >> 32), words = (u32)packed;
-        L.uniques += fresh;
-        L.dupes += n_records - fresh;   // levels.hpp:83-86
-        L.occupied += words;            // levels.hpp:79-81
+    Level& LC = ctx->levels[CHAD_LEVEL_CLUSTERS];
+    if (C) {
+        const u32 fresh = hs[SC_NEW32];
+        LC.uniques += fresh;
+        LC.dupes += 2 * C - fresh;  // levels.hpp:135-138
     }
-    ctx->roots.push_back({ctx->h_fin->root[0], ctx->h_fin->root[1]});
+    for (int d = 0; d < 20; d++) {
+        Level& L = ctx->levels[d];
+        L.uniques = ctx->h_fin->counters[d].uniques;   // levels.hpp:79-86, accumulated on the device
+        L.dupes = ctx->h_fin->counters[d].dupes;
+        L.occupied = ctx->h_fin->counters[d].occupied;
+        ctx->fin_level_nodes[d] = ctx->h_fin->level_nodes[d];
+    }
+    ctx->roots.push_back({hs[SC_ROOT], hs[SC_ROOT + 1]});
     ctx->stats.submaps++;
     if (ctx->fin_external) { *ctx->h_table_count = 0; ctx->table_count_known = 0; ctx->fin_external = false; }
     if (ctx->profiling) {
-        float a = 0.f, b = 0.f;
-        if (cudaEventElapsedTime(&a, ctx->fin_t0, ctx->fin_t1) == cudaSuccess && cudaEventElapsedTime(&b, ctx->fin_t2, ctx->fin_t3) == cudaSuccess) {
-            ctx->prof_ms[PC_FINALIZE] += a + b;
+        float a = 0.f;
+        if (cudaEventElapsedTime(&a, ctx->fin_t0, ctx->fin_t3) == cudaSuccess) {
+            ctx->prof_ms[PC_FINALIZE] += a;
             ctx->prof_launches[PC_FINALIZE]++;
         } else cudaGetLastError();
     }
@@ -755,9 +807,12 @@ int finalize_submap(chad_ctx* ctx, bool lazy) {
     }
     // no batch in flight: the exact count of the last fold may not have been read yet
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
+    ctx->fold_in_flight = false;
+    ctx->prev_fold_bound = 0;
     ctx->table_count_known = *ctx->h_table_count;
     if (ctx->table_count_known >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
-    TRY(finalize_begin(ctx, (u32)ctx->table_count_known));
+    TRY(finalize_begin(ctx, 0, false, ctx->stream));
     ctx->stats.resident_clusters = 0;
     return CHAD_OK;
 }
@@ -842,6 +897,9 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     ctx->num_sms = prop.multiProcessorCount;
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->fold_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) CREATE_TRY(cudaEventCreateWithFlags(&ctx->fold_done[b], cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&ctx->submap_closed2, cudaEventDisableTiming));
     {   // the finalize stream gets the highest priority: its ~300 tiny dependent kernels then take the first SM slot that frees up
         // instead of queueing behind the thousands of CTAs of an insert kernel
         int prio_lo = 0, prio_hi = 0;
@@ -894,8 +952,10 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     if (r == CHAD_OK) r = dev_ensure(ctx, ctx->f_level_new, 256);
     if (r != CHAD_OK) return bail(r);
     CREATE_TRY(cudaMemsetAsync(ctx->d_plan.p, 0, 2 * sizeof(BatchPlan), ctx->stream));
-    r = table_alloc(ctx, ctx->table, ctx->t_keys, ctx->t_cells, ctx->t_count, 1ull << 20);
-    if (r == CHAD_OK) r = table_alloc(ctx, ctx->table2, ctx->t2_keys, ctx->t2_cells, ctx->t2_count, 1ull << 20);
+    r = table_alloc(ctx, ctx->table, ctx->t_keys, ctx->t_cells, ctx->t_count, ctx->t_list, 1ull << 20);
+    if (r == CHAD_OK) r = table_alloc(ctx, ctx->table2, ctx->t2_keys, ctx->t2_cells, ctx->t2_count, ctx->t2_list, 1ull << 20);
+    if (r == CHAD_OK) r = dev_ensure(ctx, ctx->f_counters, sizeof(LevelCounters) * CHAD_NUM_LEVELS);
+    if (r == CHAD_OK) r = dev_ensure(ctx, ctx->f_partial, 2 * 1024 * 8);
     if (r != CHAD_OK) return bail(r);
     // NodeLevel / LeafClusterLevel constructors reserve index 0 (levels.hpp:52-54,119-120)
     for (int d = 0; d < CHAD_NUM_LEVELS; d++) {
@@ -908,6 +968,8 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     }
     CREATE_TRY(cudaStreamSynchronize(ctx->stream));
     CREATE_TRY(cudaStreamSynchronize(ctx->fin_stream));
+    r = level_counters_reset(ctx);
+    if (r != CHAD_OK) return bail(r);
 #undef CREATE_TRY
     *out = ctx;
     return CHAD_OK;
@@ -918,10 +980,11 @@ void chad_destroy(chad_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->fold_stream) cudaStreamSynchronize(ctx->fold_stream);
     if (ctx->fin_stream) cudaStreamSynchronize(ctx->fin_stream);
-    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->f_level_new, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->sh_tuples, &ctx->sh_scalars, &ctx->bt_mem, &ctx->run_mem, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
+    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->t2_list, &ctx->t_list, &ctx->f_counters, &ctx->f_partial, &ctx->f_level_new, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->sh_tuples, &ctx->sh_scalars, &ctx->bt_mem, &ctx->run_mem[0], &ctx->run_mem[1], &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
                       &ctx->sorted_keys, &ctx->sorted_order, &ctx->xyz_sorted, &ctx->normals, &ctx->seg_info, &ctx->counts, &ctx->offsets,
-                      &ctx->radix_ws, &ctx->scan_ws, &ctx->t_keys, &ctx->t_cells, &ctx->t_count, &ctx->f_ids[0], &ctx->f_ids[1], &ctx->f_slots[0],
+                      &ctx->radix_ws, &ctx->scan_ws, &ctx->t_keys, &ctx->t_cells, &ctx->t_count, &ctx->f_sorted, &ctx->f_ids[0], &ctx->f_ids[1], &ctx->f_slots[0],
                       &ctx->f_slots[1], &ctx->f_cells, &ctx->f_tsdf, &ctx->f_addr[0], &ctx->f_addr[1], &ctx->f_head, &ctx->f_head_rank, &ctx->f_cand,
                       &ctx->f_slot_of, &ctx->f_is_new, &ctx->f_rank, &ctx->f_radix_ws, &ctx->f_scan_ws, &ctx->f_scalars};
     for (DevBuf* b : bufs) dev_free(*b);
@@ -941,6 +1004,8 @@ void chad_destroy(chad_ctx* ctx) {
     if (ctx->h_fin) cudaFreeHost(ctx->h_fin);
     for (cudaEvent_t e : {ctx->submap_closed, ctx->fin_p1_done, ctx->fin_done, ctx->fin_t0, ctx->fin_t1, ctx->fin_t2, ctx->fin_t3}) if (e) cudaEventDestroy(e);
     if (ctx->fin_stream) cudaStreamDestroy(ctx->fin_stream);
+    for (cudaEvent_t e : {ctx->fold_done[0], ctx->fold_done[1], ctx->submap_closed2}) if (e) cudaEventDestroy(e);
+    if (ctx->fold_stream) cudaStreamDestroy(ctx->fold_stream);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->front_done) cudaEventDestroy(ctx->front_done);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
@@ -1107,7 +1172,11 @@ int chad_reset(chad_ctx* ctx) {
     ctx->sh_have_splitters = false;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fin_stream));
+    ctx->fold_in_flight = false;
+    ctx->prev_fold_bound = 0;
+    ctx->fold_done_valid[0] = ctx->fold_done_valid[1] = false;
     ctx->fin_state = chad_ctx::FIN_IDLE;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_plan.p, 0, 2 * sizeof(BatchPlan), ctx->stream));
     launch_table_clear(ctx->stream, ctx->table);
@@ -1119,6 +1188,7 @@ int chad_reset(chad_ctx* ctx) {
         launch_dedup_clear(ctx->stream, L.table);
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    TRY(level_counters_reset(ctx));
     *ctx->h_table_count = 0;
     ctx->table_count_known = 0;
     ctx->has_pose = false;
@@ -1443,7 +1513,7 @@ int chad_shard_finalize_from(chad_ctx* ctx, const uint64_t* keys_device, const v
         if (keys_device != ctx->f_ids[0].p) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_ids[0].p, keys_device, n_chunks * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         if (cells_device != ctx->f_cells.p) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_cells.p, cells_device, n_chunks * 64, cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    TRY(finalize_begin(ctx, (u32)n_chunks, true));
+    TRY(finalize_begin(ctx, (u32)n_chunks, true, ctx->stream));
     TRY(finalize_wait(ctx));
     ctx->has_pose = false;
     ctx->stats.resident_clusters = 0;

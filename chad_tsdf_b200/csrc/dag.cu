@@ -288,6 +288,207 @@ __global__ void __launch_bounds__(DAG_THREADS) node_resolve_kernel(const u64* __
     addr_out[e] = (u32)entries[slot_of[e]];
 }
 
+// ------------------------------------------------------------------------------------------
+// All 20 node levels in ONE persistent kernel (submap.hpp:31-61 bottom-up). The per-level kernels above need the host
+// between levels (grid sizes, exact table sizing) and ~12 launches per level; here the CTAs walk the levels together,
+// separated by a software grid barrier, and read every count from device memory: Submap::finalize is queued in one go
+// and nothing waits for the host. Once a level has few children left, CTA 0 finishes the remaining levels alone.
+// ------------------------------------------------------------------------------------------
+constexpr int LV_THREADS = 1024;
+constexpr u32 LV_SOLO = 8192;  // children from which one CTA takes over
+
+__device__ __forceinline__ void grid_barrier(u32* bar, u32& phase, u32 nctas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        phase++;
+        atomicAdd(bar, 1u);
+        const u32 target = phase * nctas;
+        while (ld_u32_volatile(bar) < target) __nanosleep(40);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// exclusive prefix of partial[0 .. nctas) (nctas <= LV_THREADS) into shared memory; returns the total
+__device__ __forceinline__ u64 partial_prefix(const u64* partial, u32 nctas, u64* s_pref, u64* s_warp) {
+    const u64 v = (threadIdx.x < nctas) ? ((const volatile u64*)partial)[threadIdx.x] : 0ull;
+    u64 total;
+    const u64 ex = block_exclusive_scan<u64>(v, s_warp, total);
+    if (threadIdx.x < nctas) s_pref[threadIdx.x] = ex;
+    __syncthreads();
+    return total;
+}
+
+__global__ void __launch_bounds__(LV_THREADS, 1) dag_levels_kernel(LevelsArgs a) {
+    __shared__ u64 s_warp[LV_THREADS / 32];
+    __shared__ u64 s_pref[LV_THREADS];
+    const u32 tid = threadIdx.x;
+    u32 cta = blockIdx.x, nctas = gridDim.x, phase = 0;
+    const u32 C = *a.d_chunks;
+    u32 n = C;   // children of the level being built
+    int cur = 0;
+    auto sync = [&]() { if (nctas == 1) __syncthreads(); else grid_barrier(a.bar, phase, gridDim.x); };
+    for (int d = 19; d >= 0; d--) {
+        if (nctas > 1 && n <= LV_SOLO) {  // uniform over the grid: n comes from memory written before the last barrier
+            if (cta != 0) return;
+            nctas = 1;
+        }
+        const u64* __restrict__ ids = a.ids[cur];
+        const u32* __restrict__ addr = a.addr[cur];
+        u64* __restrict__ ids_next = a.ids[cur ^ 1];
+        u32* __restrict__ addr_next = a.addr[cur ^ 1];
+        const LevelDev L = a.lv[d];
+        const u32 occ = a.counters[d].occupied;  // levels.hpp:77: addresses continue from _occupied_n
+        const bool empty_root = (C == 0);        // empty octree: only the root is added, twice (submap.hpp:31-46)
+        if (empty_root && d > 0) continue;
+        // ---- 1. parents: heads of the groups of children with the same id >> 3, dense index inside this CTA's slice ----
+        const u32 per = (n + nctas - 1) / nctas;
+        const u32 c0 = min(n, cta * per), c1 = min(n, c0 + per);
+        {
+            u32 carry = 0;
+            for (u32 t0 = c0; t0 < c1; t0 += LV_THREADS) {
+                const u32 i = t0 + tid;
+                const bool head = (i < c1) && (i == 0 || (ids[i] >> 3) != (ids[i - 1] >> 3));
+                u64 tot;
+                const u64 ex = block_exclusive_scan<u64>(head ? 1ull : 0ull, s_warp, tot);
+                if (i < c1) a.head_rank[i] = head ? (carry + (u32)ex) : 0xFFFFFFFFu;
+                carry += (u32)tot;
+            }
+            if (tid == 0) a.partial[cta] = carry;
+        }
+        sync();
+        const u32 P = empty_root ? 1u : (u32)partial_prefix(a.partial, nctas, s_pref, s_warp);
+        const u32 pbase = empty_root ? 0u : (u32)s_pref[cta];
+        const u32 R = 2 * P;  // records of this level: TSDF node then weight node per parent (submap.hpp:33-35)
+        // ---- 2. candidate records: 9 words = child mask + children in ascending child index, zero padded (levels.hpp:63-74) ----
+        if (empty_root) {
+            if (cta == 0 && tid < 18) a.cand[tid] = 0;
+        } else {
+            for (u32 i = c0 + tid; i < c1; i += LV_THREADS) {
+                const u32 hr = a.head_rank[i];
+                if (hr == 0xFFFFFFFFu) continue;
+                const u32 p = pbase + hr;
+                const u64 pid = ids[i] >> 3;
+                u32 rt[9], rw[9];
+#pragma unroll
+                for (int q = 0; q < 9; q++) { rt[q] = 0; rw[q] = 0; }
+                u32 c = 0;
+                for (u32 j = i; j < n && (ids[j] >> 3) == pid; j++) {
+                    const u32 bit = 1u << (u32)(ids[j] & 7ull);
+                    rt[0] |= bit; rw[0] |= bit;
+                    c++;
+#pragma unroll
+                    for (int q = 1; q < 9; q++)
+                        if ((u32)q == c) { rt[q] = addr[2 * j]; rw[q] = addr[2 * j + 1]; }
+                }
+#pragma unroll
+                for (int q = 0; q < 9; q++) {
+                    a.cand[size_t(2 * p) * 9 + q] = rt[q];
+                    a.cand[size_t(2 * p + 1) * 9 + q] = rw[q];
+                }
+                ids_next[p] = pid;
+            }
+        }
+        sync();
+        // ---- 3. probe: find-or-insert every record; a record not yet resident keeps the minimum sequence index that carried it ----
+        for (u32 e = cta * LV_THREADS + tid; e < R; e += nctas * LV_THREADS) {
+            u32 rec[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) rec[q] = a.cand[size_t(e) * 9 + q];
+            const u32 tag = node_tag(rec);
+            const u32 nchild = __popc(rec[0]);
+            const u64 mask = L.capacity - 1;
+            u64 slot = tag & mask;
+            bool done = false;
+            for (u64 probes = 0; probes < L.capacity && !done; probes++) {
+                u64 ent = ld_entry(&L.entries[slot]);
+                if (ent == 0) {
+                    const u64 mine = (u64(tag) << 32) | (REF_PENDING | e);
+                    ent = atomicCAS(&L.entries[slot], 0ull, mine);
+                    if (ent == 0) { note_first(&L.first[slot], e); a.slot_of[e] = (u32)slot; done = true; break; }
+                }
+                if ((u32)(ent >> 32) == tag) {
+                    const u32 ref = (u32)ent;
+                    const u32* other = (ref & REF_PENDING) ? (a.cand + size_t(ref & ~REF_PENDING) * 9) : (L.raw + ref);
+                    bool eq = (other[0] & 0xFFu) == rec[0];   // levels.hpp:27-44: same mask and the same children
+                    for (u32 q = 1; eq && q <= nchild; q++) eq = other[q] == rec[q];
+                    if (eq) {
+                        if (ref & REF_PENDING) note_first(&L.first[slot], e);
+                        a.slot_of[e] = (u32)slot;
+                        done = true;
+                        break;
+                    }
+                }
+                slot = (slot + 1) & mask;
+            }
+            if (!done) { atomicOr(a.d_error, ERRF_DEDUP_FULL); a.slot_of[e] = 0; }
+        }
+        sync();
+        // ---- 4. first occurrences of new records and their running size inside this CTA's slice of the sequence ----
+        const u32 per2 = (R + nctas - 1) / nctas;
+        const u32 e0 = min(R, cta * per2), e1 = min(R, e0 + per2);
+        {
+            u64 carry = 0;
+            for (u32 t0 = e0; t0 < e1; t0 += LV_THREADS) {
+                const u32 e = t0 + tid;
+                u64 v = 0;
+                if (e < e1) {
+                    const u32 slot = a.slot_of[e];
+                    const u32 ref = (u32)ld_entry(&L.entries[slot]);
+                    const bool fresh = (ref & REF_PENDING) && ld_u32_volatile(&L.first[slot]) == e;
+                    if (fresh) v = (1ull << 32) | (1u + (u32)__popc(a.cand[size_t(e) * 9]));
+                }
+                u64 tot;
+                const u64 ex = block_exclusive_scan<u64>(v, s_warp, tot);
+                if (e < e1) a.rank[e] = (carry + ex) | (v ? (1ull << 63) : 0ull);  // bit 63: this element is a first occurrence
+                carry += tot;
+            }
+            if (tid == 0) a.partial[LV_THREADS + cta] = carry;
+        }
+        sync();
+        const u64 new_total = partial_prefix(a.partial + LV_THREADS, nctas, s_pref, s_warp);  // (new records << 32) | new words
+        // ---- 5. commit the new records and resolve every element's address (levels.hpp:76-87) ----
+        for (u32 e = e0 + tid; e < e1; e += LV_THREADS) {
+            const u32 slot = a.slot_of[e];
+            const u64 rk = a.rank[e];
+            u32 address;
+            if (rk >> 63) {
+                address = occ + (u32)(s_pref[cta] + rk);  // low 32 bits: words before this record
+                const u32 words = 1u + (u32)__popc(a.cand[size_t(e) * 9]);
+                for (u32 q = 0; q < words; q++) L.raw[address + q] = a.cand[size_t(e) * 9 + q];
+                __threadfence();
+                atomicExch(&L.entries[slot], (ld_entry(&L.entries[slot]) & 0xFFFFFFFF00000000ull) | address);
+                __threadfence();
+                atomicExch(&L.first[slot], FIRST_IDLE);
+            } else {
+                while (true) {
+                    const u64 ent = ld_entry(&L.entries[slot]);
+                    if (!((u32)ent & REF_PENDING)) { address = (u32)ent; break; }
+                    const u32 f = ld_u32_volatile(&L.first[slot]);
+                    if (f != FIRST_IDLE) {  // the first occurrence has not committed yet: its address is already determined
+                        const u64 frk = ((const volatile u64*)a.rank)[f];
+                        address = occ + (u32)(s_pref[f / per2] + frk);
+                        break;
+                    }
+                }
+            }
+            addr_next[e] = address;
+        }
+        sync();
+        if (cta == 0 && tid == 0) {
+            const u32 fresh = (u32)(new_total >> 32), words = (u32)new_total;
+            a.counters[d].occupied = occ + words;   // levels.hpp:79-81
+            a.counters[d].uniques += fresh;
+            a.counters[d].dupes += R - fresh;       // levels.hpp:83-86
+            a.level_nodes[d] = P;
+        }
+        cur ^= 1;
+        n = P;
+    }
+    if (tid == 0) { a.root_out[0] = a.addr[cur][0]; a.root_out[1] = a.addr[cur][1]; }
+}
+
 __global__ void __launch_bounds__(DAG_THREADS) dedup_rehash_kernel(const u64* __restrict__ from, u64 from_capacity, u64* to, u64 to_capacity) {
     const u64 mask = to_capacity - 1;
     for (u64 s = u64(blockIdx.x) * DAG_THREADS + threadIdx.x; s < from_capacity; s += u64(gridDim.x) * DAG_THREADS) {
@@ -331,6 +532,13 @@ int launch_cluster_dedup(cudaStream_t s, const DedupTable& t, const u64* tsdf_va
     cluster_commit_kernel<<<blocks_for(max_work), DAG_THREADS, 0, s>>>(t.entries, t.first, slot_of, is_new, rank, d_chunks, tsdf_values, raw, uniques_before);
     cluster_resolve_kernel<<<blocks_for(max_chunks), DAG_THREADS, 0, s>>>(t.entries, slot_of, d_chunks, addr_out);
     return launches + 2;
+}
+
+int launch_dag_levels(cudaStream_t s, const LevelsArgs& args, int num_sms) {
+    cudaMemsetAsync(args.bar, 0, 4, s);
+    const int grid = num_sms < LV_THREADS ? num_sms : LV_THREADS;
+    dag_levels_kernel<<<grid, LV_THREADS, 0, s>>>(args);
+    return 1;
 }
 
 int launch_level_counts(cudaStream_t s, const u64* chunk_ids, const u32* d_chunks, u32 max_chunks, u32* counts20, int num_sms) {

@@ -64,7 +64,8 @@ constexpr int FOLD_WARPS = FOLD_THREADS / 32;
 
 __global__ void __launch_bounds__(FOLD_THREADS) fold_kernel(const u64* __restrict__ keys_a, const u64* __restrict__ keys_b,
                                                             const u32* __restrict__ sd_a, const u32* __restrict__ sd_b, BatchPlan* plan,
-                                                            u64* __restrict__ tkeys, uint2* __restrict__ tcells, u64 capacity, u32* tcount) {
+                                                            u64* __restrict__ tkeys, uint2* __restrict__ tcells, u64 capacity, u32* tcount,
+                                                            u64* __restrict__ tlist) {
     __shared__ u64 s_keys[FOLD_WARPS][FOLD_CHUNK];   // phase 0/1: keys; afterwards slot h = (acc bits, weight) of head h
     __shared__ u64 s_cell[FOLD_WARPS][FOLD_CHUNK];   // cell index of head h in the table
     __shared__ u32 s_sd[FOLD_WARPS][FOLD_CHUNK + FOLD_LOOK];
@@ -127,9 +128,10 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_kernel(const u64* __restric
             const bool has = h < n_heads;
             const u64 ckey = has ? s_keys[warp][s_heads[warp][h]] : 0ull;
             __syncwarp();
+            bool inserted = false;
+            u64 full = 0ull;
             if (has) {
-                const u64 full = expand_key(ckey, k);
-                bool inserted;
+                full = expand_key(ckey, k);
                 const u64 slot = table_upsert(tkeys, capacity, full >> 3, inserted);
                 if (slot == ~0ull) {
                     err |= ERRF_TABLE_FULL;
@@ -143,6 +145,15 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_kernel(const u64* __restric
                     s_keys[warp][h] = (u64(c.y) << 32) | c.x;
                 }
                 if (h + 1 == n_heads) last_key = ckey;
+            }
+            {   // new chunks join the table's chunk list (one reservation per warp)
+                const u32 nb = __ballot_sync(0xffffffffu, inserted);
+                if (nb) {
+                    u32 lbase = 0;
+                    if (lane == 0) lbase = atomicAdd(tcount, (u32)__popc(nb));
+                    lbase = __shfl_sync(0xffffffffu, lbase, 0);
+                    if (inserted) tlist[lbase + __popc(nb & lanemask_lt)] = full >> 3;
+                }
             }
             __syncwarp();
         }
@@ -227,7 +238,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_kernel(const u64* __restric
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (s_red[0]) { atomicAdd(&plan->n_new_chunks, s_red[0]); atomicAdd(tcount, s_red[0]); }
+        if (s_red[0]) atomicAdd(&plan->n_new_chunks, s_red[0]);
         if (s_red[1]) atomicOr(&plan->error, s_red[1]);
     }
 }
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) segment_count_kernel(const u64* 
 
 __global__ void __launch_bounds__(FOLD_THREADS) table_rehash_kernel(const u64* __restrict__ from_keys, const uint4* __restrict__ from_cells,
                                                                     u64 from_capacity, u64* __restrict__ to_keys, uint4* __restrict__ to_cells,
-                                                                    u64 to_capacity, u32* to_count) {
+                                                                    u64 to_capacity, u32* to_count, u64* __restrict__ to_list) {
     for (u64 s = u64(blockIdx.x) * FOLD_THREADS + threadIdx.x; s < from_capacity; s += u64(gridDim.x) * FOLD_THREADS) {
         const u64 chunk = from_keys[s];
         if (chunk == CHUNK_EMPTY) continue;
@@ -271,61 +282,73 @@ __global__ void __launch_bounds__(FOLD_THREADS) table_rehash_kernel(const u64* _
         if (slot == ~0ull) continue;  // cannot happen: the target is larger
 #pragma unroll
         for (int q = 0; q < 4; q++) to_cells[slot * 4 + q] = from_cells[s * 4 + q];
-        atomicAdd(to_count, 1u);
+        to_list[atomicAdd(to_count, 1u)] = chunk;
     }
 }
 
-// occupied chunks -> (full chunk key, slot) in arbitrary order (the sort that follows makes the
-// result deterministic); also the max range code over all resident voxels
-__global__ void __launch_bounds__(FOLD_THREADS) table_compact_kernel(const u64* __restrict__ tkeys, u64 capacity, u64* __restrict__ out_keys,
-                                                                     u32* __restrict__ out_slots, u32* d_count, u32* d_rmax) {
+// the table's chunk list -> (full chunk key, index) + the max range code over all resident voxels
+__global__ void __launch_bounds__(FOLD_THREADS) table_compact_kernel(const u64* __restrict__ tlist, const u32* __restrict__ tcount, u32 max_n,
+                                                                     u64* __restrict__ out_keys, u32* __restrict__ out_vals, u32* d_count, u32* d_rmax) {
+    const u32 n = min(*tcount, max_n);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d_count = n;
     u32 rmax = 0;
-    for (u64 s0 = u64(blockIdx.x) * FOLD_THREADS; s0 < capacity; s0 += u64(gridDim.x) * FOLD_THREADS) {
-        const u64 s = s0 + threadIdx.x;
-        const u64 chunk = (s < capacity) ? tkeys[s] : CHUNK_EMPTY;
-        const bool occ = chunk != CHUNK_EMPTY;
-        const u32 ballot = __ballot_sync(0xffffffffu, occ);
-        if (ballot == 0) continue;
-        const u32 lane = threadIdx.x & 31;
-        u32 base = 0;
-        if (lane == 0) base = atomicAdd(d_count, (u32)__popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (occ) {
-            const u32 dst = base + __popc(ballot & ((1u << lane) - 1u));
-            out_keys[dst] = chunk;
-            out_slots[dst] = (u32)s;
-            i32 x, y, z;
-            morton_decode(chunk << 3, x, y, z);
-            rmax = max(rmax, max(rcode(x), max(rcode(y), rcode(z))) | 1u);  // the chunk spans v and v+1 on every axis
-        }
+    for (u32 i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < n; i += gridDim.x * FOLD_THREADS) {
+        const u64 chunk = tlist[i];
+        out_keys[i] = chunk;
+        out_vals[i] = i;
+        i32 x, y, z;
+        morton_decode(chunk << 3, x, y, z);
+        rmax = max(rmax, max(rcode(x), max(rcode(y), rcode(z))) | 1u);  // the chunk spans v and v+1 on every axis
     }
     rmax = __reduce_max_sync(0xffffffffu, rmax);
     if ((threadIdx.x & 31) == 0 && rmax) atomicMax(d_rmax, rmax);
+}
+
+__device__ __forceinline__ u32 chunk_k(u32 rmax) {
+    u32 k = 32 - __clz(rmax);
+    if (k < 3) k = 3;
+    if (k > 20) k = 20;
+    return k;
 }
 
 // chunk sort keys: compact(full voxel key) >> 3 -> 3k bits; writes k-derived nbits for the radix sort
 __global__ void __launch_bounds__(FOLD_THREADS) chunk_sortkeys_kernel(u64* __restrict__ keys, const u32* __restrict__ d_count,
                                                                       const u32* __restrict__ d_rmax, u32* __restrict__ d_nbits) {
     const u32 n = *d_count;
-    u32 k = 32 - __clz(*d_rmax);
-    if (k < 3) k = 3;
-    if (k > 20) k = 20;
+    const u32 k = chunk_k(*d_rmax);
     if (blockIdx.x == 0 && threadIdx.x == 0) *d_nbits = 3 * k;
     for (u32 i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < n; i += gridDim.x * FOLD_THREADS) keys[i] = compact_key(keys[i] << 3, k) >> 3;
 }
 
-// sorted slots -> contiguous (full chunk key, 8 cells) for export / cluster building. The count and the buffer the
+__device__ __forceinline__ u64 table_find(const u64* __restrict__ keys, u64 capacity, u64 chunk) {
+    const u64 mask = capacity - 1;
+    u64 h = mix64(chunk) & mask;
+    for (u64 probes = 0; probes < capacity; probes++) {
+        const u64 cur = keys[h];
+        if (cur == chunk) return h;
+        if (cur == CHUNK_EMPTY) return ~0ull;
+        h = (h + 1) & mask;
+    }
+    return ~0ull;
+}
+
+// sorted chunk keys -> contiguous (full chunk key, 8 cells) for export / cluster building. The count and the buffer the
 // radix sort left its result in are read from device memory, so the host needs only an upper bound of the count.
-__global__ void __launch_bounds__(FOLD_THREADS) chunk_gather_kernel(const u64* __restrict__ tkeys, const uint4* __restrict__ tcells,
-                                                                    const u32* __restrict__ slots_a, const u32* __restrict__ slots_b,
-                                                                    const u32* __restrict__ d_count, const u32* __restrict__ d_nbits,
-                                                                    u64* __restrict__ out_keys, uint4* __restrict__ out_cells) {
+__global__ void __launch_bounds__(FOLD_THREADS) chunk_gather_kernel(const u64* __restrict__ tkeys, const uint4* __restrict__ tcells, u64 capacity,
+                                                                    const u64* __restrict__ keys_a, const u64* __restrict__ keys_b,
+                                                                    const u32* __restrict__ d_count, const u32* __restrict__ d_rmax,
+                                                                    const u32* __restrict__ d_nbits, u64* __restrict__ out_keys,
+                                                                    uint4* __restrict__ out_cells) {
     const u32 i = blockIdx.x * FOLD_THREADS + threadIdx.x;
     if (i >= *d_count) return;
-    const u32 s = radix_result_in_alt(*d_nbits) ? slots_b[i] : slots_a[i];
-    out_keys[i] = tkeys[s];
+    const u32 k = chunk_k(*d_rmax);
+    const u64 ckey = radix_result_in_alt(*d_nbits) ? keys_b[i] : keys_a[i];
+    const u64 chunk = expand_key(ckey << 3, k) >> 3;
+    const u64 s = table_find(tkeys, capacity, chunk);
+    out_keys[i] = chunk;
+    const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (int q = 0; q < 4; q++) out_cells[size_t(i) * 4 + q] = tcells[size_t(s) * 4 + q];
+    for (int q = 0; q < 4; q++) out_cells[size_t(i) * 4 + q] = (s != ~0ull) ? tcells[size_t(s) * 4 + q] : z;
 }
 
 }  // namespace
@@ -342,7 +365,7 @@ int launch_fold(cudaStream_t s, const u64* keys_a, const u64* keys_b, const u32*
     if (!max_pairs) return 0;
     u32 want = (max_pairs + FOLD_CHUNK * FOLD_WARPS - 1) / (FOLD_CHUNK * FOLD_WARPS);
     u32 cap = (u32)num_sms * 4;  // persistent: chunks are handed out by ticket
-    fold_kernel<<<want < cap ? want : cap, FOLD_THREADS, 0, s>>>(keys_a, keys_b, sd_a, sd_b, plan, t.keys, t.cells, t.capacity, t.count);
+    fold_kernel<<<want < cap ? want : cap, FOLD_THREADS, 0, s>>>(keys_a, keys_b, sd_a, sd_b, plan, t.keys, t.cells, t.capacity, t.count, t.list);
     return 1;
 }
 
@@ -356,23 +379,23 @@ int launch_segment_count(cudaStream_t s, const u64* keys_a, const u64* keys_b, u
 
 int launch_table_rehash(cudaStream_t s, const ChunkTable& from, const ChunkTable& to, int num_sms) {
     table_rehash_kernel<<<num_sms * 8, FOLD_THREADS, 0, s>>>(from.keys, reinterpret_cast<const uint4*>(from.cells), from.capacity, to.keys,
-                                                             reinterpret_cast<uint4*>(to.cells), to.capacity, to.count);
+                                                             reinterpret_cast<uint4*>(to.cells), to.capacity, to.count, to.list);
     return 1;
 }
 
-int launch_table_compact(cudaStream_t s, const ChunkTable& t, u64* out_keys, u32* out_slots, u32* d_count, u32* d_rmax, u32* d_nbits, int num_sms) {
-    cudaMemsetAsync(d_count, 0, 4, s);
+int launch_table_compact(cudaStream_t s, const ChunkTable& t, u32 max_n, u64* out_keys, u32* out_vals, u32* d_count, u32* d_rmax, u32* d_nbits, int num_sms) {
     cudaMemsetAsync(d_rmax, 0, 4, s);
-    table_compact_kernel<<<num_sms * 8, FOLD_THREADS, 0, s>>>(t.keys, t.capacity, out_keys, out_slots, d_count, d_rmax);
+    table_compact_kernel<<<num_sms * 4, FOLD_THREADS, 0, s>>>(t.list, t.count, max_n, out_keys, out_vals, d_count, d_rmax);
     chunk_sortkeys_kernel<<<num_sms * 4, FOLD_THREADS, 0, s>>>(out_keys, d_count, d_rmax, d_nbits);
     return 2;
 }
 
-int launch_chunk_gather(cudaStream_t s, const ChunkTable& t, const u32* slots_a, const u32* slots_b, const u32* d_count, const u32* d_nbits,
-                        u32 max_n, u64* out_keys, void* out_cells) {
+int launch_chunk_gather(cudaStream_t s, const ChunkTable& t, const u64* keys_a, const u64* keys_b, const u32* d_count, const u32* d_rmax,
+                        const u32* d_nbits, u32 max_n, u64* out_keys, void* out_cells) {
     if (!max_n) return 0;
-    chunk_gather_kernel<<<(max_n + FOLD_THREADS - 1) / FOLD_THREADS, FOLD_THREADS, 0, s>>>(t.keys, reinterpret_cast<const uint4*>(t.cells), slots_a, slots_b,
-                                                                                          d_count, d_nbits, out_keys, static_cast<uint4*>(out_cells));
+    chunk_gather_kernel<<<(max_n + FOLD_THREADS - 1) / FOLD_THREADS, FOLD_THREADS, 0, s>>>(t.keys, reinterpret_cast<const uint4*>(t.cells), t.capacity, keys_a,
+                                                                                          keys_b, d_count, d_rmax, d_nbits, out_keys,
+                                                                                          static_cast<uint4*>(out_cells));
     return 1;
 }
 

@@ -98,6 +98,8 @@ struct ChunkTable {
     uint2* cells;   // [capacity][8] (sd bits, weight) per voxel slot, weight 0 = absent
     u64 capacity;   // power of two
     u32* count;     // device counter of occupied chunks
+    u64* list;      // [capacity / 2] keys of the occupied chunks in insertion order (count entries): finalize reads the
+                    // submap's chunks from here instead of scanning the table
 };
 constexpr u64 CHUNK_EMPTY = ~0ull;
 int launch_table_clear(cudaStream_t s, const ChunkTable& t);
@@ -105,11 +107,11 @@ int launch_segment_count(cudaStream_t s, const u64* keys_a, const u64* keys_b, u
 int launch_fold(cudaStream_t s, const u64* keys_a, const u64* keys_b, const u32* sd_a, const u32* sd_b, u32 max_pairs, BatchPlan* plan,
                 const ChunkTable& t, int num_sms);
 int launch_table_rehash(cudaStream_t s, const ChunkTable& from, const ChunkTable& to, int num_sms);
-// occupied chunks -> (chunk sort key on *d_nbits bits, slot), arbitrary order; *d_count = number of chunks
-int launch_table_compact(cudaStream_t s, const ChunkTable& t, u64* out_keys, u32* out_slots, u32* d_count, u32* d_rmax, u32* d_nbits, int num_sms);
-// sorted slots -> contiguous (full chunk key, 8 x (sd bits, weight)); count and result buffer selected on the device
-int launch_chunk_gather(cudaStream_t s, const ChunkTable& t, const u32* slots_a, const u32* slots_b, const u32* d_count, const u32* d_nbits,
-                        u32 max_n, u64* out_keys, void* out_cells);
+// the table's chunk list -> chunk sort keys on *d_nbits bits (arbitrary order); *d_count = number of chunks
+int launch_table_compact(cudaStream_t s, const ChunkTable& t, u32 max_n, u64* out_keys, u32* out_vals, u32* d_count, u32* d_rmax, u32* d_nbits, int num_sms);
+// sorted chunk keys -> contiguous (full chunk key, 8 x (sd bits, weight)); count and result buffer selected on the device
+int launch_chunk_gather(cudaStream_t s, const ChunkTable& t, const u64* keys_a, const u64* keys_b, const u32* d_count, const u32* d_rmax,
+                        const u32* d_nbits, u32 max_n, u64* out_keys, void* out_cells);
 
 // ---- dag.cu: Submap::finalize (submap.hpp:10-106) level by level ----
 struct DedupTable {   // open addressing; entry = (hash tag << 32) | ref, 0 = empty
@@ -118,6 +120,21 @@ struct DedupTable {   // open addressing; entry = (hash tag << 32) | ref, 0 = em
     u64 capacity;     // power of two
 };
 constexpr u32 REF_PENDING = 0x80000000u;
+// the 20 node levels in one persistent kernel (dag_levels_kernel)
+struct LevelDev { u64* entries; u32* first; u64 capacity; u32* raw; };
+struct LevelCounters { u32 occupied, uniques, dupes, pad; };   // device mirror of NodeLevel::_occupied_n / _uniques_n / _dupes_n
+struct LevelsArgs {
+    LevelDev lv[20];
+    LevelCounters* counters;   // [21]
+    const u32* d_chunks;       // leaf clusters of the submap
+    u64* ids[2];               // node ids of the current children, ping-pong (ids[0] = sorted chunk ids on entry)
+    u32* addr[2];              // (TSDF, weight) addresses of the current children (addr[0] = cluster addresses on entry)
+    u32* head_rank; u32* cand; u32* slot_of; u64* rank;
+    u64* partial;              // [2][1024]
+    u32* bar;                  // grid barrier counter
+    u32* d_error; u32* root_out; u32* level_nodes;
+};
+int launch_dag_levels(cudaStream_t s, const LevelsArgs& args, int num_sms);
 int launch_dedup_clear(cudaStream_t s, const DedupTable& t);
 int launch_dedup_rehash(cudaStream_t s, const DedupTable& from, const DedupTable& to, int num_sms);
 // the chunk count is read from device memory (*d_chunks <= max_chunks): finalize part 1 runs without a host round trip

@@ -363,7 +363,8 @@ struct FoldWarp {
 __global__ void __launch_bounds__(RF_THREADS) runs_fold_kernel(const u64* __restrict__ records, const u64* __restrict__ dkeys_a,
                                                                const u64* __restrict__ dkeys_b, const uint2* __restrict__ sdesc,
                                                                const uint2* __restrict__ work, u32 work_capacity, BatchPlan* plan,
-                                                               u64* __restrict__ tkeys, uint2* tcells, u64 capacity, u32* tcount) {
+                                                               u64* __restrict__ tkeys, uint2* tcells, u64 capacity, u32* tcount,
+                                                               u64* __restrict__ tlist) {
     __shared__ __align__(16) FoldWarp s_w[RF_THREADS / 32];
     __shared__ u32 s_red[4];
     const u32 tid = threadIdx.x, lane = tid & 31;
@@ -467,9 +468,26 @@ __global__ void __launch_bounds__(RF_THREADS) runs_fold_kernel(const u64* __rest
             const u32 word0 = S.touched[lane >> 2], word1 = S.touched[(lane + 32) >> 2];
             const u32 b0 = (word0 >> ((lane & 3u) * 8u)) & 0xFFu, b1 = (word1 >> ((lane & 3u) * 8u)) & 0xFFu;
             st_segments += (u32)__popc(b0) + (u32)__popc(b1);
+            // chunks touched for the first time in this submap are inserted now and join the table's chunk list
+            const bool ins0 = b0 && slot0 == ~0ull, ins1 = b1 && slot1 == ~0ull;
+            const u32 m0 = __ballot_sync(0xffffffffu, ins0), m1 = __ballot_sync(0xffffffffu, ins1);
+            if (m0 | m1) {
+                u32 lbase = 0;
+                if (lane == 0) lbase = atomicAdd(tcount, (u32)(__popc(m0) + __popc(m1)));
+                lbase = __shfl_sync(0xffffffffu, lbase, 0);
+                if (ins0) {
+                    slot0 = table_insert(tkeys, capacity, (blk << 6) | (u64)lane);
+                    tlist[lbase + __popc(m0 & lt)] = (blk << 6) | (u64)lane;
+                    st_new++;
+                }
+                if (ins1) {
+                    slot1 = table_insert(tkeys, capacity, (blk << 6) | (u64)(lane + 32));
+                    tlist[lbase + __popc(m0) + __popc(m1 & lt)] = (blk << 6) | (u64)(lane + 32);
+                    st_new++;
+                }
+            }
             if (b0) {
                 st_chunks++;
-                if (slot0 == ~0ull) { slot0 = table_insert(tkeys, capacity, (blk << 6) | (u64)lane); st_new++; }
                 if (slot0 == ~0ull) err |= ERRF_TABLE_FULL;
                 else {
                     uint4* dst = reinterpret_cast<uint4*>(tcells + slot0 * 8);
@@ -480,7 +498,6 @@ __global__ void __launch_bounds__(RF_THREADS) runs_fold_kernel(const u64* __rest
             }
             if (b1) {
                 st_chunks++;
-                if (slot1 == ~0ull) { slot1 = table_insert(tkeys, capacity, (blk << 6) | (u64)(lane + 32)); st_new++; }
                 if (slot1 == ~0ull) err |= ERRF_TABLE_FULL;
                 else {
                     uint4* dst = reinterpret_cast<uint4*>(tcells + slot1 * 8);
@@ -510,7 +527,7 @@ __global__ void __launch_bounds__(RF_THREADS) runs_fold_kernel(const u64* __rest
     if (tid == 0) {
         if (s_red[0]) atomicAdd(&plan->n_segments, s_red[0]);
         if (s_red[1]) atomicAdd(&plan->n_chunk_heads, s_red[1]);
-        if (s_red[2]) { atomicAdd(&plan->n_new_chunks, s_red[2]); atomicAdd(tcount, s_red[2]); }
+        if (s_red[2]) atomicAdd(&plan->n_new_chunks, s_red[2]);
         if (s_red[3]) atomicOr(&plan->error, s_red[3]);
     }
 }
@@ -574,7 +591,7 @@ int launch_runs_front(cudaStream_t s, const float* xyz_sorted, const float* norm
 
 int launch_runs_fold(cudaStream_t s, const u64* records, const RunBuffers& rb, BatchPlan* plan, const ChunkTable& t, int num_sms) {
     runs_fold_kernel<<<num_sms * g_fold_ctas_per_sm, RF_THREADS, 0, s>>>(records, rb.key_a, rb.key_b, rb.sdesc, rb.work, rb.capacity, plan, t.keys, t.cells,
-                                                                              t.capacity, t.count);
+                                                                              t.capacity, t.count, t.list);
     return 1;
 }
 
