@@ -386,16 +386,16 @@ __device__ __forceinline__ u32 owner_of(u64 blk, const u64* __restrict__ splitte
 constexpr int SHARD_MAX_WORLD = 8;
 
 // per-destination update counts of this rank's ray slice
-__global__ void __launch_bounds__(BLK_THREADS) shard_count_kernel(const float* __restrict__ xyz_sorted, u32 i_begin, u32 i_end,
+__global__ void __launch_bounds__(BLK_THREADS) shard_count_kernel(const float* __restrict__ xyz_sorted, u32 n_points, const uint2* __restrict__ slices,
                                                                   const BatchScans* __restrict__ scans, float res, float trunc, float recip,
                                                                   u32 max_ray_voxels, const BatchPlan* __restrict__ plan,
                                                                   const u64* __restrict__ splitters, u32 world, u32* __restrict__ dest_count) {
-    const u32 i = i_begin + blockIdx.x * BLK_THREADS + threadIdx.x;
+    const u32 i = blockIdx.x * BLK_THREADS + threadIdx.x;
     u32 cnt[SHARD_MAX_WORLD];
 #pragma unroll
     for (int d = 0; d < SHARD_MAX_WORLD; d++) cnt[d] = 0;
-    if (i < i_end) {
-        const u32 s = scan_of(scans, plan->n_scans, i);
+    const u32 s = (i < n_points) ? scan_of(scans, plan->n_scans, i) : 0u;
+    if (i < n_points && i >= slices[s].x && i < slices[s].y) {  // this rank walks the rays whose point lies in its Morton range
         const float pos[3] = {scans->pose[s][0], scans->pose[s][1], scans->pose[s][2]};
         Ray r;
         ray_setup(r, xyz_sorted[size_t(i) * 3], xyz_sorted[size_t(i) * 3 + 1], xyz_sorted[size_t(i) * 3 + 2], pos, res, trunc, recip);
@@ -425,19 +425,19 @@ __global__ void __launch_bounds__(BLK_THREADS) shard_count_kernel(const float* _
 }
 
 // writes the slice's updates as tuples into the send buffer, grouped by destination (dest_offset = exclusive prefix of the counts)
-__global__ void __launch_bounds__(BLK_THREADS) shard_emit_kernel(const float* __restrict__ xyz_sorted, const float* __restrict__ normals, u32 i_begin,
-                                                                 u32 i_end, const BatchScans* __restrict__ scans, float res, float trunc, float recip,
+__global__ void __launch_bounds__(BLK_THREADS) shard_emit_kernel(const float* __restrict__ xyz_sorted, const float* __restrict__ normals, u32 n_points,
+                                                                 const uint2* __restrict__ slices, const BatchScans* __restrict__ scans, float res, float trunc, float recip,
                                                                  u32 max_ray_voxels, BatchPlan* plan, const u64* __restrict__ splitters, u32 world,
                                                                  const u32* __restrict__ dest_offset, u32* __restrict__ dest_cursor,
                                                                  uint4* __restrict__ tuples, u32 tuple_capacity) {
-    const u32 i = i_begin + blockIdx.x * BLK_THREADS + threadIdx.x;
+    const u32 i = blockIdx.x * BLK_THREADS + threadIdx.x;
     const u32 lane = threadIdx.x & 31;
     u64 bkey[BLK_RAY_MAX];
     u32 bsd[BLK_RAY_MAX];
     unsigned char bown[BLK_RAY_MAX];
     u32 total = 0, err = 0;
-    if (i < i_end) {
-        const u32 s = scan_of(scans, plan->n_scans, i);
+    const u32 s = (i < n_points) ? scan_of(scans, plan->n_scans, i) : 0u;
+    if (i < n_points && i >= slices[s].x && i < slices[s].y) {
         const float pos[3] = {scans->pose[s][0], scans->pose[s][1], scans->pose[s][2]};
         const float nx = normals[size_t(i) * 3], ny = normals[size_t(i) * 3 + 1], nz = normals[size_t(i) * 3 + 2];
         Ray r;
@@ -537,6 +537,30 @@ __global__ void shard_splitters_kernel(const u64* __restrict__ sorted_keys, u32 
     splitters[g] = expand_key(~sorted_keys[idx] & cmask, k) >> BLK_SHIFT;
 }
 
+// per scan: the range of sorted points whose voxel's block this rank owns. The points of a scan are in DESCENDING Morton order,
+// the ranks own ascending ranges: rank g's points are [first point with block < splitters[g], first point with block < splitters[g-1]).
+__global__ void shard_slices_kernel(const u64* __restrict__ sorted_keys, const BatchScans* __restrict__ scans, const BatchPlan* __restrict__ plan,
+                                    const u64* __restrict__ splitters, u32 rank, u32 world, uint2* __restrict__ slices) {
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= plan->n_scans) return;
+    const u32 k = plan->k;
+    const u32 cbits = 3 * k + 3;
+    const u64 cmask = (cbits >= 64) ? ~0ull : ((1ull << cbits) - 1ull);
+    const u32 b = scans->offset[s], e = scans->offset[s + 1];
+    auto first_below = [&](u64 limit) {  // first index in [b, e) whose block id is < limit (block ids descend along the scan)
+        u32 lo = b, hi = e;
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            const u64 blk = expand_key(~sorted_keys[mid] & cmask, k) >> BLK_SHIFT;
+            if (blk < limit) hi = mid; else lo = mid + 1;
+        }
+        return lo;
+    };
+    const u32 lo = (rank + 1 < world) ? first_below(splitters[rank]) : b;
+    const u32 hi = (rank > 0) ? first_below(splitters[rank - 1]) : e;
+    slices[s] = make_uint2(lo, hi);
+}
+
 inline unsigned blocks_for(u32 n) { return (n + BLK_THREADS - 1) / BLK_THREADS; }
 
 }  // namespace
@@ -598,20 +622,26 @@ int launch_shard_splitters(cudaStream_t s, const u64* sorted_keys, u32 n_first_s
     return 1;
 }
 
-int launch_shard_count(cudaStream_t s, const float* xyz_sorted, u32 i_begin, u32 i_end, const BatchScans* scans, const MapParams& mp,
-                       const BatchPlan* plan, const u64* splitters, u32 world, u32* dest_count) {
-    cudaMemsetAsync(dest_count, 0, SHARD_MAX_WORLD * 4 * 3, s);  // counts | offsets | cursors
-    if (i_end <= i_begin) return 0;
-    shard_count_kernel<<<blocks_for(i_end - i_begin), BLK_THREADS, 0, s>>>(xyz_sorted, i_begin, i_end, scans, mp.res, mp.trunc, mp.recip, mp.max_ray_voxels,
-                                                                          plan, splitters, world, dest_count);
+int launch_shard_slices(cudaStream_t s, const u64* sorted_keys, const BatchScans* scans, const BatchPlan* plan, const u64* splitters, u32 rank, u32 world,
+                        void* slices) {
+    shard_slices_kernel<<<1, MAX_BATCH_SCANS, 0, s>>>(sorted_keys, scans, plan, splitters, rank, world, static_cast<uint2*>(slices));
     return 1;
 }
 
-int launch_shard_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 i_begin, u32 i_end, const BatchScans* scans,
+int launch_shard_count(cudaStream_t s, const float* xyz_sorted, u32 n_points, const void* slices, const BatchScans* scans, const MapParams& mp,
+                       const BatchPlan* plan, const u64* splitters, u32 world, u32* dest_count) {
+    cudaMemsetAsync(dest_count, 0, SHARD_MAX_WORLD * 4 * 3, s);  // counts | offsets | cursors
+    if (!n_points) return 0;
+    shard_count_kernel<<<blocks_for(n_points), BLK_THREADS, 0, s>>>(xyz_sorted, n_points, static_cast<const uint2*>(slices), scans, mp.res, mp.trunc, mp.recip,
+                                                                   mp.max_ray_voxels, plan, splitters, world, dest_count);
+    return 1;
+}
+
+int launch_shard_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const void* slices, const BatchScans* scans,
                       const MapParams& mp, BatchPlan* plan, const u64* splitters, u32 world, const u32* dest_offset, u32* dest_cursor, void* tuples,
                       u32 tuple_capacity) {
-    if (i_end <= i_begin) return 0;
-    shard_emit_kernel<<<blocks_for(i_end - i_begin), BLK_THREADS, 0, s>>>(xyz_sorted, normals, i_begin, i_end, scans, mp.res, mp.trunc, mp.recip,
+    if (!n_points) return 0;
+    shard_emit_kernel<<<blocks_for(n_points), BLK_THREADS, 0, s>>>(xyz_sorted, normals, n_points, static_cast<const uint2*>(slices), scans, mp.res, mp.trunc, mp.recip,
                                                                          mp.max_ray_voxels, plan, splitters, world, dest_offset, dest_cursor,
                                                                          static_cast<uint4*>(tuples), tuple_capacity);
     return 1;

@@ -755,7 +755,7 @@ int finalize_part2(chad_ctx* ctx) {
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->scalars, ctx->f_scalars.p, 16 * 4 + 20 * 4, cudaMemcpyDeviceToHost, fs));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->counters, ctx->f_counters.p, sizeof(LevelCounters) * 20, cudaMemcpyDeviceToHost, fs));
     ctx->stats.d2h_bytes += 16 * 4 + 20 * 4 + sizeof(LevelCounters) * 20;
-    launch_table_clear(fs, ctx->fin_external ? ctx->table : ctx->table2);  // octree.clear(), tsdf.cpp:57
+    if (!ctx->fin_external) launch_table_clear(fs, ctx->table2);  // octree.clear(), tsdf.cpp:57 (external: done by the caller's stream)
     if (ctx->profiling) cudaEventRecord(ctx->fin_t3, fs);
     CUDA_TRY(ctx, cudaEventRecord(ctx->fin_done, fs));
     CUDA_TRY(ctx, cudaGetLastError());
@@ -784,7 +784,7 @@ int finalize_finish(chad_ctx* ctx) {
     }
     ctx->roots.push_back({hs[SC_ROOT], hs[SC_ROOT + 1]});
     ctx->stats.submaps++;
-    if (ctx->fin_external) { *ctx->h_table_count = 0; ctx->table_count_known = 0; ctx->fin_external = false; }
+    ctx->fin_external = false;
     if (ctx->profiling) {
         float a = 0.f;
         if (cudaEventElapsedTime(&a, ctx->fin_t0, ctx->fin_t3) == cudaSuccess) {
@@ -1404,16 +1404,17 @@ int chad_shard_front(chad_ctx* ctx, const float* xyz, const uint32_t* scan_offse
         return fail(ctx, CHAD_ERR_INVALID, "chad_shard_front: bad argument");
     if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    TRY(settle(ctx));
+    if (ctx->fold_pending || ctx->batch_scans || ctx->fold_in_flight) TRY(settle(ctx));  // chad_insert traffic in between
+    TRY(finalize_poll(ctx));  // (a finalize of the previous submap may still be running on its own stream: it only reads its own buffers)
     const size_t n = scan_offsets[n_scans];
     for (int d = 0; d < world; d++) send_counts[d] = 0;
     if (n == 0) return CHAD_OK;
     if (!xyz) return fail(ctx, CHAD_ERR_INVALID, "chad_shard_front: xyz is NULL");
     if (n > blocks_max_batch_points()) return fail(ctx, CHAD_ERR_CAPACITY, "sharded batch exceeds 2^23 points");
     if (n > ctx->cap_points || ctx->cap_points == 0) TRY(ensure_batch_capacity(ctx, n));
-    TRY(dev_ensure(ctx, ctx->sh_scalars, 512));
+    TRY(dev_ensure(ctx, ctx->sh_scalars, 1024));
     cudaStream_t s = ctx->stream;
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_xyz[0].p, xyz, n * 12, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_xyz[0].p, xyz, n * 12, cudaMemcpyDefault, s));  // host (pageable / pinned) or device memory
     for (int i = 0; i <= n_scans; i++) ctx->h_scans.offset[i] = scan_offsets[i];
     std::memcpy(ctx->h_scans.pose, poses, size_t(n_scans) * 12);
     *ctx->h_scans_pinned[0] = ctx->h_scans;
@@ -1429,8 +1430,9 @@ int chad_shard_front(chad_ctx* ctx, const float* xyz, const uint32_t* scan_offse
         launches += launch_shard_splitters(s, ctx->sorted_keys.as<u64>(), scan_offsets[1], plan, (u32)world, splitters);
         ctx->sh_have_splitters = true;
     }
-    const u32 i_begin = (u32)(size_t(rank) * n / world), i_end = (u32)(size_t(rank + 1) * n / world);
-    launches += launch_shard_count(s, ctx->xyz_sorted.as<float>(), i_begin, i_end, scans, ctx->mp, plan, splitters, (u32)world, dest);
+    void* slices = ctx->sh_scalars.as<unsigned char>() + 256;  // uint2[64]
+    launches += launch_shard_slices(s, ctx->sorted_keys.as<u64>(), scans, plan, splitters, (u32)rank, (u32)world, slices);
+    launches += launch_shard_count(s, ctx->xyz_sorted.as<float>(), (u32)n, slices, scans, ctx->mp, plan, splitters, (u32)world, dest);
     u32 counts[8] = {0};
     CUDA_TRY(ctx, cudaMemcpyAsync(counts, dest, 32, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
@@ -1440,7 +1442,7 @@ int chad_shard_front(chad_ctx* ctx, const float* xyz, const uint32_t* scan_offse
     if (total >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "sharded batch emits more than 2^31 updates");
     TRY(dev_ensure(ctx, ctx->sh_tuples, (total + 1) * 16));
     CUDA_TRY(ctx, cudaMemcpyAsync(dest + 8, offsets, 32, cudaMemcpyHostToDevice, s));
-    launches += launch_shard_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), i_begin, i_end, scans, ctx->mp, plan, splitters, (u32)world,
+    launches += launch_shard_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), (u32)n, slices, scans, ctx->mp, plan, splitters, (u32)world,
                                   dest + 8, dest + 16, ctx->sh_tuples.p, (u32)total);
     ctx->stats.kernel_launches += launches;
     { const int rc = stage_check(ctx); if (rc != CHAD_OK) { ctx->error += " [chad_shard_front]"; return rc; } }
@@ -1480,12 +1482,14 @@ int chad_shard_ingest(chad_ctx* ctx, const void* tuples_device, size_t n_tuples)
     }
     ctx->stats.updates += hp.n_pairs;
     ctx->stats.scan_voxels += hp.n_segments;
+    ctx->table_count_known = *ctx->h_table_count;  // exact: the previous fold's copy preceded the synchronisation above
     TRY(table_reserve(ctx, ctx->table_count_known + hp.n_chunk_heads));
     launches += launch_fold(s, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(), (u32)n_tuples, plan, ctx->table,
                             ctx->num_sms);
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_table_count, ctx->table.count, 4, cudaMemcpyDeviceToHost, s));
     ctx->stats.kernel_launches += launches;
-    return drain(ctx);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return CHAD_OK;  // the fold runs on; its deferred error flags surface at the next synchronising call
 }
 
 int chad_shard_export_chunks(chad_ctx* ctx, size_t* n_chunks, void** keys_device, void** cells_device) {
@@ -1502,22 +1506,41 @@ int chad_shard_export_chunks(chad_ctx* ctx, size_t* n_chunks, void** keys_device
     return CHAD_OK;
 }
 
-int chad_shard_finalize_from(chad_ctx* ctx, const uint64_t* keys_device, const void* cells_device, size_t n_chunks) {
+int chad_shard_clear(chad_ctx* ctx) {
+    if (!ctx) return CHAD_ERR_INVALID;
+    if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(drain(ctx));
+    launch_table_clear(ctx->stream, ctx->table);  // octree.clear(), tsdf.cpp:57
+    *ctx->h_table_count = 0;
+    ctx->table_count_known = 0;
+    ctx->has_pose = false;
+    ctx->stats.resident_clusters = 0;
+    return CHAD_OK;
+}
+
+int chad_shard_finalize_from(chad_ctx* ctx, const uint64_t* keys_device, const void* cells_device, size_t n_chunks, int clear_local) {
     if (!ctx || (n_chunks && (!keys_device || !cells_device))) return CHAD_ERR_INVALID;
     if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (n_chunks >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
-    TRY(settle(ctx));
+    if (clear_local) TRY(drain(ctx));
+    TRY(finalize_wait(ctx));  // the gathered stream goes into the finalize work buffers
     TRY(ensure_finalize_capacity(ctx, n_chunks));
     if (n_chunks) {
         if (keys_device != ctx->f_ids[0].p) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_ids[0].p, keys_device, n_chunks * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         if (cells_device != ctx->f_cells.p) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->f_cells.p, cells_device, n_chunks * 64, cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    TRY(finalize_begin(ctx, (u32)n_chunks, true, ctx->stream));
-    TRY(finalize_wait(ctx));
-    ctx->has_pose = false;
-    ctx->stats.resident_clusters = 0;
-    return CHAD_OK;
+    if (clear_local) {
+        // the shard's chunks have been exported: clear it now (octree.clear(), tsdf.cpp:57) so that the next submap's folds can
+        // start while the finalize runs on its own stream (it only reads the gathered chunk stream)
+        launch_table_clear(ctx->stream, ctx->table);
+        *ctx->h_table_count = 0;
+        ctx->table_count_known = 0;
+        ctx->has_pose = false;
+        ctx->stats.resident_clusters = 0;
+    }
+    return finalize_begin(ctx, (u32)n_chunks, true, ctx->stream);
 }
 
 int chad_device_alloc(chad_ctx* ctx, size_t bytes, void** device_ptr) {

@@ -62,9 +62,12 @@ int launch_blocks_pairs(cudaStream_t s, const float* xyz_sorted, const float* no
 constexpr int SHARD_WORLD_MAX = 8;
 int launch_shard_splitters(cudaStream_t s, const u64* sorted_keys, u32 n_first_scan, const BatchPlan* plan, u32 world, u64* splitters);
 // dest_count = u32[3][8] (counts | offsets | cursors), zeroed here
-int launch_shard_count(cudaStream_t s, const float* xyz_sorted, u32 i_begin, u32 i_end, const BatchScans* scans, const MapParams& mp,
+// slices = uint2[MAX_BATCH_SCANS]: per scan the range of sorted points whose block this rank owns
+int launch_shard_slices(cudaStream_t s, const u64* sorted_keys, const BatchScans* scans, const BatchPlan* plan, const u64* splitters, u32 rank, u32 world,
+                        void* slices);
+int launch_shard_count(cudaStream_t s, const float* xyz_sorted, u32 n_points, const void* slices, const BatchScans* scans, const MapParams& mp,
                        const BatchPlan* plan, const u64* splitters, u32 world, u32* dest_count);
-int launch_shard_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 i_begin, u32 i_end, const BatchScans* scans,
+int launch_shard_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const void* slices, const BatchScans* scans,
                       const MapParams& mp, BatchPlan* plan, const u64* splitters, u32 world, const u32* dest_offset, u32* dest_cursor, void* tuples,
                       u32 tuple_capacity);
 int launch_blocks_from_tuples(cudaStream_t s, const void* tuples, u32 n, BatchPlan* plan, const BlockTable& bt, void* scan_ws, u64* keys_a, u64* keys_b,

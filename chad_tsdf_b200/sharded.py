@@ -39,18 +39,29 @@ def device_tensor(ptr: int, n_words: int, device) -> torch.Tensor:
 class CudaShardEngine:
     """The per-rank numerical engine on a GPU: chad_shard_* of include/chad_b200.h."""
 
-    def __init__(self, sdf_res: float, sdf_trunc: float, device: int):
+    def __init__(self, sdf_res: float, sdf_trunc: float, device: int, max_batch_scans: int = 1):
         from .tsdf_map import TSDFMap
-        self.map = TSDFMap(sdf_res, sdf_trunc, device=device, max_batch_scans=1)
+        self.map = TSDFMap(sdf_res, sdf_trunc, device=device, max_batch_scans=max_batch_scans)
         self.device = torch.device("cuda", device)
         self._lib, self._h = self.map._lib, self.map._h
 
-    def front(self, xyz: np.ndarray, offsets: np.ndarray, poses: np.ndarray, rank: int, world: int, new_submap: bool):
+    def concat(self, scans: list) -> torch.Tensor:
+        """The batch's points as one device tensor. A scan may be a numpy array (staged synchronously), a page-locked CPU
+        tensor (asynchronous DMA) or a tensor that already lives on this device."""
+        parts = []
+        for p in scans:
+            t = p if isinstance(p, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(p, np.float32))
+            parts.append(t.reshape(-1, 3).to(self.device, dtype=torch.float32, non_blocking=True))
+        xyz = parts[0] if len(parts) == 1 else torch.cat(parts)
+        torch.cuda.current_stream(self.device).synchronize()  # the engine works on its own stream
+        return xyz.contiguous()
+
+    def front(self, xyz: torch.Tensor, offsets: np.ndarray, poses: np.ndarray, rank: int, world: int, new_submap: bool):
         counts = np.zeros(8, np.uint64)
-        xyz = np.ascontiguousarray(xyz, np.float32)
         offsets = np.ascontiguousarray(offsets, np.uint32)
         poses = np.ascontiguousarray(poses, np.float32)
-        self.map._check(self._lib.chad_shard_front(self._h, xyz.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p),
+        self._keep = xyz  # until the next batch: the engine copies out of it asynchronously
+        self.map._check(self._lib.chad_shard_front(self._h, C.c_void_p(xyz.data_ptr()), offsets.ctypes.data_as(C.c_void_p),
                                                    poses.ctypes.data_as(C.c_void_p), len(offsets) - 1, rank, world, int(new_submap),
                                                    counts.ctypes.data_as(C.c_void_p)))
         p = C.c_void_p()
@@ -58,6 +69,16 @@ class CudaShardEngine:
         counts = [int(c) for c in counts[:world]]
         send = device_tensor(p.value or 0, sum(counts) * TUPLE_WORDS, self.device).view(-1, TUPLE_WORDS)
         return counts, send
+
+    # the ordinary single-GPU insert path (SubmapParallelTSDFMap): host memory, or a tensor on this device
+    def insert(self, points, position) -> None:
+        if isinstance(points, torch.Tensor) and points.is_cuda:
+            self.map.insert_device(points.data_ptr(), points.numel() // 3, position)
+        else:
+            self.map.insert(points, position)
+
+    def flush(self) -> None:
+        self.map.flush()
 
     def ingest(self, tuples: torch.Tensor) -> None:
         tuples = tuples.contiguous()
@@ -70,9 +91,14 @@ class CudaShardEngine:
         cells = device_tensor(c.value or 0, n.value * CELL_WORDS, self.device).view(-1, CELL_WORDS)
         return keys, cells
 
-    def finalize_from(self, keys: torch.Tensor, cells: torch.Tensor) -> None:
+    def finalize_from(self, keys: torch.Tensor, cells: torch.Tensor, clear_local: bool = True) -> None:
         keys, cells = keys.contiguous(), cells.contiguous()
-        self.map._check(self._lib.chad_shard_finalize_from(self._h, C.c_void_p(keys.data_ptr()), C.c_void_p(cells.data_ptr()), keys.shape[0]))
+        self._keep_fin = (keys, cells)  # the engine copies out of them asynchronously
+        self.map._check(self._lib.chad_shard_finalize_from(self._h, C.c_void_p(keys.data_ptr()), C.c_void_p(cells.data_ptr()), keys.shape[0],
+                                                           1 if clear_local else 0))
+
+    def clear(self) -> None:
+        self.map._check(self._lib.chad_shard_clear(self._h))
 
     def empty(self, shape, dtype=torch.int64) -> torch.Tensor:
         return torch.empty(shape, dtype=dtype, device=self.device)
@@ -107,10 +133,7 @@ class ShardedTSDFMap:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.max_batch = max(1, min(int(max_batch_scans), 64))
-        self._scans: list[tuple[np.ndarray, np.ndarray]] = []
-        self._stage: np.ndarray | None = None   # page-locked batch buffer (the engine DMA's straight out of it)
-        self._stage_keep = None
-        self._stage_points = 0
+        self._scans: list = []   # (points, pose) of the batch being assembled
         self._first_pose: np.ndarray | None = None
         self._new_submap = True
         self.exchanged_tuples = 0
@@ -118,7 +141,8 @@ class ShardedTSDFMap:
 
     # -- the reference's API --
     def insert(self, points, position) -> None:
-        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        """points: (n, 3) float32 as a numpy array, a page-locked CPU tensor or a tensor on the engine's device."""
+        pts = points if isinstance(points, torch.Tensor) else np.ascontiguousarray(points, np.float32).reshape(-1, 3)
         pos = np.ascontiguousarray(position, np.float32).reshape(3)
         # tsdf.cpp:46-61: strictly more than 5 m from the submap's first pose, fp32 ((dx*dx + dy*dy) + dz*dz, then sqrt)
         if self._first_pose is None:
@@ -130,9 +154,7 @@ class ShardedTSDFMap:
                 self._close_submap()
                 self._first_pose = pos.copy()
         if len(pts):
-            t0 = time.perf_counter()
-            self._append(pts, pos)
-            self.phase_s["stage"] += time.perf_counter() - t0
+            self._scans.append((pts, pos))
         if len(self._scans) >= self.max_batch:
             self._process_batch()
 
@@ -146,30 +168,15 @@ class ShardedTSDFMap:
             self._first_pose = None
 
     # -- internals --
-    def _append(self, pts: np.ndarray, pos: np.ndarray) -> None:
-        need = self._stage_points + len(pts)
-        if self._stage is None or need > len(self._stage):
-            cap = max(need, len(pts) * self.max_batch)
-            try:
-                keep = torch.empty((cap, 3), dtype=torch.float32, pin_memory=torch.cuda.is_available())
-            except RuntimeError:
-                keep = torch.empty((cap, 3), dtype=torch.float32)
-            new = keep.numpy()
-            if self._stage is not None:
-                new[: self._stage_points] = self._stage[: self._stage_points]
-            self._stage, self._stage_keep = new, keep
-        self._stage[self._stage_points: need] = pts
-        self._scans.append((self._stage[self._stage_points: need], pos))
-        self._stage_points = need
-
     def _process_batch(self) -> None:
         if not self._scans:
             return
-        xyz = self._stage[: self._stage_points]
+        t0 = time.perf_counter()
+        xyz = self.engine.concat([p for p, _ in self._scans])
         offsets = np.concatenate([[0], np.cumsum([len(p) for p, _ in self._scans])]).astype(np.uint32)
         poses = np.stack([q for _, q in self._scans]).astype(np.float32)
         self._scans = []
-        self._stage_points = 0
+        self.phase_s["stage"] += time.perf_counter() - t0
         t0 = time.perf_counter()
         counts, send = self.engine.front(xyz, offsets, poses, self.rank, self.world, self._new_submap)
         t1 = time.perf_counter()
@@ -215,3 +222,86 @@ class ShardedTSDFMap:
         self.engine.finalize_from(gk, gc)
         self._new_submap = True
         self.phase_s["close"] += time.perf_counter() - t0
+
+
+class SubmapParallelTSDFMap:
+    """chad::TSDFMap semantics with the map's SUBMAPS integrated on different GPUs.
+
+    A submap is an independent octree: TSDFMap::insert clears it at every switch (tsdf.cpp:51-58) and only
+    Submap::finalize couples it to the rest of the map, through the global DAG, in submap order (submap.hpp:10-106,
+    levels.hpp). So submap s is integrated by rank s mod world alone, through the ordinary single-GPU insert path and
+    without any exchange; when it closes, its owner broadcasts the submap's sorted leaf chunks (NCCL over NVLink) and
+    every rank folds them into its replica of the DAG, in submap order. The result -- every submap's voxels and the
+    whole DAG -- is bit-identical to the single-GPU map. The submap rule only needs the poses, so every rank evaluates
+    it for every scan and simply skips the scans of the submaps it does not own (their points are never copied).
+    """
+
+    def __init__(self, engine, group=None):
+        self.engine = engine
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._first_pose: np.ndarray | None = None
+        self._submap = 0          # index of the active submap
+        self._closed = 0          # submaps already folded into the DAG (closes are collective and lag world - 1 submaps behind)
+        self.owned_scans = 0
+        self.broadcast_chunks = 0
+
+    def owner(self, submap: int) -> int:
+        return submap % self.world
+
+    def insert(self, points, position) -> None:
+        pos = np.ascontiguousarray(position, np.float32).reshape(3)
+        if self._first_pose is None:
+            self._first_pose = pos.copy()
+        else:  # tsdf.cpp:46-61: strictly more than 5 m from the submap's first pose, fp32 ((dx*dx + dy*dy) + dz*dz, then sqrt)
+            d = self._first_pose - pos
+            t = d * d
+            if np.sqrt(np.float32(np.float32(t[0] + t[1]) + t[2])) > np.float32(5.0):
+                self._submap += 1
+                self._first_pose = pos.copy()
+                # Closing a submap is collective (its owner broadcasts): do it `world - 1` switches late, so that every rank has
+                # queued the inserts of its own submap of the round first and the ranks integrate concurrently. The owner of the
+                # submap entered now closes its previous one right here, before it reuses its table.
+                self._close_until(self._submap - (self.world - 1))
+        if self.owner(self._submap) == self.rank:
+            self.engine.insert(points, pos)
+            self.owned_scans += 1
+
+    def flush(self) -> None:
+        """Everything inserted so far is applied and every submap before the active one is in the DAG (collective)."""
+        self._close_until(self._submap)
+        self.engine.flush()
+
+    def finalize_active(self) -> None:
+        """The part of TSDFMap::save before meshing (tsdf.cpp:78-81)."""
+        if self._first_pose is not None:
+            self._submap += 1
+            self._close_until(self._submap)
+            self._first_pose = None
+
+    def _close_until(self, end: int) -> None:
+        while self._closed < end:
+            self._close_submap(self._closed)
+            self._closed += 1
+
+    def _close_submap(self, submap: int) -> None:
+        src = self.owner(submap)
+        n = self.engine.empty((1,))
+        if src == self.rank:
+            keys, cells = self.engine.export_chunks()
+            n.fill_(keys.shape[0])
+        if self.world > 1:
+            src_global = src if self.group is None else dist.get_global_rank(self.group, src)
+            dist.broadcast(n, src_global, group=self.group)
+            c = int(n.item())
+            if src != self.rank:
+                keys, cells = self.engine.empty((c,)), self.engine.empty((c, CELL_WORDS))
+            if c:
+                dist.broadcast(keys, src_global, group=self.group)
+                dist.broadcast(cells, src_global, group=self.group)
+            self.engine.sync()
+        self.broadcast_chunks += int(keys.shape[0])
+        self.engine.finalize_from(keys, cells, clear_local=False)
+        if src == self.rank:
+            self.engine.clear()  # octree.clear(), tsdf.cpp:57: the owner's table is free for its next submap

@@ -143,14 +143,18 @@ int chad_timer_end(chad_ctx* ctx, float* milliseconds);
  *   chad_shard_send_buffer  device pointer of the send buffer
  *   chad_shard_ingest       received tuples (device memory, any order) -> bin, sort, fold into this rank's shard
  *   chad_shard_export_chunks  this rank's leaf chunks, ascending: device pointers to n x u64 chunk keys and n x 64 B cells
- *   chad_shard_finalize_from  Submap::finalize from the concatenation (rank order = Morton order) of all ranks' chunks;
- *                           every rank ends up with the identical DAG; the local shard is cleared */
+ *   chad_shard_finalize_from  Submap::finalize from a device-resident, ascending chunk stream -- the concatenation (rank order = Morton
+ *                           order) of all ranks' chunks, or a whole submap integrated by another rank -- queued on the finalize stream;
+ *                           every rank ends up with the identical DAG; clear_local != 0 also clears the local shard */
 int chad_shard_front(chad_ctx* ctx, const float* xyz, const uint32_t* scan_offsets, const float* poses, int n_scans, int rank, int world,
                      int new_submap, uint64_t* send_counts);
 int chad_shard_send_buffer(chad_ctx* ctx, void** tuples_device);
 int chad_shard_ingest(chad_ctx* ctx, const void* tuples_device, size_t n_tuples);
 int chad_shard_export_chunks(chad_ctx* ctx, size_t* n_chunks, void** keys_device, void** cells_device);
-int chad_shard_finalize_from(chad_ctx* ctx, const uint64_t* keys_device, const void* cells_device, size_t n_chunks);
+int chad_shard_finalize_from(chad_ctx* ctx, const uint64_t* keys_device, const void* cells_device, size_t n_chunks, int clear_local);
+/* Forget the active submap's voxels and first pose (octree.clear(), tsdf.cpp:57) without finalising anything here: the submap-parallel
+ * mode calls it on a submap's owner after chad_shard_export_chunks (the finalize happens from the broadcast chunk stream on every rank). */
+int chad_shard_clear(chad_ctx* ctx);
 
 /* ---- host-only helpers (pure CPU bit arithmetic; usable without a GPU) ------------------------ */
 /* MortonCode::encode / decode (morton.hpp:21-37): 21 bits per axis, bias 2^20, x -> bit 0. */

@@ -20,6 +20,9 @@ class NumpyShardEngine:
     def sync(self):
         pass
 
+    def concat(self, scans):
+        return np.concatenate([np.ascontiguousarray(p, np.float32).reshape(-1, 3) for p in scans])
+
     def front(self, xyz, offsets, poses, rank, world, new_submap):
         pts_sorted, keys_sorted, normals, scan_of = [], [], [], []
         for s in range(len(offsets) - 1):
@@ -44,6 +47,17 @@ class NumpyShardEngine:
         counts = [int((owner == d).sum()) for d in range(world)]
         send = np.stack([tk[order].astype(np.int64), (tr[order] | (tsd[order].astype(np.uint64) << np.uint64(32))).astype(np.int64)], axis=1) if len(tk) else np.zeros((0, 2), np.int64)
         return counts, torch.from_numpy(np.ascontiguousarray(send))
+
+    # the whole insert of one scan on this engine (SubmapParallelTSDFMap)
+    def insert(self, points, position):
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        if len(pts) == 0:
+            return
+        _, send = self.front(pts, np.array([0, len(pts)], np.uint32), np.asarray(position, np.float32).reshape(1, 3), 0, 1, True)
+        self.ingest(send)
+
+    def flush(self):
+        pass
 
     def ingest(self, tuples):
         t = tuples.numpy().view(np.uint64)
@@ -71,6 +85,10 @@ class NumpyShardEngine:
         cells[pos, (keys & np.uint64(7)).astype(np.int64)] = sd.astype(np.uint64) | (w.astype(np.uint64) << np.uint64(32))
         return torch.from_numpy(ck.astype(np.int64)), torch.from_numpy(cells.astype(np.int64))
 
-    def finalize_from(self, keys, cells):
+    def finalize_from(self, keys, cells, clear_local=True):
         self.finalized.append((keys.numpy().view(np.uint64).copy(), cells.numpy().view(np.uint64).copy()))
+        if clear_local:
+            self.vox = {}
+
+    def clear(self):
         self.vox = {}

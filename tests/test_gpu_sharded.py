@@ -12,10 +12,10 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(world, tmp_path):
+def _run(world, tmp_path, mode="morton"):
     port = 29700 + os.getpid() % 200
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "tests", "sharded_worker.py"), str(tmp_path)]
+           os.path.join(ROOT, "tests", "sharded_worker.py"), str(tmp_path), mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = [json.load(open(tmp_path / f"result{i}.json")) for i in range(world)]
@@ -40,3 +40,16 @@ def test_sharded_world2(chad_lib, oracle_lib, tmp_path):
         pytest.skip("needs 2 GPUs")
     res = _run(2, tmp_path)
     assert all(r["exchanged"] > 0 for r in res)  # updates really crossed NVLink
+
+
+def test_submap_parallel_world1(chad_lib, oracle_lib, tmp_path):
+    _run(1, tmp_path, "submaps")
+
+
+def test_submap_parallel_world2(chad_lib, oracle_lib, tmp_path):
+    """The map's submaps integrated on alternating GPUs, closed submaps broadcast over NCCL: same voxels, same DAG."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    res = _run(2, tmp_path, "submaps")
+    assert all(r["exchanged"] > 0 for r in res)

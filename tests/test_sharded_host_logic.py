@@ -67,3 +67,63 @@ def test_two_rank_sharding_reproduces_the_single_map(tmp_path, oracle_lib):
     assert np.array_equal(vk, o["bk"])
     assert np.array_equal((fc[present] & np.uint64(0xFFFFFFFF)).astype(np.uint32), o["bsd"])
     assert np.array_equal((fc[present] >> np.uint64(32)).astype(np.uint32), o["bw"])
+
+
+def _worker_submaps(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from chad_tsdf_b200 import synth
+    from chad_tsdf_b200.sharded import SubmapParallelTSDFMap
+    from oracle import bindings as ob
+    from tests.shard_cpu_engine import NumpyShardEngine
+    w = synth.Workload("t", synth.BOX_ROOM, 16, 7, -3.0, 1.8, 0.05, 0.10, seed=6)  # 7 scans, 1.8 m apart: switches at scans 3 and 6
+    eng = NumpyShardEngine(w.sdf_res, w.sdf_trunc)
+    m = SubmapParallelTSDFMap(eng)
+    o = ob.OracleMap(w.sdf_res, w.sdf_trunc)
+    closed = []  # the oracle's voxels of every closed submap
+    nsub = 0
+    for s in range(w.scans):
+        pts, pos = w.scan(s)
+        before = o.voxels()
+        got = o.insert(pts, pos)  # = submaps finalised so far
+        if got != nsub:
+            closed.append(before)
+            nsub = got
+        m.insert(pts, pos)
+    m.flush()
+    closed.append(o.voxels())
+    m.finalize_active()
+    out = {"n": len(eng.finalized), "owned": m.owned_scans}
+    for i, (fk, fc) in enumerate(eng.finalized):
+        out[f"fk{i}"], out[f"fc{i}"] = fk, fc
+    np.savez(os.path.join(out_dir, f"sp{rank}.npz"), **out)
+    if rank == 0:
+        oo = {"n": len(closed)}
+        for i, (k, sd, wt) in enumerate(closed):
+            oo[f"k{i}"], oo[f"sd{i}"], oo[f"w{i}"] = k, sd, wt
+        np.savez(os.path.join(out_dir, "sp_oracle.npz"), **oo)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_submap_parallel_reproduces_every_submap(tmp_path, oracle_lib):
+    """Submaps integrated on alternating ranks: every rank must be handed, in order, exactly the chunk stream of every
+    submap of the single map (that stream is all Submap::finalize consumes)."""
+    world = 2
+    port = 29300 + os.getpid() % 300
+    mp.spawn(_worker_submaps, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(tmp_path / f"sp{i}.npz") for i in range(world)]
+    o = np.load(tmp_path / "sp_oracle.npz")
+    n = int(o["n"])
+    assert n == 3 and int(r[0]["n"]) == n and int(r[1]["n"]) == n
+    assert int(r[0]["owned"]) + int(r[1]["owned"]) == 7 and int(r[0]["owned"]) > 0 and int(r[1]["owned"]) > 0
+    for i in range(n):
+        fk, fc = r[0][f"fk{i}"], r[0][f"fc{i}"]
+        assert np.array_equal(fk, r[1][f"fk{i}"]) and np.array_equal(fc, r[1][f"fc{i}"])
+        assert np.all(np.diff(fk.astype(np.int64)) > 0)
+        present = (fc >> np.uint64(32)) != 0
+        vk = ((fk[:, None] << np.uint64(3)) | np.arange(8, dtype=np.uint64)[None, :])[present]
+        assert np.array_equal(vk, o[f"k{i}"])
+        assert np.array_equal((fc[present] & np.uint64(0xFFFFFFFF)).astype(np.uint32), o[f"sd{i}"])
+        assert np.array_equal((fc[present] >> np.uint64(32)).astype(np.uint32), o[f"w{i}"])
