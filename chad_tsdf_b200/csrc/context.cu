@@ -843,7 +843,11 @@ int begin_scan(chad_ctx* ctx, size_t n, const float position[3], bool* skip) {
     if (ctx->batch_scans > 0 && (ctx->batch_scans >= (u32)ctx->max_batch || ctx->batch_points + n > ctx->cap_points)) TRY(process_front(ctx));
     if (n > ctx->cap_points || ctx->cap_points == 0) {
         TRY(drain(ctx));
-        TRY(ensure_batch_capacity(ctx, n > ctx->cap_points / 2 ? n * (size_t)ctx->max_batch : ctx->cap_points));
+        size_t want = n > ctx->cap_points / 2 ? n * (size_t)ctx->max_batch : ctx->cap_points;
+        // keep a batch inside the tile-run path's rank range (2^23 sorted points) unless a single scan is larger than that
+        const size_t rank_cap = (size_t)runs_max_batch_points() - 4096;
+        if (n * 9 / 8 + 1024 <= rank_cap && want * 9 / 8 + 1024 > rank_cap) want = (rank_cap - 1024) * 8 / 9;
+        TRY(ensure_batch_capacity(ctx, want));
     }
     return CHAD_OK;
 }
@@ -944,7 +948,7 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
         const u32 L = (u32)std::ceil(2.0 * ratio) + 1;
         ctx->mp.max_ray_runs = 1 + 3 * ((L + 7) / 8);
     }
-    ctx->max_batch = max_batch_scans == 0 ? 16 : max_batch_scans;
+    ctx->max_batch = max_batch_scans == 0 ? 24 : max_batch_scans;  // one batch per submap of ~21 scans on the bench trajectory
 
     int r = dev_ensure(ctx, ctx->d_scans, sizeof(BatchScans));
     if (r == CHAD_OK) r = dev_ensure(ctx, ctx->d_plan, 2 * sizeof(BatchPlan));

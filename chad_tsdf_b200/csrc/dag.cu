@@ -19,6 +19,8 @@
 #include "kernels.cuh"
 #include "scan.cuh"
 
+#include <cstdlib>
+
 namespace chadgpu {
 
 namespace {
@@ -536,7 +538,12 @@ int launch_cluster_dedup(cudaStream_t s, const DedupTable& t, const u64* tsdf_va
 
 int launch_dag_levels(cudaStream_t s, const LevelsArgs& args, int num_sms) {
     cudaMemsetAsync(args.bar, 0, 4, s);
-    const int grid = num_sms < LV_THREADS ? num_sms : LV_THREADS;
+    static const int env_ctas = [] { const char* e = std::getenv("CHAD_LEVELS_CTAS"); return e ? std::atoi(e) : 0; }();
+    // half the SMs: the CTAs spin at the grid barriers, and the insert kernels of the next submap run beside them (measured: 148 / 74 /
+    // 37 / 18 CTAs -> 11.68 / 11.39 / 11.36 / 11.82 ms per bench step)
+    int grid = num_sms / 2 < LV_THREADS ? num_sms / 2 : LV_THREADS;
+    if (grid < 1) grid = 1;
+    if (env_ctas > 0 && env_ctas <= num_sms && env_ctas <= LV_THREADS) grid = env_ctas;
     dag_levels_kernel<<<grid, LV_THREADS, 0, s>>>(args);
     return 1;
 }

@@ -28,6 +28,9 @@ constexpr u32 RUN_BLK_SHIFT = 9;           // 8^3 voxels per block
 constexpr u32 RUN_RANK_BITS = 23;          // sorted-point rank inside the batch
 constexpr u64 RUN_EMPTY = ~0ull;
 constexpr u32 RUN_BIG_BLOCK = 2048;        // updates from which a block is scheduled ahead of the others
+constexpr u32 RUN_STASH_BITS = 50;         // a descriptor key of at most this many bits carries its run's record count above them
+                                           // (the radix sort ignores -- and carries along -- the bits above the sorted width)
+__device__ __forceinline__ u64 run_key_mask(u32 nbits_blocks) { return nbits_blocks <= RUN_STASH_BITS ? ((1ull << RUN_STASH_BITS) - 1ull) : ~0ull; }
 
 constexpr int RF_THREADS = 128;             // fold: four independent warps per CTA, one block per warp at a time
 constexpr u32 RF_VOXELS = 512;
@@ -45,7 +48,7 @@ struct RayL {
 __device__ __forceinline__ void axis_setup(float p, float d, float invl, float res, float trunc, float recip, i32& c, i32& e, i32& st, float& tmax,
                                            float& delta, u32& rmax) {
     const float dir = fmul(d, invl);
-    const float dir_recip = fdiv(1.0f, dir);                  // :93
+    const float dir_recip = __frcp_rn(dir);                   // :93  (1.0f / dir, correctly rounded)
     const float start = fsub(p, fmul(dir, trunc));            // :94
     const float fin = fadd(p, fmul(dir, trunc));              // :95
     const float sv = fmul(start, recip);
@@ -68,7 +71,7 @@ __device__ __forceinline__ void axis_setup(float p, float d, float invl, float r
 __device__ __forceinline__ u32 rayl_setup(RayL& r, float px, float py, float pz, float ox, float oy, float oz, float res, float trunc, float recip) {
     r.px = px; r.py = py; r.pz = pz;
     const float dx = fsub(px, ox), dy = fsub(py, oy), dz = fsub(pz, oz);
-    const float invl = fdiv(1.0f, fsqrt(dot3(dx, dy, dz, dx, dy, dz)));  // normalize, :92
+    const float invl = __frcp_rn(fsqrt(dot3(dx, dy, dz, dx, dy, dz)));  // normalize, :92
     u32 rmax = 0;
     axis_setup(px, dx, invl, res, trunc, recip, r.cx, r.ex, r.sx, r.tx, r.dx, rmax);
     axis_setup(py, dy, invl, res, trunc, recip, r.cy, r.ey, r.sy, r.ty, r.dy, rmax);
@@ -106,14 +109,17 @@ __device__ __forceinline__ u64 packed_block_to_morton(u64 pb) {  // (Morton key 
     const u32 mask = (1u << 18) - 1u;
     return (spread3((u32)pb & mask) | (spread3((u32)(pb >> 18) & mask) << 1) | (spread3((u32)(pb >> 36) & mask) << 2));
 }
-__device__ __forceinline__ u32 tile_hash_insert(u64* s_hkey, u64 pb) {
+// find-or-insert; the slots in use are also listed (s_list[0 .. *s_nslots)), so that the tile's bookkeeping later
+// costs as much as it has distinct blocks (a few dozen), not as much as the table is wide
+__device__ __forceinline__ u32 tile_hash_insert(u64* s_hkey, unsigned short* s_list, u32* s_nslots, u64 pb) {
     u32 h = ((u32)pb * 0x9E3779B1u + (u32)(pb >> 32) * 0x85EBCA77u) >> 22;  // RUN_HASH = 2^10
     for (u32 probes = 0; probes < RUN_HASH; probes++) {
         const u64 cur = s_hkey[h];
         if (cur == pb) return h;
         if (cur == RUN_EMPTY) {
             const u64 old = atomicCAS(&s_hkey[h], RUN_EMPTY, pb);
-            if (old == RUN_EMPTY || old == pb) return h;
+            if (old == RUN_EMPTY) { s_list[atomicAdd(s_nslots, 1u)] = (unsigned short)h; return h; }
+            if (old == pb) return h;
         }
         h = (h + 1) & (RUN_HASH - 1);
     }
@@ -134,18 +140,25 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
     uint2* s_rec = reinterpret_cast<uint2*>(s_dyn);  // [RUN_THREADS][stride]: x = (slot << 9) | local voxel, y = sd bits
     __shared__ u64 s_hkey[RUN_HASH];
     __shared__ u32 s_wcnt[RUN_WARPS / 2][RUN_HASH];  // records per (warp, slot), two warps per word; later: per-warp cursors inside the slot
-    __shared__ u32 s_hbase[RUN_HASH];                // first record of the slot's run inside the tile's span
+    __shared__ unsigned short s_hbase[RUN_HASH];     // first record of the slot's run inside the tile's span (a tile holds <= 8192 records)
     __shared__ u32 s_warp[RUN_THREADS / 32];
     __shared__ u32 s_gbase, s_dbase;
     __shared__ u32 s_scan[2];  // scans of the tile's first and last point
     __shared__ u32 s_prefix[RUN_WARPS][33];  // per warp: records of the lower lanes' rays (write-out)
+    __shared__ unsigned short s_list[RUN_HASH];    // hash slots in use; their runs follow each other in this order
+    __shared__ u32 s_total;
+    __shared__ u32 s_nslots;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 stride = mrv | 1u;  // odd: the ray-major reads of the write-out and the step-major writes of the walk both spread over the banks
+    {   // clear the hash (16-byte stores)
+        uint4* hk = reinterpret_cast<uint4*>(s_hkey);
+        uint4* wc4 = reinterpret_cast<uint4*>(&s_wcnt[0][0]);
+        const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zero = make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (u32 q = 0; q < RUN_HASH / RUN_THREADS; q++) {
-        s_hkey[tid + q * RUN_THREADS] = RUN_EMPTY;
+        for (u32 q = 0; q < RUN_HASH * 8 / 16 / RUN_THREADS; q++) hk[tid + q * RUN_THREADS] = ones;
 #pragma unroll
-        for (u32 w = 0; w < RUN_WARPS / 2; w++) s_wcnt[w][tid + q * RUN_THREADS] = 0;
+        for (u32 q = 0; q < (RUN_WARPS / 2) * RUN_HASH * 4 / 16 / RUN_THREADS; q++) wc4[tid + q * RUN_THREADS] = zero;
+        if (tid == 0) s_nslots = 0;
     }
     const u32 tile0 = blockIdx.x * RUN_THREADS;
     if (tid < 2) s_scan[tid] = scan_of(scans, plan->n_scans, tid == 0 ? tile0 : min(tile0 + RUN_THREADS, n_points) - 1);
@@ -168,7 +181,7 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
         if (rmax >= (1u << 20)) err |= ERRF_RANGE;
         else {
             alive = true;
-            slot = tile_hash_insert(s_hkey, pack_block(r.cx, r.cy, r.cz));
+            slot = tile_hash_insert(s_hkey, s_list, &s_nslots, pack_block(r.cx, r.cy, r.cz));
         }
     }
     // warp-uniform walk: every lane iterates until the warp's longest ray is done, so the lanes stay converged
@@ -185,33 +198,36 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
             if (!more || crossed) {
                 if (slot != 0xFFFFFFFFu) atomicAdd(&s_wcnt[warp >> 1][slot], run << wsh); else err |= ERRF_BLOCKS_FULL;
                 run = 0;
-                if (more) slot = tile_hash_insert(s_hkey, pack_block(r.cx, r.cy, r.cz));
+                if (more) slot = tile_hash_insert(s_hkey, s_list, &s_nslots, pack_block(r.cx, r.cy, r.cz));
                 alive = more;
             }
         }
     }
     __syncthreads();
     // ---- one span of the record buffer per tile, one run per distinct block; inside a run the warps follow each other ----
-    u32 c[RUN_HASH / RUN_THREADS];
-    u32 packed = 0;  // (non-empty slots << 16) | records   (a tile holds <= 256 * 32 = 8192 records)
-#pragma unroll
-    for (u32 q = 0; q < RUN_HASH / RUN_THREADS; q++) {
-        const u32 hs = tid * (RUN_HASH / RUN_THREADS) + q;
+    const u32 nslots = min(s_nslots, RUN_HASH);
+    // pass 1 over the slots in use: per-warp cursors inside the run, records of the run
+    u32 total = 0;
+    for (u32 t0 = 0; t0 < nslots; t0 += RUN_THREADS) {
+        const u32 t = t0 + tid;
         u32 sum = 0;
+        if (t < nslots) {
+            const u32 hs = s_list[t];
 #pragma unroll
-        for (u32 w = 0; w < RUN_WARPS / 2; w++) {
-            const u32 word = s_wcnt[w][hs];
-            const u32 lo = word & 0xFFFFu, hi = word >> 16;
-            s_wcnt[w][hs] = sum | ((sum + lo) << 16);  // exclusive prefix over the warps = each warp's cursor inside the run
-            sum += lo + hi;
+            for (u32 w = 0; w < RUN_WARPS / 2; w++) {
+                const u32 word = s_wcnt[w][hs];
+                const u32 lo = word & 0xFFFFu, hi = word >> 16;
+                s_wcnt[w][hs] = sum | ((sum + lo) << 16);  // exclusive prefix over the warps = each warp's cursor inside the run
+                sum += lo + hi;
+            }
         }
-        c[q] = sum;
-        packed += sum + (sum ? (1u << 16) : 0u);
+        u32 tot;
+        const u32 ex = block_exclusive_scan<u32>(sum, s_warp, tot);
+        if (t < nslots) s_hbase[s_list[t]] = (unsigned short)(total + ex);
+        total += tot;
     }
-    u32 total;
-    u32 ex = block_exclusive_scan<u32>(packed, s_warp, total);
     if (tid == 0) {
-        const u32 nrec = total & 0xFFFFu, nd = total >> 16;
+        const u32 nrec = total, nd = nslots;
         u32 gb = 0, db = 0;
         if (nrec) { gb = atomicAdd(&plan->n_pairs, nrec); db = atomicAdd(&plan->n_runs, nd); }
         u32 e = 0;
@@ -221,24 +237,21 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
         if (e) { atomicOr(&plan->error, e); gb = 0xFFFFFFFFu; }
         s_gbase = gb;
         s_dbase = db;
+        s_total = total;
     }
     __syncthreads();
     const u32 gbase = s_gbase;
-    if (gbase != 0xFFFFFFFFu && packed) {
+    if (gbase != 0xFFFFFFFFu) {
         const u32 k = plan->k, tbits = plan->tile_bits;
-#pragma unroll
-        for (u32 q = 0; q < RUN_HASH / RUN_THREADS; q++) {
-            const u32 hs = tid * (RUN_HASH / RUN_THREADS) + q;
-            const u32 base = ex & 0xFFFFu;
-            if (c[q]) {
-                const u32 d = s_dbase + (ex >> 16);
-                const u64 cid = compact_key(packed_block_to_morton(s_hkey[hs]) << RUN_BLK_SHIFT, k) >> RUN_BLK_SHIFT;
-                desc_key[d] = (cid << tbits) | (u64)blockIdx.x;
-                desc_val[d] = d;
-                desc[d] = make_uint2(gbase + base, c[q]);
-                s_hbase[hs] = base;
-            }
-            ex += c[q] + (c[q] ? (1u << 16) : 0u);
+        const bool stash = plan->nbits_blocks <= RUN_STASH_BITS;
+        for (u32 t = tid; t < nslots; t += RUN_THREADS) {
+            const u32 hs = s_list[t];
+            const u32 d = s_dbase + t;
+            const u64 cid = compact_key(packed_block_to_morton(s_hkey[hs]) << RUN_BLK_SHIFT, k) >> RUN_BLK_SHIFT;
+            const u32 base = s_hbase[hs], next = (t + 1 < nslots) ? (u32)s_hbase[s_list[t + 1]] : s_total;
+            desc_key[d] = (cid << tbits) | (u64)blockIdx.x | (stash ? ((u64)(next - base) << RUN_STASH_BITS) : 0ull);
+            desc_val[d] = d;
+            desc[d] = make_uint2(gbase + base, next - base);
         }
     }
     __syncthreads();
@@ -269,7 +282,7 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
                 u32 old = 0;
                 if (lane == leader) old = atomicAdd(&wc[hs], (u32)__popc(m) << wsh);
                 old = __shfl_sync(m, old, leader);
-                const u32 pos = gbase + s_hbase[hs] + ((old >> wsh) & 0xFFFFu) + (u32)__popc(m & ((1u << lane) - 1u));
+                const u32 pos = gbase + (u32)s_hbase[hs] + ((old >> wsh) & 0xFFFFu) + (u32)__popc(m & ((1u << lane) - 1u));
                 records[pos] = (u64(rc.y) << 32) | (u64)(((rc.x & 511u) << RUN_RANK_BITS) | (tile0 + warp * 32 + ray));
             }
         }
@@ -289,20 +302,27 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_group_kernel(const u64* __re
     const u64* __restrict__ keys = alt ? dkeys_b : dkeys_a;
     const u32* __restrict__ vals = alt ? dvals_b : dvals_a;
     const u32 tbits = plan->tile_bits;
+    const u64 kmask = run_key_mask(plan->nbits_blocks);
+    const bool stash = plan->nbits_blocks <= RUN_STASH_BITS;
     const u32 lane = threadIdx.x & 31;
     for (u32 q0 = blockIdx.x * RUN_THREADS; q0 < n; q0 += gridDim.x * RUN_THREADS) {  // uniform per CTA
         const u32 p = q0 + threadIdx.x;
         u64 cid = 0;
         bool head = false;
         if (p < n) {
-            cid = keys[p] >> tbits;
+            cid = (keys[p] & kmask) >> tbits;
             sdesc[p] = desc[vals[p]];
-            head = (p == 0) || (keys[p - 1] >> tbits) != cid;
+            head = (p == 0) || ((keys[p - 1] & kmask) >> tbits) != cid;
         }
         u32 len = 0, recs = 0;
         if (head) {
             u32 q = p;
-            while (q < n && (keys[q] >> tbits) == cid) { recs += desc[vals[q]].y; q++; }
+            while (q < n) {
+                const u64 kq = keys[q];
+                if (((kq & kmask) >> tbits) != cid) break;
+                recs += stash ? (u32)(kq >> RUN_STASH_BITS) : desc[vals[q]].y;
+                q++;
+            }
             len = q - p;
         }
         // blocks with many updates go to the front of the list (a block is folded by ONE warp: start the long ones first),
@@ -380,6 +400,7 @@ __global__ void __launch_bounds__(RF_THREADS) runs_fold_kernel(const u64* __rest
     const u32 n_blocks = bad ? 0u : (n_big + plan->n_small_blocks), k = plan->k, tbits = plan->tile_bits;
     auto work_item = [&](u32 t) { return work[t < n_big ? t : work_capacity - 1 - (t - n_big)]; };
     const u32 lt = (1u << lane) - 1u;
+    const u64 kmask = run_key_mask(nbits);
     u32 st_segments = 0, st_chunks = 0, st_new = 0, err = 0;
     // ticket + work item of the first block
     u32 t = 0;
@@ -394,7 +415,7 @@ __global__ void __launch_bounds__(RF_THREADS) runs_fold_kernel(const u64* __rest
         u32 t_next = 0;
         uint2 w_next = make_uint2(0, 0);
         if (lane == 0) { t_next = atomicAdd(&plan->fold_ticket, 1u); if (t_next < n_blocks) w_next = work_item(t_next); }
-        const u64 blk = expand_key((dkeys[p0] >> tbits) << RUN_BLK_SHIFT, k) >> RUN_BLK_SHIFT;
+        const u64 blk = expand_key(((dkeys[p0] & kmask) >> tbits) << RUN_BLK_SHIFT, k) >> RUN_BLK_SHIFT;
         // ---- seeds: the block's 64 leaf chunks that are already resident (lane l owns chunks l and l + 32) ----
         u64 slot0 = table_find(tkeys, capacity, (blk << 6) | (u64)lane);
         u64 slot1 = table_find(tkeys, capacity, (blk << 6) | (u64)(lane + 32));
