@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) dag_levels_kernel(LevelsArgs a)
     __shared__ u64 s_warp[LV_THREADS / 32];
     __shared__ u64 s_pref[LV_THREADS];
     const u32 tid = threadIdx.x;
+    const u32 NT = blockDim.x;  // <= LV_THREADS
     u32 cta = blockIdx.x, nctas = gridDim.x, phase = 0;
     const u32 C = *a.d_chunks;
     u32 n = C;   // children of the level being built
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) dag_levels_kernel(LevelsArgs a)
         const u32 c0 = min(n, cta * per), c1 = min(n, c0 + per);
         {
             u32 carry = 0;
-            for (u32 t0 = c0; t0 < c1; t0 += LV_THREADS) {
+            for (u32 t0 = c0; t0 < c1; t0 += NT) {
                 const u32 i = t0 + tid;
                 const bool head = (i < c1) && (i == 0 || (ids[i] >> 3) != (ids[i - 1] >> 3));
                 u64 tot;
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) dag_levels_kernel(LevelsArgs a)
         if (empty_root) {
             if (cta == 0 && tid < 18) a.cand[tid] = 0;
         } else {
-            for (u32 i = c0 + tid; i < c1; i += LV_THREADS) {
+            for (u32 i = c0 + tid; i < c1; i += NT) {
                 const u32 hr = a.head_rank[i];
                 if (hr == 0xFFFFFFFFu) continue;
                 const u32 p = pbase + hr;
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) dag_levels_kernel(LevelsArgs a)
         }
         sync();
         // ---- 3. probe: find-or-insert every record; a record not yet resident keeps the minimum sequence index that carried it ----
-        for (u32 e = cta * LV_THREADS + tid; e < R; e += nctas * LV_THREADS) {
+        for (u32 e = cta * NT + tid; e < R; e += nctas * NT) {
             u32 rec[9];
 #pragma unroll
             for (int q = 0; q < 9; q++) rec[q] = a.cand[size_t(e) * 9 + q];
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) dag_levels_kernel(LevelsArgs a)
         const u32 e0 = min(R, cta * per2), e1 = min(R, e0 + per2);
         {
             u64 carry = 0;
-            for (u32 t0 = e0; t0 < e1; t0 += LV_THREADS) {
+            for (u32 t0 = e0; t0 < e1; t0 += NT) {
                 const u32 e = t0 + tid;
                 u64 v = 0;
                 if (e < e1) {
@@ -451,7 +452,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) dag_levels_kernel(LevelsArgs a)
         sync();
         const u64 new_total = partial_prefix(a.partial + LV_THREADS, nctas, s_pref, s_warp);  // (new records << 32) | new words
         // ---- 5. commit the new records and resolve every element's address (levels.hpp:76-87) ----
-        for (u32 e = e0 + tid; e < e1; e += LV_THREADS) {
+        for (u32 e = e0 + tid; e < e1; e += NT) {
             const u32 slot = a.slot_of[e];
             const u64 rk = a.rank[e];
             u32 address;
@@ -539,12 +540,17 @@ int launch_cluster_dedup(cudaStream_t s, const DedupTable& t, const u64* tsdf_va
 int launch_dag_levels(cudaStream_t s, const LevelsArgs& args, int num_sms) {
     cudaMemsetAsync(args.bar, 0, 4, s);
     static const int env_ctas = [] { const char* e = std::getenv("CHAD_LEVELS_CTAS"); return e ? std::atoi(e) : 0; }();
-    // half the SMs: the CTAs spin at the grid barriers, and the insert kernels of the next submap run beside them (measured: 148 / 74 /
-    // 37 / 18 CTAs -> 11.68 / 11.39 / 11.36 / 11.82 ms per bench step)
-    int grid = num_sms / 2 < LV_THREADS ? num_sms / 2 : LV_THREADS;
+    // one CTA of 512 threads per SM: the CTAs spin at the grid barriers while the insert kernels of the next submap run beside them, so
+    // they must leave registers and thread slots free (measured per bench step: 1024 threads x 148 / 74 / 37 CTAs -> 11.68 / 11.39 /
+    // 11.36 ms; with the fold at 3 CTAs per SM: 1024 x 74 -> 10.36 ms, 512 x 148 -> 9.70 ms)
+    int grid = num_sms < LV_THREADS ? num_sms : LV_THREADS;
     if (grid < 1) grid = 1;
     if (env_ctas > 0 && env_ctas <= num_sms && env_ctas <= LV_THREADS) grid = env_ctas;
-    dag_levels_kernel<<<grid, LV_THREADS, 0, s>>>(args);
+    static const int env_threads = [] { const char* e = std::getenv("CHAD_LEVELS_THREADS"); return e ? std::atoi(e) : 0; }();
+    int threads = 512;
+    if (env_threads >= 64 && env_threads <= LV_THREADS && env_threads % 32 == 0) threads = env_threads;
+    if (grid > threads) grid = threads;  // partial_prefix scans one partial per thread
+    dag_levels_kernel<<<grid, threads, 0, s>>>(args);
     return 1;
 }
 
