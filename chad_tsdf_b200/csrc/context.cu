@@ -93,10 +93,13 @@ struct chad_ctx {
     DevBuf run_mem[2];              // run descriptors of the tile-run path, one set per plan slot: the fold of batch i runs on
     RunBuffers rb[2]{};             // fold_stream while the front of batch i + 1 runs on `stream` (records: keys_a / keys_b by slot)
     cudaStream_t fold_stream = nullptr;
+    cudaStream_t group_stream = nullptr;  // descriptor sort + block list of a batch: beside the next point stage AND the previous fold
     cudaEvent_t fold_done[2] = {nullptr, nullptr};   // the fold that read slot b's records / descriptors / plan has finished
     bool fold_done_valid[2] = {false, false};
     bool fold_in_flight = false;    // a fold has been queued on fold_stream since the last synchronisation
-    cudaEvent_t submap_closed2 = nullptr;
+    cudaEvent_t submap_closed2 = nullptr, emit_done = nullptr;
+    DevBuf radix_ws2;               // workspace of the descriptor sort (fold stream; the point sort's runs concurrently on the main stream)
+    RadixWorkspace rws2{};
     u64 prev_fold_bound = 0;        // chunk bound of the previous fold of the active submap if its exact count may not have arrived yet
     cudaStream_t prof_stream = nullptr;  // stream the instrumentation events are recorded on
     bool pending_runs = false;      // the batch whose fold is pending went through the tile-run path
@@ -155,6 +158,8 @@ struct chad_ctx {
     struct Span { int cls; cudaEvent_t a, b; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
+    struct TimelineEntry { int cls; float t0, t1; };
+    std::vector<TimelineEntry> timeline;  // instrumented launches of the last profiled flush, ms since its first launch
     double prof_ms[PC_COUNT] = {};
     u64 prof_launches[PC_COUNT] = {};
     LaunchHook hook{nullptr, nullptr, nullptr};
@@ -195,9 +200,16 @@ void prof_end(void* user) {
 }
 // after a stream synchronisation: fold the recorded spans into the per-class totals
 void prof_resolve(chad_ctx* ctx) {
+    if (!ctx->spans.empty()) ctx->timeline.clear();
     for (auto& sp : ctx->spans) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { ctx->prof_ms[sp.cls] += ms; ctx->prof_launches[sp.cls]++; }
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            ctx->prof_ms[sp.cls] += ms;
+            ctx->prof_launches[sp.cls]++;
+            float t0 = 0.f;
+            if (cudaEventElapsedTime(&t0, ctx->spans.front().a, sp.a) == cudaSuccess) ctx->timeline.push_back({sp.cls, t0, t0 + ms});
+            else cudaGetLastError();
+        }
         else cudaGetLastError();
         ctx->event_pool.push_back(sp.a);
         ctx->event_pool.push_back(sp.b);
@@ -264,6 +276,7 @@ int table_alloc(chad_ctx* ctx, ChunkTable& t, DevBuf& keys, DevBuf& cells, DevBu
 }
 int table_reserve(chad_ctx* ctx, u64 need_chunks) {
     if (need_chunks * 2 <= ctx->table.capacity) return CHAD_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));  // a fold may still be writing the table
     ctx->fold_in_flight = false;
     const u64 new_cap = next_pow2(need_chunks * 4);
@@ -284,6 +297,7 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
     // only called while no batch is in flight
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
     const size_t np = points + points / 8 + 1024;
     const size_t pairs = np * ctx->mp.max_ray_voxels;
@@ -318,11 +332,14 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
     TRY(dev_ensure(ctx, ctx->scan_ws, scan_workspace_bytes(np > bcap ? np : bcap)));
     if (ctx->mp.max_ray_runs <= runs_max_ray_runs() && ctx->mp.max_ray_voxels <= runs_max_ray_voxels()) {
         const size_t dcap = np * ctx->mp.max_ray_runs;
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
         for (int b = 0; b < 2; b++) {
             TRY(dev_ensure(ctx, ctx->run_mem[b], runs_desc_bytes(dcap)));
             ctx->rb[b] = runs_carve(ctx->run_mem[b].p, dcap);
         }
+        TRY(dev_ensure(ctx, ctx->radix_ws2, radix_workspace_bytes(dcap)));
+        ctx->rws2 = radix_workspace_carve(ctx->radix_ws2.p, dcap);
     }
     ctx->rws = radix_workspace_carve(ctx->radix_ws.p, pairs);
     ctx->cap_points = np;
@@ -479,9 +496,15 @@ int process_front(chad_ctx* ctx) {
     // ---- pair stage ----
     const size_t max_pairs = size_t(n) * ctx->mp.max_ray_voxels;
     if (use_runs) {
-        launches += launch_runs_front(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan, ctx->rb[slot],
-                                      (slot ? ctx->keys_b : ctx->keys_a).as<u64>(), (u32)ctx->cap_pairs, ctx->rws, ctx->num_sms, hook, PC_RUNS_EMIT,
-                                      PC_RUNS_SORT);
+        launches += launch_runs_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan, ctx->rb[slot],
+                                     (slot ? ctx->keys_b : ctx->keys_a).as<u64>(), (u32)ctx->cap_pairs, hook, PC_RUNS_EMIT);
+        // the descriptor sort and the block list are only needed by the fold: they go on its stream (after the previous batch's fold)
+        CUDA_TRY(ctx, cudaEventRecord(ctx->emit_done, s));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->group_stream, ctx->emit_done, 0));
+        ctx->prof_stream = ctx->group_stream;
+        launches += launch_runs_group(ctx->group_stream, n, plan, ctx->rb[slot], ctx->rws2, ctx->num_sms, hook, PC_RUNS_SORT);
+        ctx->prof_stream = nullptr;
+        ctx->fold_in_flight = true;
     } else if (ctx->fold_in_flight) {
         // the other pair paths use both pair buffers and fold on this stream: order them after the folds still in flight
         for (int b = 0; b < 2; b++)
@@ -500,9 +523,10 @@ int process_front(chad_ctx* ctx) {
                                      max_pairs, RS_MAX_PASSES, ctx->rws, ctx->num_sms, hook, PC_PAIR_SORT_HIST);
         PROF(ctx, PC_SEGMENT_COUNT, launch_segment_count(s, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), (u32)max_pairs, plan, ctx->num_sms));
     }
-    CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->h_plan[slot], plan, sizeof(BatchPlan), cudaMemcpyDeviceToHost, s));
+    cudaStream_t plan_on = use_runs ? ctx->group_stream : s;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->h_plan[slot], plan, sizeof(BatchPlan), cudaMemcpyDeviceToHost, plan_on));
     ctx->stats.d2h_bytes += sizeof(BatchPlan);
-    CUDA_TRY(ctx, cudaEventRecord(ctx->front_done, s));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->front_done, plan_on));
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->stats.kernel_launches += launches;
     ctx->stats.batches++;
@@ -527,6 +551,7 @@ int drain(chad_ctx* ctx) {
         TRY(finalize_part2(ctx));
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
     ctx->fold_in_flight = false;
     ctx->prev_fold_bound = 0;
@@ -807,6 +832,7 @@ int finalize_submap(chad_ctx* ctx, bool lazy) {
     }
     // no batch in flight: the exact count of the last fold may not have been read yet
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
     ctx->fold_in_flight = false;
     ctx->prev_fold_bound = 0;
@@ -902,8 +928,10 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->fold_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->group_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 2; b++) CREATE_TRY(cudaEventCreateWithFlags(&ctx->fold_done[b], cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&ctx->submap_closed2, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&ctx->emit_done, cudaEventDisableTiming));
     {   // the finalize stream gets the highest priority: its ~300 tiny dependent kernels then take the first SM slot that frees up
         // instead of queueing behind the thousands of CTAs of an insert kernel
         int prio_lo = 0, prio_hi = 0;
@@ -984,9 +1012,10 @@ void chad_destroy(chad_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->group_stream) cudaStreamSynchronize(ctx->group_stream);
     if (ctx->fold_stream) cudaStreamSynchronize(ctx->fold_stream);
     if (ctx->fin_stream) cudaStreamSynchronize(ctx->fin_stream);
-    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->t2_list, &ctx->t_list, &ctx->f_counters, &ctx->f_partial, &ctx->f_level_new, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->sh_tuples, &ctx->sh_scalars, &ctx->bt_mem, &ctx->run_mem[0], &ctx->run_mem[1], &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
+    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->t2_list, &ctx->t_list, &ctx->f_counters, &ctx->f_partial, &ctx->f_level_new, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->sh_tuples, &ctx->sh_scalars, &ctx->bt_mem, &ctx->run_mem[0], &ctx->run_mem[1], &ctx->radix_ws2, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
                       &ctx->sorted_keys, &ctx->sorted_order, &ctx->xyz_sorted, &ctx->normals, &ctx->seg_info, &ctx->counts, &ctx->offsets,
                       &ctx->radix_ws, &ctx->scan_ws, &ctx->t_keys, &ctx->t_cells, &ctx->t_count, &ctx->f_sorted, &ctx->f_ids[0], &ctx->f_ids[1], &ctx->f_slots[0],
                       &ctx->f_slots[1], &ctx->f_cells, &ctx->f_tsdf, &ctx->f_addr[0], &ctx->f_addr[1], &ctx->f_head, &ctx->f_head_rank, &ctx->f_cand,
@@ -1008,8 +1037,9 @@ void chad_destroy(chad_ctx* ctx) {
     if (ctx->h_fin) cudaFreeHost(ctx->h_fin);
     for (cudaEvent_t e : {ctx->submap_closed, ctx->fin_p1_done, ctx->fin_done, ctx->fin_t0, ctx->fin_t1, ctx->fin_t2, ctx->fin_t3}) if (e) cudaEventDestroy(e);
     if (ctx->fin_stream) cudaStreamDestroy(ctx->fin_stream);
-    for (cudaEvent_t e : {ctx->fold_done[0], ctx->fold_done[1], ctx->submap_closed2}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ctx->fold_done[0], ctx->fold_done[1], ctx->submap_closed2, ctx->emit_done}) if (e) cudaEventDestroy(e);
     if (ctx->fold_stream) cudaStreamDestroy(ctx->fold_stream);
+    if (ctx->group_stream) cudaStreamDestroy(ctx->group_stream);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->front_done) cudaEventDestroy(ctx->front_done);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
@@ -1176,6 +1206,7 @@ int chad_reset(chad_ctx* ctx) {
     ctx->sh_have_splitters = false;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fin_stream));
     ctx->fold_in_flight = false;
@@ -1248,6 +1279,18 @@ int chad_profile_get(chad_ctx* ctx, int cls, const char** name, double* millisec
     if (name) *name = nm;
     if (milliseconds) *milliseconds = ctx->prof_ms[cls];
     if (launches) *launches = ctx->prof_launches[cls];
+    return CHAD_OK;
+}
+
+int chad_profile_timeline(chad_ctx* ctx, int* classes, float* begin_ms, float* end_ms, size_t capacity, size_t* count) {
+    if (!ctx || !count) return CHAD_ERR_INVALID;
+    *count = ctx->timeline.size();
+    if (!classes || !begin_ms || !end_ms) return CHAD_OK;
+    for (size_t i = 0; i < ctx->timeline.size() && i < capacity; i++) {
+        classes[i] = ctx->timeline[i].cls;
+        begin_ms[i] = ctx->timeline[i].t0;
+        end_ms[i] = ctx->timeline[i].t1;
+    }
     return CHAD_OK;
 }
 

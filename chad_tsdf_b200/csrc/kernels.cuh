@@ -90,9 +90,10 @@ u32 runs_max_ray_runs();
 size_t runs_desc_bytes(size_t capacity);
 RunBuffers runs_carve(void* mem, size_t capacity);
 struct ChunkTable;
-int launch_runs_front(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const BatchScans* scans, const MapParams& mp,
-                      BatchPlan* plan, const RunBuffers& rb, u64* records, u32 rec_capacity, const RadixWorkspace& rws, int num_sms,
-                      const LaunchHook* hook, int cls_emit, int cls_sort);
+int launch_runs_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const BatchScans* scans, const MapParams& mp,
+                     BatchPlan* plan, const RunBuffers& rb, u64* records, u32 rec_capacity, const LaunchHook* hook, int cls_emit);
+int launch_runs_group(cudaStream_t s, u32 n_points, BatchPlan* plan, const RunBuffers& rb, const RadixWorkspace& rws, int num_sms,
+                      const LaunchHook* hook, int cls_sort);
 int launch_runs_fold(cudaStream_t s, const u64* records, const RunBuffers& rb, BatchPlan* plan, const ChunkTable& t, int num_sms);
 
 // ---- fold.cu: ordered segmented fold (octree.hpp:161-163) into the resident chunk table ----

@@ -593,18 +593,24 @@ RunBuffers runs_carve(void* mem, size_t capacity) {
     return b;
 }
 
-// Everything between the point stage and the fold: walk + emit, descriptor sort, block list. Returns the kernels queued.
-int launch_runs_front(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const BatchScans* scans, const MapParams& mp,
-                      BatchPlan* plan, const RunBuffers& rb, u64* records, u32 rec_capacity, const RadixWorkspace& rws, int num_sms,
-                      const LaunchHook* hook, int cls_emit, int cls_sort) {
+// The ray walk of a batch (main stream). Returns the kernels queued.
+int launch_runs_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const BatchScans* scans, const MapParams& mp,
+                     BatchPlan* plan, const RunBuffers& rb, u64* records, u32 rec_capacity, const LaunchHook* hook, int cls_emit) {
     if (!n_points) return 0;
-    int launches = 0;
     if (hook) hook->begin(hook->user, cls_emit);
     runs_emit_kernel<<<blocks_for(n_points), RUN_THREADS, size_t(RUN_THREADS) * (mp.max_ray_voxels | 1u) * sizeof(uint2), s>>>(
         xyz_sorted, normals, n_points, scans, mp.res, mp.trunc, mp.recip, mp.max_ray_voxels, plan, records, rec_capacity, rb.key_a, rb.val_a, rb.desc,
         rb.capacity);
     if (hook) hook->end(hook->user);
-    launches++;
+    return 1;
+}
+
+// Descriptor sort + block list of a batch: only the fold needs them, so they are queued on the fold's stream and the main stream goes
+// straight on to the next batch's point stage. `rws` must not be the workspace of the point sort (it runs concurrently).
+int launch_runs_group(cudaStream_t s, u32 n_points, BatchPlan* plan, const RunBuffers& rb, const RadixWorkspace& rws, int num_sms,
+                      const LaunchHook* hook, int cls_sort) {
+    if (!n_points) return 0;
+    int launches = 0;
     if (hook) hook->begin(hook->user, cls_sort);
     const size_t max_runs = std::min<size_t>(rb.capacity, size_t(blocks_for(n_points)) * RUN_HASH);
     launches += radix_sort_pairs(s, rb.key_a, rb.val_a, rb.key_b, rb.val_b, &plan->n_runs, &plan->nbits_blocks, max_runs, RS_MAX_PASSES, rws, num_sms);

@@ -123,6 +123,19 @@ class TSDFMap:
                 out[name.value.decode()] = (ms.value, int(n.value))
         return out
 
+    def profile_timeline(self):
+        """[(kernel class name, begin ms, end ms)] of the last profiled flush, device time since its first launch."""
+        n = C.c_size_t()
+        self._check(self._lib.chad_profile_timeline(self._h, None, None, None, 0, C.byref(n)))
+        cls, t0, t1 = np.zeros(n.value, np.int32), np.zeros(n.value, np.float32), np.zeros(n.value, np.float32)
+        self._check(self._lib.chad_profile_timeline(self._h, capi.ptr(cls), capi.ptr(t0), capi.ptr(t1), n.value, C.byref(n)))
+        out = []
+        for c, a, b in zip(cls, t0, t1):
+            name = C.c_char_p()
+            self._check(self._lib.chad_profile_get(self._h, int(c), C.byref(name), None, None))
+            out.append((name.value.decode(), float(a), float(b)))
+        return out
+
     def reset_stats(self) -> None:
         self._check(self._lib.chad_reset_stats(self._h))
 

@@ -172,6 +172,9 @@ uint64_t chad_key_expand(uint64_t compact, unsigned k);
 int chad_profile_enable(chad_ctx* ctx, int on);
 int chad_profile_classes(void);
 int chad_profile_get(chad_ctx* ctx, int cls, const char** name, double* milliseconds, uint64_t* launches);
+/* The instrumented launches of the last profiled flush in launch order: class, begin and end in milliseconds since the first one
+ * (device time, all streams). Two-call protocol: NULL arrays return the count. */
+int chad_profile_timeline(chad_ctx* ctx, int* classes, float* begin_ms, float* end_ms, size_t capacity, size_t* count);
 
 #ifdef __cplusplus
 }
