@@ -266,14 +266,14 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
         const u32 T = __shfl_sync(0xffffffffu, P, 31);
         u32* sp = s_prefix[warp];
         sp[lane] = P - cnt;
+        // owner[f] = the ray of flat record f (the block hash is no longer needed: the descriptors are written)
+        unsigned char* owner = reinterpret_cast<unsigned char*>(s_hkey) + warp * (RUN_HASH * 8 / RUN_WARPS);
+        for (u32 t = 0; t < cnt; t++) owner[P - cnt + t] = (unsigned char)lane;
         __syncwarp();
         u32* wc = s_wcnt[warp >> 1];
         for (u32 f = lane; f - lane < T; f += 32) {
             const bool has = f < T;
-            u32 ray = 0;
-#pragma unroll
-            for (u32 st = 16; st > 0; st >>= 1)
-                if (sp[ray + st] <= f) ray += st;  // largest ray with prefix <= f (rays without records share their successor's prefix)
+            const u32 ray = has ? (u32)owner[f] : 0u;
             uint2 rc = make_uint2(0xFFFFFFFFu, 0);
             if (has) rc = s_rec[(warp * 32 + ray) * stride + (f - sp[ray])];
             const u32 hs = (has && (rc.x >> 9) < RUN_HASH) ? (rc.x >> 9) : (0x80000000u | lane);  // unique for idle lanes
