@@ -161,3 +161,38 @@ def test_dense_voxels_many_updates_per_voxel(chad_lib, oracle_lib):
         g.finalize_active(); o.finalize_active()
         _assert_same_state(g, o)
         g.close(); o.close()
+
+
+def test_far_from_origin_wide_keys(chad_lib, oracle_lib):
+    """A map 3.2 km from the origin: 17 significant bits per axis, so the sort keys of the points and of the tile-run descriptors are
+    wide (more radix passes, no room to stash the run lengths in the descriptor keys)."""
+    from chad_tsdf_b200 import TSDFMap
+    from oracle import bindings as ob
+    w = synth.WORKLOADS["cfg0_single_64beam"]
+    shift = np.array([3200.0, -2900.0, 40.0], np.float32)
+    for path in (2, 0):
+        g, o = TSDFMap(w.sdf_res, w.sdf_trunc, max_batch_scans=2, pair_path=path), ob.OracleMap(w.sdf_res, w.sdf_trunc)
+        for s in range(3):
+            pts, pos = w.scan(s)
+            pts, pos = (pts + shift).astype(np.float32), (pos + shift).astype(np.float32)
+            g.insert(pts, pos); o.insert(pts, pos)
+        _assert_same_state(g, o, check_levels=False)
+        g.finalize_active(); o.finalize_active()
+        _assert_same_state(g, o)
+        g.close(); o.close()
+
+
+def test_wide_truncation_band_falls_back_to_block_path(chad_lib, oracle_lib):
+    """sdf_trunc / sdf_res = 4: a ray can cross more than four 8^3 blocks, which the tile-run path does not take; the default
+    configuration must fall back to the block-binned path by itself and stay exact."""
+    from chad_tsdf_b200 import TSDFMap
+    from oracle import bindings as ob
+    w = synth.Workload("wide", synth.BOX_ROOM, 32, 3, -1.0, 0.5, 0.05, 0.20, seed=21)
+    g, o = TSDFMap(w.sdf_res, w.sdf_trunc, max_batch_scans=2), ob.OracleMap(w.sdf_res, w.sdf_trunc)
+    for s in range(w.scans):
+        pts, pos = w.scan(s)
+        g.insert(pts, pos); o.insert(pts, pos)
+    _assert_same_state(g, o, check_levels=False)
+    g.finalize_active(); o.finalize_active()
+    _assert_same_state(g, o)
+    g.close(); o.close()
