@@ -121,8 +121,9 @@ struct BatchPlan {
     u32 tile_bits;     // bits of a 256-ray tile index inside the batch
     u32 n_big_blocks;  // tile-run path: blocks listed from the front of the work list (many updates) ...
     u32 n_small_blocks;//                ... and from its back
-    u32 pad[1];
+    u32 point_shift;   // 23 when the point sort carries the input index in the low bits of its key (keys-only sort), else 0
 };
+constexpr u32 POINT_INDEX_BITS = 23;
 
 constexpr int MAX_BATCH_SCANS = 64;
 struct BatchScans {  // device resident

@@ -449,7 +449,7 @@ void queue_point_stage(chad_ctx* ctx, int slot, int b, u32 n, u32 ns) {
     PROF(ctx, PC_POINT_KEYS, launch_point_keys(s, xyz, n, scans, ctx->mp, plan, ctx->pk_a.as<u64>(), ctx->pv_a.as<u32>()));
     launches += radix_sort_pairs(s, ctx->pk_a.as<u64>(), ctx->pv_a.as<u32>(), ctx->pk_b.as<u64>(), ctx->pv_b.as<u32>(),
                                  plan_field<u32>(ctx, slot, offsetof(BatchPlan, n_points)), plan_field<u32>(ctx, slot, offsetof(BatchPlan, nbits_points)), n,
-                                 RS_MAX_PASSES, ctx->rws, ctx->num_sms, hook, PC_POINT_SORT_HIST);
+                                 RS_MAX_PASSES, ctx->rws, ctx->num_sms, hook, PC_POINT_SORT_HIST, plan_field<u32>(ctx, slot, offsetof(BatchPlan, point_shift)));
     PROF(ctx, PC_POINT_GATHER, launch_point_gather(s, xyz, n, plan, ctx->pk_a.as<u64>(), ctx->pk_b.as<u64>(), ctx->pv_a.as<u32>(),
                                                    ctx->pv_b.as<u32>(), ctx->sorted_keys.as<u64>(), ctx->sorted_order.as<u32>(),
                                                    ctx->xyz_sorted.as<float>()));
@@ -883,7 +883,10 @@ int end_scan(chad_ctx* ctx, size_t n, const float position[3]) {
     std::memcpy(ctx->h_scans.pose[ctx->batch_scans], position, 12);
     ctx->batch_scans++;
     ctx->batch_points += (u32)n;
-    if (ctx->batch_scans >= (u32)ctx->max_batch) TRY(process_front(ctx));
+    // A burst starts with a short batch: while nothing is in flight the device would only wait for the host to copy a full batch
+    // (24 scans = 1.4 ms over PCIe); once a batch is queued the following ones fill up behind it.
+    const u32 target = ctx->fold_pending ? (u32)ctx->max_batch : std::min<u32>((u32)ctx->max_batch, 4u);
+    if (ctx->batch_scans >= target) TRY(process_front(ctx));
     return CHAD_OK;
 }
 
@@ -1352,7 +1355,7 @@ int chad_stage_points(chad_ctx* ctx, const float* xyz, size_t n, const float pos
     launches += launch_point_keys(s, dxyz, (u32)n, scans, ctx->mp, plan, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>());
     launches += radix_sort_pairs(s, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), ctx->keys_b.as<u64>(), ctx->vals_b.as<u32>(),
                                  plan_field<u32>(ctx, 0, offsetof(BatchPlan, n_points)), plan_field<u32>(ctx, 0, offsetof(BatchPlan, nbits_points)), n,
-                                 RS_MAX_PASSES, ctx->rws, ctx->num_sms);
+                                 RS_MAX_PASSES, ctx->rws, ctx->num_sms, nullptr, 0, plan_field<u32>(ctx, 0, offsetof(BatchPlan, point_shift)));
     launches += launch_point_gather(s, dxyz, (u32)n, plan, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(),
                                     ctx->sorted_keys.as<u64>(), ctx->sorted_order.as<u32>(), ctx->xyz_sorted.as<float>());
     launches += launch_normals(s, ctx->xyz_sorted.as<float>(), ctx->sorted_keys.as<u64>(), (u32)n, scans, plan, ctx->seg_info.as<u32>(),

@@ -42,7 +42,7 @@ __device__ __forceinline__ bool voxel_of(float px, float py, float pz, float rec
 __global__ void __launch_bounds__(PT_THREADS) plan_reset_kernel(BatchPlan* plan, u32 n_points, u32 n_scans) {
     plan->rmax = 0; plan->k = 0; plan->nbits_points = 0; plan->nbits_pairs = 0;
     plan->n_points = n_points; plan->n_scans = n_scans; plan->n_pairs = 0;
-    plan->n_segments = 0; plan->n_chunk_heads = 0; plan->n_new_chunks = 0; plan->fold_ticket = 0; plan->n_blocks = 0; plan->sort_ticket = 0; plan->n_runs = 0; plan->nbits_blocks = 0; plan->tile_bits = 0; plan->n_big_blocks = 0; plan->n_small_blocks = 0;
+    plan->n_segments = 0; plan->n_chunk_heads = 0; plan->n_new_chunks = 0; plan->fold_ticket = 0; plan->n_blocks = 0; plan->sort_ticket = 0; plan->n_runs = 0; plan->nbits_blocks = 0; plan->tile_bits = 0; plan->n_big_blocks = 0; plan->n_small_blocks = 0; plan->point_shift = 0;
     // plan->error is sticky: cleared by the host when it reports it
 }
 
@@ -93,6 +93,8 @@ __global__ void plan_finalize_kernel(BatchPlan* plan, u32 margin) {
         if (3 * k - 6 + tbits > 64) plan->nbits_blocks = 0xFFFFFFFFu;  // the tile-run path reports ERRF_KEY_BUDGET; paths 0 / 1 do not use it
     }
     plan->nbits_points = nb;
+    // the input index (the sort's payload) fits under the key: one 8-byte array goes through the sort instead of 8 + 4 bytes
+    plan->point_shift = (nb + POINT_INDEX_BITS <= 64 && plan->n_points <= (1u << POINT_INDEX_BITS)) ? POINT_INDEX_BITS : 0u;
 }
 
 // sort key of a point: (scan << (3k+3)) | (~compact(morton) & mask): ascending sort == per scan
@@ -113,8 +115,9 @@ __global__ void __launch_bounds__(PT_THREADS) point_keys_kernel(const float* __r
     const u64 cmask = (cbits >= 64) ? ~0ull : ((1ull << cbits) - 1ull);
     const u64 inv = ~compact_key(full, k) & cmask;
     const u32 s = scan_of(scans, plan->n_scans, i);
-    sortkeys[i] = (cbits >= 64 ? 0ull : (u64(s) << cbits)) | inv;
-    index[i] = i;
+    const u64 sk = (cbits >= 64 ? 0ull : (u64(s) << cbits)) | inv;
+    if (plan->point_shift) sortkeys[i] = (sk << POINT_INDEX_BITS) | (u64)i;
+    else { sortkeys[i] = sk; index[i] = i; }
 }
 
 __global__ void __launch_bounds__(PT_THREADS) point_gather_kernel(const float* __restrict__ xyz, u32 n_points, const BatchPlan* __restrict__ plan,
@@ -125,8 +128,10 @@ __global__ void __launch_bounds__(PT_THREADS) point_gather_kernel(const float* _
     const u32 i = blockIdx.x * PT_THREADS + threadIdx.x;
     if (i >= n_points) return;
     const bool alt = radix_result_in_alt(plan->nbits_points);
-    const u64 key = alt ? keys_b[i] : keys_a[i];
-    const u32 src = alt ? idx_b[i] : idx_a[i];
+    u64 key = alt ? keys_b[i] : keys_a[i];
+    u32 src;
+    if (plan->point_shift) { src = (u32)key & ((1u << POINT_INDEX_BITS) - 1u); key >>= POINT_INDEX_BITS; }
+    else src = alt ? idx_b[i] : idx_a[i];
     sorted_keys[i] = key;
     sorted_order[i] = src;
     const float x = __ldg(&xyz[size_t(src) * 3]), y = __ldg(&xyz[size_t(src) * 3 + 1]), z = __ldg(&xyz[size_t(src) * 3 + 2]);

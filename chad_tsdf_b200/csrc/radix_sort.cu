@@ -36,10 +36,11 @@ __device__ __forceinline__ u32 block_exclusive_scan_256(u32 v, u32* s_warp_total
 }
 
 __global__ void __launch_bounds__(RS_THREADS) radix_histogram_kernel(const u64* __restrict__ keys, const u32* __restrict__ d_n,
-                                                                     const u32* __restrict__ d_nbits, u32* __restrict__ hist,
-                                                                     u32* __restrict__ lookback0) {
+                                                                     const u32* __restrict__ d_nbits, const u32* __restrict__ d_shift0,
+                                                                     u32* __restrict__ hist, u32* __restrict__ lookback0) {
     __shared__ u32 s_hist[RS_MAX_PASSES][RS_RADIX];
     const u32 n = *d_n;
+    const u32 shift0 = d_shift0 ? *d_shift0 : 0u;  // the sorted bits are [shift0, shift0 + nbits); lower bits ride along (packed payload)
     u32 npasses = radix_num_passes(*d_nbits);
     if (npasses > RS_MAX_PASSES) npasses = RS_MAX_PASSES;
     const u32 tid = threadIdx.x, lane = tid & 31;
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_histogram_kernel(const u64* 
         for (int j = 0; j < RS_ITEMS; j++) {
             const u32 idx = base + j * RS_THREADS + tid;
             const bool valid = idx < n;
-            const u64 key = valid ? keys[idx] : 0ull;
+            const u64 key = valid ? (keys[idx] >> shift0) : 0ull;
             // digit 0 is close to uniform: plain shared atomics. Digits >= 1 are Morton-coherent (whole warps share
             // them): ONE match.any on key >> 8 groups the lanes whose upper digits all agree, one lane per group adds.
             if (valid) atomicAdd(&s_hist[0][(u32)(key & (RS_RADIX - 1))], 1u);
@@ -75,14 +76,17 @@ __global__ void __launch_bounds__(RS_THREADS) radix_histogram_kernel(const u64* 
 
 __global__ void __launch_bounds__(RS_THREADS, RS_CTAS_PER_SM)
     radix_onesweep_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
-                          u32* __restrict__ vals_out, const u32* __restrict__ d_n, const u32* __restrict__ d_nbits, u32 pass,
-                          const u32* __restrict__ hist, u32* __restrict__ tile_counter, u32* lookback_cur, u32* __restrict__ lookback_next) {
+                          u32* __restrict__ vals_out, const u32* __restrict__ d_n, const u32* __restrict__ d_nbits,
+                          const u32* __restrict__ d_shift0, u32 pass, const u32* __restrict__ hist, u32* __restrict__ tile_counter,
+                          u32* lookback_cur, u32* __restrict__ lookback_next) {
     const u32 npasses = radix_num_passes(*d_nbits);
     if (pass >= npasses) return;
+    const u32 shift0 = d_shift0 ? *d_shift0 : 0u;
+    const bool keys_only = shift0 != 0;  // the payload is packed into the key bits below shift0: no value array to move
     const u32 n = *d_n;
     const u32 num_tiles = (n + RS_TILE - 1) / RS_TILE;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 shift = pass * RS_RADIX_BITS;
+    const u32 shift = shift0 + pass * RS_RADIX_BITS;
     const u32 lanemask_lt = (1u << lane) - 1u;
 
     extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_CTAS_PER_SM)
             const u32 idx = base + j * 32;
             const bool valid = idx < n;
             key[j] = valid ? keys_in[idx] : ~0ull;
-            val[j] = valid ? vals_in[idx] : 0u;
+            val[j] = (valid && !keys_only) ? vals_in[idx] : 0u;
         }
         // ---- stable rank inside (warp, digit): match.any multi-split ----
         // all matches first (independent -> pipelined; ncu r01: the match latency was 25 % of the stall samples when each
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_CTAS_PER_SM)
                 const u32 d = (u32)((key[j] >> shift) & (RS_RADIX - 1));
                 const u32 pos = s_tile_start[d] + s_warp_hist[warp][d] + rank[j];
                 s_keys[pos] = key[j];
-                s_vals[pos] = val[j];
+                if (!keys_only) s_vals[pos] = val[j];
             }
         }
         // ---- decoupled look-back, AFTER the staging so that the predecessors had time to publish their prefixes:
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_CTAS_PER_SM)
             const u32 d = (u32)((k >> shift) & (RS_RADIX - 1));
             const u32 dst = s_gbase[d] + e;
             keys_out[dst] = k;
-            vals_out[dst] = s_vals[e];
+            if (!keys_only) vals_out[dst] = s_vals[e];
         }
         __syncthreads();
     }
@@ -215,7 +219,8 @@ cudaError_t radix_sort_init() {
 }
 
 int radix_sort_pairs(cudaStream_t stream, u64* keys, u32* vals, u64* keys_alt, u32* vals_alt, const u32* d_n, const u32* d_nbits,
-                     size_t max_n, int max_passes, const RadixWorkspace& ws, int num_sms, const LaunchHook* hook, int cls_base) {
+                     size_t max_n, int max_passes, const RadixWorkspace& ws, int num_sms, const LaunchHook* hook, int cls_base,
+                     const u32* d_shift0) {
     if (max_n == 0) return 0;
     if (max_passes > RS_MAX_PASSES) max_passes = RS_MAX_PASSES;
     size_t max_tiles = (max_n + RS_TILE - 1) / RS_TILE;
@@ -223,14 +228,14 @@ int radix_sort_pairs(cudaStream_t stream, u64* keys, u32* vals, u64* keys_alt, u
     cudaMemsetAsync(ws.hist, 0, (size_t(RS_MAX_PASSES) * 256 + 64) * 4, stream);
     int hist_grid = (int)(max_tiles < size_t(num_sms) * 4 ? max_tiles : size_t(num_sms) * 4);
     if (hook) hook->begin(hook->user, cls_base);
-    radix_histogram_kernel<<<hist_grid, RS_THREADS, 0, stream>>>(keys, d_n, d_nbits, ws.hist, ws.lookback[0]);
+    radix_histogram_kernel<<<hist_grid, RS_THREADS, 0, stream>>>(keys, d_n, d_nbits, d_shift0, ws.hist, ws.lookback[0]);
     if (hook) hook->end(hook->user);
     launches++;
     int grid = (int)(max_tiles < size_t(num_sms) * RS_CTAS_PER_SM ? max_tiles : size_t(num_sms) * RS_CTAS_PER_SM);
     u64* kin = keys; u32* vin = vals; u64* kout = keys_alt; u32* vout = vals_alt;
     for (int p = 0; p < max_passes; p++) {
         if (hook) hook->begin(hook->user, cls_base + 1 + p);
-        radix_onesweep_kernel<<<grid, RS_THREADS, RS_SMEM_BYTES, stream>>>(kin, vin, kout, vout, d_n, d_nbits, (u32)p, ws.hist,
+        radix_onesweep_kernel<<<grid, RS_THREADS, RS_SMEM_BYTES, stream>>>(kin, vin, kout, vout, d_n, d_nbits, d_shift0, (u32)p, ws.hist,
                                                                             ws.tile_counter, ws.lookback[p & 1], ws.lookback[(p + 1) & 1]);
         if (hook) hook->end(hook->user);
         launches++;

@@ -69,7 +69,9 @@ __host__ __device__ __forceinline__ bool radix_result_in_alt(u32 nbits) { return
 // hook/cls_base: optional instrumentation; class cls_base = histogram, cls_base + 1 + p = pass p.
 int radix_sort_pairs(cudaStream_t stream, u64* keys, u32* vals, u64* keys_alt, u32* vals_alt, const u32* d_n,
                      const u32* d_nbits, size_t max_n, int max_passes, const RadixWorkspace& ws, int num_sms,
-                     const LaunchHook* hook = nullptr, int cls_base = 0);
+                     const LaunchHook* hook = nullptr, int cls_base = 0, const u32* d_shift0 = nullptr);
+// d_shift0 (optional, device): when *d_shift0 != 0 the sorted bits are [*d_shift0, *d_shift0 + nbits) of the key and the bits
+// below carry the payload (keys-only sort: the value arrays are not touched).
 cudaError_t radix_sort_init();  // opt in to > 48 KB dynamic shared memory
 
 }  // namespace chadgpu
