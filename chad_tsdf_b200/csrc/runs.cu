@@ -448,13 +448,12 @@ __global__ void __launch_bounds__(RF_THREADS) runs_fold_kernel(const u64* __rest
             S.rprefix[lane] = P - dl.y;
             S.rstart[lane] = dl.x - (P - dl.y);  // record f of the flat sequence lives at rstart[run] + f
             __syncwarp();
+            // the positions fetched by a lane only grow (by 32 per iteration): its run cursor walks forward, usually by 0 or 1
+            u32 frun = 0;
             auto fetch = [&](u32 f) -> u64 {
                 if (f >= T) return ~0ull;
-                u32 run = 0;
-#pragma unroll
-                for (u32 st = 16; st > 0; st >>= 1)
-                    if (S.rprefix[run + st] <= f) run += st;
-                return records[S.rstart[run] + f];
+                while (S.rprefix[frun + 1] <= f) frun++;  // rprefix[32] is a sentinel
+                return records[S.rstart[frun] + f];
             };
             u64 buf[RF_DEPTH];
 #pragma unroll
