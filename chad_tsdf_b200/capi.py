@@ -67,6 +67,7 @@ SYMBOLS = {
     "chad_shard_export_chunks": (C.c_int, [_P, C.POINTER(C.c_size_t), C.POINTER(_P), C.POINTER(_P)]),
     "chad_shard_finalize_from": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int]),
     "chad_shard_clear": (C.c_int, [_P]),
+    "chad_query_voxels": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t, _P]),
     "chad_profile_timeline": (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "chad_morton_encode": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32]),
     "chad_morton_decode": (None, [C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

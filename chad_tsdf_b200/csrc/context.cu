@@ -1197,6 +1197,30 @@ int chad_export_level(chad_ctx* ctx, int level, void* dst, size_t capacity_words
     return CHAD_OK;
 }
 
+int chad_query_voxels(chad_ctx* ctx, uint32_t submap, const uint64_t* keys, size_t n, uint8_t* bytes) {
+    if (!ctx || (n && (!keys || !bytes))) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(settle(ctx));
+    if (submap >= ctx->roots.size()) return fail(ctx, CHAD_ERR_INVALID, "submap index out of range");
+    if (n >= (1ull << 31)) return fail(ctx, CHAD_ERR_INVALID, "too many queries");
+    if (n == 0) return CHAD_OK;
+    DevBuf dk, db;
+    TRY(dev_ensure(ctx, dk, n * 8));
+    int rc = dev_ensure(ctx, db, n);
+    if (rc != CHAD_OK) { dev_free(dk); return rc; }
+    DagReadArgs a{};
+    for (int d = 0; d < 20; d++) a.raw[d] = ctx->levels[d].raw.as<u32>();
+    a.clusters = ctx->levels[CHAD_LEVEL_CLUSTERS].raw.as<u64>();
+    cudaError_t e = cudaMemcpyAsync(dk.p, keys, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) { ctx->stats.kernel_launches += launch_dag_query(ctx->stream, a, ctx->roots[submap][0], dk.as<u64>(), (u32)n, db.as<u8>()); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bytes, db.p, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dev_free(dk);
+    dev_free(db);
+    if (e != cudaSuccess) return fail(ctx, CHAD_ERR_CUDA, std::string("chad_query_voxels: ") + cudaGetErrorString(e));
+    return CHAD_OK;
+}
+
 int chad_reset(chad_ctx* ctx) {
     if (!ctx) return CHAD_ERR_INVALID;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));

@@ -492,6 +492,26 @@ __global__ void __launch_bounds__(LV_THREADS, 1) dag_levels_kernel(LevelsArgs a)
     if (tid == 0) { a.root_out[0] = a.addr[cur][0]; a.root_out[1] = a.addr[cur][1]; }
 }
 
+// ------------------------------------------------------------------------------------------
+// DAG read path on the device: NodeLevels::get_child_addr (levels.hpp:147-161) down the 20 node levels, then
+// try_get_lc (levels.hpp:177-192) and the voxel's byte of the leaf cluster (cluster.hpp:34-52). One thread per query.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DAG_THREADS) dag_query_kernel(DagReadArgs a, u32 root, const u64* __restrict__ keys, u32 n, u8* __restrict__ out) {
+    const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const u64 key = keys[i];
+    u32 addr = root;
+    u8 byte = 0xFF;  // absent
+    for (u32 depth = 0; depth <= 20 && addr != 0; depth++) {
+        if (depth == 20) { byte = (u8)(a.clusters[addr] >> (8 * (key & 7ull))); break; }
+        const u32 child_i = (u32)(key >> (3 * (20 - depth))) & 7u;   // depth d picks Morton triple 20 - d
+        const u32 mask = a.raw[depth][addr];
+        const u32 bit = 1u << child_i;
+        addr = (mask & bit) ? a.raw[depth][addr + 1 + __popc(mask & (bit - 1) & 0xFFu)] : 0u;
+    }
+    out[i] = byte;
+}
+
 __global__ void __launch_bounds__(DAG_THREADS) dedup_rehash_kernel(const u64* __restrict__ from, u64 from_capacity, u64* to, u64 to_capacity) {
     const u64 mask = to_capacity - 1;
     for (u64 s = u64(blockIdx.x) * DAG_THREADS + threadIdx.x; s < from_capacity; s += u64(gridDim.x) * DAG_THREADS) {
@@ -551,6 +571,12 @@ int launch_dag_levels(cudaStream_t s, const LevelsArgs& args, int num_sms) {
     if (env_threads >= 64 && env_threads <= LV_THREADS && env_threads % 32 == 0) threads = env_threads;
     if (grid > threads) grid = threads;  // partial_prefix scans one partial per thread
     dag_levels_kernel<<<grid, threads, 0, s>>>(args);
+    return 1;
+}
+
+int launch_dag_query(cudaStream_t s, const DagReadArgs& args, u32 root, const u64* keys, u32 n, u8* out) {
+    if (!n) return 0;
+    dag_query_kernel<<<blocks_for(n), DAG_THREADS, 0, s>>>(args, root, keys, n, out);
     return 1;
 }
 

@@ -139,6 +139,9 @@ struct LevelsArgs {
     u32* d_error; u32* root_out; u32* level_nodes;
 };
 int launch_dag_levels(cudaStream_t s, const LevelsArgs& args, int num_sms);
+// device-side DAG reader: bytes of the queried voxels in the TSDF tree rooted at `root` (0xFF = absent)
+struct DagReadArgs { const u32* raw[20]; const u64* clusters; };
+int launch_dag_query(cudaStream_t s, const DagReadArgs& args, u32 root, const u64* keys, u32 n, u8* out);
 int launch_dedup_clear(cudaStream_t s, const DedupTable& t);
 int launch_dedup_rehash(cudaStream_t s, const DedupTable& from, const DedupTable& to, int num_sms);
 // the chunk count is read from device memory (*d_chunks <= max_chunks): finalize part 1 runs without a host round trip

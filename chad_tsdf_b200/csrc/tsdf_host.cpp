@@ -2,9 +2,12 @@
 // /root/reference/src/chad/tsdf.cpp:27-86 (constructor, destructor, insert, save).
 #include "chad/tsdf.hpp"
 
+#include <algorithm>
 #include <bit>
 #include <cstdio>
+#include <cstring>
 #include <stdexcept>
+#include <unordered_map>
 
 #include "chad_b200.h"
 
@@ -70,6 +73,76 @@ void TSDFMap::save(const std::string& filename) {
     const uint64_t n = levels.leaf_clusters.size();
     put(&n, 8);
     put(levels.leaf_clusters.data(), n * 8);
+    std::fclose(f);
+}
+
+// The reference's ChadGrid constructor (lvr2.cpp:32-130) + ChadGrid::saveGrid (lvr2.cpp:170-200) on the host copy of the DAG.
+void TSDFMap::save_grid(const std::string& filename, size_t submap) {
+    check(_ctx, chad_finalize_active(_ctx), "save_grid");  // tsdf.cpp:78-81
+    if (submap >= submap_count()) throw std::runtime_error("chad::TSDFMap::save_grid: no such submap");
+    const HostNodeLevels levels = node_levels();
+    const uint32_t root = submap_roots(submap)[0];
+    struct QueryPoint { float x, y, z, sd; };
+    std::vector<QueryPoint> query_points;
+    constexpr uint32_t INVALID = 0xFFFFFFFFu;  // lvr2 FastBox::INVALID_INDEX
+    std::unordered_map<uint64_t, std::array<uint32_t, 8>> cells;
+    static const int32_t cell_offsets[8][3] = { {0, 0, 0}, {-1, 0, 0}, {-1, -1, 0}, {0, -1, 0}, {0, 0, -1}, {-1, 0, -1}, {-1, -1, -1}, {0, -1, -1} };  // lvr2.cpp:88-98
+    std::array<uint8_t, HostNodeLevels::MAX_DEPTH> path_child{};
+    std::array<uint32_t, HostNodeLevels::MAX_DEPTH> path_addr{};
+    path_addr[0] = root;
+    uint32_t depth = 0;
+    while (true) {  // lvr2.cpp:33-113
+        const uint8_t child_i = path_child[depth]++;
+        if (child_i == 8) {
+            if (depth > 0) depth--;
+            else break;
+        } else if (depth < HostNodeLevels::MAX_DEPTH - 1) {
+            const uint32_t child_addr = levels.get_child_addr(depth, path_addr[depth], child_i);
+            if (child_addr > 0) {
+                depth++;
+                path_child[depth] = 0;
+                path_addr[depth] = child_addr;
+            }
+        } else {
+            uint64_t cluster;
+            if (!levels.try_get_lc(path_addr[depth], child_i, cluster)) continue;
+            uint64_t code = 0;  // Morton code of the cluster from the path (lvr2.cpp:59-65)
+            for (uint64_t k = 0; k < 63 / 3 - 1; k++) code |= uint64_t(path_child[k] - 1) << uint64_t(60 - k * 3);
+            int32_t cx, cy, cz;
+            chad_morton_decode(code, &cx, &cy, &cz);
+            uint32_t leaf_i = 0;
+            for (int32_t z = 0; z <= 1; z++) for (int32_t y = 0; y <= 1; y++) for (int32_t x = 0; x <= 1; x++, leaf_i++) {
+                const uint64_t bits = (cluster >> (leaf_i * 8)) & 0xFF;  // TSDFs::try_get, cluster.hpp:34-52
+                if (bits == 0xFF) continue;
+                float sd = float(bits) - 127.0f;
+                sd *= float(1.0 / 127.0f);
+                sd *= _sdf_trunc;
+                const int32_t lx = cx + x, ly = cy + y, lz = cz + z;
+                const uint32_t qi = (uint32_t)query_points.size();
+                query_points.push_back({ float(lx) * _sdf_res, float(ly) * _sdf_res, float(lz) * _sdf_res, sd });
+                for (size_t i = 0; i < 8; i++) {
+                    const uint64_t cell = chad_morton_encode(lx + cell_offsets[i][0], ly + cell_offsets[i][1], lz + cell_offsets[i][2]);
+                    auto [it, fresh] = cells.try_emplace(cell);
+                    if (fresh) it->second.fill(INVALID);
+                    it->second[i] = qi;
+                }
+            }
+        }
+    }
+    std::vector<uint64_t> complete;  // lvr2.cpp:115-129: cells with a missing corner are culled
+    for (const auto& [code, verts] : cells)
+        if (std::find(verts.begin(), verts.end(), INVALID) == verts.end()) complete.push_back(code);
+    std::sort(complete.begin(), complete.end());
+    std::FILE* f = std::fopen(filename.c_str(), "wb");
+    if (!f) throw std::runtime_error("chad::TSDFMap::save_grid: cannot open " + filename);
+    auto put = [&](const void* p, size_t n) { if (n && std::fwrite(p, 1, n, f) != n) { std::fclose(f); throw std::runtime_error("chad::TSDFMap::save_grid: write failed"); } };
+    const float header = _sdf_trunc;  // the reference writes m_truncsize under the name voxel_res (lvr2.cpp:176-177)
+    const size_t nq = query_points.size(), nc = complete.size();
+    put(&header, sizeof(float));
+    put(&nq, sizeof(size_t));
+    put(&nc, sizeof(size_t));
+    put(query_points.data(), nq * sizeof(QueryPoint));
+    for (uint64_t code : complete) put(cells[code].data(), 8 * sizeof(uint32_t));
     std::fclose(f);
 }
 

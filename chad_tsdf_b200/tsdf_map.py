@@ -88,6 +88,13 @@ class TSDFMap:
         assert got.value == n.value
         return keys, sd, w
 
+    def query_voxels(self, submap: int, keys) -> np.ndarray:
+        """Quantised TSDF bytes (0xFF = absent) of the given Morton keys in finalised submap `submap`, read from the DAG on the device."""
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        out = np.empty(k.shape[0], np.uint8)
+        self._check(self._lib.chad_query_voxels(self._h, submap, capi.ptr(k), k.shape[0], capi.ptr(out)))
+        return out
+
     def level(self, level: int):
         n = C.c_size_t()
         self._check(self._lib.chad_level_words(self._h, level, C.byref(n)))

@@ -95,6 +95,11 @@ namespace chad {
         void save(const std::string& filename);
 
         // ---- additions (not in the reference) ----
+        // The reference's save() hands the first submap to LVR2 as a "ChadGrid" (lvr2.cpp:32-113) whose saveGrid writes a
+        // `.grid` file (lvr2.cpp:170-200). LVR2 is out of scope here, but the grid itself only needs the DAG: this writes the
+        // same file for finalised submap `submap` (query points in the reference's traversal order; complete cells in
+        // ascending Morton order of the cell -- the reference's order is its unordered_map's iteration order).
+        void save_grid(const std::string& filename, size_t submap = 0);
         void flush();                                   // wait for queued inserts
         size_t submap_count();
         std::array<uint32_t, 2> submap_roots(size_t i); // root_addr_tsdf, root_addr_weight (submap.hpp:108-109)

@@ -92,6 +92,11 @@ int chad_level_words(chad_ctx* ctx, int level, size_t* words);
 int chad_level_counters(chad_ctx* ctx, int level, uint32_t* uniques, uint32_t* dupes);
 int chad_export_level(chad_ctx* ctx, int level, void* dst, size_t capacity_words);
 
+/* DAG read path on the device (NodeLevels::get_child_addr / try_get_lc, levels.hpp:147-192, and the leaf byte of
+ * cluster.hpp:34-52): for n Morton keys (host), the quantised TSDF byte of that voxel in finalised submap `submap`'s tree,
+ * 0xFF where the voxel does not exist. Decode: (byte - 127) / 127 * sdf_trunc. */
+int chad_query_voxels(chad_ctx* ctx, uint32_t submap, const uint64_t* keys, size_t n, uint8_t* bytes);
+
 /* How the band-voxel updates of a batch are grouped per voxel before the fold: 2 = tile runs + fused per-block sort and fold (default: runs.cu), 0 = block-binned (hashed
  * 8x8x8-voxel blocks + shared-memory sort), 1 = global onesweep radix sort. All give bit-identical results. */
 int chad_set_pair_path(chad_ctx* ctx, int mode);

@@ -20,6 +20,7 @@ int main(int argc, char** argv) {
     chad::TSDFMap map{ 0.05f, 0.1f };
     map.insert(points, { 0.0f, 0.0f, 0.0f });
     map.save("facade_demo.chad");
+    map.save_grid("facade_demo.grid");  // the reference's hashgrid.grid (lvr2.cpp:170-200) for the first submap
     const auto levels = map.node_levels();
     const auto roots = map.submap_roots(0);
     // depth-first walk of the TSDF tree

@@ -28,3 +28,22 @@ def test_facade_demo_runs_on_gpu(chad_lib, tmp_path):
     assert blob[:8] == b"CHADDAG1"
     res, trunc, nsub = struct.unpack_from("<ffI", blob, 8)
     assert (np.float32(res), np.float32(trunc), nsub) == (np.float32(0.05), np.float32(0.1), 1)
+    # the reference's .grid file (lvr2.cpp:170-200): header, query points (leaf corner position + decoded distance), complete cells
+    g = open(tmp_path / "facade_demo.grid", "rb").read()
+    hdr, nq, nc = struct.unpack_from("<fQQ", g, 0)
+    assert np.float32(hdr) == np.float32(0.1)  # the reference stores the truncation distance in this field
+    leaves = int(r.stdout.split(" leaves")[0].split()[-1])
+    assert nq == leaves and nc > 0
+    qp = np.frombuffer(g, np.float32, nq * 4, 20).reshape(nq, 4)
+    cells = np.frombuffer(g, np.uint32, nc * 8, 20 + nq * 16).reshape(nc, 8)
+    assert len(g) == 20 + nq * 16 + nc * 32
+    assert cells.max() < nq
+    assert np.all(np.abs(qp[:, 3]) <= np.float32(0.1) + 1e-6)
+    # a complete cell's corners sit on the voxel lattice at the reference's eight offsets from the cell (lvr2.cpp:88-98)
+    off = np.array([[0, 0, 0], [-1, 0, 0], [-1, -1, 0], [0, -1, 0], [0, 0, -1], [-1, 0, -1], [-1, -1, -1], [0, -1, -1]], np.float32) * np.float32(0.05)
+    corner0 = qp[cells[:, 0], :3]
+    for i in range(1, 8):
+        assert np.allclose(qp[cells[:, i], :3] - corner0, -off[i], atol=1e-4)
+    # decoded distances follow the analytic sphere like the walk above
+    rad = np.linalg.norm(qp[:, :3].astype(np.float64), axis=1)
+    assert np.mean(np.abs(qp[:, 3] - np.clip(5.0 - rad, -0.1, 0.1)) > 0.03) < 0.02

@@ -196,3 +196,27 @@ def test_wide_truncation_band_falls_back_to_block_path(chad_lib, oracle_lib):
     g.finalize_active(); o.finalize_active()
     _assert_same_state(g, o)
     g.close(); o.close()
+
+
+def test_device_dag_reader_matches_the_quantised_voxels(chad_lib, oracle_lib):
+    """chad_query_voxels walks the finalised DAG on the device (get_child_addr / try_get_lc, levels.hpp:147-192): every voxel of the
+    closed submap must come back with the byte cluster.hpp:13-26 quantises its distance to, every other key as 0xFF."""
+    from chad_tsdf_b200 import TSDFMap
+    from oracle import bindings as ob
+    w = synth.WORKLOADS["cfg0_single_64beam"]
+    g, o = TSDFMap(w.sdf_res, w.sdf_trunc), ob.OracleMap(w.sdf_res, w.sdf_trunc)
+    pts, pos = w.scan(0)
+    g.insert(pts, pos); o.insert(pts, pos)
+    keys, sd_bits, _ = o.voxels()
+    g.finalize_active(); o.finalize_active()
+    sd = sd_bits.view(np.float32)
+    t = np.float32(1.0) / np.float32(w.sdf_trunc)
+    q = np.clip(sd * t, np.float32(-1.0), np.float32(1.0)) * np.float32(127.0) + np.float32(127.0)   # cluster.hpp:19-26, fp32, truncation
+    expect = q.astype(np.uint64).astype(np.uint8)
+    got = g.query_voxels(0, keys)
+    assert np.array_equal(got, expect)
+    absent = np.setdiff1d(keys + np.uint64(1 << 30), keys)[:10000]  # same region, far-away keys
+    assert np.all(g.query_voxels(0, absent) == 0xFF)
+    empty_neighbours = np.setdiff1d(keys ^ np.uint64(1), keys)       # the other voxel of a pair: mostly absent leaves of PRESENT clusters
+    assert np.all(g.query_voxels(0, empty_neighbours) == 0xFF)
+    g.close(); o.close()
