@@ -126,16 +126,14 @@ struct chad_ctx {
     u32 fin_chunks = 0;           // exact count (known after part 1)
     u32 fin_level_nodes[20] = {}; // exact node count per level (known after part 1)
     cudaEvent_t submap_closed = nullptr, fin_p1_done = nullptr, fin_done = nullptr;
-    cudaEvent_t fin_t0 = nullptr, fin_t1 = nullptr, fin_t2 = nullptr, fin_t3 = nullptr;  // profiling: part 1 = t0..t1, part 2 = t2..t3
+    cudaEvent_t fin_t0 = nullptr, fin_t3 = nullptr;  // profiling: the whole finalize
     struct FinHost {              // pinned read-back area
         u32 scalars[16];
         u32 level_nodes[20];
-        u64 level_new[20];        // per level: (new records << 32) | new words
         u32 root[2];
         LevelCounters counters[CHAD_NUM_LEVELS];
     }* h_fin = nullptr;
     DevBuf f_counters, f_partial;  // device LevelCounters[21]; partial sums of the persistent levels kernel
-    DevBuf f_level_new;           // device u64[20]
     bool fin_external = false;    // the finalize in flight consumes a caller-provided chunk stream (sharded mode): clear `table`, not `table2`
 
     // Morton-range sharding (multi-GPU, driven from the host language binding)
@@ -145,9 +143,8 @@ struct chad_ctx {
     // finalize work buffers
     size_t cap_chunks = 0;
     DevBuf f_sorted;  // full chunk keys in ascending order (gather output)
-    DevBuf f_ids[2], f_slots[2], f_cells, f_tsdf, f_addr[2], f_head, f_head_rank, f_cand, f_slot_of, f_is_new, f_rank, f_radix_ws, f_scan_ws, f_scalars;
+    DevBuf f_ids[2], f_slots[2], f_cells, f_tsdf, f_addr[2], f_head_rank, f_cand, f_slot_of, f_is_new, f_rank, f_radix_ws, f_scan_ws, f_scalars;
     RadixWorkspace f_rws{};
-    u64* h_scalars = nullptr;  // pinned, 8 x u64
 
     Level levels[CHAD_NUM_LEVELS];
     chad_stats stats{};
@@ -605,7 +602,6 @@ int ensure_finalize_capacity(chad_ctx* ctx, size_t chunks) {
     }
     TRY(dev_ensure(ctx, ctx->f_cells, nc * 64));
     TRY(dev_ensure(ctx, ctx->f_tsdf, nc * 8));
-    TRY(dev_ensure(ctx, ctx->f_head, nc * 4));
     TRY(dev_ensure(ctx, ctx->f_head_rank, nc * 4));
     TRY(dev_ensure(ctx, ctx->f_cand, nc * 2 * 9 * 4));
     TRY(dev_ensure(ctx, ctx->f_slot_of, (nc * 2 + 2) * 4));
@@ -944,7 +940,7 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     CREATE_TRY(cudaEventCreateWithFlags(&ctx->submap_closed, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&ctx->fin_p1_done, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&ctx->fin_done, cudaEventDisableTiming));
-    for (cudaEvent_t* e : {&ctx->fin_t0, &ctx->fin_t1, &ctx->fin_t2, &ctx->fin_t3}) CREATE_TRY(cudaEventCreate(e));
+    for (cudaEvent_t* e : {&ctx->fin_t0, &ctx->fin_t3}) CREATE_TRY(cudaEventCreate(e));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_fin), sizeof(chad_ctx::FinHost)));
     std::memset(ctx->h_fin, 0, sizeof(chad_ctx::FinHost));
     for (int b = 0; b < 2; b++) {
@@ -960,7 +956,6 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_table_count), 64));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_table_count2), 64));
     *ctx->h_table_count2 = 0;
-    CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_scalars), 64));
     *ctx->h_table_count = 0;
     CREATE_TRY(radix_sort_init());
     CREATE_TRY(blocks_init());
@@ -984,7 +979,6 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     int r = dev_ensure(ctx, ctx->d_scans, sizeof(BatchScans));
     if (r == CHAD_OK) r = dev_ensure(ctx, ctx->d_plan, 2 * sizeof(BatchPlan));
     if (r == CHAD_OK) r = dev_ensure(ctx, ctx->f_scalars, 256);
-    if (r == CHAD_OK) r = dev_ensure(ctx, ctx->f_level_new, 256);
     if (r != CHAD_OK) return bail(r);
     CREATE_TRY(cudaMemsetAsync(ctx->d_plan.p, 0, 2 * sizeof(BatchPlan), ctx->stream));
     r = table_alloc(ctx, ctx->table, ctx->t_keys, ctx->t_cells, ctx->t_count, ctx->t_list, 1ull << 20);
@@ -1018,10 +1012,10 @@ void chad_destroy(chad_ctx* ctx) {
     if (ctx->group_stream) cudaStreamSynchronize(ctx->group_stream);
     if (ctx->fold_stream) cudaStreamSynchronize(ctx->fold_stream);
     if (ctx->fin_stream) cudaStreamSynchronize(ctx->fin_stream);
-    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->t2_list, &ctx->t_list, &ctx->f_counters, &ctx->f_partial, &ctx->f_level_new, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->sh_tuples, &ctx->sh_scalars, &ctx->bt_mem, &ctx->run_mem[0], &ctx->run_mem[1], &ctx->radix_ws2, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
+    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->t2_list, &ctx->t_list, &ctx->f_counters, &ctx->f_partial, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->sh_tuples, &ctx->sh_scalars, &ctx->bt_mem, &ctx->run_mem[0], &ctx->run_mem[1], &ctx->radix_ws2, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
                       &ctx->sorted_keys, &ctx->sorted_order, &ctx->xyz_sorted, &ctx->normals, &ctx->seg_info, &ctx->counts, &ctx->offsets,
                       &ctx->radix_ws, &ctx->scan_ws, &ctx->t_keys, &ctx->t_cells, &ctx->t_count, &ctx->f_sorted, &ctx->f_ids[0], &ctx->f_ids[1], &ctx->f_slots[0],
-                      &ctx->f_slots[1], &ctx->f_cells, &ctx->f_tsdf, &ctx->f_addr[0], &ctx->f_addr[1], &ctx->f_head, &ctx->f_head_rank, &ctx->f_cand,
+                      &ctx->f_slots[1], &ctx->f_cells, &ctx->f_tsdf, &ctx->f_addr[0], &ctx->f_addr[1], &ctx->f_head_rank, &ctx->f_cand,
                       &ctx->f_slot_of, &ctx->f_is_new, &ctx->f_rank, &ctx->f_radix_ws, &ctx->f_scan_ws, &ctx->f_scalars};
     for (DevBuf* b : bufs) dev_free(*b);
     for (auto& L : ctx->levels) { dev_free(L.raw); dev_free(L.entries); dev_free(L.first); }
@@ -1038,12 +1032,11 @@ void chad_destroy(chad_ctx* ctx) {
     if (ctx->h_table_count) cudaFreeHost(ctx->h_table_count);
     if (ctx->h_table_count2) cudaFreeHost(ctx->h_table_count2);
     if (ctx->h_fin) cudaFreeHost(ctx->h_fin);
-    for (cudaEvent_t e : {ctx->submap_closed, ctx->fin_p1_done, ctx->fin_done, ctx->fin_t0, ctx->fin_t1, ctx->fin_t2, ctx->fin_t3}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ctx->submap_closed, ctx->fin_p1_done, ctx->fin_done, ctx->fin_t0, ctx->fin_t3}) if (e) cudaEventDestroy(e);
     if (ctx->fin_stream) cudaStreamDestroy(ctx->fin_stream);
     for (cudaEvent_t e : {ctx->fold_done[0], ctx->fold_done[1], ctx->submap_closed2, ctx->emit_done}) if (e) cudaEventDestroy(e);
     if (ctx->fold_stream) cudaStreamDestroy(ctx->fold_stream);
     if (ctx->group_stream) cudaStreamDestroy(ctx->group_stream);
-    if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     if (ctx->front_done) cudaEventDestroy(ctx->front_done);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);

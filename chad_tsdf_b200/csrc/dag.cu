@@ -9,6 +9,7 @@
 // for each node of that level in ascending Morton order, TSDF record then weight record, and the
 // sequences of different levels are independent. That makes each level a
 // data-parallel first-occurrence dedup:
+// (clusters: one small kernel per step below; node levels: the same five steps inside dag_levels_kernel)
 //   probe   : find-or-insert every record of the sequence in the level's resident hash set; records
 //             not yet resident keep the MINIMUM sequence index that carried them (atomicMin);
 //   mark    : a record is new iff it is the first occurrence of a non-resident value;
@@ -151,143 +152,11 @@ __global__ void __launch_bounds__(DAG_THREADS) cluster_resolve_kernel(const u64*
 // ------------------------------------------------------------------------------------------
 // node levels: submap.hpp:31-61, levels.hpp:57-88
 // ------------------------------------------------------------------------------------------
-// Number of nodes every level will receive, from the sorted chunk ids alone: chunk i starts a new level-d node iff
-// (id >> 3(20-d)) differs from its predecessor's, i.e. iff the highest differing bit of the two ids is >= 3(20-d).
-// counts[d] = nodes at level d (d = 0..19), so the host can size every level exactly with ONE read-back.
-__global__ void __launch_bounds__(DAG_THREADS) level_counts_kernel(const u64* __restrict__ chunk_ids, const u32* __restrict__ d_chunks,
-                                                                   u32* __restrict__ counts /*[20]*/) {
-    __shared__ u32 s_cnt[20];
-    if (threadIdx.x < 20) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const u32 n = *d_chunks;
-    for (u32 i = blockIdx.x * DAG_THREADS + threadIdx.x; i < n; i += gridDim.x * DAG_THREADS) {
-        u32 levels;  // number of levels (counted from level 19 upwards) at which chunk i opens a new node
-        if (i == 0) levels = 20;
-        else {
-            const u64 x = chunk_ids[i] ^ chunk_ids[i - 1];
-            const u32 hb = 63 - __clzll(x);      // highest differing bit (ids are distinct)
-            levels = min(20u, hb / 3);           // opens level d iff hb >= 3(20-d)  <=>  20-d <= hb/3
-        }
-        // warp-aggregate: lanes opening at least j levels
-        for (u32 j = 1; j <= 20; j++) {
-            const u32 m = __ballot_sync(__activemask(), levels >= j);
-            if (m == 0) break;
-            if ((threadIdx.x & 31) == (u32)(__ffs(m) - 1)) atomicAdd(&s_cnt[20 - j], (u32)__popc(m));
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < 20 && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
-}
-
-__global__ void __launch_bounds__(DAG_THREADS) group_heads_kernel(const u64* __restrict__ child_ids, u32 n, u32* __restrict__ head) {
-    const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
-    if (i >= n) return;
-    head[i] = (i == 0 || (child_ids[i] >> 3) != (child_ids[i - 1] >> 3)) ? 1u : 0u;
-}
-
-// One thread per parent (sitting on its first child): two candidate records, TSDF then weight, each
-// 9 words = child mask + children compacted in ascending child index, zero padded (levels.hpp:63-74).
-__global__ void __launch_bounds__(DAG_THREADS) node_candidates_kernel(const u64* __restrict__ child_ids, const u32* __restrict__ child_addr,
-                                                                      const u32* __restrict__ head, const u32* __restrict__ head_rank, u32 n,
-                                                                      u32* __restrict__ cand, u64* __restrict__ parent_ids) {
-    const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
-    if (i >= n || !head[i]) return;
-    const u32 p = head_rank[i];
-    const u64 pid = child_ids[i] >> 3;
-    u32 rt[9], rw[9];
-#pragma unroll
-    for (int q = 0; q < 9; q++) { rt[q] = 0; rw[q] = 0; }
-    u32 c = 0;
-    for (u32 j = i; j < n && (child_ids[j] >> 3) == pid; j++) {
-        const u32 bit = 1u << (u32)(child_ids[j] & 7ull);
-        rt[0] |= bit; rw[0] |= bit;
-        c++;
-        // static indexing keeps the records in registers
-#pragma unroll
-        for (int q = 1; q < 9; q++)
-            if ((u32)q == c) { rt[q] = child_addr[2 * j]; rw[q] = child_addr[2 * j + 1]; }
-    }
-#pragma unroll
-    for (int q = 0; q < 9; q++) {
-        cand[size_t(2 * p) * 9 + q] = rt[q];
-        cand[size_t(2 * p + 1) * 9 + q] = rw[q];
-    }
-    parent_ids[p] = pid;
-}
-
 __device__ __forceinline__ u32 node_tag(const u32* __restrict__ rec) {
     u64 h = rec[0];
 #pragma unroll
     for (int q = 1; q < 9; q++) h = mix64(h ^ (u64(rec[q]) << 8) ^ (u64(q) << 48));
     return (u32)(mix64(h) >> 32);
-}
-
-__global__ void __launch_bounds__(DAG_THREADS) node_probe_kernel(u64* entries, u32* first, u64 capacity, const u32* __restrict__ cand, u32 n_records,
-                                                                 const u32* __restrict__ raw, u32* __restrict__ slot_of, u32* d_error) {
-    const u32 e = blockIdx.x * DAG_THREADS + threadIdx.x;
-    if (e >= n_records) return;
-    u32 rec[9];
-#pragma unroll
-    for (int q = 0; q < 9; q++) rec[q] = cand[size_t(e) * 9 + q];
-    const u32 tag = node_tag(rec);
-    const u32 nchild = __popc(rec[0]);
-    const u64 mask = capacity - 1;
-    u64 slot = tag & mask;
-    for (u64 probes = 0; probes < capacity; probes++) {
-        u64 ent = ld_entry(&entries[slot]);
-        if (ent == 0) {
-            const u64 mine = (u64(tag) << 32) | (REF_PENDING | e);
-            ent = atomicCAS(&entries[slot], 0ull, mine);
-            if (ent == 0) { note_first(&first[slot], e); slot_of[e] = (u32)slot; return; }
-        }
-        if ((u32)(ent >> 32) == tag) {
-            const u32 ref = (u32)ent;
-            // levels.hpp:27-44: same mask and the same children
-            const u32* other = (ref & REF_PENDING) ? (cand + size_t(ref & ~REF_PENDING) * 9) : (raw + ref);
-            bool eq = (other[0] & 0xFFu) == rec[0];
-            for (u32 q = 1; eq && q <= nchild; q++) eq = other[q] == rec[q];
-            if (eq) {
-                if (ref & REF_PENDING) note_first(&first[slot], e);
-                slot_of[e] = (u32)slot;
-                return;
-            }
-        }
-        slot = (slot + 1) & mask;
-    }
-    atomicOr(d_error, ERRF_DEDUP_FULL);
-    slot_of[e] = 0;
-}
-
-// packed (words << 0) | (1 << 32) for new records, 0 otherwise
-__global__ void __launch_bounds__(DAG_THREADS) node_mark_kernel(const u64* __restrict__ entries, const u32* __restrict__ first,
-                                                                const u32* __restrict__ slot_of, const u32* __restrict__ cand, u32 n_records,
-                                                                u64* __restrict__ is_new) {
-    const u32 e = blockIdx.x * DAG_THREADS + threadIdx.x;
-    if (e >= n_records) return;
-    const u32 slot = slot_of[e];
-    const u32 ref = (u32)entries[slot];
-    const bool fresh = (ref & REF_PENDING) && first[slot] == e;
-    is_new[e] = fresh ? ((1ull << 32) | (1u + (u32)__popc(cand[size_t(e) * 9]))) : 0ull;
-}
-
-__global__ void __launch_bounds__(DAG_THREADS) node_commit_kernel(u64* entries, u32* first, const u32* __restrict__ slot_of,
-                                                                  const u64* __restrict__ is_new, const u64* __restrict__ rank, u32 n_records,
-                                                                  const u32* __restrict__ cand, u32* __restrict__ raw, u32 occupied_before) {
-    const u32 e = blockIdx.x * DAG_THREADS + threadIdx.x;
-    if (e >= n_records || is_new[e] == 0) return;
-    const u32 slot = slot_of[e];
-    const u32 addr = occupied_before + (u32)rank[e];  // levels.hpp:77: address = _occupied_n before the add
-    const u32 words = (u32)is_new[e];
-    for (u32 q = 0; q < words; q++) raw[addr + q] = cand[size_t(e) * 9 + q];
-    entries[slot] = (entries[slot] & 0xFFFFFFFF00000000ull) | addr;
-    first[slot] = FIRST_IDLE;
-}
-
-__global__ void __launch_bounds__(DAG_THREADS) node_resolve_kernel(const u64* __restrict__ entries, const u32* __restrict__ slot_of, u32 n_records,
-                                                                   u32* __restrict__ addr_out) {
-    const u32 e = blockIdx.x * DAG_THREADS + threadIdx.x;
-    if (e >= n_records) return;
-    addr_out[e] = (u32)entries[slot_of[e]];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -578,38 +447,6 @@ int launch_dag_query(cudaStream_t s, const DagReadArgs& args, u32 root, const u6
     if (!n) return 0;
     dag_query_kernel<<<blocks_for(n), DAG_THREADS, 0, s>>>(args, root, keys, n, out);
     return 1;
-}
-
-int launch_level_counts(cudaStream_t s, const u64* chunk_ids, const u32* d_chunks, u32 max_chunks, u32* counts20, int num_sms) {
-    cudaMemsetAsync(counts20, 0, 20 * 4, s);
-    if (!max_chunks) return 0;
-    const u32 want = blocks_for(max_chunks), cap = (u32)num_sms * 4;
-    level_counts_kernel<<<want < cap ? want : cap, DAG_THREADS, 0, s>>>(chunk_ids, d_chunks, counts20);
-    return 1;
-}
-
-int launch_group_heads(cudaStream_t s, const u64* child_ids, u32 n_children, u32* head, u32* head_rank, void* scan_ws, u32* d_parents) {
-    if (!n_children) { cudaMemsetAsync(d_parents, 0, 4, s); return 0; }
-    group_heads_kernel<<<blocks_for(n_children), DAG_THREADS, 0, s>>>(child_ids, n_children, head);
-    return 1 + exclusive_scan<u32, u32>(s, head, head_rank, n_children, scan_ws, d_parents);
-}
-
-int launch_node_candidates(cudaStream_t s, const u64* child_ids, const u32* child_addr, const u32* head, const u32* head_rank, u32 n_children,
-                           u32* cand, u64* parent_ids) {
-    if (!n_children) return 0;
-    node_candidates_kernel<<<blocks_for(n_children), DAG_THREADS, 0, s>>>(child_ids, child_addr, head, head_rank, n_children, cand, parent_ids);
-    return 1;
-}
-
-int launch_node_dedup(cudaStream_t s, const DedupTable& t, const u32* cand, u32 n_records, u32* raw, u32 occupied_before, u32* slot_of,
-                      u64* is_new, u64* rank, void* scan_ws, u32* addr_out, u64* d_new_packed, u32* d_error) {
-    if (!n_records) { cudaMemsetAsync(d_new_packed, 0, 8, s); return 0; }
-    node_probe_kernel<<<blocks_for(n_records), DAG_THREADS, 0, s>>>(t.entries, t.first, t.capacity, cand, n_records, raw, slot_of, d_error);
-    node_mark_kernel<<<blocks_for(n_records), DAG_THREADS, 0, s>>>(t.entries, t.first, slot_of, cand, n_records, is_new);
-    int launches = 2 + exclusive_scan<u64, u64>(s, is_new, rank, n_records, scan_ws, d_new_packed);
-    node_commit_kernel<<<blocks_for(n_records), DAG_THREADS, 0, s>>>(t.entries, t.first, slot_of, is_new, rank, n_records, cand, raw, occupied_before);
-    node_resolve_kernel<<<blocks_for(n_records), DAG_THREADS, 0, s>>>(t.entries, slot_of, n_records, addr_out);
-    return launches + 2;
 }
 
 }  // namespace chadgpu

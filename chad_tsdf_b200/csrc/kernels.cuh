@@ -149,15 +149,5 @@ int launch_cluster_build(cudaStream_t s, const void* gathered_cells, const u32* 
 // cluster level: sequence tsdf_0, W, tsdf_1, W, ...; addr_out[2i] / addr_out[2i+1] = tsdf / weight cluster address of chunk i
 int launch_cluster_dedup(cudaStream_t s, const DedupTable& t, const u64* tsdf_values, const u32* d_chunks, u32 max_chunks, u64* raw, u32 uniques_before,
                          u32* slot_of, u32* is_new, u32* rank, void* scan_ws, u32* addr_out, u32* d_new_count, u32* d_error);
-// counts20[d] = number of level-d nodes the sorted chunk ids will produce
-int launch_level_counts(cudaStream_t s, const u64* chunk_ids, const u32* d_chunks, u32 max_chunks, u32* counts20, int num_sms);
-// children (ids ascending) -> head flags, dense parent index on the heads, *d_parents = parent count
-int launch_group_heads(cudaStream_t s, const u64* child_ids, u32 n_children, u32* head, u32* head_rank, void* scan_ws, u32* d_parents);
-// 2 candidate records (TSDF, weight) of 9 words per parent + the parent ids
-int launch_node_candidates(cudaStream_t s, const u64* child_ids, const u32* child_addr, const u32* head, const u32* head_rank, u32 n_children,
-                           u32* cand, u64* parent_ids);
-// node level dedup over n_records = 2 * parents candidates; *d_new_packed = (new records << 32) | new words
-int launch_node_dedup(cudaStream_t s, const DedupTable& t, const u32* cand, u32 n_records, u32* raw, u32 occupied_before, u32* slot_of,
-                      u64* is_new, u64* rank, void* scan_ws, u32* addr_out, u64* d_new_packed, u32* d_error);
 
 }  // namespace chadgpu
