@@ -38,6 +38,7 @@ SYMBOLS = {
     "chad_destroy": (None, [_P]),
     "chad_last_error": (C.c_char_p, [_P]),
     "chad_insert": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "chad_insert_async": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "chad_insert_device": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "chad_flush": (C.c_int, [_P]),
     "chad_finalize_active": (C.c_int, [_P]),

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cstdint>
 #include <string>
 #include <vector>
 
@@ -54,6 +55,10 @@ size_t next_pow2(size_t v) {
 struct chad_ctx {
     int device = 0, num_sms = 148;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t xyz_free[2] = {nullptr, nullptr};      // the point stage has finished reading d_xyz[b]: the batch after next may fill it
+    bool xyz_free_valid[2] = {false, false};
+    cudaEvent_t scans_uploaded[2] = {nullptr, nullptr}; // h_scans_pinned[b] has been copied to the device: the host may rewrite it
+    bool scans_uploaded_valid[2] = {false, false};
     MapParams mp{};
     int max_batch = 16;
     std::string error;
@@ -78,13 +83,13 @@ struct chad_ctx {
     DevBuf d_scans, d_plan;       // d_plan = BatchPlan[2]: the batch being queued and the batch whose fold is pending
     BatchPlan* h_plan = nullptr;  // pinned BatchPlan[2]
     int plan_slot = 0;            // slot of the batch being assembled
-    int pending_slot = 0;         // slot of the batch whose fold is pending
+    struct PendingFold { int slot; bool runs; u32 max_pairs; bool close; };
+    PendingFold pend[2];          // batches whose front is queued but whose fold is not (oldest first): the fold needs the batch's block
+    int n_pend = 0;               // count on the host (table sizing), so it is launched as soon as the front's read-back has arrived --
+                                  // by any later API call that finds it there, at the latest when the batch's plan slot is needed again
     u32* h_table_count = nullptr; // pinned: chunk count of `table` after its last fold
     u32* h_table_count2 = nullptr; // pinned: same for `table2`
-    cudaEvent_t front_done = nullptr;
-    bool fold_pending = false;
-    bool close_pending = false;   // the batch whose fold is pending is the last one of its submap: finalize starts right after that fold
-    u32 pending_max_pairs = 0;
+    cudaEvent_t front_done[2] = {nullptr, nullptr};  // per plan slot: the front's plan read-back has arrived
 
     // batch work buffers
     DevBuf bt_mem;                  // block table of the block-binned pair path
@@ -102,7 +107,7 @@ struct chad_ctx {
     RadixWorkspace rws2{};
     u64 prev_fold_bound = 0;        // chunk bound of the previous fold of the active submap if its exact count may not have arrived yet
     cudaStream_t prof_stream = nullptr;  // stream the instrumentation events are recorded on
-    bool pending_runs = false;      // the batch whose fold is pending went through the tile-run path
+    cudaStream_t last_fold_stream = nullptr;  // stream the most recent fold (and the copy of the table counter behind it) was queued on
     BatchPlan* h_plan_fold = nullptr;  // pinned BatchPlan[2]: the plan as the fused fold left it (distinct voxels, deferred errors)
     bool fold_stats_pending[2] = {false, false};
     DevBuf pk_a, pk_b, pv_a, pv_b;  // point-sort ping-pong (N-sized): separate from the pair buffers so that the next batch's point
@@ -364,15 +369,26 @@ void account_fold_stats(chad_ctx* ctx, int only_slot = -1) {
     }
 }
 
-// launch the fold of the batch whose front has been queued (see the file comment)
-int complete_pending_fold(chad_ctx* ctx) {
-    if (!ctx->fold_pending) return CHAD_OK;
-    ctx->fold_pending = false;
-    const int slot = ctx->pending_slot;
-    CUDA_TRY(ctx, cudaEventSynchronize(ctx->front_done));
+// Launch the fold of the oldest batch whose front has been queued. block = false: only if its read-back has arrived already
+// (*launched tells). The folds are launched in batch order.
+int complete_one_fold(chad_ctx* ctx, bool block, bool* launched) {
+    *launched = false;
+    if (ctx->n_pend == 0) return CHAD_OK;
+    const chad_ctx::PendingFold pf = ctx->pend[0];
+    const int slot = pf.slot;
+    if (!block) {
+        const cudaError_t q = cudaEventQuery(ctx->front_done[slot]);
+        if (q == cudaErrorNotReady) { cudaGetLastError(); return CHAD_OK; }
+        CUDA_TRY(ctx, q);
+    } else {
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->front_done[slot]));
+    }
+    ctx->pend[0] = ctx->pend[1];
+    ctx->n_pend--;
+    *launched = true;
     account_fold_stats(ctx, slot);  // the pair stage of this batch waited for the fold that used this slot before
     BatchPlan plan = ctx->h_plan[slot];
-    const bool runs = ctx->pending_runs;
+    const bool runs = pf.runs;
     ctx->table_count_known = *ctx->h_table_count;
     ctx->stats.updates += plan.n_pairs;
     ctx->stats.key_bits_points = plan.nbits_points;
@@ -387,7 +403,6 @@ int complete_pending_fold(chad_ctx* ctx) {
         ctx->stats.scan_voxels += plan.n_segments;
     }
     if (plan.error) {
-        ctx->close_pending = false;
         CUDA_TRY(ctx, cudaMemsetAsync(plan_field<u32>(ctx, slot, offsetof(BatchPlan, error)), 0, 4, ctx->stream));
         return error_from_flags(ctx, plan.error);
     }
@@ -401,7 +416,7 @@ int complete_pending_fold(chad_ctx* ctx) {
         // the fused fold runs on its own stream, concurrently with the next batch's front (point stage, ray walk, descriptor sort)
         cudaStream_t fs = ctx->fold_stream;
         fold_on = fs;
-        CUDA_TRY(ctx, cudaStreamWaitEvent(fs, ctx->front_done, 0));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(fs, ctx->front_done[slot], 0));
         ctx->prof_stream = fs;
         if (plan.n_pairs) PROF(ctx, PC_RUNS_FOLD, launch_runs_fold(fs, (slot ? ctx->keys_b : ctx->keys_a).as<u64>(), ctx->rb[slot], plan_ptr(ctx, slot), ctx->table, ctx->num_sms));
         ctx->prof_stream = nullptr;
@@ -413,24 +428,37 @@ int complete_pending_fold(chad_ctx* ctx) {
     } else {
         ctx->prev_fold_bound = 0;
         PROF(ctx, PC_FOLD, launch_fold(ctx->stream, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(),
-                                       ctx->pending_max_pairs, plan_ptr(ctx, slot), ctx->table, ctx->num_sms));
+                                       pf.max_pairs, plan_ptr(ctx, slot), ctx->table, ctx->num_sms));
     }
     ctx->stats.kernel_launches += launches;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_table_count, ctx->table.count, 4, cudaMemcpyDeviceToHost, fold_on));
     ctx->stats.d2h_bytes += 4;
+    ctx->last_fold_stream = fold_on;
     if (runs) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->fold_done[slot], ctx->fold_stream));
         ctx->fold_done_valid[slot] = true;
     }
     CUDA_TRY(ctx, cudaGetLastError());
-    if (ctx->close_pending) {  // that was the submap's last batch: swap tables and start its asynchronous finalize
-        ctx->close_pending = false;
+    if (pf.close) {  // that was the submap's last batch: swap tables and start its asynchronous finalize
         const u64 bound = count_bound;
         if (bound >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
         (void)bound;
         TRY(finalize_begin(ctx, 0, false, fold_on));
         ctx->stats.resident_clusters = 0;
     }
+    return CHAD_OK;
+}
+
+// every pending fold, waiting for the fronts
+int complete_pending_fold(chad_ctx* ctx) {
+    bool launched;
+    while (ctx->n_pend) TRY(complete_one_fold(ctx, true, &launched));
+    return CHAD_OK;
+}
+// the pending folds whose front has already reported
+int poll_folds(chad_ctx* ctx) {
+    bool launched = true;
+    while (ctx->n_pend && launched) TRY(complete_one_fold(ctx, false, &launched));
     return CHAD_OK;
 }
 
@@ -466,8 +494,11 @@ int process_front(chad_ctx* ctx) {
     const u32 n = ctx->batch_points, ns = ctx->batch_scans;
     cudaStream_t s = ctx->stream;
     ctx->h_scans.offset[ns] = n;
+    if (ctx->scans_uploaded_valid[b]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->scans_uploaded[b]));  // (two batches ago: long done)
     *ctx->h_scans_pinned[b] = ctx->h_scans;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scans.p, ctx->h_scans_pinned[b], sizeof(BatchScans), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->scans_uploaded[b], s));
+    ctx->scans_uploaded_valid[b] = true;
     CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[b], ctx->copy_stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->copy_done[b], 0));
     if (ctx->stage_busy[b]) CUDA_TRY(ctx, cudaEventRecord(ctx->stage_copied[b], ctx->copy_stream));
@@ -476,9 +507,14 @@ int process_front(chad_ctx* ctx) {
     const BatchScans* scans = ctx->d_scans.as<BatchScans>();
     u64 launches = 0;
     const LaunchHook* hook = ctx->profiling ? &ctx->hook : nullptr;
-    // this slot's plan / records / descriptors were last used by the fold of two batches ago (on fold_stream)
+    // this slot's plan / records / descriptors were last used by the batch of two batches ago: its fold must have been launched ...
+    while (ctx->n_pend && ctx->pend[0].slot == slot) { bool launched; TRY(complete_one_fold(ctx, true, &launched)); }
+    if (ctx->n_pend == 2) { bool launched; TRY(complete_one_fold(ctx, true, &launched)); }
+    // ... and the device waits for it (on fold_stream) before touching the slot
     if (ctx->fold_done_valid[slot]) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->fold_done[slot], 0));
     queue_point_stage(ctx, slot, b, n, ns);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->xyz_free[b], s));  // the point stage is the only reader of d_xyz[b]
+    ctx->xyz_free_valid[b] = true;
     const bool use_runs = ctx->pair_path == 2 && n <= runs_max_batch_points() && ctx->rb[0].capacity != 0;
     const bool use_blocks = !use_runs && ctx->pair_path != 1 && n <= blocks_max_batch_points();
     if (!use_blocks && !use_runs) {
@@ -488,8 +524,10 @@ int process_front(chad_ctx* ctx) {
     }
     ctx->stats.kernel_launches += launches;
     launches = 0;
-    // ---- the previous batch's fold: its pairs live in the buffers the pair stage is about to reuse ----
-    TRY(complete_pending_fold(ctx));
+    // ---- the previous batch's fold. The tile-run path keeps its updates in per-slot buffers, so the fold is launched only if its
+    //      front has reported already (the host does not wait here: it goes on to queue this batch and to copy the next scans);
+    //      the other paths reuse the pair buffers and fold on this stream: everything before them must be queued first ----
+    if (use_runs) TRY(poll_folds(ctx)); else TRY(complete_pending_fold(ctx));
     // ---- pair stage ----
     const size_t max_pairs = size_t(n) * ctx->mp.max_ray_voxels;
     if (use_runs) {
@@ -523,15 +561,12 @@ int process_front(chad_ctx* ctx) {
     cudaStream_t plan_on = use_runs ? ctx->group_stream : s;
     CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->h_plan[slot], plan, sizeof(BatchPlan), cudaMemcpyDeviceToHost, plan_on));
     ctx->stats.d2h_bytes += sizeof(BatchPlan);
-    CUDA_TRY(ctx, cudaEventRecord(ctx->front_done, plan_on));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->front_done[slot], plan_on));
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->stats.kernel_launches += launches;
     ctx->stats.batches++;
-    ctx->fold_pending = true;
-    ctx->pending_runs = use_runs;
-    ctx->pending_slot = slot;
+    ctx->pend[ctx->n_pend++] = chad_ctx::PendingFold{slot, use_runs, (u32)max_pairs, false};
     ctx->plan_slot ^= 1;
-    ctx->pending_max_pairs = (u32)max_pairs;
     ctx->cur ^= 1;
     ctx->batch_points = 0;
     ctx->batch_scans = 0;
@@ -821,20 +856,14 @@ int finalize_finish(chad_ctx* ctx) {
 // device here. lazy = false (chad_finalize_active): queue everything now.
 int finalize_submap(chad_ctx* ctx, bool lazy) {
     TRY(process_front(ctx));
-    if (ctx->fold_pending) {
-        ctx->close_pending = true;
+    if (ctx->n_pend) {
+        ctx->pend[ctx->n_pend - 1].close = true;  // the submap's last batch: the finalize begins right after its fold
         if (lazy) return CHAD_OK;
         return complete_pending_fold(ctx);  // waits for the front of the last batch, queues its fold, begins the finalize
     }
-    // no batch in flight: the exact count of the last fold may not have been read yet
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
-    ctx->fold_in_flight = false;
-    ctx->prev_fold_bound = 0;
-    ctx->table_count_known = *ctx->h_table_count;
-    if (ctx->table_count_known >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
-    TRY(finalize_begin(ctx, 0, false, ctx->stream));
+    // every fold of the submap has been launched already: the copy of the table counter that followed the last one is in flight on
+    // that fold's stream (or has arrived); the finalize is queued when it is there -- no host wait here either
+    TRY(finalize_begin(ctx, 0, false, ctx->last_fold_stream ? ctx->last_fold_stream : ctx->stream));
     ctx->stats.resident_clusters = 0;
     return CHAD_OK;
 }
@@ -843,6 +872,7 @@ int begin_scan(chad_ctx* ctx, size_t n, const float position[3], bool* skip) {
     *skip = false;
     if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
     TRY(finalize_poll(ctx));
+    TRY(poll_folds(ctx));
     // tsdf.cpp:46-61: a pose more than 5 m (strictly) from the submap's FIRST pose finalises the submap;
     // the triggering scan goes entirely into the new one
     if (!ctx->has_pose) {
@@ -874,6 +904,16 @@ int begin_scan(chad_ctx* ctx, size_t n, const float position[3], bool* skip) {
     return CHAD_OK;
 }
 
+// first scan of a batch into d_xyz[cur]: the transfers must not overtake the point stage of the batch that used the buffer before
+// (the host no longer waits for that batch: it may be two batches ahead of the device)
+int guard_batch_buffer(chad_ctx* ctx) {
+    const int b = ctx->cur;
+    if (ctx->batch_scans == 0 && ctx->xyz_free_valid[b]) {
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->xyz_free[b], 0));
+    }
+    return CHAD_OK;
+}
+
 int end_scan(chad_ctx* ctx, size_t n, const float position[3]) {
     ctx->h_scans.offset[ctx->batch_scans] = ctx->batch_points;
     std::memcpy(ctx->h_scans.pose[ctx->batch_scans], position, 12);
@@ -881,7 +921,7 @@ int end_scan(chad_ctx* ctx, size_t n, const float position[3]) {
     ctx->batch_points += (u32)n;
     // A burst starts with a short batch: while nothing is in flight the device would only wait for the host to copy a full batch
     // (24 scans = 1.4 ms over PCIe); once a batch is queued the following ones fill up behind it.
-    const u32 target = ctx->fold_pending ? (u32)ctx->max_batch : std::min<u32>((u32)ctx->max_batch, 4u);
+    const u32 target = ctx->n_pend ? (u32)ctx->max_batch : std::min<u32>((u32)ctx->max_batch, 4u);
     if (ctx->batch_scans >= target) TRY(process_front(ctx));
     return CHAD_OK;
 }
@@ -926,6 +966,10 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     ctx->num_sms = prop.multiProcessorCount;
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        CREATE_TRY(cudaEventCreateWithFlags(&ctx->xyz_free[b], cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&ctx->scans_uploaded[b], cudaEventDisableTiming));
+    }
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->fold_stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->group_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 2; b++) CREATE_TRY(cudaEventCreateWithFlags(&ctx->fold_done[b], cudaEventDisableTiming));
@@ -948,7 +992,7 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
         CREATE_TRY(cudaEventCreateWithFlags(&ctx->copy_done[b], cudaEventDisableTiming));
         CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_scans_pinned[b]), sizeof(BatchScans)));
     }
-    CREATE_TRY(cudaEventCreateWithFlags(&ctx->front_done, cudaEventDisableTiming));
+    for (int b = 0; b < 2; b++) CREATE_TRY(cudaEventCreateWithFlags(&ctx->front_done[b], cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreate(&ctx->t0));
     CREATE_TRY(cudaEventCreate(&ctx->t1));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_plan), 2 * sizeof(BatchPlan)));
@@ -1037,27 +1081,36 @@ void chad_destroy(chad_ctx* ctx) {
     for (cudaEvent_t e : {ctx->fold_done[0], ctx->fold_done[1], ctx->submap_closed2, ctx->emit_done}) if (e) cudaEventDestroy(e);
     if (ctx->fold_stream) cudaStreamDestroy(ctx->fold_stream);
     if (ctx->group_stream) cudaStreamDestroy(ctx->group_stream);
-    if (ctx->front_done) cudaEventDestroy(ctx->front_done);
+    for (int b = 0; b < 2; b++) if (ctx->front_done[b]) cudaEventDestroy(ctx->front_done[b]);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int b = 0; b < 2; b++) {
+        if (ctx->xyz_free[b]) cudaEventDestroy(ctx->xyz_free[b]);
+        if (ctx->scans_uploaded[b]) cudaEventDestroy(ctx->scans_uploaded[b]);
+    }
     delete ctx;
 }
 
-int chad_insert(chad_ctx* ctx, const float* xyz, size_t n, const float position[3]) {
+static int insert_host(chad_ctx* ctx, const float* xyz, size_t n, const float position[3], bool wait_for_copy) {
     if (!ctx) return CHAD_ERR_INVALID;
     if (!position || (n && !xyz)) return fail(ctx, CHAD_ERR_INVALID, "NULL argument");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const bool pinned = n && is_pinned_host(xyz);
+    if (!wait_for_copy && n && !pinned) return fail(ctx, CHAD_ERR_INVALID, "chad_insert_async needs page-locked (cudaHostAlloc / cudaHostRegister) memory");
     bool skip;
     TRY(begin_scan(ctx, n, position, &skip));
     if (skip) return CHAD_OK;
+    TRY(guard_batch_buffer(ctx));
     const int b = ctx->cur;
     float* dst = ctx->d_xyz[b].as<float>() + size_t(ctx->batch_points) * 3;
-    if (is_pinned_host(xyz)) {
-        // page-locked caller memory: DMA straight from it and wait for the copy, so the caller may reuse the buffer
+    if (pinned) {
+        // page-locked caller memory: DMA straight from it. chad_insert waits for the copy, so the caller may reuse the buffer at once
+        // (one 3 MB transfer at a time reaches 36-44 of the link's 55 GB/s on an idle GPU: profiles/h2d_probe.py); chad_insert_async
+        // leaves it in flight. Beside the insert kernels either way moves 26-33 GB/s (profiles/timeline.py 24 host)
         CUDA_TRY(ctx, cudaMemcpyAsync(dst, xyz, n * 12, cudaMemcpyHostToDevice, ctx->copy_stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        if (wait_for_copy) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
     } else {
         if (ctx->stage_busy[b] && ctx->batch_scans == 0) {  // first scan of a new batch: the staging buffer may still be draining
             CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_copied[b]));
@@ -1072,6 +1125,9 @@ int chad_insert(chad_ctx* ctx, const float* xyz, size_t n, const float position[
     return end_scan(ctx, n, position);
 }
 
+int chad_insert(chad_ctx* ctx, const float* xyz, size_t n, const float position[3]) { return insert_host(ctx, xyz, n, position, true); }
+int chad_insert_async(chad_ctx* ctx, const float* xyz, size_t n, const float position[3]) { return insert_host(ctx, xyz, n, position, false); }
+
 int chad_insert_device(chad_ctx* ctx, const float* xyz_device, size_t n, const float position[3]) {
     if (!ctx) return CHAD_ERR_INVALID;
     if (!position || (n && !xyz_device)) return fail(ctx, CHAD_ERR_INVALID, "NULL argument");
@@ -1079,6 +1135,7 @@ int chad_insert_device(chad_ctx* ctx, const float* xyz_device, size_t n, const f
     bool skip;
     TRY(begin_scan(ctx, n, position, &skip));
     if (skip) return CHAD_OK;
+    TRY(guard_batch_buffer(ctx));
     float* dst = ctx->d_xyz[ctx->cur].as<float>() + size_t(ctx->batch_points) * 3;
     CUDA_TRY(ctx, cudaMemcpyAsync(dst, xyz_device, n * 12, cudaMemcpyDeviceToDevice, ctx->copy_stream));
     return end_scan(ctx, n, position);
@@ -1220,8 +1277,7 @@ int chad_reset(chad_ctx* ctx) {
     ctx->sticky_error = CHAD_OK;
     ctx->batch_points = 0;
     ctx->batch_scans = 0;
-    ctx->fold_pending = false;
-    ctx->close_pending = false;
+    ctx->n_pend = 0;
     ctx->fold_stats_pending[0] = ctx->fold_stats_pending[1] = false;
     ctx->sh_have_splitters = false;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
@@ -1471,7 +1527,7 @@ int chad_shard_front(chad_ctx* ctx, const float* xyz, const uint32_t* scan_offse
         return fail(ctx, CHAD_ERR_INVALID, "chad_shard_front: bad argument");
     if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (ctx->fold_pending || ctx->batch_scans || ctx->fold_in_flight) TRY(settle(ctx));  // chad_insert traffic in between
+    if (ctx->n_pend || ctx->batch_scans || ctx->fold_in_flight) TRY(settle(ctx));  // chad_insert traffic in between
     TRY(finalize_poll(ctx));  // (a finalize of the previous submap may still be running on its own stream: it only reads its own buffers)
     const size_t n = scan_offsets[n_scans];
     for (int d = 0; d < world; d++) send_counts[d] = 0;

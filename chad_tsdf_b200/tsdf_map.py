@@ -44,8 +44,10 @@ class TSDFMap:
             raise capi.ChadError(rc, self._lib.chad_last_error(self._h).decode())
 
     # -- the reference's API --
-    def insert(self, points, position) -> None:
-        """TSDFMap::insert(points, position): points = (n, 3) float32 (any host memory; pinned memory is DMA'd directly)."""
+    def insert(self, points, position, wait_for_copy: bool = True) -> None:
+        """TSDFMap::insert(points, position): points = (n, 3) float32 (any host memory; pinned memory is DMA'd directly).
+        wait_for_copy=False (page-locked memory only, chad_insert_async): the transfer stays in flight and `points` must not change
+        until flush()."""
         if hasattr(points, "data_ptr"):  # torch tensor (host, possibly pinned) -- no numpy round trip
             assert points.dtype.is_floating_point and points.element_size() == 4 and points.is_contiguous() and not points.is_cuda
             n, p = points.numel() // 3, C.c_void_p(points.data_ptr())
@@ -53,7 +55,8 @@ class TSDFMap:
             points = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
             n, p = points.shape[0], capi.ptr(points)
         pos = np.ascontiguousarray(position, dtype=np.float32).reshape(3)
-        self._check(self._lib.chad_insert(self._h, p, n, capi.ptr(pos)))
+        f = self._lib.chad_insert if wait_for_copy else self._lib.chad_insert_async
+        self._check(f(self._h, p, n, capi.ptr(pos)))
 
     def insert_device(self, device_ptr: int, n: int, position) -> None:
         pos = np.ascontiguousarray(position, dtype=np.float32).reshape(3)

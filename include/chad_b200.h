@@ -68,6 +68,10 @@ const char* chad_last_error(const chad_ctx* ctx);
  * be running when the call returns; the submap switch rule (> 5 m from the submap's first pose,
  * tsdf.cpp:51-58) is applied here. */
 int chad_insert(chad_ctx* ctx, const float* xyz, size_t n, const float position[3]);
+/* Same for PAGE-LOCKED host memory, without waiting for the copy: the transfers of consecutive scans then follow each other at
+ * the link's full rate (a caller that recycles one buffer per scan needs chad_insert). `xyz` must stay valid and unchanged until
+ * the next chad_flush (or any other synchronising call). Fails with CHAD_ERR_INVALID for pageable memory. */
+int chad_insert_async(chad_ctx* ctx, const float* xyz, size_t n, const float position[3]);
 /* Same, but `xyz_device` already lives in this context's device memory (no host copy). */
 int chad_insert_device(chad_ctx* ctx, const float* xyz_device, size_t n, const float position[3]);
 /* Wait until every queued insert has been applied; reports deferred device errors. */

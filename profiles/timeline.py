@@ -7,6 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from chad_tsdf_b200 import TSDFMap, synth  # noqa: E402
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+host = len(sys.argv) > 2 and sys.argv[2] == "host"  # page-locked host inputs through chad_insert_async instead of device-resident ones
 w = synth.WORKLOADS["cfg1_traj100_128beam"]
 scans = [w.scan(s) for s in range(w.scans)]
 m = TSDFMap(w.sdf_res, w.sdf_trunc, max_batch_scans=batch)
@@ -15,12 +16,23 @@ for pts, _ in scans:
     p = m.device_alloc(pts.nbytes)
     m.upload(p, pts)
     ptrs.append((p, len(pts)))
+pinned = []
+if host:
+    import torch
+    for pts, _ in scans:
+        t = torch.empty((len(pts), 3), dtype=torch.float32, pin_memory=True)
+        t.numpy()[...] = pts
+        pinned.append(t)
 for rep in range(3):
     m.reset()
     if rep == 2:
         m.profile_enable(True)
-    for (p, n), (_, pos) in zip(ptrs, scans):
-        m.insert_device(p, n, pos)
+    if host:
+        for t, (_, pos) in zip(pinned, scans):
+            m.insert(t, pos, False)
+    else:
+        for (p, n), (_, pos) in zip(ptrs, scans):
+            m.insert_device(p, n, pos)
     m.flush()
 tl = m.profile_timeline()
 prev_end = 0.0
