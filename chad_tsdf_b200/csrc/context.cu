@@ -921,7 +921,8 @@ int end_scan(chad_ctx* ctx, size_t n, const float position[3]) {
     ctx->batch_points += (u32)n;
     // A burst starts with a short batch: while nothing is in flight the device would only wait for the host to copy a full batch
     // (24 scans = 1.4 ms over PCIe); once a batch is queued the following ones fill up behind it.
-    const u32 target = ctx->n_pend ? (u32)ctx->max_batch : std::min<u32>((u32)ctx->max_batch, 4u);
+    static const u32 first_batch = [] { const char* e = std::getenv("CHAD_FIRST_BATCH"); const int v = e ? std::atoi(e) : 4; return (u32)(v < 1 ? 1 : v); }();
+    const u32 target = ctx->n_pend ? (u32)ctx->max_batch : std::min<u32>((u32)ctx->max_batch, first_batch);
     if (ctx->batch_scans >= target) TRY(process_front(ctx));
     return CHAD_OK;
 }

@@ -3,6 +3,8 @@ by Submap::finalize, run twice in-process (first run = warm-up). Usage: python p
 import os
 import sys
 
+os.environ.setdefault("CHAD_FIRST_BATCH", "64")  # no short first batch: the profile shows full batches
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from chad_tsdf_b200 import TSDFMap, synth  # noqa: E402
 
