@@ -3,12 +3,13 @@
 // consecutive scans, and the level-by-level driver of Submap::finalize
 // (/root/reference/include/chad/detail/submap.hpp:10-106).
 //
-// Scheduling. insert() copies the scan into the current batch (pinned staging + async H2D on a
-// copy stream) and returns. When a batch is full, its "front" (plan, point sort, normals, band
-// enumeration, pair sort, segment count) is queued on the compute stream; the "fold" of a batch is
-// queued just before the next batch's front (or at flush), after the host has read the batch's
-// exact distinct-chunk count and grown the resident table if needed. So the device never waits on
-// the host except for one event per batch, and table growth is exact instead of worst-case.
+// Scheduling. insert() copies the scan into the current batch (page-locked caller memory is DMA'd
+// directly, pageable memory goes through a pinned staging ring) on the copy stream and returns. When a batch is full its
+// "front" (plan, point sort, normals, ray walk) is queued on the main stream, the descriptor sort + block list on the
+// group stream, and the batch joins a queue of at most two pending folds. A fold needs the batch's block count on the host
+// (table sizing), so it is launched -- on the fold stream, beside the next batch's front -- by the first API call that
+// finds the front's read-back there, at the latest when the batch's buffers are needed again two batches later: the
+// host never waits inside the steady state. Submap::finalize runs on its own high-priority stream (finalize_begin).
 #include <array>
 #include <cmath>
 #include <cstddef>

@@ -1,17 +1,19 @@
-// Tile-run grouping of the band-voxel updates with the fold fused into the per-block sort: the default replacement
-// for the octree's per-voxel grouping and running average (/root/reference/include/chad/detail/octree.hpp:31-78,
-// 86-164). Successor of blocks.cu (which stays as pair path 0): ncu r01b showed the count / emit / sort / fold chain
-// issue bound (1360 warp instructions per warp in the count walk alone, DRAM below 17 % everywhere), so this path
-//   * walks every ray ONCE (no counting pass): a CTA takes a tile of 256 consecutive sorted rays, keeps the tile's
-//     updates in shared memory, groups them by 8x8x8-voxel block with a shared-memory hash, reserves one contiguous
-//     span of the record buffer with ONE global atomic and writes one "run" per (tile, block) plus a 16-byte run
-//     descriptor -- no global hash table, no per-ray global atomics;
-//   * sorts the run descriptors by block id (a few hundred thousand keys: the existing onesweep sort);
-//   * gives every block to one CTA that reads the block's runs, sorts its records by (voxel, sorted-point rank) in
-//     shared memory and folds them IN PLACE into the resident leaf-chunk table: one hash probe per 2x2x2 chunk instead
-//     of one per voxel, and the sorted (key, sd) stream never goes back to HBM.
-// The reference's update order inside a voxel (sorted point rank, then ray step; a ray touches a voxel at most once)
-// is restored exactly by the rank sort, so results are bit-identical to paths 0 / 1 and to the CPU reference.
+// Tile-run grouping of the band-voxel updates and the streaming fold: the default replacement for the octree's
+// per-voxel grouping and running average (/root/reference/include/chad/detail/octree.hpp:31-78,86-164). Successor of
+// blocks.cu (which stays as pair path 0): ncu r01b showed the count / emit / sort / fold chain issue bound (1360 warp
+// instructions per warp in the count walk alone, DRAM below 17 % everywhere), so this path removes work:
+//   * runs_emit_kernel walks every ray ONCE (no counting pass): a CTA takes a tile of 256 consecutive sorted rays, keeps
+//     the tile's updates in shared memory, groups them by 8x8x8-voxel block with a shared-memory hash, reserves one
+//     contiguous span of the record buffer with ONE global atomic and writes one "run" per (tile, block) -- its records
+//     in (ray, step) = rank order -- plus a 16-byte run descriptor. No global hash table, no per-ray global atomics.
+//   * The run descriptors (a few hundred thousand) are sorted by (block, tile) with the onesweep sort: the concatenation
+//     of a block's runs then IS its update stream in the reference's order (sorted point rank, then ray step; a ray
+//     touches a voxel at most once).
+//   * runs_fold_kernel gives every block to one WARP that streams that sequence, 32 updates per iteration, into a
+//     shared-memory copy of the block's 64 leaf chunks (lanes that share a voxel go in lane order) and writes the
+//     touched chunks back: one table probe per 2x2x2 chunk instead of one per voxel, nothing is sorted, and the
+//     (key, sd) stream never goes back to HBM.
+// Results are bit-identical to paths 0 / 1 and to the CPU reference.
 #include "kernels.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
