@@ -24,12 +24,26 @@ CASES = {
 }
 SPHERE_POINTS = 100_000  # the reference demo's workload shape (main.cpp:7-38)
 
+# BASELINE.json's configs at FULL size (or, for the two that take the reference minutes to hours, a prefix long enough to
+# cross many submap switches), pinned in golden_full.json by make_golden.py --full. The GPU path is checked against
+# these pins without running any CPU model on the GPU box; the oracle restatement is checked against them on the CPU.
+FULL_CASES = {
+    # configs[1] = the bench workload, whole: 100 scans x 262 144 points, four submap switches inside insert
+    "full_cfg1_traj100_128beam": synth.WORKLOADS["cfg1_traj100_128beam"],
+    # configs[2], whole: 20 dense indoor scans at 0.02 m voxels / 0.06 m truncation
+    "full_cfg2_fine_indoor": synth.WORKLOADS["cfg2_fine_indoor"],
+    # configs[3], the first 120 m of the 5 km drive: 19 submap switches inside insert, 0.10 m voxels
+    "full_cfg3_urban_first120": synth.WORKLOADS["cfg3_urban_5km"].truncated(120),
+    # configs[4]'s trajectory (0.025 m per scan), first 240 scans: submaps of 201 scans = nine default batches each
+    "full_cfg4_traj1000_first240": synth.WORKLOADS["cfg4_traj1000_128beam"].truncated(240),
+}
+
 
 def case_scans(name):
     """[(points, pose)] of a golden case."""
     if name == "sphere_demo_100k":
         return [(synth.sphere_demo_points(SPHERE_POINTS), np.zeros(3, np.float32))], 0.05, 0.10
-    w = CASES[name]
+    w = CASES[name] if name in CASES else FULL_CASES[name]
     return [w.scan(s) for s in range(w.scans)], w.sdf_res, w.sdf_trunc
 
 

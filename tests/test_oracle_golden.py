@@ -8,6 +8,9 @@ import pytest
 from tests.golden import cases
 
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+GOLDEN_FULL = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_full.json")))
+# the two long prefixes take the single-threaded oracle 2.5 minutes: CHAD_SLOW_TESTS=1 runs them too (green)
+FULL_ON_CPU = [n for n in cases.FULL_CASES if os.environ.get("CHAD_SLOW_TESTS") or n in ("full_cfg1_traj100_128beam", "full_cfg2_fine_indoor")]
 
 
 @pytest.mark.parametrize("name", cases.ALL_CASES)
@@ -29,4 +32,19 @@ def test_oracle_matches_reference_golden(oracle_lib, name):
     assert d["final"]["roots"] == g["stable"]["final"]["roots"]
     for lv, (a, b) in enumerate(zip(d["final"]["levels"], g["stable"]["final"]["levels"])):
         assert a == b, f"DAG level {lv}"
+    m.close()
+
+
+@pytest.mark.parametrize("name", FULL_ON_CPU)
+def test_oracle_matches_reference_golden_at_full_size(oracle_lib, name):
+    """The restatement against the reference on BASELINE.json's configs at full size (configs[1] = the bench workload)."""
+    scans, _, _ = cases.case_scans(name)
+    g = GOLDEN_FULL[name]
+    assert cases.input_digest(scans) == g["input_sha256"], "the synthetic generator is not bit-reproducible on this machine"
+    del scans
+    m, d = cases.run_case(lambda r, t: oracle_lib.OracleMap(r, t), name)
+    for k, v in g["verbatim"]["before_finalize"].items():
+        assert d["before_finalize"][k] == v, f"tier A {k}"
+    assert d["before_finalize"] == g["stable"]["before_finalize"]
+    assert d["final"] == g["stable"]["final"]
     m.close()
