@@ -50,6 +50,7 @@ SYMBOLS = {
     "chad_level_counters": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "chad_export_level": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     "chad_set_pair_path": (C.c_int, [_P, C.c_int]),
+    "chad_pipeline_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "chad_reset": (C.c_int, [_P]),
     "chad_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "chad_reset_stats": (C.c_int, [_P]),

@@ -31,6 +31,8 @@ namespace {
 
 thread_local std::string g_create_error;
 
+constexpr int MAX_SLOTS = 3;  // plan slots = batches between the start of a point stage and the end of the batch's fold
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -81,39 +83,47 @@ struct chad_ctx {
     u32 batch_points = 0, batch_scans = 0;
     BatchScans h_scans{};
     BatchScans* h_scans_pinned[2] = {nullptr, nullptr};
-    DevBuf d_scans, d_plan;       // d_plan = BatchPlan[2]: the batch being queued and the batch whose fold is pending
-    BatchPlan* h_plan = nullptr;  // pinned BatchPlan[2]
+    DevBuf d_scans, d_plan;       // d_plan = BatchPlan[MAX_SLOTS]: the batch being queued and the batches whose fold is pending / running
+    BatchPlan* h_plan = nullptr;  // pinned BatchPlan[MAX_SLOTS]
     int plan_slot = 0;            // slot of the batch being assembled
+    int n_slots = 2;              // slots in use: 2, or 3 with overlap_walk (a batch's walk, descriptor sort and fold then span two point stages)
     struct PendingFold { int slot; bool runs; u32 max_pairs; bool close; };
-    PendingFold pend[2];          // batches whose front is queued but whose fold is not (oldest first): the fold needs the batch's block
+    PendingFold pend[MAX_SLOTS];  // batches whose front is queued but whose fold is not (oldest first): the fold needs the batch's block
     int n_pend = 0;               // count on the host (table sizing), so it is launched as soon as the front's read-back has arrived --
                                   // by any later API call that finds it there, at the latest when the batch's plan slot is needed again
     u32* h_table_count = nullptr; // pinned: chunk count of `table` after its last fold
     u32* h_table_count2 = nullptr; // pinned: same for `table2`
-    cudaEvent_t front_done[2] = {nullptr, nullptr};  // per plan slot: the front's plan read-back has arrived
+    cudaEvent_t front_done[MAX_SLOTS] = {};  // per plan slot: the front's plan read-back has arrived
 
     // batch work buffers
     DevBuf bt_mem;                  // block table of the block-binned pair path
     BlockTable bt{};
     int pair_path = 2;              // 2 = tile runs + fused block sort/fold (default), 0 = block-binned, 1 = global radix sort
-    DevBuf run_mem[2];              // run descriptors of the tile-run path, one set per plan slot: the fold of batch i runs on
-    RunBuffers rb[2]{};             // fold_stream while the front of batch i + 1 runs on `stream` (records: keys_a / keys_b by slot)
+    DevBuf run_mem[MAX_SLOTS];      // run descriptors of the tile-run path, one set per plan slot: the fold of batch i runs on
+    RunBuffers rb[MAX_SLOTS]{};     // fold_stream while the front of batch i + 1 runs on `stream` (records: keys_a / keys_b / keys_c by slot)
     cudaStream_t fold_stream = nullptr;
     cudaStream_t group_stream = nullptr;  // descriptor sort + block list of a batch: beside the next point stage AND the previous fold
-    cudaEvent_t fold_done[2] = {nullptr, nullptr};   // the fold that read slot b's records / descriptors / plan has finished
-    bool fold_done_valid[2] = {false, false};
+    cudaStream_t walk_stream = nullptr;   // overlap_walk: the ray walk of batch i, beside the point stage of batch i + 1 on `stream`
+    bool overlap_walk = false;            // (sorted points, normals and the scan table are then double buffered by plan slot)
+    cudaEvent_t points_done[MAX_SLOTS] = {};  // per plan slot: the point stage has written xyz_sorted / normals of the slot
+    cudaEvent_t fold_done[MAX_SLOTS] = {};    // the fold that read slot b's records / descriptors / plan has finished
+    bool fold_done_valid[MAX_SLOTS] = {};
     bool fold_in_flight = false;    // a fold has been queued on fold_stream since the last synchronisation
     cudaEvent_t submap_closed2 = nullptr, emit_done = nullptr;
     DevBuf radix_ws2;               // workspace of the descriptor sort (fold stream; the point sort's runs concurrently on the main stream)
     RadixWorkspace rws2{};
-    u64 prev_fold_bound = 0;        // chunk bound of the previous fold of the active submap if its exact count may not have arrived yet
+    u64 prev_fold_bound[MAX_SLOTS - 1] = {};  // chunk bounds of the last n_slots - 1 folds of the active submap (newest first): their exact
+                                    // counts may not have arrived yet when the next fold's table is sized
     cudaStream_t prof_stream = nullptr;  // stream the instrumentation events are recorded on
     cudaStream_t last_fold_stream = nullptr;  // stream the most recent fold (and the copy of the table counter behind it) was queued on
-    BatchPlan* h_plan_fold = nullptr;  // pinned BatchPlan[2]: the plan as the fused fold left it (distinct voxels, deferred errors)
-    bool fold_stats_pending[2] = {false, false};
+    BatchPlan* h_plan_fold = nullptr;  // pinned BatchPlan[MAX_SLOTS]: the plan as the fused fold left it (distinct voxels, deferred errors)
+    bool fold_stats_pending[MAX_SLOTS] = {};
     DevBuf pk_a, pk_b, pv_a, pv_b;  // point-sort ping-pong (N-sized): separate from the pair buffers so that the next batch's point
                                     // stage can be queued while the previous batch's pairs still wait for their fold
     DevBuf keys_a, keys_b, vals_a, vals_b, sorted_keys, sorted_order, xyz_sorted, normals, seg_info, counts, offsets, radix_ws, scan_ws;
+    DevBuf xyz_sorted2[MAX_SLOTS - 1], normals2[MAX_SLOTS - 1], d_scans2[MAX_SLOTS - 1];  // plan slots 1 and 2 (slot 0 uses xyz_sorted / normals /
+                                    // d_scans, like the stage and shard calls)
+    DevBuf keys_c;                  // update records of plan slot 2 (slots 0 / 1: keys_a / keys_b)
     RadixWorkspace rws{};
 
     // resident chunk tables: `table` belongs to the active submap; the other one is being finalised / is spare
@@ -247,6 +257,12 @@ void dev_free(DevBuf& b) {
 }
 BatchPlan* plan_ptr(chad_ctx* ctx, int slot) { return ctx->d_plan.as<BatchPlan>() + slot; }
 template <typename T> T* plan_field(chad_ctx* ctx, int slot, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<char*>(plan_ptr(ctx, slot)) + off); }
+// what the point stage of a batch hands to its ray walk, per plan slot
+float* slot_xyz_sorted(chad_ctx* ctx, int slot) { return (slot ? ctx->xyz_sorted2[slot - 1] : ctx->xyz_sorted).as<float>(); }
+float* slot_normals(chad_ctx* ctx, int slot) { return (slot ? ctx->normals2[slot - 1] : ctx->normals).as<float>(); }
+BatchScans* slot_scans(chad_ctx* ctx, int slot) { return (slot ? ctx->d_scans2[slot - 1] : ctx->d_scans).as<BatchScans>(); }
+u64* slot_records(chad_ctx* ctx, int slot) { return (slot == 0 ? ctx->keys_a : slot == 1 ? ctx->keys_b : ctx->keys_c).as<u64>(); }
+void fold_bounds_reset(chad_ctx* ctx) { for (u64& b : ctx->prev_fold_bound) b = 0; }
 
 int error_from_flags(chad_ctx* ctx, u32 flags) {
     if (!flags) return CHAD_OK;
@@ -300,6 +316,7 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
     // only called while no batch is in flight
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->walk_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
     const size_t np = points + points / 8 + 1024;
@@ -323,6 +340,11 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
     TRY(dev_ensure(ctx, ctx->sorted_order, np * 4));
     TRY(dev_ensure(ctx, ctx->xyz_sorted, np * 12));
     TRY(dev_ensure(ctx, ctx->normals, np * 12));
+    for (int q = 0; q + 1 < ctx->n_slots; q++) {
+        TRY(dev_ensure(ctx, ctx->xyz_sorted2[q], np * 12));
+        TRY(dev_ensure(ctx, ctx->normals2[q], np * 12));
+    }
+    if (ctx->n_slots > 2) TRY(dev_ensure(ctx, ctx->keys_c, pairs * 8));
     TRY(dev_ensure(ctx, ctx->seg_info, np * 4));
     TRY(dev_ensure(ctx, ctx->counts, np * 4));
     TRY(dev_ensure(ctx, ctx->offsets, np * 4));
@@ -335,9 +357,7 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
     TRY(dev_ensure(ctx, ctx->scan_ws, scan_workspace_bytes(np > bcap ? np : bcap)));
     if (ctx->mp.max_ray_runs <= runs_max_ray_runs() && ctx->mp.max_ray_voxels <= runs_max_ray_voxels()) {
         const size_t dcap = np * ctx->mp.max_ray_runs;
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < ctx->n_slots; b++) {
             TRY(dev_ensure(ctx, ctx->run_mem[b], runs_desc_bytes(dcap)));
             ctx->rb[b] = runs_carve(ctx->run_mem[b].p, dcap);
         }
@@ -363,7 +383,7 @@ int level_counters_reset(chad_ctx* ctx) {
 // the fused fold of the tile-run path reports the batch's distinct voxels after the fact: collect what has arrived.
 // Only called when the stream has passed the copies (after an event / stream synchronisation that follows them).
 void account_fold_stats(chad_ctx* ctx, int only_slot = -1) {
-    for (int slot = 0; slot < 2; slot++) {
+    for (int slot = 0; slot < MAX_SLOTS; slot++) {
         if (!ctx->fold_stats_pending[slot] || (only_slot >= 0 && slot != only_slot)) continue;
         ctx->fold_stats_pending[slot] = false;
         ctx->stats.scan_voxels += ctx->h_plan_fold[slot].n_segments;
@@ -384,7 +404,7 @@ int complete_one_fold(chad_ctx* ctx, bool block, bool* launched) {
     } else {
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->front_done[slot]));
     }
-    ctx->pend[0] = ctx->pend[1];
+    for (int q = 0; q + 1 < ctx->n_pend; q++) ctx->pend[q] = ctx->pend[q + 1];
     ctx->n_pend--;
     *launched = true;
     account_fold_stats(ctx, slot);  // the pair stage of this batch waited for the fold that used this slot before
@@ -407,9 +427,11 @@ int complete_one_fold(chad_ctx* ctx, bool block, bool* launched) {
         CUDA_TRY(ctx, cudaMemsetAsync(plan_field<u32>(ctx, slot, offsetof(BatchPlan, error)), 0, 4, ctx->stream));
         return error_from_flags(ctx, plan.error);
     }
-    // *h_table_count is exact as of the last fold whose copy has arrived; the previous fold may still be running on
-    // fold_stream, so its bound is added: an upper bound of the chunk count after this fold either way
-    const u64 count_bound = ctx->table_count_known + ctx->prev_fold_bound + plan.n_chunk_heads;
+    // *h_table_count is exact as of the last fold whose copy has arrived. This batch's point stage waited for the fold of n_slots batches
+    // ago, so at most the n_slots - 1 folds before this one may still be queued or running on fold_stream: their bounds are added --
+    // an upper bound of the chunk count after this fold either way
+    u64 count_bound = ctx->table_count_known + plan.n_chunk_heads;
+    for (int q = 0; q + 1 < ctx->n_slots; q++) count_bound += ctx->prev_fold_bound[q];
     TRY(table_reserve(ctx, count_bound));
     u64 launches = 0;
     cudaStream_t fold_on = ctx->stream;
@@ -419,15 +441,16 @@ int complete_one_fold(chad_ctx* ctx, bool block, bool* launched) {
         fold_on = fs;
         CUDA_TRY(ctx, cudaStreamWaitEvent(fs, ctx->front_done[slot], 0));
         ctx->prof_stream = fs;
-        if (plan.n_pairs) PROF(ctx, PC_RUNS_FOLD, launch_runs_fold(fs, (slot ? ctx->keys_b : ctx->keys_a).as<u64>(), ctx->rb[slot], plan_ptr(ctx, slot), ctx->table, ctx->num_sms));
+        if (plan.n_pairs) PROF(ctx, PC_RUNS_FOLD, launch_runs_fold(fs, slot_records(ctx, slot), ctx->rb[slot], plan_ptr(ctx, slot), ctx->table, ctx->num_sms));
         ctx->prof_stream = nullptr;
         CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->h_plan_fold[slot], plan_ptr(ctx, slot), sizeof(BatchPlan), cudaMemcpyDeviceToHost, fs));
         ctx->stats.d2h_bytes += sizeof(BatchPlan);
         ctx->fold_stats_pending[slot] = true;
-        ctx->prev_fold_bound = plan.n_chunk_heads;
+        for (int q = MAX_SLOTS - 2; q > 0; q--) ctx->prev_fold_bound[q] = ctx->prev_fold_bound[q - 1];
+        ctx->prev_fold_bound[0] = plan.n_chunk_heads;
         ctx->fold_in_flight = true;
     } else {
-        ctx->prev_fold_bound = 0;
+        fold_bounds_reset(ctx);
         PROF(ctx, PC_FOLD, launch_fold(ctx->stream, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(),
                                        pf.max_pairs, plan_ptr(ctx, slot), ctx->table, ctx->num_sms));
     }
@@ -441,9 +464,7 @@ int complete_one_fold(chad_ctx* ctx, bool block, bool* launched) {
     }
     CUDA_TRY(ctx, cudaGetLastError());
     if (pf.close) {  // that was the submap's last batch: swap tables and start its asynchronous finalize
-        const u64 bound = count_bound;
-        if (bound >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
-        (void)bound;
+        if (count_bound >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
         TRY(finalize_begin(ctx, 0, false, fold_on));
         ctx->stats.resident_clusters = 0;
     }
@@ -467,7 +488,7 @@ int poll_folds(chad_ctx* ctx) {
 void queue_point_stage(chad_ctx* ctx, int slot, int b, u32 n, u32 ns) {
     cudaStream_t s = ctx->stream;
     BatchPlan* plan = plan_ptr(ctx, slot);
-    const BatchScans* scans = ctx->d_scans.as<BatchScans>();
+    const BatchScans* scans = slot_scans(ctx, slot);
     const float* xyz = ctx->d_xyz[b].as<float>();
     u64 launches = 0;
     const LaunchHook* hook = ctx->profiling ? &ctx->hook : nullptr;
@@ -478,9 +499,9 @@ void queue_point_stage(chad_ctx* ctx, int slot, int b, u32 n, u32 ns) {
                                  RS_MAX_PASSES, ctx->rws, ctx->num_sms, hook, PC_POINT_SORT_HIST, plan_field<u32>(ctx, slot, offsetof(BatchPlan, point_shift)));
     PROF(ctx, PC_POINT_GATHER, launch_point_gather(s, xyz, n, plan, ctx->pk_a.as<u64>(), ctx->pk_b.as<u64>(), ctx->pv_a.as<u32>(),
                                                    ctx->pv_b.as<u32>(), ctx->sorted_keys.as<u64>(), ctx->sorted_order.as<u32>(),
-                                                   ctx->xyz_sorted.as<float>()));
-    PROF(ctx, PC_NORMALS, launch_normals(s, ctx->xyz_sorted.as<float>(), ctx->sorted_keys.as<u64>(), n, scans, plan, ctx->seg_info.as<u32>(),
-                                         ctx->normals.as<float>()));
+                                                   slot_xyz_sorted(ctx, slot)));
+    PROF(ctx, PC_NORMALS, launch_normals(s, slot_xyz_sorted(ctx, slot), ctx->sorted_keys.as<u64>(), n, scans, plan, ctx->seg_info.as<u32>(),
+                                         slot_normals(ctx, slot)));
     ctx->stats.kernel_launches += launches;
 }
 
@@ -495,31 +516,32 @@ int process_front(chad_ctx* ctx) {
     const u32 n = ctx->batch_points, ns = ctx->batch_scans;
     cudaStream_t s = ctx->stream;
     ctx->h_scans.offset[ns] = n;
-    if (ctx->scans_uploaded_valid[b]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->scans_uploaded[b]));  // (two batches ago: long done)
-    *ctx->h_scans_pinned[b] = ctx->h_scans;
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scans.p, ctx->h_scans_pinned[b], sizeof(BatchScans), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->scans_uploaded[b], s));
-    ctx->scans_uploaded_valid[b] = true;
     CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[b], ctx->copy_stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->copy_done[b], 0));
     if (ctx->stage_busy[b]) CUDA_TRY(ctx, cudaEventRecord(ctx->stage_copied[b], ctx->copy_stream));
 
     BatchPlan* plan = plan_ptr(ctx, slot);
-    const BatchScans* scans = ctx->d_scans.as<BatchScans>();
+    const BatchScans* scans = slot_scans(ctx, slot);
     u64 launches = 0;
     const LaunchHook* hook = ctx->profiling ? &ctx->hook : nullptr;
-    // this slot's plan / records / descriptors were last used by the batch of two batches ago: its fold must have been launched ...
+    // this slot's plan / scan table / sorted points / records / descriptors were last used by the batch of two batches ago: its fold
+    // (which follows its ray walk and its descriptor sort) must have been launched ...
     while (ctx->n_pend && ctx->pend[0].slot == slot) { bool launched; TRY(complete_one_fold(ctx, true, &launched)); }
-    if (ctx->n_pend == 2) { bool launched; TRY(complete_one_fold(ctx, true, &launched)); }
+    if (ctx->n_pend == ctx->n_slots) { bool launched; TRY(complete_one_fold(ctx, true, &launched)); }
     // ... and the device waits for it (on fold_stream) before touching the slot
     if (ctx->fold_done_valid[slot]) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->fold_done[slot], 0));
+    if (ctx->scans_uploaded_valid[b]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->scans_uploaded[b]));  // (two batches ago: long done)
+    *ctx->h_scans_pinned[b] = ctx->h_scans;
+    CUDA_TRY(ctx, cudaMemcpyAsync(slot_scans(ctx, slot), ctx->h_scans_pinned[b], sizeof(BatchScans), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->scans_uploaded[b], s));
+    ctx->scans_uploaded_valid[b] = true;
     queue_point_stage(ctx, slot, b, n, ns);
     CUDA_TRY(ctx, cudaEventRecord(ctx->xyz_free[b], s));  // the point stage is the only reader of d_xyz[b]
     ctx->xyz_free_valid[b] = true;
     const bool use_runs = ctx->pair_path == 2 && n <= runs_max_batch_points() && ctx->rb[0].capacity != 0;
     const bool use_blocks = !use_runs && ctx->pair_path != 1 && n <= blocks_max_batch_points();
     if (!use_blocks && !use_runs) {
-        PROF(ctx, PC_BAND_COUNT, launch_band_count(s, ctx->xyz_sorted.as<float>(), n, scans, ctx->mp, plan, ctx->counts.as<u32>()));
+        PROF(ctx, PC_BAND_COUNT, launch_band_count(s, slot_xyz_sorted(ctx, slot), n, scans, ctx->mp, plan, ctx->counts.as<u32>()));
         PROF(ctx, PC_BAND_SCAN, (exclusive_scan<u32, u32>(s, ctx->counts.as<u32>(), ctx->offsets.as<u32>(), n, ctx->scan_ws.p, (u32*)nullptr,
                                                           plan_field<u32>(ctx, slot, offsetof(BatchPlan, n_pairs)))));
     }
@@ -528,14 +550,26 @@ int process_front(chad_ctx* ctx) {
     // ---- the previous batch's fold. The tile-run path keeps its updates in per-slot buffers, so the fold is launched only if its
     //      front has reported already (the host does not wait here: it goes on to queue this batch and to copy the next scans);
     //      the other paths reuse the pair buffers and fold on this stream: everything before them must be queued first ----
-    if (use_runs) TRY(poll_folds(ctx)); else TRY(complete_pending_fold(ctx));
+    //      (so does a tile-run batch that follows a batch of another path, e.g. a scan beyond the tile-run path's 2^23 points: its
+    //      sorted updates sit in the record buffers until its fold has been queued)
+    bool other_path_pending = false;
+    for (int q = 0; q < ctx->n_pend; q++) other_path_pending |= !ctx->pend[q].runs;
+    if (use_runs && !other_path_pending) TRY(poll_folds(ctx)); else TRY(complete_pending_fold(ctx));
     // ---- pair stage ----
     const size_t max_pairs = size_t(n) * ctx->mp.max_ray_voxels;
     if (use_runs) {
-        launches += launch_runs_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan, ctx->rb[slot],
-                                     (slot ? ctx->keys_b : ctx->keys_a).as<u64>(), (u32)ctx->cap_pairs, hook, PC_RUNS_EMIT);
-        // the descriptor sort and the block list are only needed by the fold: they go on its stream (after the previous batch's fold)
-        CUDA_TRY(ctx, cudaEventRecord(ctx->emit_done, s));
+        // overlap_walk: the walk only reads what the point stage left in this slot's buffers, so it runs on its own stream and the main
+        // stream goes straight on to the next batch's point stage (which writes the other slot's buffers)
+        cudaStream_t ws = ctx->overlap_walk ? ctx->walk_stream : s;
+        if (ctx->overlap_walk) {
+            CUDA_TRY(ctx, cudaEventRecord(ctx->points_done[slot], s));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ws, ctx->points_done[slot], 0));
+            ctx->prof_stream = ws;
+        }
+        launches += launch_runs_emit(ws, slot_xyz_sorted(ctx, slot), slot_normals(ctx, slot), n, scans, ctx->mp, plan, ctx->rb[slot],
+                                     slot_records(ctx, slot), (u32)ctx->cap_pairs, hook, PC_RUNS_EMIT);
+        // the descriptor sort and the block list are only needed by the fold: they go on their own stream
+        CUDA_TRY(ctx, cudaEventRecord(ctx->emit_done, ws));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->group_stream, ctx->emit_done, 0));
         ctx->prof_stream = ctx->group_stream;
         launches += launch_runs_group(ctx->group_stream, n, plan, ctx->rb[slot], ctx->rws2, ctx->num_sms, hook, PC_RUNS_SORT);
@@ -543,16 +577,17 @@ int process_front(chad_ctx* ctx) {
         ctx->fold_in_flight = true;
     } else if (ctx->fold_in_flight) {
         // the other pair paths use both pair buffers and fold on this stream: order them after the folds still in flight
-        for (int b = 0; b < 2; b++)
+        for (int b = 0; b < MAX_SLOTS; b++)
             if (ctx->fold_done_valid[b]) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->fold_done[b], 0));
     }
     if (use_runs) {
+        // (queued above)
     } else if (use_blocks) {
-        launches += launch_blocks_pairs(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan, ctx->bt, ctx->scan_ws.p,
+        launches += launch_blocks_pairs(s, slot_xyz_sorted(ctx, slot), slot_normals(ctx, slot), n, scans, ctx->mp, plan, ctx->bt, ctx->scan_ws.p,
                                         ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(), (u32)ctx->cap_pairs,
                                         ctx->num_sms, hook, PC_BLOCKS_COUNT, PC_BLOCKS_SCAN, PC_BLOCKS_EMIT, PC_BLOCKS_SORT);
     } else {
-        PROF(ctx, PC_BAND_EMIT, launch_band_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), n, scans, ctx->mp, plan,
+        PROF(ctx, PC_BAND_EMIT, launch_band_emit(s, slot_xyz_sorted(ctx, slot), slot_normals(ctx, slot), n, scans, ctx->mp, plan,
                                                  ctx->offsets.as<u32>(), ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), (u32)ctx->cap_pairs, false));
         launches += radix_sort_pairs(s, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), ctx->keys_b.as<u64>(), ctx->vals_b.as<u32>(),
                                      plan_field<u32>(ctx, slot, offsetof(BatchPlan, n_pairs)), plan_field<u32>(ctx, slot, offsetof(BatchPlan, nbits_pairs)),
@@ -567,7 +602,7 @@ int process_front(chad_ctx* ctx) {
     ctx->stats.kernel_launches += launches;
     ctx->stats.batches++;
     ctx->pend[ctx->n_pend++] = chad_ctx::PendingFold{slot, use_runs, (u32)max_pairs, false};
-    ctx->plan_slot ^= 1;
+    ctx->plan_slot = (ctx->plan_slot + 1) % ctx->n_slots;
     ctx->cur ^= 1;
     ctx->batch_points = 0;
     ctx->batch_scans = 0;
@@ -584,17 +619,18 @@ int drain(chad_ctx* ctx) {
         TRY(finalize_part2(ctx));
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->walk_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
     ctx->fold_in_flight = false;
-    ctx->prev_fold_bound = 0;
+    fold_bounds_reset(ctx);
     account_fold_stats(ctx);
     prof_resolve(ctx);
     ctx->table_count_known = *ctx->h_table_count;
     ctx->stats.resident_clusters = ctx->table_count_known;
     // deferred flags raised by the fold (either plan slot)
     u32 flags = 0;
-    for (int slot = 0; slot < 2; slot++) {
+    for (int slot = 0; slot < MAX_SLOTS; slot++) {
         u32 f = 0;
         CUDA_TRY(ctx, cudaMemcpy(&f, plan_field<u32>(ctx, slot, offsetof(BatchPlan, error)), 4, cudaMemcpyDeviceToHost));
         if (f) CUDA_TRY(ctx, cudaMemset(plan_field<u32>(ctx, slot, offsetof(BatchPlan, error)), 0, 4));
@@ -758,7 +794,7 @@ int finalize_begin(chad_ctx* ctx, u32 max_chunks, bool external, cudaStream_t co
     std::swap(ctx->h_table_count, ctx->h_table_count2);  // the closed table's last count copy lands in h_table_count2
     *ctx->h_table_count = 0;
     ctx->table_count_known = 0;
-    ctx->prev_fold_bound = 0;
+    fold_bounds_reset(ctx);
     CUDA_TRY(ctx, cudaEventRecord(ctx->fin_p1_done, count_stream));
     ctx->fin_state = chad_ctx::FIN_PART1;
     return CHAD_OK;
@@ -974,7 +1010,9 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     }
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->fold_stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->group_stream, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; b++) CREATE_TRY(cudaEventCreateWithFlags(&ctx->fold_done[b], cudaEventDisableTiming));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->walk_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < MAX_SLOTS; b++) CREATE_TRY(cudaEventCreateWithFlags(&ctx->points_done[b], cudaEventDisableTiming));
+    for (int b = 0; b < MAX_SLOTS; b++) CREATE_TRY(cudaEventCreateWithFlags(&ctx->fold_done[b], cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&ctx->submap_closed2, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&ctx->emit_done, cudaEventDisableTiming));
     {   // the finalize stream gets the highest priority: its ~300 tiny dependent kernels then take the first SM slot that frees up
@@ -994,11 +1032,11 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
         CREATE_TRY(cudaEventCreateWithFlags(&ctx->copy_done[b], cudaEventDisableTiming));
         CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_scans_pinned[b]), sizeof(BatchScans)));
     }
-    for (int b = 0; b < 2; b++) CREATE_TRY(cudaEventCreateWithFlags(&ctx->front_done[b], cudaEventDisableTiming));
+    for (int b = 0; b < MAX_SLOTS; b++) CREATE_TRY(cudaEventCreateWithFlags(&ctx->front_done[b], cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreate(&ctx->t0));
     CREATE_TRY(cudaEventCreate(&ctx->t1));
-    CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_plan), 2 * sizeof(BatchPlan)));
-    CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_plan_fold), 2 * sizeof(BatchPlan)));
+    CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_plan), MAX_SLOTS * sizeof(BatchPlan)));
+    CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_plan_fold), MAX_SLOTS * sizeof(BatchPlan)));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_table_count), 64));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_table_count2), 64));
     *ctx->h_table_count2 = 0;
@@ -1007,6 +1045,9 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     CREATE_TRY(blocks_init());
     CREATE_TRY(runs_init());
     if (const char* env = std::getenv("CHAD_PAIR_PATH")) { const int m = std::atoi(env); if (m >= 0 && m <= 2) ctx->pair_path = m; }
+    if (const char* env = std::getenv("CHAD_OVERLAP_WALK")) ctx->overlap_walk = std::atoi(env) != 0;
+    ctx->n_slots = ctx->overlap_walk ? 3 : 2;
+    if (const char* env = std::getenv("CHAD_PLAN_SLOTS")) { const int v = std::atoi(env); if (v >= 2 && v <= MAX_SLOTS) ctx->n_slots = v; }
 
     ctx->mp.res = sdf_res;
     ctx->mp.trunc = sdf_trunc;
@@ -1023,10 +1064,11 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     ctx->max_batch = max_batch_scans == 0 ? 24 : max_batch_scans;  // one batch per submap of ~21 scans on the bench trajectory
 
     int r = dev_ensure(ctx, ctx->d_scans, sizeof(BatchScans));
-    if (r == CHAD_OK) r = dev_ensure(ctx, ctx->d_plan, 2 * sizeof(BatchPlan));
+    for (int q = 0; q < MAX_SLOTS - 1; q++) if (r == CHAD_OK) r = dev_ensure(ctx, ctx->d_scans2[q], sizeof(BatchScans));
+    if (r == CHAD_OK) r = dev_ensure(ctx, ctx->d_plan, MAX_SLOTS * sizeof(BatchPlan));
     if (r == CHAD_OK) r = dev_ensure(ctx, ctx->f_scalars, 256);
     if (r != CHAD_OK) return bail(r);
-    CREATE_TRY(cudaMemsetAsync(ctx->d_plan.p, 0, 2 * sizeof(BatchPlan), ctx->stream));
+    CREATE_TRY(cudaMemsetAsync(ctx->d_plan.p, 0, MAX_SLOTS * sizeof(BatchPlan), ctx->stream));
     r = table_alloc(ctx, ctx->table, ctx->t_keys, ctx->t_cells, ctx->t_count, ctx->t_list, 1ull << 20);
     if (r == CHAD_OK) r = table_alloc(ctx, ctx->table2, ctx->t2_keys, ctx->t2_cells, ctx->t2_count, ctx->t2_list, 1ull << 20);
     if (r == CHAD_OK) r = dev_ensure(ctx, ctx->f_counters, sizeof(LevelCounters) * CHAD_NUM_LEVELS);
@@ -1055,10 +1097,11 @@ void chad_destroy(chad_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->walk_stream) cudaStreamSynchronize(ctx->walk_stream);
     if (ctx->group_stream) cudaStreamSynchronize(ctx->group_stream);
     if (ctx->fold_stream) cudaStreamSynchronize(ctx->fold_stream);
     if (ctx->fin_stream) cudaStreamSynchronize(ctx->fin_stream);
-    DevBuf* bufs[] = {&ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->t2_list, &ctx->t_list, &ctx->f_counters, &ctx->f_partial, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->sh_tuples, &ctx->sh_scalars, &ctx->bt_mem, &ctx->run_mem[0], &ctx->run_mem[1], &ctx->radix_ws2, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
+    DevBuf* bufs[] = {&ctx->xyz_sorted2[0], &ctx->normals2[0], &ctx->d_scans2[0], &ctx->xyz_sorted2[1], &ctx->normals2[1], &ctx->d_scans2[1], &ctx->keys_c, &ctx->run_mem[2], &ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->t2_list, &ctx->t_list, &ctx->f_counters, &ctx->f_partial, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->sh_tuples, &ctx->sh_scalars, &ctx->bt_mem, &ctx->run_mem[0], &ctx->run_mem[1], &ctx->radix_ws2, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
                       &ctx->sorted_keys, &ctx->sorted_order, &ctx->xyz_sorted, &ctx->normals, &ctx->seg_info, &ctx->counts, &ctx->offsets,
                       &ctx->radix_ws, &ctx->scan_ws, &ctx->t_keys, &ctx->t_cells, &ctx->t_count, &ctx->f_sorted, &ctx->f_ids[0], &ctx->f_ids[1], &ctx->f_slots[0],
                       &ctx->f_slots[1], &ctx->f_cells, &ctx->f_tsdf, &ctx->f_addr[0], &ctx->f_addr[1], &ctx->f_head_rank, &ctx->f_cand,
@@ -1080,10 +1123,12 @@ void chad_destroy(chad_ctx* ctx) {
     if (ctx->h_fin) cudaFreeHost(ctx->h_fin);
     for (cudaEvent_t e : {ctx->submap_closed, ctx->fin_p1_done, ctx->fin_done, ctx->fin_t0, ctx->fin_t3}) if (e) cudaEventDestroy(e);
     if (ctx->fin_stream) cudaStreamDestroy(ctx->fin_stream);
-    for (cudaEvent_t e : {ctx->fold_done[0], ctx->fold_done[1], ctx->submap_closed2, ctx->emit_done}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ctx->fold_done[0], ctx->fold_done[1], ctx->fold_done[2], ctx->submap_closed2, ctx->emit_done}) if (e) cudaEventDestroy(e);
     if (ctx->fold_stream) cudaStreamDestroy(ctx->fold_stream);
     if (ctx->group_stream) cudaStreamDestroy(ctx->group_stream);
-    for (int b = 0; b < 2; b++) if (ctx->front_done[b]) cudaEventDestroy(ctx->front_done[b]);
+    if (ctx->walk_stream) cudaStreamDestroy(ctx->walk_stream);
+    for (int b = 0; b < MAX_SLOTS; b++) if (ctx->points_done[b]) cudaEventDestroy(ctx->points_done[b]);
+    for (int b = 0; b < MAX_SLOTS; b++) if (ctx->front_done[b]) cudaEventDestroy(ctx->front_done[b]);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1280,18 +1325,19 @@ int chad_reset(chad_ctx* ctx) {
     ctx->batch_points = 0;
     ctx->batch_scans = 0;
     ctx->n_pend = 0;
-    ctx->fold_stats_pending[0] = ctx->fold_stats_pending[1] = false;
+    for (bool& f : ctx->fold_stats_pending) f = false;
     ctx->sh_have_splitters = false;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->walk_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fin_stream));
     ctx->fold_in_flight = false;
-    ctx->prev_fold_bound = 0;
-    ctx->fold_done_valid[0] = ctx->fold_done_valid[1] = false;
+    fold_bounds_reset(ctx);
+    for (bool& f : ctx->fold_done_valid) f = false;
     ctx->fin_state = chad_ctx::FIN_IDLE;
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_plan.p, 0, 2 * sizeof(BatchPlan), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_plan.p, 0, MAX_SLOTS * sizeof(BatchPlan), ctx->stream));
     launch_table_clear(ctx->stream, ctx->table);
     launch_table_clear(ctx->stream, ctx->table2);
     *ctx->h_table_count2 = 0;
@@ -1315,6 +1361,13 @@ int chad_set_pair_path(chad_ctx* ctx, int mode) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     TRY(settle(ctx));
     ctx->pair_path = mode;
+    return CHAD_OK;
+}
+
+int chad_pipeline_info(chad_ctx* ctx, int* plan_slots, int* walk_overlapped) {
+    if (!ctx || !plan_slots || !walk_overlapped) return CHAD_ERR_INVALID;
+    *plan_slots = ctx->n_slots;
+    *walk_overlapped = ctx->overlap_walk ? 1 : 0;
     return CHAD_OK;
 }
 

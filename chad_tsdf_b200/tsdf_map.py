@@ -113,8 +113,14 @@ class TSDFMap:
         return s.as_dict()
 
     def set_pair_path(self, mode: int) -> None:
-        """0 = block-binned grouping of the voxel updates (default), 1 = global radix sort. Identical results."""
+        """2 = tile runs + streaming fold (default), 0 = block-binned grouping of the voxel updates, 1 = global radix sort. Identical results."""
         self._check(self._lib.chad_set_pair_path(self._h, mode))
+
+    def pipeline_info(self) -> dict:
+        """Plan slots (batches in flight) and whether a batch's ray walk runs beside the next batch's point stage."""
+        slots, overlapped = C.c_int(0), C.c_int(0)
+        self._check(self._lib.chad_pipeline_info(self._h, C.byref(slots), C.byref(overlapped)))
+        return {"plan_slots": slots.value, "walk_overlapped": bool(overlapped.value)}
 
     def reset(self) -> None:
         """Forget the whole map but keep the device buffers (== a freshly constructed map)."""

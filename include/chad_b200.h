@@ -105,6 +105,11 @@ int chad_query_voxels(chad_ctx* ctx, uint32_t submap, const uint64_t* keys, size
  * 8x8x8-voxel blocks + shared-memory sort), 1 = global onesweep radix sort. All give bit-identical results. */
 int chad_set_pair_path(chad_ctx* ctx, int mode);
 
+/* How the batches are pipelined on the device (context.cu header): *plan_slots = batches that can be between the start of their point
+ * stage and the end of their fold at the same time (2 or 3), *walk_overlapped != 0 when the ray walk of a batch runs on its own stream
+ * beside the next batch's point stage. Set at chad_create from CHAD_OVERLAP_WALK / CHAD_PLAN_SLOTS; never changes the results. */
+int chad_pipeline_info(chad_ctx* ctx, int* plan_slots, int* walk_overlapped);
+
 /* Forget everything (active submap, all DAG levels, submap roots, sticky errors) but keep the device
  * buffers: equivalent to destroying the map and constructing a new one with the same parameters. */
 int chad_reset(chad_ctx* ctx);

@@ -220,3 +220,23 @@ def test_device_dag_reader_matches_the_quantised_voxels(chad_lib, oracle_lib):
     empty_neighbours = np.setdiff1d(keys ^ np.uint64(1), keys)       # the other voxel of a pair: mostly absent leaves of PRESENT clusters
     assert np.all(g.query_voxels(0, empty_neighbours) == 0xFF)
     g.close(); o.close()
+
+
+def test_scan_beyond_the_tile_run_rank_range_then_ordinary_scans(chad_lib, oracle_lib):
+    """Maximum sizes: one scan of more than 2^23 points does not fit the tile-run path's 23-bit point rank and goes through the
+    global-sort path by itself; the ordinary scans after it are tile-run batches again. The big batch's sorted updates wait in the
+    buffers the tile-run path uses for its records, so its fold must be queued before the next batch's ray walk writes them."""
+    from chad_tsdf_b200 import TSDFMap
+    from oracle import bindings as ob
+    n_big = (1 << 23) + 5000
+    pts = synth.sphere_demo_points(n_big + 3 * 40_000)
+    pos = np.zeros(3, np.float32)
+    g, o = TSDFMap(0.05, 0.1, max_batch_scans=1), ob.OracleMap(0.05, 0.1)
+    cuts = [0, n_big, n_big + 40_000, n_big + 80_000, n_big + 120_000]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        g.insert(pts[a:b], pos); o.insert(pts[a:b], pos)
+    _assert_same_state(g, o, check_levels=False)
+    g.finalize_active(); o.finalize_active()
+    _assert_same_state(g, o)
+    assert g.stats()["points"] == len(pts)
+    g.close(); o.close()
