@@ -38,3 +38,4 @@ fi
 CHAD_OVERLAP_WALK=$BEST timeout 330 python -m pytest tests -m gpu -x -q $DESEL > gpurun_out/ab_suite.log 2>&1; echo "suite (overlap=$BEST): rc=$?"
 tail -4 gpurun_out/ab_suite.log
 echo "$BEST" > gpurun_out/ab_best.txt
+CHAD_OVERLAP_WALK=$BEST timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/ab_smoke.log 2>&1; echo "smoke: rc=$?"; tail -1 gpurun_out/ab_smoke.log
