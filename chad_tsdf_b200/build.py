@@ -40,6 +40,18 @@ def build_facade_demo(verbose: bool = False) -> str:
     return out
 
 
+def build_facade_overloads(verbose: bool = False) -> str:
+    """tests/cpp/facade_overloads.cpp: every insert() overload / constructor of the reference's class, the glm and Eigen ones
+    compiled against the stand-in headers under tests/cpp/shims (neither library is installed here)."""
+    out = os.path.join(ROOT, "tests", "cpp", "facade_overloads")
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++20", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "cpp", "shims"),
+           os.path.join(ROOT, "tests", "cpp", "facade_overloads.cpp"), "-o", out, "-L", PKG, "-lchad_b200", f"-Wl,-rpath,{PKG}"]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return out
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
