@@ -104,7 +104,9 @@ struct chad_ctx {
     cudaStream_t fold_stream = nullptr;
     cudaStream_t group_stream = nullptr;  // descriptor sort + block list of a batch: beside the next point stage AND the previous fold
     cudaStream_t walk_stream = nullptr;   // overlap_walk: the ray walk of batch i, beside the point stage of batch i + 1 on `stream`
-    bool overlap_walk = true;             // (sorted points, normals and the scan table are then buffered per plan slot); CHAD_OVERLAP_WALK=0: off
+    bool overlap_walk = false;            // (sorted points, normals and the scan table are then buffered per plan slot). CHAD_OVERLAP_WALK=1
+                                          // turns it on; off by default: measured 9.24 vs 9.29 ms per bench step (profiles/ab_overlap_r01.md) --
+                                          // the walk's 16 384 CTAs are dispatched before the next point stage's kernels get an SM either way
     cudaEvent_t points_done[MAX_SLOTS] = {};  // per plan slot: the point stage has written xyz_sorted / normals of the slot
     cudaEvent_t fold_done[MAX_SLOTS] = {};    // the fold that read slot b's records / descriptors / plan has finished
     bool fold_done_valid[MAX_SLOTS] = {};

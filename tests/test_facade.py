@@ -58,3 +58,14 @@ def test_facade_demo_runs_on_gpu(chad_lib, tmp_path):
     # decoded distances follow the analytic sphere like the walk above
     rad = np.linalg.norm(qp[:, :3].astype(np.float64), axis=1)
     assert np.mean(np.abs(qp[:, 3] - np.clip(5.0 - rad, -0.1, 0.1)) > 0.03) < 0.02
+
+
+@pytest.mark.gpu
+def test_facade_overloads_build_the_identical_map(chad_lib, tmp_path):
+    """The same 20 000 points through every insert overload and construct-and-insert constructor (std::array, raw pointer with pose
+    pointer / pose scalars, glm::vec3, Eigen::Vector3f): ten maps, identical roots and DAG size."""
+    from chad_tsdf_b200 import build
+    exe = build.build_facade_overloads()
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "10 maps" in r.stdout and "identical: yes" in r.stdout
