@@ -159,4 +159,53 @@ bool HostNodeLevels::try_get_lc(uint32_t parent_addr, uint8_t child_i, uint64_t&
     cluster = leaf_clusters[addr];
     return true;
 }
+uint8_t HostNodeLevels::query(uint32_t root_addr, uint64_t morton_key) const {
+    // depth d picks the child (key >> 3(20 - d)) & 7 (octree.hpp:44-56); the depth-19 node's children are leaf clusters whose
+    // byte `key & 7` is the voxel (cluster.hpp:13-32)
+    uint32_t addr = root_addr;
+    if (addr == 0 || addr >= nodes[0].size()) return 0xFF;
+    for (uint32_t depth = 0; depth + 1 < MAX_DEPTH; depth++) {
+        addr = get_child_addr(depth, addr, uint8_t((morton_key >> (3 * (20 - depth))) & 7));
+        if (addr == 0) return 0xFF;
+    }
+    uint64_t cluster;
+    if (!try_get_lc(addr, uint8_t((morton_key >> 3) & 7), cluster)) return 0xFF;
+    return uint8_t(cluster >> (8 * (morton_key & 7)));
+}
+
+SavedMap load_dag(const std::string& filename) {
+    std::FILE* f = std::fopen(filename.c_str(), "rb");
+    if (!f) throw std::runtime_error("chad::load_dag: cannot open " + filename);
+    auto fail = [&](const char* what) { std::fclose(f); throw std::runtime_error("chad::load_dag: " + filename + ": " + what); };
+    auto get = [&](void* p, size_t n) { if (n && std::fread(p, 1, n, f) != n) fail("truncated file"); };
+    std::fseek(f, 0, SEEK_END);
+    const uint64_t file_bytes = (uint64_t)std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    char magic[8];
+    get(magic, 8);
+    if (std::memcmp(magic, "CHADDAG1", 8) != 0) fail("not a CHADDAG1 file");
+    SavedMap m;
+    uint32_t n_sub = 0;
+    get(&m.sdf_res, 4);
+    get(&m.sdf_trunc, 4);
+    get(&n_sub, 4);
+    if (uint64_t(n_sub) * 8 > file_bytes) fail("submap count exceeds the file size");
+    m.roots.resize(n_sub);
+    for (auto& r : m.roots) get(r.data(), 8);
+    for (auto& lv : m.levels.nodes) {
+        uint64_t n = 0;
+        get(&n, 8);
+        if (n > file_bytes / 4) fail("level size exceeds the file size");
+        lv.resize(n);
+        get(lv.data(), n * 4);
+    }
+    uint64_t n = 0;
+    get(&n, 8);
+    if (n > file_bytes / 8) fail("cluster count exceeds the file size");
+    m.levels.leaf_clusters.resize(n);
+    get(m.levels.leaf_clusters.data(), n * 8);
+    if ((uint64_t)std::ftell(f) != file_bytes) fail("trailing bytes");
+    std::fclose(f);
+    return m;
+}
 }  // namespace chad

@@ -35,7 +35,21 @@ namespace chad {
         uint32_t get_child_addr(uint32_t depth, uint32_t parent_addr, uint8_t child_i) const;
         // NodeLevels::try_get_lc (levels.hpp:177-192)
         bool try_get_lc(uint32_t parent_addr, uint8_t child_i, uint64_t& cluster) const;
+        // Single-voxel read through the tree under `root_addr` (a submap's root_addr_tsdf or root_addr_weight): the root-to-leaf
+        // walk the reference's readers make with get_child_addr / try_get_lc, for one Morton key (morton.hpp:21-28). Returns the
+        // voxel's quantised byte (cluster.hpp:13-32; decode (byte - 127) / 127 * sdf_trunc), 0xFF where the voxel does not exist.
+        // Host counterpart of chad_query_voxels.
+        uint8_t query(uint32_t root_addr, uint64_t morton_key) const;
     };
+
+    // What TSDFMap::save wrote (flat CHADDAG1 dump): map parameters, the roots of every finalised
+    // submap (submap.hpp:108-109) and the host copy of the DAG. Pure host code: no GPU needed to read a map back.
+    struct SavedMap {
+        float sdf_res = 0.0f, sdf_trunc = 0.0f;
+        std::vector<std::array<uint32_t, 2>> roots;  // per submap: root_addr_tsdf, root_addr_weight
+        HostNodeLevels levels;
+    };
+    SavedMap load_dag(const std::string& filename);  // throws std::runtime_error on a malformed or truncated file
 
     class TSDFMap {
     public:

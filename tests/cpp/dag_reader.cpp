@@ -1,0 +1,35 @@
+// Reads a CHADDAG1 file back with chad::load_dag (pure host code, no GPU) and answers single-voxel queries through
+// chad::HostNodeLevels::query -- the walk the reference's readers make (levels.hpp:147-192).
+// usage: dag_reader <file.chad> <submap> <keys.u64> <out.u8>   -> prints "res trunc n_submaps root_tsdf root_weight n_keys"
+#include <cstdio>
+#include <cstdlib>
+#include <exception>
+
+#include "chad/tsdf.hpp"
+
+int main(int argc, char** argv) {
+    if (argc != 5) { std::fprintf(stderr, "usage: dag_reader <file.chad> <submap> <keys.u64> <out.u8>\n"); return 2; }
+    try {
+        const chad::SavedMap m = chad::load_dag(argv[1]);
+        const size_t submap = std::strtoul(argv[2], nullptr, 10);
+        if (submap >= m.roots.size()) { std::fprintf(stderr, "no such submap\n"); return 3; }
+        std::FILE* fk = std::fopen(argv[3], "rb");
+        if (!fk) return 4;
+        std::fseek(fk, 0, SEEK_END);
+        const size_t n = (size_t)std::ftell(fk) / 8;
+        std::fseek(fk, 0, SEEK_SET);
+        std::vector<uint64_t> keys(n);
+        if (n && std::fread(keys.data(), 8, n, fk) != n) return 4;
+        std::fclose(fk);
+        std::vector<uint8_t> out(n);
+        for (size_t i = 0; i < n; i++) out[i] = m.levels.query(m.roots[submap][0], keys[i]);
+        std::FILE* fo = std::fopen(argv[4], "wb");
+        if (!fo || (n && std::fwrite(out.data(), 1, n, fo) != n)) return 5;
+        std::fclose(fo);
+        std::printf("%.9g %.9g %zu %u %u %zu\n", m.sdf_res, m.sdf_trunc, m.roots.size(), m.roots[submap][0], m.roots[submap][1], n);
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "%s\n", e.what());
+        return 1;
+    }
+}

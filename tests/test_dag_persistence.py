@@ -1,0 +1,99 @@
+"""CPU: the saved-map reader of the C++ facade (chad::load_dag + HostNodeLevels::query, host-only code in libchad_b200.so).
+A CHADDAG1 file is written HERE from the oracle's DAG, following the format as INTEGRATION.md section 4 states it (an independent
+writer), read back by the library, and every voxel of the closed submaps must come back with the byte cluster.hpp:13-26
+quantises its distance to -- the same check tests/test_gpu_parity.py makes for the device-side reader (chad_query_voxels)."""
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from chad_tsdf_b200 import synth
+
+
+def _write_chaddag1(path, m, res, trunc):
+    with open(path, "wb") as f:
+        f.write(b"CHADDAG1")
+        roots = m.roots()
+        f.write(struct.pack("<ffI", res, trunc, len(roots)))
+        for r in roots:
+            f.write(struct.pack("<II", *r))
+        for lv in range(20):
+            arr, _, _ = m.level(lv)
+            f.write(struct.pack("<Q", len(arr)))
+            f.write(np.ascontiguousarray(arr, dtype="<u4").tobytes())
+        arr, _, _ = m.level(20)
+        f.write(struct.pack("<Q", len(arr)))
+        f.write(np.ascontiguousarray(arr, dtype="<u8").tobytes())
+
+
+def _quantise(sd_bits, trunc):
+    sd = sd_bits.view(np.float32)
+    t = np.float32(1.0) / np.float32(trunc)
+    q = np.clip(sd * t, np.float32(-1.0), np.float32(1.0)) * np.float32(127.0) + np.float32(127.0)  # cluster.hpp:19-26, fp32, truncation
+    return q.astype(np.uint64).astype(np.uint8)
+
+
+def _query(exe, chad_file, submap, keys, tmp_path):
+    kf, of = tmp_path / f"keys{submap}.u64", tmp_path / f"out{submap}.u8"
+    np.ascontiguousarray(keys, dtype="<u8").tofile(kf)
+    r = subprocess.run([exe, str(chad_file), str(submap), str(kf), str(of)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout.split(), np.fromfile(of, np.uint8)
+
+
+def test_saved_map_reads_back_on_the_host(chad_lib, oracle_lib, tmp_path):
+    from chad_tsdf_b200 import build
+    exe = build.build_dag_reader()
+    w = synth.Workload("persist", synth.BOX_ROOM, 32, 2, 0.0, 6.0, 0.05, 0.10)  # two scans 6 m apart: two submaps
+    o = oracle_lib.OracleMap(w.sdf_res, w.sdf_trunc)
+    per_submap = []                 # voxels of each submap as the oracle holds them right before the submap is closed
+    pts, pos = w.scan(0)
+    o.insert(pts, pos)
+    per_submap.append(o.voxels())
+    pts, pos = w.scan(1)
+    o.insert(pts, pos)              # closes the first submap (tsdf.cpp:51-58) ...
+    per_submap.append(o.voxels())
+    o.finalize_active()             # ... and save() closes the second one (tsdf.cpp:78-81)
+    roots = o.roots()
+    assert len(roots) == 2
+    chad_file = tmp_path / "map.chad"
+    _write_chaddag1(chad_file, o, w.sdf_res, w.sdf_trunc)
+    for submap, (keys, sd_bits, _) in enumerate(per_submap):
+        head, got = _query(exe, chad_file, submap, keys, tmp_path)
+        assert (np.float32(head[0]), np.float32(head[1]), int(head[2])) == (np.float32(w.sdf_res), np.float32(w.sdf_trunc), 2)
+        assert (int(head[3]), int(head[4])) == tuple(roots[submap])
+        assert np.array_equal(got, _quantise(sd_bits, w.sdf_trunc)), f"submap {submap}: voxel bytes differ"
+        far = np.setdiff1d(keys + np.uint64(1 << 30), keys)[:5000]
+        assert np.all(_query(exe, chad_file, submap, far, tmp_path)[1] == 0xFF)
+        pair = np.setdiff1d(keys ^ np.uint64(1), keys)          # absent leaves of present clusters
+        assert np.all(_query(exe, chad_file, submap, pair, tmp_path)[1] == 0xFF)
+    # the other submap's voxels are a different tree: a voxel only one submap holds is absent from the other
+    only0 = np.setdiff1d(per_submap[0][0], per_submap[1][0])[:5000]
+    assert len(only0) and np.all(_query(exe, chad_file, 1, only0, tmp_path)[1] == 0xFF)
+    o.close()
+
+
+@pytest.mark.parametrize("damage", ["magic", "truncate", "trailing"])
+def test_malformed_files_are_rejected(chad_lib, oracle_lib, tmp_path, damage):
+    from chad_tsdf_b200 import build
+    exe = build.build_dag_reader()
+    o = oracle_lib.OracleMap(0.05, 0.1)
+    pts = synth.sphere_demo_points(5000)
+    o.insert(pts, np.zeros(3, np.float32))
+    o.finalize_active()
+    good = tmp_path / "good.chad"
+    _write_chaddag1(good, o, 0.05, 0.1)
+    o.close()
+    blob = bytearray(open(good, "rb").read())
+    if damage == "magic":
+        blob[:8] = b"CHADDAG2"
+    elif damage == "truncate":
+        blob = blob[: len(blob) // 2]
+    else:
+        blob += b"\0\0\0\0"
+    bad = tmp_path / "bad.chad"
+    open(bad, "wb").write(bytes(blob))
+    (tmp_path / "k.u64").write_bytes(b"")
+    r = subprocess.run([exe, str(bad), "0", str(tmp_path / "k.u64"), str(tmp_path / "o.u8")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "chad::load_dag" in r.stderr

@@ -1,0 +1,38 @@
+"""GPU: TSDFMap::save -> chad::load_dag round trip (the file the C++ class writes is read back by the library's host-side reader).
+Named to run last: it was added after the round's last GPU run (its pieces -- save() on the GPU, load_dag / query on the CPU against
+the oracle -- are each covered by tests that did run)."""
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_saved_map_round_trip(chad_lib, tmp_path):
+    from chad_tsdf_b200 import build, capi
+    demo, reader = build.build_facade_demo(), build.build_dag_reader()
+    r = subprocess.run([demo, "150000"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lib = capi.load()
+    # a 12^3 neighbourhood of the voxel where the 5 m sphere crosses the x axis, and the same neighbourhood far outside the band
+    g = np.arange(-6, 6)
+    near = np.array([lib.chad_morton_encode(100 + int(x), int(y), int(z)) for x in g for y in g for z in g], np.uint64)
+    far = np.array([lib.chad_morton_encode(160 + int(x), int(y), int(z)) for x in g for y in g for z in g], np.uint64)
+    out = {}
+    for name, keys in (("near", near), ("far", far)):
+        kf, of = tmp_path / f"{name}.u64", tmp_path / f"{name}.u8"
+        keys.tofile(kf)
+        q = subprocess.run([reader, str(tmp_path / "facade_demo.chad"), "0", str(kf), str(of)], capture_output=True, text=True, timeout=60)
+        assert q.returncode == 0, q.stdout + q.stderr
+        head = q.stdout.split()
+        assert (np.float32(head[0]), np.float32(head[1]), int(head[2]), int(head[3]), int(head[4])) == (np.float32(0.05), np.float32(0.1), 1, 1, 10)
+        out[name] = np.fromfile(of, np.uint8)
+    assert np.all(out["far"] == 0xFF)
+    present = out["near"] != 0xFF
+    assert present.sum() > 20  # the truncation band is four voxels thick there
+    # decoded distances follow the analytic sphere (inward normals: positive inside), cf. tests/cpp/facade_demo.cpp
+    xyz = np.array([[100 + x, y, z] for x in g for y in g for z in g], np.float64) * 0.05
+    sd = (out["near"][present].astype(np.float64) - 127.0) / 127.0 * 0.1
+    expect = np.clip(5.0 - np.linalg.norm(xyz[present], axis=1), -0.1, 0.1)
+    assert np.mean(np.abs(sd - expect) > 0.03) < 0.1
