@@ -1,6 +1,6 @@
-"""GPU: TSDFMap::save -> chad::load_dag round trip (the file the C++ class writes is read back by the library's host-side reader).
-Named to run last: it was added after the round's last GPU run (its pieces -- save() on the GPU, load_dag / query on the CPU against
-the oracle -- are each covered by tests that did run)."""
+"""GPU: TSDFMap::save -> chad::load_dag round trip: the file the C++ class writes on the GPU box is read back by the library's
+host-side reader and queried voxel by voxel (green on B200; the reader itself is also checked on the CPU against the oracle,
+tests/test_dag_persistence.py)."""
 import subprocess
 
 import numpy as np
