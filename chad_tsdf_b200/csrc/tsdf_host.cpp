@@ -80,8 +80,10 @@ void TSDFMap::save(const std::string& filename) {
 void TSDFMap::save_grid(const std::string& filename, size_t submap) {
     check(_ctx, chad_finalize_active(_ctx), "save_grid");  // tsdf.cpp:78-81
     if (submap >= submap_count()) throw std::runtime_error("chad::TSDFMap::save_grid: no such submap");
-    const HostNodeLevels levels = node_levels();
-    const uint32_t root = submap_roots(submap)[0];
+    write_grid(node_levels(), submap_roots(submap)[0], _sdf_res, _sdf_trunc, filename);
+}
+
+void write_grid(const HostNodeLevels& levels, uint32_t root, float _sdf_res, float _sdf_trunc, const std::string& filename) {
     struct QueryPoint { float x, y, z, sd; };
     std::vector<QueryPoint> query_points;
     constexpr uint32_t INVALID = 0xFFFFFFFFu;  // lvr2 FastBox::INVALID_INDEX
@@ -134,8 +136,8 @@ void TSDFMap::save_grid(const std::string& filename, size_t submap) {
         if (std::find(verts.begin(), verts.end(), INVALID) == verts.end()) complete.push_back(code);
     std::sort(complete.begin(), complete.end());
     std::FILE* f = std::fopen(filename.c_str(), "wb");
-    if (!f) throw std::runtime_error("chad::TSDFMap::save_grid: cannot open " + filename);
-    auto put = [&](const void* p, size_t n) { if (n && std::fwrite(p, 1, n, f) != n) { std::fclose(f); throw std::runtime_error("chad::TSDFMap::save_grid: write failed"); } };
+    if (!f) throw std::runtime_error("chad::write_grid: cannot open " + filename);
+    auto put = [&](const void* p, size_t n) { if (n && std::fwrite(p, 1, n, f) != n) { std::fclose(f); throw std::runtime_error("chad::write_grid: write failed"); } };
     const float header = _sdf_trunc;  // the reference writes m_truncsize under the name voxel_res (lvr2.cpp:176-177)
     const size_t nq = query_points.size(), nc = complete.size();
     put(&header, sizeof(float));

@@ -50,6 +50,9 @@ namespace chad {
         HostNodeLevels levels;
     };
     SavedMap load_dag(const std::string& filename);  // throws std::runtime_error on a malformed or truncated file
+    // The reference's ChadGrid constructor + saveGrid (lvr2.cpp:32-130,170-200) for the tree under `root_addr_tsdf`: what
+    // TSDFMap::save_grid writes, usable on a loaded map as well (pure host code).
+    void write_grid(const HostNodeLevels& levels, uint32_t root_addr_tsdf, float sdf_res, float sdf_trunc, const std::string& filename);
 
     class TSDFMap {
     public:

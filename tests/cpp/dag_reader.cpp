@@ -1,13 +1,27 @@
 // Reads a CHADDAG1 file back with chad::load_dag (pure host code, no GPU) and answers single-voxel queries through
 // chad::HostNodeLevels::query -- the walk the reference's readers make (levels.hpp:147-192).
 // usage: dag_reader <file.chad> <submap> <keys.u64> <out.u8>   -> prints "res trunc n_submaps root_tsdf root_weight n_keys"
+//        dag_reader grid <file.chad> <submap> <out.grid>      -> the reference's hashgrid.grid (lvr2.cpp:170-200) of that submap
 #include <cstdio>
 #include <cstdlib>
 #include <exception>
+#include <string>
 
 #include "chad/tsdf.hpp"
 
 int main(int argc, char** argv) {
+    if (argc == 5 && std::string(argv[1]) == "grid") {  // dag_reader grid <file.chad> <submap> <out.grid>
+        try {
+            const chad::SavedMap m = chad::load_dag(argv[2]);
+            const size_t submap = std::strtoul(argv[3], nullptr, 10);
+            if (submap >= m.roots.size()) { std::fprintf(stderr, "no such submap\n"); return 3; }
+            chad::write_grid(m.levels, m.roots[submap][0], m.sdf_res, m.sdf_trunc, argv[4]);
+            return 0;
+        } catch (const std::exception& e) {
+            std::fprintf(stderr, "%s\n", e.what());
+            return 1;
+        }
+    }
     if (argc != 5) { std::fprintf(stderr, "usage: dag_reader <file.chad> <submap> <keys.u64> <out.u8>\n"); return 2; }
     try {
         const chad::SavedMap m = chad::load_dag(argv[1]);

@@ -2,6 +2,7 @@
 A CHADDAG1 file is written HERE from the oracle's DAG, following the format as INTEGRATION.md section 4 states it (an independent
 writer), read back by the library, and every voxel of the closed submaps must come back with the byte cluster.hpp:13-26
 quantises its distance to -- the same check tests/test_gpu_parity.py makes for the device-side reader (chad_query_voxels)."""
+import ctypes as C
 import struct
 import subprocess
 
@@ -97,3 +98,59 @@ def test_malformed_files_are_rejected(chad_lib, oracle_lib, tmp_path, damage):
     (tmp_path / "k.u64").write_bytes(b"")
     r = subprocess.run([exe, str(bad), "0", str(tmp_path / "k.u64"), str(tmp_path / "o.u8")], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "chad::load_dag" in r.stderr
+
+
+def test_grid_file_of_a_loaded_map_matches_the_oracle(chad_lib, oracle_lib, tmp_path):
+    """chad::write_grid = the reference's ChadGrid constructor + saveGrid (lvr2.cpp:32-130,170-200) on a map read back with
+    load_dag: one query point per voxel of the submap, at the voxel's lower corner (lvr2.cpp:81-85), with the decoded distance
+    (cluster.hpp:46-50); a cell is kept only when all eight of its corner voxels exist (lvr2.cpp:115-129), its corners listed
+    at the reference's offsets (lvr2.cpp:88-98)."""
+    from chad_tsdf_b200 import build, capi
+    exe = build.build_dag_reader()
+    lib = capi.load()
+    w = synth.Workload("grid", synth.BOX_ROOM, 16, 1, 0.0, 0.0, 0.05, 0.10)
+    o = oracle_lib.OracleMap(w.sdf_res, w.sdf_trunc)
+    # a densely sampled 1 m x 1 m wall patch 3 m in front of the sensor: a solid slab of band voxels, so complete cells exist
+    rng = np.random.default_rng(5)
+    pts = np.empty((20000, 3), np.float32)
+    pts[:, 0] = 3.0 + rng.normal(0.0, 0.005, len(pts))
+    pts[:, 1:] = rng.random((len(pts), 2)) - 0.5
+    pos = np.zeros(3, np.float32)
+    o.insert(pts, pos)
+    keys, sd_bits, _ = o.voxels()
+    o.finalize_active()
+    chad_file, grid_file = tmp_path / "m.chad", tmp_path / "m.grid"
+    _write_chaddag1(chad_file, o, w.sdf_res, w.sdf_trunc)
+    o.close()
+    r = subprocess.run([exe, "grid", str(chad_file), "0", str(grid_file)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    g = open(grid_file, "rb").read()
+    hdr, nq, nc = struct.unpack_from("<fQQ", g, 0)
+    assert np.float32(hdr) == np.float32(w.sdf_trunc)  # the reference stores the truncation distance here (SURVEY section 9 Q15)
+    assert nq == len(keys) and len(g) == 20 + nq * 16 + nc * 32
+    qp = np.frombuffer(g, np.float32, nq * 4, 20).reshape(nq, 4)
+    cells = np.frombuffer(g, np.uint32, nc * 8, 20 + nq * 16).reshape(nc, 8)
+    # query points come in the tree's traversal order = ascending Morton key = the oracle's voxel order
+    xyz = np.empty((len(keys), 3), np.int32)
+    for i, k in enumerate(keys):
+        x, y, z = (C.c_int32(), C.c_int32(), C.c_int32())
+        lib.chad_morton_decode(int(k), C.byref(x), C.byref(y), C.byref(z))
+        xyz[i] = (x.value, y.value, z.value)
+    assert np.array_equal(qp[:, :3], xyz.astype(np.float32) * np.float32(w.sdf_res))
+    byte = _quantise(sd_bits, w.sdf_trunc)
+    decoded = (byte.astype(np.float32) - np.float32(127.0)) * np.float32(1.0 / 127.0) * np.float32(w.sdf_trunc)
+    assert np.array_equal(qp[:, 3], decoded)
+    # complete cells, recomputed here from the voxel set: cell c has corner i at voxel c - offset[i]
+    off = np.array([[0, 0, 0], [-1, 0, 0], [-1, -1, 0], [0, -1, 0], [0, 0, -1], [-1, 0, -1], [-1, -1, -1], [0, -1, -1]], np.int32)
+    index = {tuple(v): i for i, v in enumerate(xyz.tolist())}
+    expect = {}
+    for v in index:
+        for o_ in off:  # voxel v is corner i of cell v + offset[i]
+            c = (v[0] + o_[0], v[1] + o_[1], v[2] + o_[2])
+            if c in expect:
+                continue
+            corners = [index.get((c[0] - q[0], c[1] - q[1], c[2] - q[2])) for q in off]
+            expect[c] = corners if None not in corners else None
+    complete = sorted((lib.chad_morton_encode(*c), corners) for c, corners in expect.items() if corners is not None)
+    assert nc == len(complete) and nc > 0
+    assert np.array_equal(cells, np.array([c for _, c in complete], np.uint32))  # ascending Morton order of the cell
