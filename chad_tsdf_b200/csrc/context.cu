@@ -10,6 +10,8 @@
 // (table sizing), so it is launched -- on the fold stream, beside the next batch's front -- by the first API call that
 // finds the front's read-back there, at the latest when the batch's buffers are needed again two batches later: the
 // host never waits inside the steady state. Submap::finalize runs on its own high-priority stream (finalize_begin).
+// Optional (CHAD_OVERLAP_WALK=1, off by default -- measured no gain, profiles/ab_overlap_r01.md): the ray walk on its own
+// stream beside the next batch's point stage, with three plan slots instead of two.
 #include <array>
 #include <cmath>
 #include <cstddef>
@@ -526,7 +528,7 @@ int process_front(chad_ctx* ctx) {
     const BatchScans* scans = slot_scans(ctx, slot);
     u64 launches = 0;
     const LaunchHook* hook = ctx->profiling ? &ctx->hook : nullptr;
-    // this slot's plan / scan table / sorted points / records / descriptors were last used by the batch of two batches ago: its fold
+    // this slot's plan / scan table / sorted points / records / descriptors were last used by the batch of n_slots batches ago: its fold
     // (which follows its ray walk and its descriptor sort) must have been launched ...
     while (ctx->n_pend && ctx->pend[0].slot == slot) { bool launched; TRY(complete_one_fold(ctx, true, &launched)); }
     if (ctx->n_pend == ctx->n_slots) { bool launched; TRY(complete_one_fold(ctx, true, &launched)); }
