@@ -7,6 +7,8 @@ TAG=${1:-rXX}
 mkdir -p gpurun_out
 timeout 420 python -m pytest tests -m gpu -x -q > gpurun_out/t_$TAG.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/t_$TAG.log
 timeout 60 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+# the random-scene parameter sweep through the CUDA path (written after round 1's last GPU minute; make it unconditional once green)
+CHAD_GPU_SWEEP=1 timeout 120 python -m pytest tests/test_zz_saved_map_gpu.py -m gpu -q > gpurun_out/t_${TAG}_sweep.log 2>&1; echo "sweep rc=$?"; tail -2 gpurun_out/t_${TAG}_sweep.log
 timeout 120 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
 timeout 200 python bench.py --impl reference > gpurun_out/bench_${TAG}_ref.json 2> gpurun_out/bench_${TAG}_ref.err; echo "reference arm rc=$?"
 python - <<PY
