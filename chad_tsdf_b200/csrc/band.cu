@@ -16,7 +16,7 @@ constexpr int BAND_THREADS = 256;
 
 __global__ void __launch_bounds__(BAND_THREADS) band_count_kernel(const float* __restrict__ xyz_sorted, u32 n_points,
                                                                   const BatchScans* __restrict__ scans, float res, float trunc, float recip,
-                                                                  u32 max_ray_voxels, const BatchPlan* __restrict__ plan, u32* __restrict__ counts) {
+                                                                  u32 max_ray_voxels, BatchPlan* __restrict__ plan, u32* __restrict__ counts) {
     const u32 i = blockIdx.x * BAND_THREADS + threadIdx.x;
     if (i >= n_points) return;
     const u32 s = scan_of(scans, plan->n_scans, i);
@@ -24,7 +24,10 @@ __global__ void __launch_bounds__(BAND_THREADS) band_count_kernel(const float* _
     Ray r;
     ray_setup(r, xyz_sorted[size_t(i) * 3], xyz_sorted[size_t(i) * 3 + 1], xyz_sorted[size_t(i) * 3 + 2], pos, res, trunc, recip);
     u32 c = 1;  // the start voxel is always emitted (:121-122)
-    while (c < max_ray_voxels && ray_advance(r)) c++;
+    while (ray_advance(r)) {
+        if (c >= max_ray_voxels) { atomicOr(&plan->error, ERRF_PAIR_CAPACITY); break; }  // the analytic per-ray bound was exceeded: report it
+        c++;
+    }
     counts[i] = c;
 }
 
@@ -75,8 +78,8 @@ inline unsigned blocks_for(u32 n) { return (n + BAND_THREADS - 1) / BAND_THREADS
 int launch_band_count(cudaStream_t s, const float* xyz_sorted, u32 n_points, const BatchScans* scans, const MapParams& mp,
                       const BatchPlan* plan, u32* counts) {
     if (!n_points) return 0;
-    band_count_kernel<<<blocks_for(n_points), BAND_THREADS, 0, s>>>(xyz_sorted, n_points, scans, mp.res, mp.trunc, mp.recip, mp.max_ray_voxels, plan,
-                                                                    counts);
+    band_count_kernel<<<blocks_for(n_points), BAND_THREADS, 0, s>>>(xyz_sorted, n_points, scans, mp.res, mp.trunc, mp.recip, mp.max_ray_voxels,
+                                                                    const_cast<BatchPlan*>(plan), counts);
     return 1;
 }
 

@@ -108,9 +108,9 @@ __global__ void __launch_bounds__(BLK_THREADS) blocks_count_kernel(const float* 
         while (true) {
             run++;
             total++;
-            bool more = total < max_ray_voxels;
             int axis = 0;
-            if (more) more = ray_advance(r, axis);
+            bool more = ray_advance(r, axis);
+            if (more && total >= max_ray_voxels) { err |= ERRF_PAIR_CAPACITY; more = false; }  // analytic per-ray bound exceeded: report it
             u64 next_full = full;
             if (more) next_full = morton_step(full, axis, axis == 0 ? r.step[0] : (axis == 1 ? r.step[1] : r.step[2]));
             if (!more || (next_full >> BLK_SHIFT) != blk) {  // the run ends

@@ -66,6 +66,7 @@ struct chad_ctx {
     bool scans_uploaded_valid[2] = {false, false};
     MapParams mp{};
     int max_batch = 16;
+    u32 first_batch = 4;  // scans of a batch that starts a burst (nothing in flight): see end_scan. CHAD_FIRST_BATCH, read at chad_create
     std::string error;
     int sticky_error = CHAD_OK;
 
@@ -940,6 +941,10 @@ int begin_scan(chad_ctx* ctx, size_t n, const float position[3], bool* skip) {
         // keep a batch inside the tile-run path's rank range (2^23 sorted points) unless a single scan is larger than that
         const size_t rank_cap = (size_t)runs_max_batch_points() - 4096;
         if (n * 9 / 8 + 1024 <= rank_cap && want * 9 / 8 + 1024 > rank_cap) want = (rank_cap - 1024) * 8 / 9;
+        // ... and inside the 2^30 band-voxel limit of the pair buffers: a large scan gets a smaller batch (down to the scan alone)
+        // instead of an error -- the reference accepts any scan size
+        const size_t pair_cap = (((1ull << 30) - 1) / ctx->mp.max_ray_voxels - 1024) * 8 / 9 - 1;
+        if (want > pair_cap && n <= pair_cap) want = pair_cap;
         TRY(ensure_batch_capacity(ctx, want));
     }
     return CHAD_OK;
@@ -962,8 +967,7 @@ int end_scan(chad_ctx* ctx, size_t n, const float position[3]) {
     ctx->batch_points += (u32)n;
     // A burst starts with a short batch: while nothing is in flight the device would only wait for the host to copy a full batch
     // (24 scans = 1.4 ms over PCIe); once a batch is queued the following ones fill up behind it.
-    static const u32 first_batch = [] { const char* e = std::getenv("CHAD_FIRST_BATCH"); const int v = e ? std::atoi(e) : 4; return (u32)(v < 1 ? 1 : v); }();
-    const u32 target = ctx->n_pend ? (u32)ctx->max_batch : std::min<u32>((u32)ctx->max_batch, first_batch);
+    const u32 target = ctx->n_pend ? (u32)ctx->max_batch : std::min<u32>((u32)ctx->max_batch, ctx->first_batch);
     if (ctx->batch_scans >= target) TRY(process_front(ctx));
     return CHAD_OK;
 }
@@ -1050,6 +1054,7 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     CREATE_TRY(runs_init());
     if (const char* env = std::getenv("CHAD_PAIR_PATH")) { const int m = std::atoi(env); if (m >= 0 && m <= 2) ctx->pair_path = m; }
     if (const char* env = std::getenv("CHAD_OVERLAP_WALK")) ctx->overlap_walk = std::atoi(env) != 0;
+    if (const char* env = std::getenv("CHAD_FIRST_BATCH")) { const int v = std::atoi(env); ctx->first_batch = (u32)(v < 1 ? 1 : v); }
     ctx->n_slots = ctx->overlap_walk ? 3 : 2;
     if (const char* env = std::getenv("CHAD_PLAN_SLOTS")) { const int v = std::atoi(env); if (v >= 2 && v <= MAX_SLOTS) ctx->n_slots = v; }
 
@@ -1290,8 +1295,8 @@ int chad_level_counters(chad_ctx* ctx, int level, uint32_t* uniques, uint32_t* d
 int chad_export_level(chad_ctx* ctx, int level, void* dst, size_t capacity_words) {
     if (!ctx || !dst || level < 0 || level >= CHAD_NUM_LEVELS) return CHAD_ERR_INVALID;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    size_t words;
-    chad_level_words(ctx, level, &words);
+    size_t words = 0;
+    TRY(chad_level_words(ctx, level, &words));
     if (capacity_words < words) return fail(ctx, CHAD_ERR_INVALID, "export capacity too small");
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fin_stream));
     CUDA_TRY(ctx, cudaMemcpy(dst, ctx->levels[level].raw.p, words * (level == CHAD_LEVEL_CLUSTERS ? 8 : 4), cudaMemcpyDeviceToHost));

@@ -432,13 +432,38 @@ int launch_dag_levels(cudaStream_t s, const LevelsArgs& args, int num_sms) {
     // one CTA of 512 threads per SM: the CTAs spin at the grid barriers while the insert kernels of the next submap run beside them, so
     // they must leave registers and thread slots free (measured per bench step: 1024 threads x 148 / 74 / 37 CTAs -> 11.68 / 11.39 /
     // 11.36 ms; with the fold at 3 CTAs per SM: 1024 x 74 -> 10.36 ms, 512 x 148 -> 9.70 ms)
-    int grid = num_sms < LV_THREADS ? num_sms : LV_THREADS;
-    if (grid < 1) grid = 1;
-    if (env_ctas > 0 && env_ctas <= num_sms && env_ctas <= LV_THREADS) grid = env_ctas;
     static const int env_threads = [] { const char* e = std::getenv("CHAD_LEVELS_THREADS"); return e ? std::atoi(e) : 0; }();
     int threads = 512;
     if (env_threads >= 64 && env_threads <= LV_THREADS && env_threads % 32 == 0) threads = env_threads;
+    // The software grid barrier needs every CTA resident at the same time. A cooperative launch makes the driver guarantee it (the grid
+    // starts only once all of it fits, whatever else -- other contexts, MPS partitions, the persistent fold -- holds SM resources) and
+    // the grid is bounded by what the occupancy calculator says one device can hold. If the device cannot launch cooperatively the
+    // levels are built by ONE CTA (the kernel's solo path: __syncthreads only), which cannot deadlock.
+    static const int coop_ok = [] {
+        const char* e = std::getenv("CHAD_LEVELS_COOP");
+        if (e && std::atoi(e) == 0) return 0;
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+        return v ? 1 : -1;
+    }();
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dag_levels_kernel, threads, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+    int grid = num_sms < LV_THREADS ? num_sms : LV_THREADS;
+    if (env_ctas > 0 && env_ctas <= num_sms && env_ctas <= LV_THREADS) grid = env_ctas;
     if (grid > threads) grid = threads;  // partial_prefix scans one partial per thread
+    if (per_sm < 1) grid = 1;
+    else if (grid > per_sm * num_sms) grid = per_sm * num_sms;
+    if (grid < 1) grid = 1;
+    if (coop_ok == 1 && grid > 1) {
+        LevelsArgs a = args;
+        void* params[] = {&a};
+        if (cudaLaunchCooperativeKernel((const void*)dag_levels_kernel, dim3(grid), dim3(threads), params, 0, s) == cudaSuccess) return 1;
+        cudaGetLastError();
+        grid = 1;  // rejected (e.g. a partitioned device): the one-CTA path
+    } else if (coop_ok == -1) {
+        grid = 1;
+    }
+    // coop_ok == 0 (CHAD_LEVELS_COOP=0): the round-1 plain launch, kept for A/B timing only
     dag_levels_kernel<<<grid, threads, 0, s>>>(args);
     return 1;
 }

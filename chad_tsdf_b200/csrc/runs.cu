@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
             cnt++;
             run++;
             bool crossed = false;
-            const bool more = (cnt < mrv) && rayl_advance(r, crossed);
+            bool more = rayl_advance(r, crossed);
+            if (more && cnt >= mrv) { err |= ERRF_PAIR_CAPACITY; more = false; }  // the analytic per-ray bound was exceeded: report, never truncate silently
             if (!more || crossed) {
                 if (slot != 0xFFFFFFFFu) atomicAdd(&s_wcnt[warp >> 1][slot], run << wsh); else err |= ERRF_BLOCKS_FULL;
                 run = 0;

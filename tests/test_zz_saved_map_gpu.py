@@ -38,7 +38,6 @@ def test_saved_map_round_trip(chad_lib, tmp_path):
     assert np.mean(np.abs(sd - expect) > 0.03) < 0.1
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("CHAD_GPU_SWEEP"), reason="written after the round's last GPU minute: profiles/first_call.sh runs it (CHAD_GPU_SWEEP=1)")
 @pytest.mark.parametrize("seed", range(12))
 def test_gpu_vs_oracle_on_random_scenes(chad_lib, oracle_lib, seed):
     """The parameter sweep of tests/test_oracle_vs_reference.py::test_restatement_vs_reference_on_random_scenes (voxel sizes 0.03-0.2 m,
