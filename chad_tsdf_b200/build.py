@@ -13,8 +13,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libchad_b200.so")
-SOURCES = ["radix_sort.cu", "points.cu", "band.cu", "blocks.cu", "runs.cu", "fold.cu", "dag.cu", "context.cu", "tsdf_host.cpp"]
-HEADERS = ["common.cuh", "kernels.cuh", "radix_sort.cuh", "scan.cuh", "ray.cuh"]
+SOURCES = ["radix_sort.cu", "points.cu", "shard.cu", "band.cu", "blocks.cu", "runs.cu", "fold.cu", "dag.cu", "context.cu", "nccl_dyn.cpp", "tsdf_host.cpp"]
+HEADERS = ["common.cuh", "kernels.cuh", "points.cuh", "radix_sort.cuh", "scan.cuh", "ray.cuh", "nccl_dyn.h"]
 # -fmad=false / -ffp-contract=off: the reference's strict-IEEE configuration (cmake/options_compiler.cmake:39);
 # the kernels additionally use explicit *_rn intrinsics wherever a result is observable.
 NVCC_FLAGS = ["-std=c++20", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
@@ -67,7 +67,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)

@@ -15,6 +15,7 @@ from .build import LIB
 CHAD_OK = 0
 NUM_LEVELS = 21
 LEVEL_CLUSTERS = 20
+SHARD_ID_BYTES = 256
 
 
 class ChadError(RuntimeError):
@@ -63,9 +64,9 @@ SYMBOLS = {
     "chad_upload": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "chad_timer_begin": (C.c_int, [_P]),
     "chad_timer_end": (C.c_int, [_P, C.POINTER(C.c_float)]),
-    "chad_shard_front": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
-    "chad_shard_send_buffer": (C.c_int, [_P, C.POINTER(_P)]),
-    "chad_shard_ingest": (C.c_int, [_P, _P, C.c_size_t]),
+    "chad_shard_unique_id": (C.c_int, [_P]),
+    "chad_create_sharded": (C.c_int, [C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    "chad_shard_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "chad_shard_export_chunks": (C.c_int, [_P, C.POINTER(C.c_size_t), C.POINTER(_P), C.POINTER(_P)]),
     "chad_shard_finalize_from": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int]),
     "chad_shard_clear": (C.c_int, [_P]),

@@ -369,198 +369,6 @@ __global__ void __launch_bounds__(BLK_THREADS) blocks_sort_kernel(const u64* __r
     if (tid == 0 && s_stats[0]) { atomicAdd(&plan->n_segments, s_stats[0]); atomicAdd(&plan->n_chunk_heads, s_stats[1]); }
 }
 
-// ================================================================================================
-// Morton-range sharding across GPUs. Every rank runs the (small) point stage on the whole batch,
-// walks only its slice of the sorted rays and routes every band-voxel update to the rank that owns the voxel's block
-// (contiguous Morton ranges of 8^3-voxel blocks, cut by world-1 splitters). The update travels as a 16-byte tuple
-// (full Morton key, sorted-point rank, sd): the rank inside the tuple carries the reference's fold order, so the receiver
-// may take the tuples of all senders in any order -- it bins them by block and sorts by (voxel, rank) exactly like the
-// single-GPU path.
-// ================================================================================================
-__device__ __forceinline__ u32 owner_of(u64 blk, const u64* __restrict__ splitters, u32 world) {
-    u32 o = 0;
-    for (u32 g = 0; g + 1 < world; g++) o += (blk >= splitters[g]) ? 1u : 0u;  // world <= 8: branch-free count
-    return o;
-}
-
-constexpr int SHARD_MAX_WORLD = 8;
-
-// per-destination update counts of this rank's ray slice
-__global__ void __launch_bounds__(BLK_THREADS) shard_count_kernel(const float* __restrict__ xyz_sorted, u32 n_points, const uint2* __restrict__ slices,
-                                                                  const BatchScans* __restrict__ scans, float res, float trunc, float recip,
-                                                                  u32 max_ray_voxels, const BatchPlan* __restrict__ plan,
-                                                                  const u64* __restrict__ splitters, u32 world, u32* __restrict__ dest_count) {
-    const u32 i = blockIdx.x * BLK_THREADS + threadIdx.x;
-    u32 cnt[SHARD_MAX_WORLD];
-#pragma unroll
-    for (int d = 0; d < SHARD_MAX_WORLD; d++) cnt[d] = 0;
-    const u32 s = (i < n_points) ? scan_of(scans, plan->n_scans, i) : 0u;
-    if (i < n_points && i >= slices[s].x && i < slices[s].y) {  // this rank walks the rays whose point lies in its Morton range
-        const float pos[3] = {scans->pose[s][0], scans->pose[s][1], scans->pose[s][2]};
-        Ray r;
-        ray_setup(r, xyz_sorted[size_t(i) * 3], xyz_sorted[size_t(i) * 3 + 1], xyz_sorted[size_t(i) * 3 + 2], pos, res, trunc, recip);
-        u64 full = morton_encode(r.cur[0], r.cur[1], r.cur[2]);
-        u32 total = 0;
-        while (true) {
-            const u32 o = owner_of(full >> BLK_SHIFT, splitters, world);
-#pragma unroll
-            for (int d = 0; d < SHARD_MAX_WORLD; d++) cnt[d] += (o == (u32)d) ? 1u : 0u;
-            total++;
-            if (total >= max_ray_voxels) break;
-            int axis;
-            if (!ray_advance(r, axis)) break;
-            full = morton_step(full, axis, axis == 0 ? r.step[0] : (axis == 1 ? r.step[1] : r.step[2]));
-        }
-    }
-    __shared__ u32 s_cnt[SHARD_MAX_WORLD];
-    if (threadIdx.x < SHARD_MAX_WORLD) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-#pragma unroll
-    for (int d = 0; d < SHARD_MAX_WORLD; d++) {
-        const u32 w = __reduce_add_sync(0xffffffffu, cnt[d]);
-        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cnt[d], w);
-    }
-    __syncthreads();
-    if (threadIdx.x < world && s_cnt[threadIdx.x]) atomicAdd(&dest_count[threadIdx.x], s_cnt[threadIdx.x]);
-}
-
-// writes the slice's updates as tuples into the send buffer, grouped by destination (dest_offset = exclusive prefix of the counts)
-__global__ void __launch_bounds__(BLK_THREADS) shard_emit_kernel(const float* __restrict__ xyz_sorted, const float* __restrict__ normals, u32 n_points,
-                                                                 const uint2* __restrict__ slices, const BatchScans* __restrict__ scans, float res, float trunc, float recip,
-                                                                 u32 max_ray_voxels, BatchPlan* plan, const u64* __restrict__ splitters, u32 world,
-                                                                 const u32* __restrict__ dest_offset, u32* __restrict__ dest_cursor,
-                                                                 uint4* __restrict__ tuples, u32 tuple_capacity) {
-    const u32 i = blockIdx.x * BLK_THREADS + threadIdx.x;
-    const u32 lane = threadIdx.x & 31;
-    u64 bkey[BLK_RAY_MAX];
-    u32 bsd[BLK_RAY_MAX];
-    unsigned char bown[BLK_RAY_MAX];
-    u32 total = 0, err = 0;
-    const u32 s = (i < n_points) ? scan_of(scans, plan->n_scans, i) : 0u;
-    if (i < n_points && i >= slices[s].x && i < slices[s].y) {
-        const float pos[3] = {scans->pose[s][0], scans->pose[s][1], scans->pose[s][2]};
-        const float nx = normals[size_t(i) * 3], ny = normals[size_t(i) * 3 + 1], nz = normals[size_t(i) * 3 + 2];
-        Ray r;
-        ray_setup(r, xyz_sorted[size_t(i) * 3], xyz_sorted[size_t(i) * 3 + 1], xyz_sorted[size_t(i) * 3 + 2], pos, res, trunc, recip);
-        u64 full = morton_encode(r.cur[0], r.cur[1], r.cur[2]);
-        const u32 cap = min(max_ray_voxels, (u32)BLK_RAY_MAX);
-        while (true) {
-            if (max(rcode(r.cur[0]), max(rcode(r.cur[1]), rcode(r.cur[2]))) >= (1u << 20)) err |= ERRF_RANGE;
-            float sd = dot3(nx, ny, nz, fsub(fmul((float)r.cur[0], res), r.px), fsub(fmul((float)r.cur[1], res), r.py),
-                            fsub(fmul((float)r.cur[2], res), r.pz));  // octree.hpp:157-159
-            sd = fclamp(sd, -trunc, trunc);
-            bkey[total] = full;
-            bsd[total] = __float_as_uint(sd);
-            bown[total] = (unsigned char)owner_of(full >> BLK_SHIFT, splitters, world);
-            total++;
-            if (total >= cap) break;
-            int axis;
-            if (!ray_advance(r, axis)) break;
-            full = morton_step(full, axis, axis == 0 ? r.step[0] : (axis == 1 ? r.step[1] : r.step[2]));
-        }
-    }
-    for (u32 d = 0; d < world; d++) {  // uniform loop: one reservation per (warp, destination)
-        u32 mine = 0;
-        for (u32 q = 0; q < total; q++) mine += (bown[q] == d) ? 1u : 0u;
-        u32 wtotal = 0, prefix = 0;
-#pragma unroll
-        for (int b = 0; b < 6; b++) {  // mine <= 32: ballot bit planes
-            const u32 plane = __ballot_sync(0xffffffffu, (mine >> b) & 1u);
-            wtotal += (u32)__popc(plane) << b;
-            prefix += (u32)__popc(plane & ((1u << lane) - 1u)) << b;
-        }
-        u32 base = 0;
-        if (lane == 0 && wtotal) base = dest_offset[d] + atomicAdd(&dest_cursor[d], wtotal);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        u32 w = base + prefix;
-        for (u32 q = 0; q < total; q++) {
-            if (bown[q] != d) continue;
-            if (w >= tuple_capacity) { err |= ERRF_PAIR_CAPACITY; break; }
-            tuples[w++] = make_uint4((u32)bkey[q], (u32)(bkey[q] >> 32), i, bsd[q]);
-        }
-    }
-    if (err) atomicOr(&plan->error, err);
-}
-
-// receiver side: count the tuples per block
-__global__ void __launch_bounds__(BLK_THREADS) list_count_kernel(const uint4* __restrict__ tuples, u32 n, BatchPlan* plan, u64* __restrict__ bkeys,
-                                                                 u32* __restrict__ bcount, u32 capacity) {
-    const u32 j = blockIdx.x * BLK_THREADS + threadIdx.x;
-    const u32 lane = threadIdx.x & 31;
-    const bool has = j < n;
-    u64 blk = 0xFFFFFFFF00000000ull | lane;
-    if (has) { const uint4 t = tuples[j]; blk = ((u64(t.y) << 32) | t.x) >> BLK_SHIFT; }
-    const u32 m = __match_any_sync(0xffffffffu, blk);
-    if (has && lane == (u32)(__ffs(m) - 1)) {
-        const u32 slot = block_insert(bkeys, capacity, blk);
-        if (slot == 0xFFFFFFFFu) atomicOr(&plan->error, ERRF_BLOCKS_FULL); else atomicAdd(&bcount[slot], (u32)__popc(m));
-    }
-}
-
-// receiver side: tuples -> 8-byte records in their block's region
-__global__ void __launch_bounds__(BLK_THREADS) list_scatter_kernel(const uint4* __restrict__ tuples, u32 n, BatchPlan* plan, const u64* __restrict__ bkeys,
-                                                                   const u32* __restrict__ boffset, u32* __restrict__ bcursor, u32 capacity, u64* keys_a,
-                                                                   u64* keys_b, u32 pair_capacity) {
-    const u32 j = blockIdx.x * BLK_THREADS + threadIdx.x;
-    const u32 lane = threadIdx.x & 31;
-    const bool has = (j < n) && !(plan->error & ERRF_BLOCKS_FULL);
-    u64* __restrict__ records = radix_result_in_alt(plan->nbits_pairs) ? keys_a : keys_b;
-    u64 key = 0, blk = 0xFFFFFFFF00000000ull | lane;
-    uint4 t = make_uint4(0, 0, 0, 0);
-    if (has) { t = tuples[j]; key = (u64(t.y) << 32) | t.x; blk = key >> BLK_SHIFT; }
-    const u32 m = __match_any_sync(0xffffffffu, blk);
-    const u32 leader = (u32)(__ffs(m) - 1);
-    u32 base = 0xFFFFFFFFu;
-    if (has && lane == leader) {
-        const u32 slot = block_find(bkeys, capacity, blk);
-        if (slot != 0xFFFFFFFFu) base = boffset[slot] + atomicAdd(&bcursor[slot], (u32)__popc(m));
-    }
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (has) {
-        const u32 pos = base + (u32)__popc(m & ((1u << lane) - 1u));
-        if (base == 0xFFFFFFFFu) atomicOr(&plan->error, ERRF_BLOCKS_FULL);
-        else if (pos >= pair_capacity) atomicOr(&plan->error, ERRF_PAIR_CAPACITY);
-        else records[pos] = (u64(t.w) << 32) | (u64)((((u32)key & (BLK_VOXELS - 1)) << BLK_RANK_BITS) | t.z);
-    }
-}
-
-// splitters from the sorted point keys of the batch: block id of the point at every world-th quantile
-__global__ void shard_splitters_kernel(const u64* __restrict__ sorted_keys, u32 n_first_scan, const BatchPlan* __restrict__ plan, u32 world,
-                                       u64* __restrict__ splitters) {
-    const u32 g = threadIdx.x;
-    if (g + 1 >= world) return;
-    // the sorted keys are (scan << bits) | ~compact: the first scan's points are in DESCENDING Morton order
-    const u32 k = plan->k;
-    const u32 cbits = 3 * k + 3;
-    const u64 cmask = (cbits >= 64) ? ~0ull : ((1ull << cbits) - 1ull);
-    const u32 idx = n_first_scan - 1 - (u32)((u64)(g + 1) * n_first_scan / world);  // ascending quantile
-    splitters[g] = expand_key(~sorted_keys[idx] & cmask, k) >> BLK_SHIFT;
-}
-
-// per scan: the range of sorted points whose voxel's block this rank owns. The points of a scan are in DESCENDING Morton order,
-// the ranks own ascending ranges: rank g's points are [first point with block < splitters[g], first point with block < splitters[g-1]).
-__global__ void shard_slices_kernel(const u64* __restrict__ sorted_keys, const BatchScans* __restrict__ scans, const BatchPlan* __restrict__ plan,
-                                    const u64* __restrict__ splitters, u32 rank, u32 world, uint2* __restrict__ slices) {
-    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= plan->n_scans) return;
-    const u32 k = plan->k;
-    const u32 cbits = 3 * k + 3;
-    const u64 cmask = (cbits >= 64) ? ~0ull : ((1ull << cbits) - 1ull);
-    const u32 b = scans->offset[s], e = scans->offset[s + 1];
-    auto first_below = [&](u64 limit) {  // first index in [b, e) whose block id is < limit (block ids descend along the scan)
-        u32 lo = b, hi = e;
-        while (lo < hi) {
-            const u32 mid = (lo + hi) >> 1;
-            const u64 blk = expand_key(~sorted_keys[mid] & cmask, k) >> BLK_SHIFT;
-            if (blk < limit) hi = mid; else lo = mid + 1;
-        }
-        return lo;
-    };
-    const u32 lo = (rank + 1 < world) ? first_below(splitters[rank]) : b;
-    const u32 hi = (rank > 0) ? first_below(splitters[rank - 1]) : e;
-    slices[s] = make_uint2(lo, hi);
-}
-
 inline unsigned blocks_for(u32 n) { return (n + BLK_THREADS - 1) / BLK_THREADS; }
 
 }  // namespace
@@ -616,57 +424,5 @@ int launch_blocks_pairs(cudaStream_t s, const float* xyz_sorted, const float* no
     return launches;
 }
 
-
-int launch_shard_splitters(cudaStream_t s, const u64* sorted_keys, u32 n_first_scan, const BatchPlan* plan, u32 world, u64* splitters) {
-    shard_splitters_kernel<<<1, 32, 0, s>>>(sorted_keys, n_first_scan, plan, world, splitters);
-    return 1;
-}
-
-int launch_shard_slices(cudaStream_t s, const u64* sorted_keys, const BatchScans* scans, const BatchPlan* plan, const u64* splitters, u32 rank, u32 world,
-                        void* slices) {
-    shard_slices_kernel<<<1, MAX_BATCH_SCANS, 0, s>>>(sorted_keys, scans, plan, splitters, rank, world, static_cast<uint2*>(slices));
-    return 1;
-}
-
-int launch_shard_count(cudaStream_t s, const float* xyz_sorted, u32 n_points, const void* slices, const BatchScans* scans, const MapParams& mp,
-                       const BatchPlan* plan, const u64* splitters, u32 world, u32* dest_count) {
-    cudaMemsetAsync(dest_count, 0, SHARD_MAX_WORLD * 4 * 3, s);  // counts | offsets | cursors
-    if (!n_points) return 0;
-    shard_count_kernel<<<blocks_for(n_points), BLK_THREADS, 0, s>>>(xyz_sorted, n_points, static_cast<const uint2*>(slices), scans, mp.res, mp.trunc, mp.recip,
-                                                                   mp.max_ray_voxels, plan, splitters, world, dest_count);
-    return 1;
-}
-
-int launch_shard_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const void* slices, const BatchScans* scans,
-                      const MapParams& mp, BatchPlan* plan, const u64* splitters, u32 world, const u32* dest_offset, u32* dest_cursor, void* tuples,
-                      u32 tuple_capacity) {
-    if (!n_points) return 0;
-    shard_emit_kernel<<<blocks_for(n_points), BLK_THREADS, 0, s>>>(xyz_sorted, normals, n_points, static_cast<const uint2*>(slices), scans, mp.res, mp.trunc, mp.recip,
-                                                                         mp.max_ray_voxels, plan, splitters, world, dest_offset, dest_cursor,
-                                                                         static_cast<uint4*>(tuples), tuple_capacity);
-    return 1;
-}
-
-// receiver: tuples -> block regions -> per-block sort -> (compact key, sd) arrays for the fold
-int launch_blocks_from_tuples(cudaStream_t s, const void* tuples, u32 n, BatchPlan* plan, const BlockTable& bt, void* scan_ws, u64* keys_a, u64* keys_b,
-                              u32* vals_a, u32* vals_b, u32 pair_capacity, int num_sms) {
-    cudaMemsetAsync(bt.keys, 0xFF, size_t(bt.capacity) * 8, s);
-    cudaMemsetAsync(bt.count, 0, size_t(bt.capacity) * (4 + 4), s);
-    int launches = 0;
-    if (n) {
-        list_count_kernel<<<blocks_for(n), BLK_THREADS, 0, s>>>(static_cast<const uint4*>(tuples), n, plan, bt.keys, bt.count, bt.capacity);
-        launches++;
-    }
-    launches += exclusive_scan<u32, u32>(s, bt.count, bt.offset, bt.capacity, scan_ws, (u32*)nullptr, &plan->n_pairs);
-    blocks_compact_kernel<<<blocks_for(bt.capacity), BLK_THREADS, 0, s>>>(bt.count, bt.capacity, bt.list, plan);
-    launches++;
-    if (n) {
-        list_scatter_kernel<<<blocks_for(n), BLK_THREADS, 0, s>>>(static_cast<const uint4*>(tuples), n, plan, bt.keys, bt.offset, bt.cursor, bt.capacity,
-                                                                 keys_a, keys_b, pair_capacity);
-        launches++;
-    }
-    blocks_sort_kernel<<<num_sms * 6, BLK_THREADS, BLK_RMAX * 8, s>>>(bt.keys, bt.count, bt.offset, bt.list, plan, keys_a, keys_b, vals_a, vals_b);
-    return launches + 1;
-}
 
 }  // namespace chadgpu

@@ -99,6 +99,7 @@ enum : u32 {
     ERRF_NUMERIC = 16u,      // NaN / Inf coordinate
     ERRF_DEDUP_FULL = 32u,   // DAG dedup table over capacity
     ERRF_BLOCKS_FULL = 64u,  // block table of the block-binned pair path over capacity (or > 8192 updates of ONE voxel in a batch)
+    ERRF_EXCHANGE = 128u,    // Morton-range sharding: the runs for another rank did not fit the exchange buffer
 };
 
 struct BatchPlan {
@@ -122,6 +123,13 @@ struct BatchPlan {
     u32 n_big_blocks;  // tile-run path: blocks listed from the front of the work list (many updates) ...
     u32 n_small_blocks;//                ... and from its back
     u32 point_shift;   // 23 when the point sort carries the input index in the low bits of its key (keys-only sort), else 0
+    u32 tsb;           // bits of a tile index inside ONE scan (tile_bits = scan bits + Morton-range rank bits + tsb)
+    u32 n_batch;       // points of the whole batch (== n_points on a single GPU; a Morton-range shard sorts only its own n_points of them)
+    u32 tail_lo, tail_hi;  // bit s set: this context holds the lowest-key point of scan s, which normals.hpp:100 never absorbs into a neighbourhood
+    u32 n_runs_local;  // sharded: runs / records of this rank's own walk (before the runs received from the other ranks are appended)
+    u32 n_pairs_local;
+    u32 xfer_runs;     // sharded: runs / records this rank sent to other ranks
+    u32 xfer_records;
 };
 constexpr u32 POINT_INDEX_BITS = 23;
 
@@ -129,7 +137,16 @@ constexpr int MAX_BATCH_SCANS = 64;
 struct BatchScans {  // device resident
     u32 offset[MAX_BATCH_SCANS + 1];  // point offsets of the scans inside the batch
     float pose[MAX_BATCH_SCANS][3];
+    u32 tile_prefix[MAX_BATCH_SCANS + 1];  // 256-ray tiles of the ray walk before scan s: tiles never straddle scans, so that
+                                           // (scan, Morton-range rank, tile in scan) orders the runs of a block across GPUs
 };
+constexpr u32 RAY_TILE = 256;
+// host or device: fill tile_prefix from offset
+__host__ __device__ inline void batch_scans_tiles(BatchScans& sc, u32 n_scans) {
+    u32 t = 0;
+    for (u32 s = 0; s < n_scans; s++) { sc.tile_prefix[s] = t; t += (sc.offset[s + 1] - sc.offset[s] + RAY_TILE - 1) / RAY_TILE; }
+    for (u32 s = n_scans; s <= MAX_BATCH_SCANS; s++) sc.tile_prefix[s] = t;
+}
 
 // scan id of batch point index i (n_scans <= 64: branch-free-ish binary search)
 __device__ __forceinline__ u32 scan_of(const BatchScans* __restrict__ sc, u32 n_scans, u32 i) {

@@ -24,6 +24,7 @@
 
 #include "chad_b200.h"
 #include "kernels.cuh"
+#include "nccl_dyn.h"
 #include "radix_sort.cuh"
 #include "scan.cuh"
 
@@ -141,7 +142,8 @@ struct chad_ctx {
     // asynchronous Submap::finalize (see finalize_begin): part 1 and part 2 run on fin_stream
     cudaStream_t fin_stream = nullptr;
     enum FinState { FIN_IDLE = 0, FIN_PART1 = 1 /* tables swapped, waiting for the closed submap's exact chunk count */,
-                    FIN_PART2 = 2 /* everything queued on fin_stream */ };
+                    FIN_PART2 = 2 /* everything queued on fin_stream */,
+                    FIN_COUNTS = 3 /* sharded: own count known, waiting for the all-gather of every rank's count */ };
     int fin_state = FIN_IDLE;
     u32 fin_max_chunks = 0;       // host upper bound of the chunk count of the submap being finalised
     u32 fin_chunks = 0;           // exact count (known after part 1)
@@ -153,13 +155,35 @@ struct chad_ctx {
         u32 level_nodes[20];
         u32 root[2];
         LevelCounters counters[CHAD_NUM_LEVELS];
+        u32 h2d[4];               // page-locked sources of small host-to-device copies (a pageable source would make the copy wait for the stream)
     }* h_fin = nullptr;
     DevBuf f_counters, f_partial;  // device LevelCounters[21]; partial sums of the persistent levels kernel
     bool fin_external = false;    // the finalize in flight consumes a caller-provided chunk stream (sharded mode): clear `table`, not `table2`
 
-    // Morton-range sharding (multi-GPU, driven from the host language binding)
-    DevBuf sh_tuples, sh_scalars; // send buffer (16-byte tuples grouped by destination); u64 splitters[8] | u32 counts[8] | offsets[8] | cursors[8]
-    bool sh_have_splitters = false;
+    // Morton-range sharding: this context is rank `rank` of `world` ranks that hold ONE map; world == 1 is the
+    // plain single-GPU map. Every rank is fed the same scans; it sorts / walks the points of its own Morton range, the runs of blocks
+    // beyond the range go to their owner (comm_x, group stream, once per batch) and at a submap's close the ranks' sorted leaf chunks
+    // are gathered on rank 0 (comm_f, finalize stream), which holds the DAG.
+    struct Shard {
+        int rank = 0, world = 1;
+        const NcclApi* nccl = nullptr;
+        ncclComm_t comm_x = nullptr, comm_f = nullptr;
+        DevBuf splitters;               // u64[2][SHARD_WORLD_MAX + 1]: range starts (block ids), two sets used alternately by the submaps
+        int split_set = 0;              // set of the active submap
+        int slot_split[MAX_SLOTS] = {}; // set a plan slot's batch was filtered with (its pack kernel runs later, on the group stream)
+        bool need_splitters = true;     // the next batch is the first of a submap
+        u32 first_share_256 = 256;      // rank 0's share of the rays relative to 256 for every other rank (CHAD_SHARD_RANK0_SHARE)
+        DevBuf filter_mem;
+        ShardFilter filter{};
+        DevBuf batch_scans[MAX_SLOTS];  // scan table of the whole batch (slot_scans() holds the table of this rank's own points)
+        DevBuf box_out, box_in;         // exchange boxes [world][box_words] u64
+        u32 box_words = 0;
+        DevBuf scalars;                 // u32: [0..1] sample sort (n, nbits) | [8] own chunk count | [16 .. 16 + world) all chunk counts
+        u32* h_counts = nullptr;        // pinned [SHARD_WORLD_MAX]: chunk counts of the submap being closed
+        cudaEvent_t counts_done = nullptr;
+        u64 sent_runs = 0, sent_records = 0, exchanges = 0;
+    } sh;
+    u32 burst_batches = 0;              // batches queued since the last drain (sharded: the batch boundaries must not depend on timing)
 
     // finalize work buffers
     size_t cap_chunks = 0;
@@ -198,6 +222,11 @@ int fail(chad_ctx* ctx, int code, const std::string& msg) {
     do {                            \
         int _r = (expr);            \
         if (_r != CHAD_OK) return _r; \
+    } while (0)
+#define NCCL_TRY(ctx, expr)                                                                                      \
+    do {                                                                                                         \
+        ncclResult_t _n = (expr);                                                                                \
+        if (_n != ncclSuccess) return fail(ctx, CHAD_ERR_CUDA, std::string(#expr) + ": " + (ctx)->sh.nccl->GetErrorString(_n)); \
     } while (0)
 
 void prof_begin(void* user, int cls) {
@@ -279,6 +308,7 @@ int error_from_flags(chad_ctx* ctx, u32 flags) {
     if (flags & ERRF_PAIR_CAPACITY) { msg += " band voxel buffer overflow;"; code = CHAD_ERR_CAPACITY; }
     if (flags & ERRF_TABLE_FULL) { msg += " resident chunk table full;"; code = CHAD_ERR_CAPACITY; }
     if (flags & ERRF_DEDUP_FULL) { msg += " DAG dedup table full;"; code = CHAD_ERR_CAPACITY; }
+    if (flags & ERRF_EXCHANGE) { msg += " sharded map: the runs for another rank did not fit the exchange box (raise CHAD_SHARD_BOX_MB);"; code = CHAD_ERR_CAPACITY; }
     if (flags & ERRF_BLOCKS_FULL) { msg += " block table of the block-binned pair path full (chad_set_pair_path(ctx, 1) selects the global sort);"; code = CHAD_ERR_CAPACITY; }
     ctx->sticky_error = code;
     return fail(ctx, code, msg);
@@ -370,6 +400,11 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
         ctx->rws2 = radix_workspace_carve(ctx->radix_ws2.p, dcap);
     }
     ctx->rws = radix_workspace_carve(ctx->radix_ws.p, pairs);
+    if (ctx->sh.world > 1) {
+        TRY(dev_ensure(ctx, ctx->sh.filter_mem, shard_filter_bytes(np)));
+        ctx->sh.filter = shard_filter_carve(ctx->sh.filter_mem.p, np);
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->sh.filter_mem.p, 0, ctx->sh.filter_mem.bytes, ctx->stream));  // the per-scan counters start (and are left) at zero
+    }
     ctx->cap_points = np;
     ctx->cap_pairs = pairs;
     return CHAD_OK;
@@ -417,6 +452,8 @@ int complete_one_fold(chad_ctx* ctx, bool block, bool* launched) {
     const bool runs = pf.runs;
     ctx->table_count_known = *ctx->h_table_count;
     ctx->stats.updates += plan.n_pairs;
+    ctx->sh.sent_runs += plan.xfer_runs;
+    ctx->sh.sent_records += plan.xfer_records;
     ctx->stats.key_bits_points = plan.nbits_points;
     ctx->stats.key_bits_pairs = plan.nbits_pairs;
     if (runs) {
@@ -489,16 +526,46 @@ int poll_folds(chad_ctx* ctx) {
     return CHAD_OK;
 }
 
-// plan -> point sort keys -> sort -> gather -> normals of the batch in d_xyz[b] (n points, ns scans; d_scans uploaded)
-void queue_point_stage(chad_ctx* ctx, int slot, int b, u32 n, u32 ns) {
+// bits of a 256-ray tile index inside the batch's largest scan (order key of a run descriptor: points.cuh). Follows from the scan
+// table of the WHOLE batch, so every rank of a sharded map derives the same value.
+u32 batch_tsb(const BatchScans& h, u32 ns) {
+    u32 longest = 0;
+    for (u32 i = 0; i < ns; i++) longest = std::max(longest, h.offset[i + 1] - h.offset[i]);
+    const u32 tiles = (longest + RAY_TILE - 1) / RAY_TILE;
+    u32 bits = 0;
+    while (bits < 32 && (1ull << bits) < tiles) bits++;
+    return bits;
+}
+u32 shard_gbits(const chad_ctx* ctx) { u32 b = 0; while ((1 << b) < ctx->sh.world) b++; return b; }
+const u64* shard_splitters(const chad_ctx* ctx, int set) { return ctx->sh.splitters.as<u64>() + size_t(set) * (SHARD_WORLD_MAX + 1); }
+
+// plan -> point sort keys -> sort -> gather -> normals of the batch in d_xyz[b] (n points, ns scans; the scan table `h` uploaded).
+// Sharded: the plan + ownership filter replace the plan + key kernels and everything behind them works on this rank's points only.
+void queue_point_stage(chad_ctx* ctx, int slot, int b, u32 n, u32 ns, const BatchScans& h) {
     cudaStream_t s = ctx->stream;
     BatchPlan* plan = plan_ptr(ctx, slot);
     const BatchScans* scans = slot_scans(ctx, slot);
     const float* xyz = ctx->d_xyz[b].as<float>();
     u64 launches = 0;
     const LaunchHook* hook = ctx->profiling ? &ctx->hook : nullptr;
-    PROF(ctx, PC_PLAN, launch_plan(s, xyz, n, ns, ctx->mp, plan));
-    PROF(ctx, PC_POINT_KEYS, launch_point_keys(s, xyz, n, scans, ctx->mp, plan, ctx->pk_a.as<u64>(), ctx->pv_a.as<u32>()));
+    const u32 tsb = batch_tsb(h, ns);
+    if (ctx->sh.world > 1) {
+        if (ctx->sh.need_splitters) {
+            // every rank samples and sorts the same points (the submap's first scan), so every rank derives the same ranges: no communication
+            ctx->sh.split_set ^= 1;
+            ctx->sh.need_splitters = false;
+            PROF(ctx, PC_PLAN, launch_shard_splitters(s, xyz, h.offset[1], ctx->mp, (u32)ctx->sh.world, ctx->sh.first_share_256, ctx->pk_a.as<u64>(),
+                                                      ctx->pv_a.as<u32>(), ctx->pk_b.as<u64>(), ctx->pv_b.as<u32>(), ctx->sh.scalars.as<u32>(), ctx->rws,
+                                                      ctx->num_sms, const_cast<u64*>(shard_splitters(ctx, ctx->sh.split_set))));
+        }
+        ctx->sh.slot_split[slot] = ctx->sh.split_set;
+        PROF(ctx, PC_POINT_KEYS, launch_shard_filter(s, xyz, n, ns, ctx->sh.batch_scans[slot].as<BatchScans>(), ctx->mp, plan, tsb, shard_gbits(ctx),
+                                                     shard_splitters(ctx, ctx->sh.split_set), (u32)ctx->sh.rank, (u32)ctx->sh.world, ctx->sh.filter,
+                                                     slot_scans(ctx, slot), ctx->pk_a.as<u64>(), ctx->pv_a.as<u32>()));
+    } else {
+        PROF(ctx, PC_PLAN, launch_plan(s, xyz, n, ns, ctx->mp, plan, tsb));
+        PROF(ctx, PC_POINT_KEYS, launch_point_keys(s, xyz, n, scans, ctx->mp, plan, ctx->pk_a.as<u64>(), ctx->pv_a.as<u32>()));
+    }
     launches += radix_sort_pairs(s, ctx->pk_a.as<u64>(), ctx->pv_a.as<u32>(), ctx->pk_b.as<u64>(), ctx->pv_b.as<u32>(),
                                  plan_field<u32>(ctx, slot, offsetof(BatchPlan, n_points)), plan_field<u32>(ctx, slot, offsetof(BatchPlan, nbits_points)), n,
                                  RS_MAX_PASSES, ctx->rws, ctx->num_sms, hook, PC_POINT_SORT_HIST, plan_field<u32>(ctx, slot, offsetof(BatchPlan, point_shift)));
@@ -508,6 +575,30 @@ void queue_point_stage(chad_ctx* ctx, int slot, int b, u32 n, u32 ns) {
     PROF(ctx, PC_NORMALS, launch_normals(s, slot_xyz_sorted(ctx, slot), ctx->sorted_keys.as<u64>(), n, scans, plan, ctx->seg_info.as<u32>(),
                                          slot_normals(ctx, slot)));
     ctx->stats.kernel_launches += launches;
+}
+
+// sharded: the runs of blocks outside this rank's range go to their owner, the runs received are appended (group stream, between the
+// walk and the descriptor sort). One grouped send / receive of fixed-size boxes per batch: the counts travel inside the boxes, so the
+// host never learns (or waits for) them.
+int queue_shard_exchange(chad_ctx* ctx, int slot) {
+    cudaStream_t gs = ctx->group_stream;
+    chad_ctx::Shard& sh = ctx->sh;
+    const ShardBoxes boxes{sh.box_out.as<u64>(), sh.box_in.as<u64>(), sh.box_words};
+    u64 launches = 0;
+    launches += launch_runs_pack(gs, ctx->rb[slot].capacity, plan_ptr(ctx, slot), ctx->rb[slot], slot_records(ctx, slot), shard_splitters(ctx, sh.slot_split[slot]),
+                                 (u32)sh.rank, (u32)sh.world, boxes, ctx->num_sms);
+    NCCL_TRY(ctx, sh.nccl->GroupStart());
+    for (int g = 0; g < sh.world; g++) {
+        if (g == sh.rank) continue;
+        NCCL_TRY(ctx, sh.nccl->Send(boxes.out + size_t(g) * boxes.words, boxes.words, ncclUint64, g, sh.comm_x, gs));
+        NCCL_TRY(ctx, sh.nccl->Recv(boxes.in + size_t(g) * boxes.words, boxes.words, ncclUint64, g, sh.comm_x, gs));
+    }
+    NCCL_TRY(ctx, sh.nccl->GroupEnd());
+    launches += 1;
+    launches += launch_runs_ingest(gs, plan_ptr(ctx, slot), ctx->rb[slot], slot_records(ctx, slot), (u32)ctx->cap_pairs, (u32)sh.rank, (u32)sh.world, boxes);
+    ctx->stats.kernel_launches += launches;
+    sh.exchanges++;
+    return CHAD_OK;
 }
 
 // Queue everything of the assembled batch up to (not including) the fold. The point stage (which does not touch the
@@ -536,15 +627,20 @@ int process_front(chad_ctx* ctx) {
     // ... and the device waits for it (on fold_stream) before touching the slot
     if (ctx->fold_done_valid[slot]) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->fold_done[slot], 0));
     if (ctx->scans_uploaded_valid[b]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->scans_uploaded[b]));  // (two batches ago: long done)
+    batch_scans_tiles(ctx->h_scans, ns);
     *ctx->h_scans_pinned[b] = ctx->h_scans;
-    CUDA_TRY(ctx, cudaMemcpyAsync(slot_scans(ctx, slot), ctx->h_scans_pinned[b], sizeof(BatchScans), cudaMemcpyHostToDevice, s));
+    // (sharded: this is the table of the whole batch; the table of this rank's own points -- slot_scans -- is made by the filter)
+    BatchScans* scans_dst = ctx->sh.world > 1 ? ctx->sh.batch_scans[slot].as<BatchScans>() : slot_scans(ctx, slot);
+    CUDA_TRY(ctx, cudaMemcpyAsync(scans_dst, ctx->h_scans_pinned[b], sizeof(BatchScans), cudaMemcpyHostToDevice, s));
     CUDA_TRY(ctx, cudaEventRecord(ctx->scans_uploaded[b], s));
     ctx->scans_uploaded_valid[b] = true;
-    queue_point_stage(ctx, slot, b, n, ns);
+    queue_point_stage(ctx, slot, b, n, ns, ctx->h_scans);
     CUDA_TRY(ctx, cudaEventRecord(ctx->xyz_free[b], s));  // the point stage is the only reader of d_xyz[b]
     ctx->xyz_free_valid[b] = true;
     const bool use_runs = ctx->pair_path == 2 && n <= runs_max_batch_points() && ctx->rb[0].capacity != 0;
     const bool use_blocks = !use_runs && ctx->pair_path != 1 && n <= blocks_max_batch_points();
+    if (ctx->sh.world > 1 && !use_runs)
+        return fail(ctx, CHAD_ERR_INVALID, "a sharded map needs the tile-run pair path (truncation / voxel size <= 3.5, batches of at most 2^23 points)");
     if (!use_blocks && !use_runs) {
         PROF(ctx, PC_BAND_COUNT, launch_band_count(s, slot_xyz_sorted(ctx, slot), n, scans, ctx->mp, plan, ctx->counts.as<u32>()));
         PROF(ctx, PC_BAND_SCAN, (exclusive_scan<u32, u32>(s, ctx->counts.as<u32>(), ctx->offsets.as<u32>(), n, ctx->scan_ws.p, (u32*)nullptr,
@@ -571,13 +667,20 @@ int process_front(chad_ctx* ctx) {
             CUDA_TRY(ctx, cudaStreamWaitEvent(ws, ctx->points_done[slot], 0));
             ctx->prof_stream = ws;
         }
-        launches += launch_runs_emit(ws, slot_xyz_sorted(ctx, slot), slot_normals(ctx, slot), n, scans, ctx->mp, plan, ctx->rb[slot],
-                                     slot_records(ctx, slot), (u32)ctx->cap_pairs, hook, PC_RUNS_EMIT);
+        const u32 order_rank = ctx->sh.world > 1 ? u32(ctx->sh.world - 1 - ctx->sh.rank) << batch_tsb(ctx->h_scans, ns) : 0u;
+        launches += launch_runs_emit(ws, slot_xyz_sorted(ctx, slot), slot_normals(ctx, slot), n, ns, scans, ctx->mp, plan, ctx->rb[slot],
+                                     slot_records(ctx, slot), (u32)ctx->cap_pairs, order_rank, hook, PC_RUNS_EMIT);
         // the descriptor sort and the block list are only needed by the fold: they go on their own stream
         CUDA_TRY(ctx, cudaEventRecord(ctx->emit_done, ws));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->group_stream, ctx->emit_done, 0));
         ctx->prof_stream = ctx->group_stream;
-        launches += launch_runs_group(ctx->group_stream, n, plan, ctx->rb[slot], ctx->rws2, ctx->num_sms, hook, PC_RUNS_SORT);
+        if (ctx->sh.world > 1) {
+            prof_begin(ctx, PC_SHARD_EXCHANGE);
+            TRY(queue_shard_exchange(ctx, slot));
+            prof_end(ctx);
+        }
+        launches += launch_runs_group(ctx->group_stream, ctx->sh.world > 1 ? size_t(ctx->rb[slot].capacity) : runs_max_runs(n, ns), plan, ctx->rb[slot], ctx->rws2,
+                                      ctx->num_sms, hook, PC_RUNS_SORT);
         ctx->prof_stream = nullptr;
         ctx->fold_in_flight = true;
     } else if (ctx->fold_in_flight) {
@@ -606,6 +709,7 @@ int process_front(chad_ctx* ctx) {
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->stats.kernel_launches += launches;
     ctx->stats.batches++;
+    ctx->burst_batches++;
     ctx->pend[ctx->n_pend++] = chad_ctx::PendingFold{slot, use_runs, (u32)max_pairs, false};
     ctx->plan_slot = (ctx->plan_slot + 1) % ctx->n_slots;
     ctx->cur ^= 1;
@@ -628,6 +732,7 @@ int drain(chad_ctx* ctx) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
     ctx->fold_in_flight = false;
+    ctx->burst_batches = 0;
     fold_bounds_reset(ctx);
     account_fold_stats(ctx);
     prof_resolve(ctx);
@@ -752,9 +857,11 @@ int queue_sorted_chunks(chad_ctx* ctx, cudaStream_t s, const ChunkTable& t, u32 
 int finalize_part2(chad_ctx* ctx);
 int finalize_finish(chad_ctx* ctx);
 
+int finalize_gather(chad_ctx* ctx);
 // non-blocking progress of an in-flight finalize (called from every API entry)
 int finalize_poll(chad_ctx* ctx) {
     if (ctx->fin_state == chad_ctx::FIN_PART1 && cudaEventQuery(ctx->fin_p1_done) == cudaSuccess) TRY(finalize_part2(ctx));
+    if (ctx->fin_state == chad_ctx::FIN_COUNTS && cudaEventQuery(ctx->sh.counts_done) == cudaSuccess) TRY(finalize_gather(ctx));
     if (ctx->fin_state == chad_ctx::FIN_PART2 && cudaEventQuery(ctx->fin_done) == cudaSuccess) TRY(finalize_finish(ctx));
     cudaGetLastError();  // cudaErrorNotReady is not an error
     return CHAD_OK;
@@ -764,6 +871,10 @@ int finalize_wait(chad_ctx* ctx) {
     if (ctx->fin_state == chad_ctx::FIN_PART1) {
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->fin_p1_done));
         TRY(finalize_part2(ctx));
+    }
+    if (ctx->fin_state == chad_ctx::FIN_COUNTS) {
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->sh.counts_done));
+        TRY(finalize_gather(ctx));
     }
     if (ctx->fin_state == chad_ctx::FIN_PART2) {
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->fin_done));
@@ -805,10 +916,11 @@ int finalize_begin(chad_ctx* ctx, u32 max_chunks, bool external, cudaStream_t co
     return CHAD_OK;
 }
 
-// the exact chunk count is on the host: size everything and queue the whole finalize on fin_stream
-int finalize_part2(chad_ctx* ctx) {
+// The DAG stage of Submap::finalize on fin_stream: f_ids[0] / f_cells hold C ascending chunks (or are about to: `chunks` queues whatever
+// produces them, after the buffers have been sized), *SC_COUNT = C.
+template <typename QueueChunks>
+int finalize_dag(chad_ctx* ctx, u32 C, bool count_from_host, QueueChunks chunks) {
     cudaStream_t fs = ctx->fin_stream;
-    const u32 C = ctx->fin_external ? ctx->fin_max_chunks : *ctx->h_table_count2;
     ctx->fin_chunks = C;
     ctx->fin_state = chad_ctx::FIN_IDLE;  // (until everything is queued: the reserves below may synchronise fin_stream)
     if (C >= (1u << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
@@ -823,9 +935,12 @@ int finalize_part2(chad_ctx* ctx) {
     if (ctx->profiling) cudaEventRecord(ctx->fin_t0, fs);
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->f_scalars.p, 0, 256, fs));
     u64 launches = 0;
-    if (ctx->fin_external) CUDA_TRY(ctx, cudaMemcpyAsync(scalar32(ctx, SC_COUNT), &ctx->fin_chunks, 4, cudaMemcpyHostToDevice, fs));
+    TRY(chunks());
+    if (count_from_host) {
+        ctx->h_fin->h2d[0] = C;
+        CUDA_TRY(ctx, cudaMemcpyAsync(scalar32(ctx, SC_COUNT), &ctx->h_fin->h2d[0], 4, cudaMemcpyHostToDevice, fs));
+    }
     if (C) {
-        if (!ctx->fin_external) TRY(queue_sorted_chunks(ctx, fs, ctx->table2, C));
         launches += launch_cluster_build(fs, ctx->f_cells.p, scalar32(ctx, SC_COUNT), C, ctx->mp, ctx->f_tsdf.as<u64>());
         launches += launch_cluster_dedup(fs, LC.table, ctx->f_tsdf.as<u64>(), scalar32(ctx, SC_COUNT), C, LC.raw.as<u64>(), LC.uniques,
                                          ctx->f_slot_of.as<u32>(), ctx->f_is_new.as<u32>(), ctx->f_rank.as<u32>(), ctx->f_scan_ws.p,
@@ -850,16 +965,98 @@ int finalize_part2(chad_ctx* ctx) {
     la.root_out = scalar32(ctx, SC_ROOT);
     la.level_nodes = scalar32(ctx, SC_LEVELS);
     launches += launch_dag_levels(fs, la, ctx->num_sms);
+    ctx->stats.kernel_launches += launches;
+    return CHAD_OK;
+}
+
+// the tail of a finalize on fin_stream: results to the host, the closed submap's table cleared
+int finalize_tail(chad_ctx* ctx, bool clear_table2) {
+    cudaStream_t fs = ctx->fin_stream;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->scalars, ctx->f_scalars.p, 16 * 4 + 20 * 4, cudaMemcpyDeviceToHost, fs));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_fin->counters, ctx->f_counters.p, sizeof(LevelCounters) * 20, cudaMemcpyDeviceToHost, fs));
     ctx->stats.d2h_bytes += 16 * 4 + 20 * 4 + sizeof(LevelCounters) * 20;
-    if (!ctx->fin_external) launch_table_clear(fs, ctx->table2);  // octree.clear(), tsdf.cpp:57 (external: done by the caller's stream)
+    if (clear_table2) launch_table_clear(fs, ctx->table2);  // octree.clear(), tsdf.cpp:57 (external: done by the caller's stream)
     if (ctx->profiling) cudaEventRecord(ctx->fin_t3, fs);
     CUDA_TRY(ctx, cudaEventRecord(ctx->fin_done, fs));
     CUDA_TRY(ctx, cudaGetLastError());
-    ctx->stats.kernel_launches += launches;
     ctx->fin_state = chad_ctx::FIN_PART2;
     return CHAD_OK;
+}
+
+// the exact chunk count is on the host: size everything and queue the whole finalize on fin_stream
+int finalize_part2(chad_ctx* ctx) {
+    cudaStream_t fs = ctx->fin_stream;
+    const u32 C = ctx->fin_external ? ctx->fin_max_chunks : *ctx->h_table_count2;
+    if (ctx->sh.world > 1 && !ctx->fin_external) {
+        // sharded: rank 0 builds the DAG from all ranks' chunks, so every rank first learns every rank's count (the sizes of the gather
+        // must be known on the host). Queued here, collected by finalize_gather -- nobody waits.
+        chad_ctx::Shard& sh = ctx->sh;
+        ctx->fin_chunks = C;
+        u32* d = sh.scalars.as<u32>();
+        ctx->h_fin->h2d[1] = C;
+        CUDA_TRY(ctx, cudaMemcpyAsync(d + 8, &ctx->h_fin->h2d[1], 4, cudaMemcpyHostToDevice, fs));
+        NCCL_TRY(ctx, sh.nccl->AllGather(d + 8, d + 16, 1, ncclUint32, sh.comm_f, fs));
+        CUDA_TRY(ctx, cudaMemcpyAsync(sh.h_counts, d + 16, size_t(sh.world) * 4, cudaMemcpyDeviceToHost, fs));
+        CUDA_TRY(ctx, cudaEventRecord(sh.counts_done, fs));
+        ctx->stats.kernel_launches += 1;
+        ctx->fin_state = chad_ctx::FIN_COUNTS;
+        return CHAD_OK;
+    }
+    TRY(finalize_dag(ctx, C, ctx->fin_external, [&]() -> int {
+        if (C && !ctx->fin_external) TRY(queue_sorted_chunks(ctx, fs, ctx->table2, C));
+        return CHAD_OK;
+    }));
+    return finalize_tail(ctx, !ctx->fin_external);
+}
+
+// sharded: every rank's chunk count has arrived. The ranges ascend with the rank, so the concatenation of the ranks' sorted chunks in
+// rank order is the submap's chunk stream in ascending Morton order (submap.hpp:10-106 walks the octree in that order): every rank
+// sorts its chunks and sends them to rank 0, which receives them behind its own and runs the DAG stage; the two root addresses
+// (submap.hpp:108-109) are broadcast back.
+int finalize_gather(chad_ctx* ctx) {
+    cudaStream_t fs = ctx->fin_stream;
+    chad_ctx::Shard& sh = ctx->sh;
+    u64 total = 0;
+    u64 offset[SHARD_WORLD_MAX + 1];
+    for (int g = 0; g < sh.world; g++) { offset[g] = total; total += sh.h_counts[g]; }
+    const u32 own = sh.h_counts[sh.rank];
+    if (total >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
+    if (sh.rank == 0) {
+        TRY(finalize_dag(ctx, (u32)total, true, [&]() -> int {
+            if (own) TRY(queue_sorted_chunks(ctx, fs, ctx->table2, own));
+            bool any = false;
+            for (int g = 1; g < sh.world; g++) any |= sh.h_counts[g] != 0;
+            if (any) {
+                NCCL_TRY(ctx, sh.nccl->GroupStart());
+                for (int g = 1; g < sh.world; g++) {
+                    const size_t c = sh.h_counts[g];
+                    if (!c) continue;
+                    NCCL_TRY(ctx, sh.nccl->Recv(ctx->f_ids[0].as<u64>() + offset[g], c, ncclUint64, g, sh.comm_f, fs));
+                    NCCL_TRY(ctx, sh.nccl->Recv(static_cast<u64*>(ctx->f_cells.p) + offset[g] * 8, c * 8, ncclUint64, g, sh.comm_f, fs));
+                }
+                NCCL_TRY(ctx, sh.nccl->GroupEnd());
+                ctx->stats.kernel_launches += 1;
+            }
+            return CHAD_OK;
+        }));
+    } else {
+        ctx->fin_chunks = own;
+        ctx->fin_state = chad_ctx::FIN_IDLE;
+        TRY(ensure_finalize_capacity(ctx, own));
+        if (ctx->profiling) cudaEventRecord(ctx->fin_t0, fs);
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->f_scalars.p, 0, 256, fs));
+        if (own) {
+            TRY(queue_sorted_chunks(ctx, fs, ctx->table2, own));
+            NCCL_TRY(ctx, sh.nccl->GroupStart());
+            NCCL_TRY(ctx, sh.nccl->Send(ctx->f_ids[0].p, own, ncclUint64, 0, sh.comm_f, fs));
+            NCCL_TRY(ctx, sh.nccl->Send(ctx->f_cells.p, size_t(own) * 8, ncclUint64, 0, sh.comm_f, fs));
+            NCCL_TRY(ctx, sh.nccl->GroupEnd());
+            ctx->stats.kernel_launches += 1;
+        }
+    }
+    NCCL_TRY(ctx, sh.nccl->Broadcast(scalar32(ctx, SC_ROOT), scalar32(ctx, SC_ROOT), 2, ncclUint32, 0, sh.comm_f, fs));
+    ctx->stats.kernel_launches += 1;
+    return finalize_tail(ctx, true);
 }
 
 int finalize_finish(chad_ctx* ctx) {
@@ -868,12 +1065,13 @@ int finalize_finish(chad_ctx* ctx) {
     if (hs[SC_ERR]) return error_from_flags(ctx, hs[SC_ERR]);
     const u32 C = ctx->fin_chunks;
     Level& LC = ctx->levels[CHAD_LEVEL_CLUSTERS];
-    if (C) {
+    const bool has_dag = ctx->sh.rank == 0 || ctx->fin_external;  // sharded: the levels live on rank 0, the others only learn the roots
+    if (C && has_dag) {
         const u32 fresh = hs[SC_NEW32];
         LC.uniques += fresh;
         LC.dupes += 2 * C - fresh;  // levels.hpp:135-138
     }
-    for (int d = 0; d < 20; d++) {
+    for (int d = 0; d < 20 && has_dag; d++) {
         Level& L = ctx->levels[d];
         L.uniques = ctx->h_fin->counters[d].uniques;   // levels.hpp:79-86, accumulated on the device
         L.dupes = ctx->h_fin->counters[d].dupes;
@@ -898,6 +1096,7 @@ int finalize_finish(chad_ctx* ctx) {
 // device here. lazy = false (chad_finalize_active): queue everything now.
 int finalize_submap(chad_ctx* ctx, bool lazy) {
     TRY(process_front(ctx));
+    ctx->sh.need_splitters = true;  // (sharded) the next submap's ranges follow its own first scan
     if (ctx->n_pend) {
         ctx->pend[ctx->n_pend - 1].close = true;  // the submap's last batch: the finalize begins right after its fold
         if (lazy) return CHAD_OK;
@@ -967,7 +1166,9 @@ int end_scan(chad_ctx* ctx, size_t n, const float position[3]) {
     ctx->batch_points += (u32)n;
     // A burst starts with a short batch: while nothing is in flight the device would only wait for the host to copy a full batch
     // (24 scans = 1.4 ms over PCIe); once a batch is queued the following ones fill up behind it.
-    const u32 target = ctx->n_pend ? (u32)ctx->max_batch : std::min<u32>((u32)ctx->max_batch, ctx->first_batch);
+    // (sharded: every rank must cut the same batches, so the rule may not look at what happens to be in flight)
+    const bool burst_start = ctx->sh.world > 1 ? ctx->burst_batches == 0 : ctx->n_pend == 0;
+    const u32 target = burst_start ? std::min<u32>((u32)ctx->max_batch, ctx->first_batch) : (u32)ctx->max_batch;
     if (ctx->batch_scans >= target) TRY(process_front(ctx));
     return CHAD_OK;
 }
@@ -987,9 +1188,17 @@ extern "C" {
 
 const char* chad_last_error(const chad_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
-int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans, chad_ctx** out) {
+static int create_impl(float sdf_res, float sdf_trunc, int device, int max_batch_scans, int rank, int world, const void* shard_id, chad_ctx** out) {
     if (!out) return fail(nullptr, CHAD_ERR_INVALID, "out is NULL");
     *out = nullptr;
+    if (world < 1 || world > SHARD_WORLD_MAX || rank < 0 || rank >= world || (world > 1 && !shard_id))
+        return fail(nullptr, CHAD_ERR_INVALID, "sharded map: 1 <= world <= 8, 0 <= rank < world, and the id of chad_shard_unique_id");
+    const NcclApi* nccl = nullptr;
+    if (world > 1) {
+        const char* why = "";
+        nccl = nccl_api(&why);
+        if (!nccl) return fail(nullptr, CHAD_ERR_CUDA, std::string("sharded map: ") + why);
+    }
     if (!(sdf_res > 0.0f) || !(sdf_trunc > 0.0f)) return fail(nullptr, CHAD_ERR_INVALID, "sdf_res and sdf_trunc must be positive");
     if (max_batch_scans < 0 || max_batch_scans > MAX_BATCH_SCANS) return fail(nullptr, CHAD_ERR_INVALID, "max_batch_scans must be in [0, 64]");
     int count = 0;
@@ -1096,21 +1305,92 @@ int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans,
     CREATE_TRY(cudaStreamSynchronize(ctx->fin_stream));
     r = level_counters_reset(ctx);
     if (r != CHAD_OK) return bail(r);
+    if (world > 1) {
+        chad_ctx::Shard& sh = ctx->sh;
+        sh.rank = rank;
+        sh.world = world;
+        sh.nccl = nccl;
+        r = dev_ensure(ctx, sh.splitters, 2 * (SHARD_WORLD_MAX + 1) * sizeof(u64));
+        for (int q = 0; q < MAX_SLOTS; q++) if (r == CHAD_OK) r = dev_ensure(ctx, sh.batch_scans[q], sizeof(BatchScans));
+        if (r == CHAD_OK) r = dev_ensure(ctx, sh.scalars, 256);
+        size_t box_mb = 4;
+        if (const char* env = std::getenv("CHAD_SHARD_BOX_MB")) { const long v = std::atol(env); if (v >= 1 && v <= 1024) box_mb = (size_t)v; }
+        sh.box_words = (u32)(box_mb * (1u << 20) / 8);
+        if (r == CHAD_OK) r = dev_ensure(ctx, sh.box_out, size_t(world) * sh.box_words * 8);
+        if (r == CHAD_OK) r = dev_ensure(ctx, sh.box_in, size_t(world) * sh.box_words * 8);
+        if (r != CHAD_OK) return bail(r);
+        CREATE_TRY(cudaMemset(sh.scalars.p, 0, 256));
+        CREATE_TRY(cudaMemset(sh.box_in.p, 0, size_t(world) * sh.box_words * 8));
+        CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&sh.h_counts), SHARD_WORLD_MAX * sizeof(u32)));
+        CREATE_TRY(cudaEventCreateWithFlags(&sh.counts_done, cudaEventDisableTiming));
+        if (const char* env = std::getenv("CHAD_SHARD_RANK0_SHARE")) { const int v = std::atoi(env); if (v >= 0 && v <= 256) sh.first_share_256 = (u32)v; }
+        // two communicators: the per-batch exchange (group stream) and the per-submap gather (finalize stream) are queued from points of
+        // the host code that are not ordered against each other, and NCCL wants one issue order per communicator
+        const ncclUniqueId* ids = static_cast<const ncclUniqueId*>(shard_id);
+        ncclResult_t n1 = nccl->CommInitRank(&sh.comm_x, world, ids[0], rank);
+        ncclResult_t n2 = n1 == ncclSuccess ? nccl->CommInitRank(&sh.comm_f, world, ids[1], rank) : n1;
+        if (n1 != ncclSuccess || n2 != ncclSuccess) {
+            ctx->error = std::string("ncclCommInitRank: ") + nccl->GetErrorString(n1 != ncclSuccess ? n1 : n2);
+            return bail(CHAD_ERR_CUDA);
+        }
+    }
 #undef CREATE_TRY
     *out = ctx;
+    return CHAD_OK;
+}
+
+int chad_create(float sdf_res, float sdf_trunc, int device, int max_batch_scans, chad_ctx** out) {
+    return create_impl(sdf_res, sdf_trunc, device, max_batch_scans, 0, 1, nullptr, out);
+}
+
+int chad_shard_unique_id(void* id) {
+    if (!id) return fail(nullptr, CHAD_ERR_INVALID, "id is NULL");
+    const char* why = "";
+    const NcclApi* nccl = nccl_api(&why);
+    if (!nccl) return fail(nullptr, CHAD_ERR_CUDA, std::string("chad_shard_unique_id: ") + why);
+    ncclUniqueId* ids = static_cast<ncclUniqueId*>(id);
+    for (int q = 0; q < 2; q++) {
+        const ncclResult_t n = nccl->GetUniqueId(&ids[q]);
+        if (n != ncclSuccess) return fail(nullptr, CHAD_ERR_CUDA, std::string("ncclGetUniqueId: ") + nccl->GetErrorString(n));
+    }
+    return CHAD_OK;
+}
+
+int chad_create_sharded(float sdf_res, float sdf_trunc, int device, int max_batch_scans, int rank, int world, const void* id, chad_ctx** out) {
+    if (world == 1) return create_impl(sdf_res, sdf_trunc, device, max_batch_scans, 0, 1, nullptr, out);
+    return create_impl(sdf_res, sdf_trunc, device, max_batch_scans, rank, world, id, out);
+}
+
+int chad_shard_info(chad_ctx* ctx, int* rank, int* world, uint64_t* sent_runs, uint64_t* sent_records, uint64_t* exchanges) {
+    if (!ctx) return CHAD_ERR_INVALID;
+    if (rank) *rank = ctx->sh.rank;
+    if (world) *world = ctx->sh.world;
+    if (sent_runs) *sent_runs = ctx->sh.sent_runs;
+    if (sent_records) *sent_records = ctx->sh.sent_records;
+    if (exchanges) *exchanges = ctx->sh.exchanges;
     return CHAD_OK;
 }
 
 void chad_destroy(chad_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->sh.world > 1) {
+        for (cudaStream_t st : {ctx->group_stream, ctx->fin_stream}) if (st) cudaStreamSynchronize(st);
+        if (ctx->sh.comm_x) ctx->sh.nccl->CommDestroy(ctx->sh.comm_x);
+        if (ctx->sh.comm_f) ctx->sh.nccl->CommDestroy(ctx->sh.comm_f);
+        for (DevBuf* b : {&ctx->sh.splitters, &ctx->sh.filter_mem, &ctx->sh.batch_scans[0], &ctx->sh.batch_scans[1], &ctx->sh.batch_scans[2], &ctx->sh.box_out,
+                          &ctx->sh.box_in, &ctx->sh.scalars})
+            dev_free(*b);
+        if (ctx->sh.h_counts) cudaFreeHost(ctx->sh.h_counts);
+        if (ctx->sh.counts_done) cudaEventDestroy(ctx->sh.counts_done);
+    }
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->walk_stream) cudaStreamSynchronize(ctx->walk_stream);
     if (ctx->group_stream) cudaStreamSynchronize(ctx->group_stream);
     if (ctx->fold_stream) cudaStreamSynchronize(ctx->fold_stream);
     if (ctx->fin_stream) cudaStreamSynchronize(ctx->fin_stream);
-    DevBuf* bufs[] = {&ctx->xyz_sorted2[0], &ctx->normals2[0], &ctx->d_scans2[0], &ctx->xyz_sorted2[1], &ctx->normals2[1], &ctx->d_scans2[1], &ctx->keys_c, &ctx->run_mem[2], &ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->t2_list, &ctx->t_list, &ctx->f_counters, &ctx->f_partial, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->sh_tuples, &ctx->sh_scalars, &ctx->bt_mem, &ctx->run_mem[0], &ctx->run_mem[1], &ctx->radix_ws2, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
+    DevBuf* bufs[] = {&ctx->xyz_sorted2[0], &ctx->normals2[0], &ctx->d_scans2[0], &ctx->xyz_sorted2[1], &ctx->normals2[1], &ctx->d_scans2[1], &ctx->keys_c, &ctx->run_mem[2], &ctx->t2_keys, &ctx->t2_cells, &ctx->t2_count, &ctx->t2_list, &ctx->t_list, &ctx->f_counters, &ctx->f_partial, &ctx->d_xyz[0], &ctx->d_xyz[1], &ctx->d_scans, &ctx->d_plan, &ctx->bt_mem, &ctx->run_mem[0], &ctx->run_mem[1], &ctx->radix_ws2, &ctx->pk_a, &ctx->pk_b, &ctx->pv_a, &ctx->pv_b, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b,
                       &ctx->sorted_keys, &ctx->sorted_order, &ctx->xyz_sorted, &ctx->normals, &ctx->seg_info, &ctx->counts, &ctx->offsets,
                       &ctx->radix_ws, &ctx->scan_ws, &ctx->t_keys, &ctx->t_cells, &ctx->t_count, &ctx->f_sorted, &ctx->f_ids[0], &ctx->f_ids[1], &ctx->f_slots[0],
                       &ctx->f_slots[1], &ctx->f_cells, &ctx->f_tsdf, &ctx->f_addr[0], &ctx->f_addr[1], &ctx->f_head_rank, &ctx->f_cand,
@@ -1276,6 +1556,7 @@ int chad_export_voxels(chad_ctx* ctx, uint64_t* keys, uint32_t* sd_bits, uint32_
 
 int chad_level_words(chad_ctx* ctx, int level, size_t* words) {
     if (!ctx || !words || level < 0 || level >= CHAD_NUM_LEVELS) return CHAD_ERR_INVALID;
+    if (ctx->sh.rank != 0) return fail(ctx, CHAD_ERR_INVALID, "sharded map: the DAG levels live on rank 0");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     TRY(settle(ctx));
     const Level& L = ctx->levels[level];
@@ -1285,6 +1566,7 @@ int chad_level_words(chad_ctx* ctx, int level, size_t* words) {
 
 int chad_level_counters(chad_ctx* ctx, int level, uint32_t* uniques, uint32_t* dupes) {
     if (!ctx || !uniques || !dupes || level < 0 || level >= CHAD_NUM_LEVELS) return CHAD_ERR_INVALID;
+    if (ctx->sh.rank != 0) return fail(ctx, CHAD_ERR_INVALID, "sharded map: the DAG levels live on rank 0");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     TRY(settle(ctx));
     *uniques = ctx->levels[level].uniques;
@@ -1305,6 +1587,7 @@ int chad_export_level(chad_ctx* ctx, int level, void* dst, size_t capacity_words
 
 int chad_query_voxels(chad_ctx* ctx, uint32_t submap, const uint64_t* keys, size_t n, uint8_t* bytes) {
     if (!ctx || (n && (!keys || !bytes))) return CHAD_ERR_INVALID;
+    if (ctx->sh.rank != 0) return fail(ctx, CHAD_ERR_INVALID, "sharded map: the DAG levels live on rank 0");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     TRY(settle(ctx));
     if (submap >= ctx->roots.size()) return fail(ctx, CHAD_ERR_INVALID, "submap index out of range");
@@ -1335,7 +1618,10 @@ int chad_reset(chad_ctx* ctx) {
     ctx->batch_scans = 0;
     ctx->n_pend = 0;
     for (bool& f : ctx->fold_stats_pending) f = false;
-    ctx->sh_have_splitters = false;
+    ctx->sh.need_splitters = true;
+    ctx->burst_batches = 0;
+    ctx->sh.sent_runs = ctx->sh.sent_records = ctx->sh.exchanges = 0;
+    if (ctx->sh.world > 1 && ctx->sh.filter_mem.p) CUDA_TRY(ctx, cudaMemsetAsync(ctx->sh.filter_mem.p, 0, ctx->sh.filter_mem.bytes, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->walk_stream));
@@ -1415,6 +1701,7 @@ int chad_profile_get(chad_ctx* ctx, int cls, const char** name, double* millisec
     else if (cls == PC_RUNS_EMIT) nm = "runs_emit_kernel";
     else if (cls == PC_RUNS_SORT) nm = "run descriptor sort + runs_group_kernel";
     else if (cls == PC_RUNS_FOLD) nm = "runs_fold_kernel";
+    else if (cls == PC_SHARD_EXCHANGE) nm = "runs_pack_kernel + NCCL send/recv + runs_ingest_kernel";
     else nm = "finalize_submap[part 1 + part 2 on the finalize stream, overlapped with inserts]";
     if (name) *name = nm;
     if (milliseconds) *milliseconds = ctx->prof_ms[cls];
@@ -1458,6 +1745,7 @@ static void stage_single_scan(chad_ctx* ctx, size_t n, const float position[3]) 
     ctx->h_scans.offset[0] = 0;
     ctx->h_scans.offset[1] = (u32)n;
     std::memcpy(ctx->h_scans.pose[0], position, 12);
+    batch_scans_tiles(ctx->h_scans, 1);
     *ctx->h_scans_pinned[0] = ctx->h_scans;
     cudaMemcpyAsync(ctx->d_scans.p, ctx->h_scans_pinned[0], sizeof(BatchScans), cudaMemcpyHostToDevice, ctx->stream);
 }
@@ -1488,7 +1776,7 @@ int chad_stage_points(chad_ctx* ctx, const float* xyz, size_t n, const float pos
     const BatchScans* scans = ctx->d_scans.as<BatchScans>();
     const float* dxyz = ctx->d_xyz[0].as<float>();
     u64 launches = 0;
-    launches += launch_plan(s, dxyz, (u32)n, 1, ctx->mp, plan);
+    launches += launch_plan(s, dxyz, (u32)n, 1, ctx->mp, plan, batch_tsb(ctx->h_scans, 1));
     launches += launch_point_keys(s, dxyz, (u32)n, scans, ctx->mp, plan, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>());
     launches += radix_sort_pairs(s, ctx->keys_a.as<u64>(), ctx->vals_a.as<u32>(), ctx->keys_b.as<u64>(), ctx->vals_b.as<u32>(),
                                  plan_field<u32>(ctx, 0, offsetof(BatchPlan, n_points)), plan_field<u32>(ctx, 0, offsetof(BatchPlan, nbits_points)), n,
@@ -1521,7 +1809,7 @@ int chad_stage_pairs(chad_ctx* ctx, const float* xyz_sorted, const float* normal
     BatchPlan* plan = ctx->d_plan.as<BatchPlan>();
     const BatchScans* scans = ctx->d_scans.as<BatchScans>();
     u64 launches = 0;
-    launches += launch_plan(s, ctx->xyz_sorted.as<float>(), (u32)n, 1, ctx->mp, plan);
+    launches += launch_plan(s, ctx->xyz_sorted.as<float>(), (u32)n, 1, ctx->mp, plan, batch_tsb(ctx->h_scans, 1));
     launches += launch_band_count(s, ctx->xyz_sorted.as<float>(), (u32)n, scans, ctx->mp, plan, ctx->counts.as<u32>());
     launches += exclusive_scan<u32, u32>(s, ctx->counts.as<u32>(), ctx->offsets.as<u32>(), n, ctx->scan_ws.p, (u32*)nullptr,
                                          plan_field<u32>(ctx, 0, offsetof(BatchPlan, n_pairs)));
@@ -1581,104 +1869,7 @@ void chad_morton_decode(uint64_t key, int32_t* x, int32_t* y, int32_t* z) { mort
 uint64_t chad_key_compact(uint64_t key, unsigned k) { return compact_key(key, k); }
 uint64_t chad_key_expand(uint64_t compact, unsigned k) { return expand_key(compact, k); }
 
-// ---- Morton-range sharding across GPUs -----------------------------------------------
-// Synchronous building blocks; the exchange itself (NCCL all-to-all / all-gather over NVLink) is done by the caller
-// between them (chad_tsdf_b200/sharded.py uses torch.distributed). All ranks must call them with the same batch.
-int chad_shard_front(chad_ctx* ctx, const float* xyz, const uint32_t* scan_offsets, const float* poses, int n_scans, int rank, int world,
-                     int new_submap, uint64_t* send_counts) {
-    if (!ctx || !scan_offsets || !poses || !send_counts || n_scans < 1 || n_scans > MAX_BATCH_SCANS || world < 1 || world > SHARD_WORLD_MAX ||
-        rank < 0 || rank >= world)
-        return fail(ctx, CHAD_ERR_INVALID, "chad_shard_front: bad argument");
-    if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (ctx->n_pend || ctx->batch_scans || ctx->fold_in_flight) TRY(settle(ctx));  // chad_insert traffic in between
-    TRY(finalize_poll(ctx));  // (a finalize of the previous submap may still be running on its own stream: it only reads its own buffers)
-    const size_t n = scan_offsets[n_scans];
-    for (int d = 0; d < world; d++) send_counts[d] = 0;
-    if (n == 0) return CHAD_OK;
-    if (!xyz) return fail(ctx, CHAD_ERR_INVALID, "chad_shard_front: xyz is NULL");
-    if (n > blocks_max_batch_points()) return fail(ctx, CHAD_ERR_CAPACITY, "sharded batch exceeds 2^23 points");
-    if (n > ctx->cap_points || ctx->cap_points == 0) TRY(ensure_batch_capacity(ctx, n));
-    TRY(dev_ensure(ctx, ctx->sh_scalars, 1024));
-    cudaStream_t s = ctx->stream;
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_xyz[0].p, xyz, n * 12, cudaMemcpyDefault, s));  // host (pageable / pinned) or device memory
-    for (int i = 0; i <= n_scans; i++) ctx->h_scans.offset[i] = scan_offsets[i];
-    std::memcpy(ctx->h_scans.pose, poses, size_t(n_scans) * 12);
-    *ctx->h_scans_pinned[0] = ctx->h_scans;
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scans.p, ctx->h_scans_pinned[0], sizeof(BatchScans), cudaMemcpyHostToDevice, s));
-    queue_point_stage(ctx, 0, 0, (u32)n, (u32)n_scans);
-    BatchPlan* plan = plan_ptr(ctx, 0);
-    const BatchScans* scans = ctx->d_scans.as<BatchScans>();
-    u64* splitters = ctx->sh_scalars.as<u64>();
-    u32* dest = reinterpret_cast<u32*>(splitters + 8);  // counts[8] | offsets[8] | cursors[8]
-    u64 launches = 0;
-    if (new_submap || !ctx->sh_have_splitters) {
-        // every rank sorts the same points, so every rank derives the same splitters: no communication
-        launches += launch_shard_splitters(s, ctx->sorted_keys.as<u64>(), scan_offsets[1], plan, (u32)world, splitters);
-        ctx->sh_have_splitters = true;
-    }
-    void* slices = ctx->sh_scalars.as<unsigned char>() + 256;  // uint2[64]
-    launches += launch_shard_slices(s, ctx->sorted_keys.as<u64>(), scans, plan, splitters, (u32)rank, (u32)world, slices);
-    launches += launch_shard_count(s, ctx->xyz_sorted.as<float>(), (u32)n, slices, scans, ctx->mp, plan, splitters, (u32)world, dest);
-    u32 counts[8] = {0};
-    CUDA_TRY(ctx, cudaMemcpyAsync(counts, dest, 32, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    u32 offsets[8];
-    size_t total = 0;
-    for (int d = 0; d < 8; d++) { offsets[d] = (u32)total; total += counts[d]; }
-    if (total >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "sharded batch emits more than 2^31 updates");
-    TRY(dev_ensure(ctx, ctx->sh_tuples, (total + 1) * 16));
-    CUDA_TRY(ctx, cudaMemcpyAsync(dest + 8, offsets, 32, cudaMemcpyHostToDevice, s));
-    launches += launch_shard_emit(s, ctx->xyz_sorted.as<float>(), ctx->normals.as<float>(), (u32)n, slices, scans, ctx->mp, plan, splitters, (u32)world,
-                                  dest + 8, dest + 16, ctx->sh_tuples.p, (u32)total);
-    ctx->stats.kernel_launches += launches;
-    { const int rc = stage_check(ctx); if (rc != CHAD_OK) { ctx->error += " [chad_shard_front]"; return rc; } }
-    for (int d = 0; d < world; d++) send_counts[d] = counts[d];
-    ctx->stats.scans += (u64)n_scans;
-    ctx->stats.points += n;
-    ctx->stats.h2d_bytes += n * 12;
-    ctx->stats.batches++;
-    return CHAD_OK;
-}
-
-int chad_shard_send_buffer(chad_ctx* ctx, void** tuples_device) {
-    if (!ctx || !tuples_device) return CHAD_ERR_INVALID;
-    *tuples_device = ctx->sh_tuples.p;
-    return CHAD_OK;
-}
-
-int chad_shard_ingest(chad_ctx* ctx, const void* tuples_device, size_t n_tuples) {
-    if (!ctx || (n_tuples && !tuples_device)) return CHAD_ERR_INVALID;
-    if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (ctx->cap_points == 0) TRY(ensure_batch_capacity(ctx, 1));
-    if (n_tuples > ctx->cap_pairs) return fail(ctx, CHAD_ERR_CAPACITY, "chad_shard_ingest: more updates than the pair buffers hold");
-    cudaStream_t s = ctx->stream;
-    BatchPlan* plan = plan_ptr(ctx, 0);
-    u64 launches = 0;
-    launches += launch_blocks_from_tuples(s, tuples_device, (u32)n_tuples, plan, ctx->bt, ctx->scan_ws.p, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(),
-                                          ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(), (u32)ctx->cap_pairs, ctx->num_sms);
-    CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->h_plan[0], plan, sizeof(BatchPlan), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    const BatchPlan hp = ctx->h_plan[0];
-    if (hp.error) {
-        CUDA_TRY(ctx, cudaMemset(plan_field<u32>(ctx, 0, offsetof(BatchPlan, error)), 0, 4));
-        const int rc = error_from_flags(ctx, hp.error);
-        ctx->error += " [chad_shard_ingest: " + std::to_string(n_tuples) + " tuples, " + std::to_string(hp.n_pairs) + " binned, " + std::to_string(hp.n_blocks) + " blocks, table " + std::to_string(ctx->bt.capacity) + "]";
-        return rc;
-    }
-    ctx->stats.updates += hp.n_pairs;
-    ctx->stats.scan_voxels += hp.n_segments;
-    ctx->table_count_known = *ctx->h_table_count;  // exact: the previous fold's copy preceded the synchronisation above
-    TRY(table_reserve(ctx, ctx->table_count_known + hp.n_chunk_heads));
-    launches += launch_fold(s, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), ctx->vals_a.as<u32>(), ctx->vals_b.as<u32>(), (u32)n_tuples, plan, ctx->table,
-                            ctx->num_sms);
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_table_count, ctx->table.count, 4, cudaMemcpyDeviceToHost, s));
-    ctx->stats.kernel_launches += launches;
-    CUDA_TRY(ctx, cudaGetLastError());
-    return CHAD_OK;  // the fold runs on; its deferred error flags surface at the next synchronising call
-}
-
+// ---- one submap integrated by another rank (submap-parallel mode of chad_tsdf_b200/sharded.py): chunk stream in, chunk stream out ----
 int chad_shard_export_chunks(chad_ctx* ctx, size_t* n_chunks, void** keys_device, void** cells_device) {
     if (!ctx || !n_chunks || !keys_device || !cells_device) return CHAD_ERR_INVALID;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));

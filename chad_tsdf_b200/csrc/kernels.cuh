@@ -18,11 +18,12 @@ struct MapParams {
 enum ProfClass {
     PC_PLAN = 0, PC_POINT_KEYS, PC_POINT_SORT_HIST, PC_POINT_SORT_PASS0, PC_POINT_GATHER = PC_POINT_SORT_PASS0 + 8, PC_NORMALS, PC_BAND_COUNT,
     PC_BAND_SCAN, PC_BAND_EMIT, PC_PAIR_SORT_HIST, PC_PAIR_SORT_PASS0, PC_SEGMENT_COUNT = PC_PAIR_SORT_PASS0 + 8, PC_FOLD, PC_FINALIZE,
-    PC_BLOCKS_COUNT, PC_BLOCKS_SCAN, PC_BLOCKS_EMIT, PC_BLOCKS_SORT, PC_RUNS_EMIT, PC_RUNS_SORT, PC_RUNS_FOLD, PC_COUNT
+    PC_BLOCKS_COUNT, PC_BLOCKS_SCAN, PC_BLOCKS_EMIT, PC_BLOCKS_SORT, PC_RUNS_EMIT, PC_RUNS_SORT, PC_RUNS_FOLD, PC_SHARD_EXCHANGE, PC_COUNT
 };
 
 // ---- points.cu: voxelise + Morton (morton.hpp:59-80), sort keys, gather, normals (normals.hpp) ----
-int launch_plan(cudaStream_t s, const float* xyz, u32 n_points, u32 n_scans, const MapParams& mp, BatchPlan* plan);
+// tsb = bits of a 256-ray tile index inside the batch's largest scan (run descriptor order key, see points.cuh)
+int launch_plan(cudaStream_t s, const float* xyz, u32 n_points, u32 n_scans, const MapParams& mp, BatchPlan* plan, u32 tsb);
 int launch_point_keys(cudaStream_t s, const float* xyz, u32 n_points, const BatchScans* scans, const MapParams& mp, const BatchPlan* plan,
                       u64* sortkeys, u32* index);
 // keys_a/keys_b, idx_a/idx_b: the two radix buffers; the sorted result is picked with plan->nbits_points
@@ -58,23 +59,28 @@ int launch_blocks_pairs(cudaStream_t s, const float* xyz_sorted, const float* no
                         BatchPlan* plan, const BlockTable& bt, void* scan_ws, u64* keys_a, u64* keys_b, u32* vals_a, u32* vals_b, u32 pair_capacity,
                         int num_sms, const LaunchHook* hook, int cls_count, int cls_scan, int cls_emit, int cls_sort);
 
-// Morton-range sharding (multi-GPU): sender side (ray slice -> 16-byte tuples grouped by destination) and receiver side
+// ---- shard.cu: Morton-range sharding of one map across GPUs, point-stage side ----
 constexpr int SHARD_WORLD_MAX = 8;
-int launch_shard_splitters(cudaStream_t s, const u64* sorted_keys, u32 n_first_scan, const BatchPlan* plan, u32 world, u64* splitters);
-// dest_count = u32[3][8] (counts | offsets | cursors), zeroed here
-// slices = uint2[MAX_BATCH_SCANS]: per scan the range of sorted points whose block this rank owns
-int launch_shard_slices(cudaStream_t s, const u64* sorted_keys, const BatchScans* scans, const BatchPlan* plan, const u64* splitters, u32 rank, u32 world,
-                        void* slices);
-int launch_shard_count(cudaStream_t s, const float* xyz_sorted, u32 n_points, const void* slices, const BatchScans* scans, const MapParams& mp,
-                       const BatchPlan* plan, const u64* splitters, u32 world, u32* dest_count);
-int launch_shard_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const void* slices, const BatchScans* scans,
-                      const MapParams& mp, BatchPlan* plan, const u64* splitters, u32 world, const u32* dest_offset, u32* dest_cursor, void* tuples,
-                      u32 tuple_capacity);
-int launch_blocks_from_tuples(cudaStream_t s, const void* tuples, u32 n, BatchPlan* plan, const BlockTable& bt, void* scan_ws, u64* keys_a, u64* keys_b,
-                              u32* vals_a, u32* vals_b, u32 pair_capacity, int num_sms);
+struct RadixWorkspace;
+struct ShardFilter {    // work arrays of the ownership filter
+    u32* scan_own;      // [MAX_BATCH_SCANS + 1] points of scan s this rank owns (zero between batches)
+    u32* scan_lower;    // [MAX_BATCH_SCANS + 1] points of scan s owned by lower ranks
+    u32* tile_cnt;      // [max_tiles] owned points per 256-point tile of the batch -> their exclusive prefix
+    u32 max_tiles;
+};
+size_t shard_filter_bytes(size_t max_points);
+ShardFilter shard_filter_carve(void* mem, size_t max_points);
+int launch_plan_reset(cudaStream_t s, BatchPlan* plan, u32 n_points, u32 n_scans);
+// splitters[0 .. world] (block ids = Morton key >> 9; [0] = 0, [world] = ~0) from a sorted sample of the submap's first scan
+int launch_shard_splitters(cudaStream_t s, const float* xyz_first_scan, u32 n_first_scan, const MapParams& mp, u32 world, u32 first_share_256,
+                           u64* keys_a, u32* vals_a, u64* keys_b, u32* vals_b, u32* d_scalars, const RadixWorkspace& rws, int num_sms,
+                           u64* splitters);
+// plan + ownership filter of a batch (replaces launch_plan + launch_point_keys): plan->n_points = owned points, own_scans = their scan table
+int launch_shard_filter(cudaStream_t s, const float* xyz, u32 n_points, u32 n_scans, const BatchScans* scans, const MapParams& mp, BatchPlan* plan,
+                        u32 tsb, u32 gbits, const u64* splitters, u32 rank, u32 world, const ShardFilter& f, BatchScans* own_scans, u64* sortkeys,
+                        u32* index);
 
 // ---- runs.cu: tile-run grouping with the fold fused into the per-block sort (default pair path) ----
-struct RadixWorkspace;
 struct RunBuffers {   // run descriptors of a batch: sort ping-pong (block id, descriptor index), descriptor = (first record, records)
     u64 *key_a, *key_b;
     u32 *val_a, *val_b;
@@ -90,11 +96,26 @@ u32 runs_max_ray_runs();
 size_t runs_desc_bytes(size_t capacity);
 RunBuffers runs_carve(void* mem, size_t capacity);
 struct ChunkTable;
-int launch_runs_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const BatchScans* scans, const MapParams& mp,
-                     BatchPlan* plan, const RunBuffers& rb, u64* records, u32 rec_capacity, const LaunchHook* hook, int cls_emit);
-int launch_runs_group(cudaStream_t s, u32 n_points, BatchPlan* plan, const RunBuffers& rb, const RadixWorkspace& rws, int num_sms,
+u32 runs_max_tiles(u32 n_points, u32 n_scans);
+size_t runs_max_runs(u32 n_points, u32 n_scans);
+int launch_runs_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, u32 n_scans, const BatchScans* scans,
+                     const MapParams& mp, BatchPlan* plan, const RunBuffers& rb, u64* records, u32 rec_capacity, u32 order_rank,
+                     const LaunchHook* hook, int cls_emit);
+int launch_runs_group(cudaStream_t s, size_t max_runs, BatchPlan* plan, const RunBuffers& rb, const RadixWorkspace& rws, int num_sms,
                       const LaunchHook* hook, int cls_sort);
 int launch_runs_fold(cudaStream_t s, const u64* records, const RunBuffers& rb, BatchPlan* plan, const ChunkTable& t, int num_sms);
+// Morton-range sharding, walk side: the runs of blocks another rank owns are moved into that rank's exchange box, the boxes received
+// from the other ranks are appended to this rank's records / descriptors (between launch_runs_emit and launch_runs_group).
+// A box is `words` u64: [0] = runs | records << 32, [1] = flags, then (key, first | length << 32) per run from the front and the
+// records from the back.
+struct ShardBoxes {
+    u64* out;   // [world][words] one box per destination (the own one is unused)
+    u64* in;    // [world][words] one box per source
+    u32 words;
+};
+int launch_runs_pack(cudaStream_t s, size_t max_runs, BatchPlan* plan, const RunBuffers& rb, u64* records, const u64* splitters, u32 rank, u32 world,
+                     const ShardBoxes& boxes, int num_sms);
+int launch_runs_ingest(cudaStream_t s, BatchPlan* plan, const RunBuffers& rb, u64* records, u32 rec_capacity, u32 rank, u32 world, const ShardBoxes& boxes);
 
 // ---- fold.cu: ordered segmented fold (octree.hpp:161-163) into the resident chunk table ----
 struct ChunkTable {

@@ -6,43 +6,19 @@
 //                                   -- include/chad/detail/normals.hpp:10-148
 // All citations are into /root/reference.
 #include "kernels.cuh"
+#include "points.cuh"
 #include "radix_sort.cuh"
 
 namespace chadgpu {
 
 namespace {
 
-constexpr int PT_THREADS = 256;
-
-// Coalesced float4 staging of a tile of AoS xyz points (12 B each) into shared memory.
-// `xyz` must be 16-byte aligned; tile_base (in points) must be a multiple of 4.
-__device__ __forceinline__ void load_xyz_tile(const float* __restrict__ xyz, u32 tile_base, u32 n_points, float* s_xyz) {
-    const u32 pts = min((u32)PT_THREADS, n_points - tile_base);
-    const u32 nf = pts * 3;
-    const float* src = xyz + size_t(tile_base) * 3;
-    const u32 nvec = nf >> 2;
-    const float4* src4 = reinterpret_cast<const float4*>(src);
-    float4* dst4 = reinterpret_cast<float4*>(s_xyz);
-    for (u32 v = threadIdx.x; v < nvec; v += PT_THREADS) dst4[v] = __ldg(&src4[v]);
-    for (u32 f = (nvec << 2) + threadIdx.x; f < nf; f += PT_THREADS) s_xyz[f] = __ldg(&src[f]);
-    __syncthreads();
-}
-
-// morton.hpp:71-73: v = ivec3(floor(p * recip)), fp32
-__device__ __forceinline__ bool voxel_of(float px, float py, float pz, float recip, i32& vx, i32& vy, i32& vz) {
-    const float fx = floorf(fmul(px, recip)), fy = floorf(fmul(py, recip)), fz = floorf(fmul(pz, recip));
-    const float lim = 1048576.0f;  // 2^20
-    const bool ok = (fabsf(fx) < lim) && (fabsf(fy) < lim) && (fabsf(fz) < lim);  // false for NaN / Inf too
-    vx = ok ? (i32)fx : 0;
-    vy = ok ? (i32)fy : 0;
-    vz = ok ? (i32)fz : 0;
-    return ok;
-}
-
 __global__ void __launch_bounds__(PT_THREADS) plan_reset_kernel(BatchPlan* plan, u32 n_points, u32 n_scans) {
     plan->rmax = 0; plan->k = 0; plan->nbits_points = 0; plan->nbits_pairs = 0;
     plan->n_points = n_points; plan->n_scans = n_scans; plan->n_pairs = 0;
     plan->n_segments = 0; plan->n_chunk_heads = 0; plan->n_new_chunks = 0; plan->fold_ticket = 0; plan->n_blocks = 0; plan->sort_ticket = 0; plan->n_runs = 0; plan->nbits_blocks = 0; plan->tile_bits = 0; plan->n_big_blocks = 0; plan->n_small_blocks = 0; plan->point_shift = 0;
+    plan->tsb = 0; plan->n_batch = n_points; plan->tail_lo = 0xFFFFFFFFu; plan->tail_hi = 0xFFFFFFFFu;
+    plan->n_runs_local = 0; plan->n_pairs_local = 0; plan->xfer_runs = 0; plan->xfer_records = 0;
     // plan->error is sticky: cleared by the host when it reports it
 }
 
@@ -74,28 +50,7 @@ __global__ void __launch_bounds__(PT_THREADS) plan_bbox_kernel(const float* __re
     }
 }
 
-__global__ void plan_finalize_kernel(BatchPlan* plan, u32 margin) {
-    const u32 reach = plan->rmax + margin;  // every band voxel of the batch has range code <= reach
-    u32 k = 32 - __clz(reach);              // smallest k with reach < 2^k
-    if (k < 3) k = 3;                       // keep at least the 4^3 neighbourhood bits below the top triple
-    if (k > 20) { k = 20; atomicOr(&plan->error, ERRF_RANGE); }
-    const u32 n_scans = plan->n_scans;
-    const u32 sbits = (n_scans > 1) ? (32 - __clz(n_scans - 1)) : 0;
-    u32 nb = 3 * k + 3 + sbits;
-    if (nb > 64) { nb = 64; atomicOr(&plan->error, ERRF_KEY_BUDGET); }
-    plan->k = k;
-    plan->nbits_pairs = 3 * k + 3;
-    {   // run descriptors of the tile-run pair path sort by (compact block id, tile)
-        const u32 tiles = (plan->n_points + 255u) / 256u;
-        const u32 tbits = (tiles > 1) ? (32 - __clz(tiles - 1)) : 0;
-        plan->tile_bits = tbits;
-        plan->nbits_blocks = 3 * k - 6 + tbits;
-        if (3 * k - 6 + tbits > 64) plan->nbits_blocks = 0xFFFFFFFFu;  // the tile-run path reports ERRF_KEY_BUDGET; paths 0 / 1 do not use it
-    }
-    plan->nbits_points = nb;
-    // the input index (the sort's payload) fits under the key: one 8-byte array goes through the sort instead of 8 + 4 bytes
-    plan->point_shift = (nb + POINT_INDEX_BITS <= 64 && plan->n_points <= (1u << POINT_INDEX_BITS)) ? POINT_INDEX_BITS : 0u;
-}
+__global__ void plan_finalize_kernel(BatchPlan* plan, u32 margin, u32 tsb) { plan_finalize_body(plan, margin, tsb, 0u); }
 
 // sort key of a point: (scan << (3k+3)) | (~compact(morton) & mask): ascending sort == per scan
 // descending Morton (morton.hpp:85-89); the stable LSD sort breaks ties by input index (canonical).
@@ -107,15 +62,9 @@ __global__ void __launch_bounds__(PT_THREADS) point_keys_kernel(const float* __r
     load_xyz_tile(xyz, tile_base, n_points, s_xyz);
     const u32 i = tile_base + threadIdx.x;
     if (i >= n_points) return;
-    const u32 k = plan->k;
     i32 vx, vy, vz;
     voxel_of(s_xyz[threadIdx.x * 3], s_xyz[threadIdx.x * 3 + 1], s_xyz[threadIdx.x * 3 + 2], recip, vx, vy, vz);
-    const u64 full = morton_encode(vx, vy, vz);
-    const u32 cbits = 3 * k + 3;
-    const u64 cmask = (cbits >= 64) ? ~0ull : ((1ull << cbits) - 1ull);
-    const u64 inv = ~compact_key(full, k) & cmask;
-    const u32 s = scan_of(scans, plan->n_scans, i);
-    const u64 sk = (cbits >= 64 ? 0ull : (u64(s) << cbits)) | inv;
+    const u64 sk = point_sort_key(morton_encode(vx, vy, vz), plan->k, scan_of(scans, plan->n_scans, i));
     if (plan->point_shift) sortkeys[i] = (sk << POINT_INDEX_BITS) | (u64)i;
     else { sortkeys[i] = sk; index[i] = i; }
 }
@@ -126,7 +75,7 @@ __global__ void __launch_bounds__(PT_THREADS) point_gather_kernel(const float* _
                                                                   u64* __restrict__ sorted_keys, u32* __restrict__ sorted_order,
                                                                   float* __restrict__ xyz_sorted) {
     const u32 i = blockIdx.x * PT_THREADS + threadIdx.x;
-    if (i >= n_points) return;
+    if (i >= n_points || i >= plan->n_points) return;  // (a Morton-range shard sorts only its own points of the batch)
     const bool alt = radix_result_in_alt(plan->nbits_points);
     u64 key = alt ? keys_b[i] : keys_a[i];
     u32 src;
@@ -148,12 +97,15 @@ __global__ void __launch_bounds__(PT_THREADS) point_gather_kernel(const float* _
 __global__ void __launch_bounds__(PT_THREADS) segment_kernel(const u64* __restrict__ sorted_keys, u32 n_points, const BatchScans* __restrict__ scans,
                                                              const BatchPlan* __restrict__ plan, u32* __restrict__ seg_info) {
     const u32 i = blockIdx.x * PT_THREADS + threadIdx.x;
-    if (i >= n_points) return;
+    if (i >= n_points || i >= plan->n_points) return;
     const u64 block_id = sorted_keys[i] >> 6;  // includes the scan bits
     if (i > 0 && (sorted_keys[i - 1] >> 6) == block_id) return;
     const u32 s = scan_of(scans, plan->n_scans, i);
     const u32 scan_end = scans->offset[s + 1];
-    const u32 last = scan_end - 1;  // normals.hpp:100: the scan's last point is never absorbed
+    // normals.hpp:100: the scan's last point is never absorbed. Of a sharded map only the rank that holds
+    // the scan's lowest key has that point (plan->tail_*); on the others no point is special
+    const bool tail = ((s < 32 ? plan->tail_lo >> s : plan->tail_hi >> (s - 32)) & 1u) != 0;
+    const u32 last = tail ? scan_end - 1 : 0xFFFFFFFFu;
     u32 it = i;
     while (it < scan_end && (sorted_keys[it] >> 6) == block_id) {
         const u64 key_it = sorted_keys[it];
@@ -180,7 +132,7 @@ __global__ void __launch_bounds__(PT_THREADS) normals_kernel(const float* __rest
                                                              const BatchPlan* __restrict__ plan, const u32* __restrict__ seg_info,
                                                              float* __restrict__ normals) {
     const u32 i = blockIdx.x * PT_THREADS + threadIdx.x;
-    if (i >= n_points) return;
+    if (i >= n_points || i >= plan->n_points) return;
     const u32 info = seg_info[i];
     if (info == 0) return;  // member of a neighbourhood whose first point writes the shared normal
     const u32 s = scan_of(scans, plan->n_scans, i);
@@ -250,7 +202,7 @@ __global__ void __launch_bounds__(PT_THREADS) normals_kernel(const float* __rest
 __global__ void __launch_bounds__(PT_THREADS) point_full_keys_kernel(const u64* __restrict__ sorted_keys, u32 n_points,
                                                                      const BatchPlan* __restrict__ plan, u64* __restrict__ full_keys) {
     const u32 i = blockIdx.x * PT_THREADS + threadIdx.x;
-    if (i >= n_points) return;
+    if (i >= n_points || i >= plan->n_points) return;
     const u32 k = plan->k;
     const u32 cbits = 3 * k + 3;
     const u64 cmask = (cbits >= 64) ? ~0ull : ((1ull << cbits) - 1ull);
@@ -267,14 +219,19 @@ inline unsigned blocks_for(u32 n) { return (n + PT_THREADS - 1) / PT_THREADS; }
 
 }  // namespace
 
-int launch_plan(cudaStream_t s, const float* xyz, u32 n_points, u32 n_scans, const MapParams& mp, BatchPlan* plan) {
+int launch_plan_reset(cudaStream_t s, BatchPlan* plan, u32 n_points, u32 n_scans) {
+    plan_reset_kernel<<<1, 1, 0, s>>>(plan, n_points, n_scans);
+    return 1;
+}
+
+int launch_plan(cudaStream_t s, const float* xyz, u32 n_points, u32 n_scans, const MapParams& mp, BatchPlan* plan, u32 tsb) {
     plan_reset_kernel<<<1, 1, 0, s>>>(plan, n_points, n_scans);
     int launches = 1;
     if (n_points) {
         plan_bbox_kernel<<<blocks_for(n_points), PT_THREADS, 0, s>>>(xyz, n_points, mp.recip, plan);
         launches++;
     }
-    plan_finalize_kernel<<<1, 1, 0, s>>>(plan, mp.band_margin);
+    plan_finalize_kernel<<<1, 1, 0, s>>>(plan, mp.band_margin, tsb);
     return launches + 1;
 }
 

@@ -15,6 +15,7 @@
 //     (key, sd) stream never goes back to HBM.
 // Results are bit-identical to paths 0 / 1 and to the CPU reference.
 #include "kernels.cuh"
+#include "points.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
 
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
                                                                 const BatchScans* __restrict__ scans, float res, float trunc, float recip, u32 mrv,
                                                                 BatchPlan* plan, u64* __restrict__ records, u32 rec_capacity,
                                                                 u64* __restrict__ desc_key, u32* __restrict__ desc_val, uint2* __restrict__ desc,
-                                                                u32 desc_capacity) {
+                                                                u32 desc_capacity, u32 order_rank) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     uint2* s_rec = reinterpret_cast<uint2*>(s_dyn);  // [RUN_THREADS][stride]: x = (slot << 9) | local voxel, y = sd bits
     __shared__ u64 s_hkey[RUN_HASH];
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
     __shared__ unsigned short s_hbase[RUN_HASH];     // first record of the slot's run inside the tile's span (a tile holds <= 8192 records)
     __shared__ u32 s_warp[RUN_THREADS / 32];
     __shared__ u32 s_gbase, s_dbase;
-    __shared__ u32 s_scan[2];  // scans of the tile's first and last point
+    __shared__ u32 s_scan[4];  // the tile's scan, first ray, end, order key
     __shared__ u32 s_prefix[RUN_WARPS][33];  // per warp: records of the lower lanes' rays (write-out)
     __shared__ unsigned short s_list[RUN_HASH];    // hash slots in use; their runs follow each other in this order
     __shared__ u32 s_total;
@@ -163,10 +164,27 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
         for (u32 q = 0; q < (RUN_WARPS / 2) * RUN_HASH * 4 / 16 / RUN_THREADS; q++) wc4[tid + q * RUN_THREADS] = zero;
         if (tid == 0) s_nslots = 0;
     }
-    const u32 tile0 = blockIdx.x * RUN_THREADS;
-    if (tid < 2) s_scan[tid] = scan_of(scans, plan->n_scans, tid == 0 ? tile0 : min(tile0 + RUN_THREADS, n_points) - 1);
+    // Tiles never straddle scans: tile t of scan s holds the sorted rays offset[s] + 256 t .. of that scan, so that the order key
+    // (scan | Morton-range rank, descending | tile in scan) sorts the runs of a block in the reference's update order, also when the
+    // block's runs come from several GPUs
+    if (tid == 0) {
+        const u32 ns = plan->n_scans;
+        u32 lo = 0, hi = ns;  // tile_prefix[lo] <= blockIdx.x < tile_prefix[hi] when the tile exists
+        while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (scans->tile_prefix[mid] <= blockIdx.x) lo = mid; else hi = mid; }
+        const bool exists = ns > 0 && blockIdx.x < scans->tile_prefix[ns];
+        const u32 t = blockIdx.x - scans->tile_prefix[lo];
+        const u32 first = scans->offset[lo] + t * RUN_THREADS;
+        s_scan[0] = lo;
+        s_scan[1] = exists ? first : 0xFFFFFFFFu;
+        s_scan[2] = exists ? min(first + RUN_THREADS, scans->offset[lo + 1]) : 0u;
+        s_scan[3] = (lo << (plan->tile_bits - bits_for(ns))) | order_rank | t;  // order_rank = (world - 1 - rank) << tsb
+    }
     if (lane == 0) s_prefix[warp][32] = 0xFFFFFFFFu;  // sentinel of the write-out's binary search
     __syncthreads();
+    const u32 tile0 = s_scan[1];
+    if (tile0 == 0xFFFFFFFFu) return;  // (the grid is sized from an upper bound of the tile count)
+    const u32 tile_end = min(min(s_scan[2], n_points), plan->n_points);
+    const u32 okey = s_scan[3];
     const u32 i = tile0 + tid;
     u32 cnt = 0, err = 0;
     RayL r;
@@ -174,10 +192,8 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
     bool alive = false;
     u32 slot = 0, run = 0;
     const u32 wsh = (warp & 1u) * 16u;
-    if (i < n_points) {
-        u32 s = s_scan[0];
-        const u32 s_last = s_scan[1];
-        while (s < s_last && scans->offset[s + 1] <= i) s++;  // a tile rarely straddles scans
+    if (i < tile_end) {
+        const u32 s = s_scan[0];
         nx = normals[size_t(i) * 3]; ny = normals[size_t(i) * 3 + 1]; nz = normals[size_t(i) * 3 + 2];
         const u32 rmax = rayl_setup(r, xyz_sorted[size_t(i) * 3], xyz_sorted[size_t(i) * 3 + 1], xyz_sorted[size_t(i) * 3 + 2], scans->pose[s][0],
                                     scans->pose[s][1], scans->pose[s][2], res, trunc, recip);
@@ -253,7 +269,7 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
             const u32 d = s_dbase + t;
             const u64 cid = compact_key(packed_block_to_morton(s_hkey[hs]) << RUN_BLK_SHIFT, k) >> RUN_BLK_SHIFT;
             const u32 base = s_hbase[hs], next = (t + 1 < nslots) ? (u32)s_hbase[s_list[t + 1]] : s_total;
-            desc_key[d] = (cid << tbits) | (u64)blockIdx.x | (stash ? ((u64)(next - base) << RUN_STASH_BITS) : 0ull);
+            desc_key[d] = (cid << tbits) | (u64)okey | (stash ? ((u64)(next - base) << RUN_STASH_BITS) : 0ull);
             desc_val[d] = d;
             desc[d] = make_uint2(gbase + base, next - base);
         }
@@ -332,7 +348,7 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_group_kernel(const u64* __re
         // blocks with many updates go to the front of the list (a block is folded by ONE warp: start the long ones first),
         // the others are listed from the back
         const bool big = head && recs >= RUN_BIG_BLOCK;
-        const bool small = head && !big;
+        const bool small = head && !big && recs > 0;  // recs == 0: a block of another Morton range, its runs have been sent to their owner
         const u32 bb = __ballot_sync(0xffffffffu, big), bs = __ballot_sync(0xffffffffu, small);
         u32 base_b = 0, base_s = 0;
         if (lane == 0) {
@@ -556,6 +572,105 @@ __global__ void __launch_bounds__(RF_THREADS) runs_fold_kernel(const u64* __rest
     }
 }
 
+// ---- Morton-range sharding: runs of blocks another rank owns travel to that rank -------------
+// A ray's band reaches at most a few voxels beyond its point's range, so a few per thousand of the runs are foreign. They
+// are moved whole: the key (compact block id, order key) is valid on every rank (k and the order key layout follow from
+// the whole batch), so the receiver appends records and descriptors to its own and the descriptor sort interleaves them
+// with the local runs in the reference's update order.
+__device__ __forceinline__ u32 run_owner(u64 blk, const u64* __restrict__ splitters, u32 world) {
+    u32 g = 0;
+    for (u32 q = 1; q < world; q++) g += (splitters[q] <= blk) ? 1u : 0u;
+    return g;
+}
+
+__global__ void __launch_bounds__(RUN_THREADS) runs_pack_kernel(const u64* __restrict__ records, u64* __restrict__ desc_key, uint2* __restrict__ desc,
+                                                                BatchPlan* plan, const u64* __restrict__ splitters, u32 rank, u32 world,
+                                                                u64* __restrict__ out, u32 words) {
+    const u32 n = plan->n_runs;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { plan->n_runs_local = n; plan->n_pairs_local = plan->n_pairs; }
+    if (plan->nbits_blocks > 64) return;
+    const u32 k = plan->k, tbits = plan->tile_bits, lane = threadIdx.x & 31;
+    const u64 kmask = run_key_mask(plan->nbits_blocks);
+    u32 sent_runs = 0, sent_records = 0;
+    for (u32 d0 = blockIdx.x * RUN_THREADS; d0 < n; d0 += gridDim.x * RUN_THREADS) {  // uniform per CTA
+        const u32 d = d0 + threadIdx.x;
+        u64 key = 0;
+        uint2 dd = make_uint2(0, 0);
+        u32 owner = rank;
+        if (d < n) {
+            key = desc_key[d] & kmask;
+            dd = desc[d];
+            owner = run_owner(expand_key(((key >> tbits) << RUN_BLK_SHIFT), k) >> RUN_BLK_SHIFT, splitters, world);
+        }
+        const bool foreign = owner != rank;
+        u32 todo = __ballot_sync(0xffffffffu, foreign);
+        while (todo) {  // the warp moves one foreign run at a time
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const u32 first = __shfl_sync(0xffffffffu, dd.x, l), len = __shfl_sync(0xffffffffu, dd.y, l), ow = __shfl_sync(0xffffffffu, owner, l);
+            const u64 rkey = __shfl_sync(0xffffffffu, key, l);
+            u64* box = out + size_t(ow) * words;
+            u64 old = 0;
+            if (lane == 0) old = atomicAdd(&box[0], (u64(len) << 32) | 1ull);  // runs in the low half, records in the high half
+            old = __shfl_sync(0xffffffffu, old, 0);
+            const u32 dpos = (u32)old, rpos = (u32)(old >> 32);
+            if (2ull + 2ull * (dpos + 1ull) + rpos + len <= (u64)words) {
+                if (lane == 0) { box[2 + 2 * dpos] = rkey; box[3 + 2 * dpos] = (u64)rpos | (u64(len) << 32); }
+                for (u32 q = lane; q < len; q += 32) box[words - 1 - (rpos + q)] = records[first + q];
+            } else if (lane == 0) {
+                atomicOr(&box[1], 1ull);
+                atomicOr(&plan->error, ERRF_EXCHANGE);
+            }
+            if (lane == 0) { sent_runs++; sent_records += len; }
+        }
+        if (foreign) {  // the local copy of the run is dead: no records, so the block is not listed for the fold
+            desc_key[d] = key;  // (stashed record count removed)
+            desc[d] = make_uint2(dd.x, 0);
+        }
+    }
+    if (sent_runs) { atomicAdd(&plan->xfer_runs, sent_runs); atomicAdd(&plan->xfer_records, sent_records); }
+}
+
+// grid (CTAs per source, world): the box received from rank blockIdx.y is appended to the local records / descriptors
+__global__ void __launch_bounds__(RUN_THREADS) runs_ingest_kernel(u64* __restrict__ records, u32 rec_capacity, u64* __restrict__ desc_key,
+                                                                  u32* __restrict__ desc_val, uint2* __restrict__ desc, u32 desc_capacity, BatchPlan* plan,
+                                                                  u32 rank, u32 world, const u64* __restrict__ in, u32 words) {
+    const u32 src = blockIdx.y;
+    if (src == rank || plan->nbits_blocks > 64) return;
+    // every CTA derives every source's place from the headers: sources are appended in rank order behind the local runs
+    u64 total_r = plan->n_pairs_local, total_d = plan->n_runs_local;
+    u64 my_r = 0, my_d = 0;
+    u32 my_nd = 0, my_nr = 0;
+    bool bad = false;
+    for (u32 g = 0; g < world; g++) {
+        if (g == rank) continue;
+        const u64 hdr = in[size_t(g) * words];
+        const u32 nd = (u32)hdr, nr = (u32)(hdr >> 32);
+        bad |= (in[size_t(g) * words + 1] & 1ull) != 0 || (2ull + 2ull * nd + nr > (u64)words);
+        if (g == src) { my_r = total_r; my_d = total_d; my_nd = nd; my_nr = nr; }
+        total_r += nr;
+        total_d += nd;
+    }
+    bad |= total_r > (u64)rec_capacity || total_d > (u64)desc_capacity;
+    const u32 writer = rank == 0 ? 1u : 0u;  // one thread publishes the totals
+    if (src == writer && blockIdx.x == 0 && threadIdx.x == 0) {
+        if (bad) atomicOr(&plan->error, ERRF_EXCHANGE);
+        else { plan->n_pairs = (u32)total_r; plan->n_runs = (u32)total_d; }
+    }
+    if (bad) return;
+    const u64* __restrict__ box = in + size_t(src) * words;
+    const bool stash = plan->nbits_blocks <= RUN_STASH_BITS;
+    for (u32 j = blockIdx.x * RUN_THREADS + threadIdx.x; j < my_nd; j += gridDim.x * RUN_THREADS) {
+        const u64 key = box[2 + 2 * j], fl = box[3 + 2 * j];
+        const u32 first = (u32)fl, len = (u32)(fl >> 32);
+        const u32 d = (u32)my_d + j;
+        desc_key[d] = key | (stash ? ((u64)len << RUN_STASH_BITS) : 0ull);
+        desc_val[d] = d;
+        desc[d] = make_uint2((u32)my_r + first, len);
+    }
+    for (u32 q = blockIdx.x * RUN_THREADS + threadIdx.x; q < my_nr; q += gridDim.x * RUN_THREADS) records[(u32)my_r + q] = box[words - 1 - q];
+}
+
 inline unsigned blocks_for(u32 n) { return (n + RUN_THREADS - 1) / RUN_THREADS; }
 
 }  // namespace
@@ -576,6 +691,8 @@ cudaError_t runs_init() {
 }
 
 u32 runs_max_batch_points() { return 1u << RUN_RANK_BITS; }
+u32 runs_max_tiles(u32 n_points, u32 n_scans) { return (n_points + RUN_THREADS - 1) / RUN_THREADS + n_scans; }  // every scan may end in a partial tile
+size_t runs_max_runs(u32 n_points, u32 n_scans) { return size_t(runs_max_tiles(n_points, n_scans)) * RUN_HASH; }
 u32 runs_max_ray_voxels() { return 32; }
 u32 runs_max_ray_runs() { return RUN_HASH / RUN_THREADS; }
 
@@ -595,31 +712,50 @@ RunBuffers runs_carve(void* mem, size_t capacity) {
     return b;
 }
 
-// The ray walk of a batch (main stream). Returns the kernels queued.
-int launch_runs_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, const BatchScans* scans, const MapParams& mp,
-                     BatchPlan* plan, const RunBuffers& rb, u64* records, u32 rec_capacity, const LaunchHook* hook, int cls_emit) {
+// The ray walk of a batch (main stream). Returns the kernels queued. n_points / n_scans: host upper bounds (a Morton-range shard walks
+// only its own rays: their count and the tile table are in device memory). order_rank = (world - 1 - rank) << tsb, 0 on one GPU.
+int launch_runs_emit(cudaStream_t s, const float* xyz_sorted, const float* normals, u32 n_points, u32 n_scans, const BatchScans* scans,
+                     const MapParams& mp, BatchPlan* plan, const RunBuffers& rb, u64* records, u32 rec_capacity, u32 order_rank,
+                     const LaunchHook* hook, int cls_emit) {
     if (!n_points) return 0;
     if (hook) hook->begin(hook->user, cls_emit);
-    runs_emit_kernel<<<blocks_for(n_points), RUN_THREADS, size_t(RUN_THREADS) * (mp.max_ray_voxels | 1u) * sizeof(uint2), s>>>(
+    runs_emit_kernel<<<runs_max_tiles(n_points, n_scans), RUN_THREADS, size_t(RUN_THREADS) * (mp.max_ray_voxels | 1u) * sizeof(uint2), s>>>(
         xyz_sorted, normals, n_points, scans, mp.res, mp.trunc, mp.recip, mp.max_ray_voxels, plan, records, rec_capacity, rb.key_a, rb.val_a, rb.desc,
-        rb.capacity);
+        rb.capacity, order_rank);
     if (hook) hook->end(hook->user);
     return 1;
 }
 
 // Descriptor sort + block list of a batch: only the fold needs them, so they are queued on the fold's stream and the main stream goes
 // straight on to the next batch's point stage. `rws` must not be the workspace of the point sort (it runs concurrently).
-int launch_runs_group(cudaStream_t s, u32 n_points, BatchPlan* plan, const RunBuffers& rb, const RadixWorkspace& rws, int num_sms,
+// max_runs: host upper bound of plan->n_runs.
+int launch_runs_group(cudaStream_t s, size_t max_runs, BatchPlan* plan, const RunBuffers& rb, const RadixWorkspace& rws, int num_sms,
                       const LaunchHook* hook, int cls_sort) {
-    if (!n_points) return 0;
+    if (!max_runs) return 0;
     int launches = 0;
     if (hook) hook->begin(hook->user, cls_sort);
-    const size_t max_runs = std::min<size_t>(rb.capacity, size_t(blocks_for(n_points)) * RUN_HASH);
+    max_runs = std::min<size_t>(rb.capacity, max_runs);
     launches += radix_sort_pairs(s, rb.key_a, rb.val_a, rb.key_b, rb.val_b, &plan->n_runs, &plan->nbits_blocks, max_runs, RS_MAX_PASSES, rws, num_sms);
     runs_group_kernel<<<(unsigned)std::min<size_t>(blocks_for((u32)max_runs), size_t(num_sms) * 8), RUN_THREADS, 0, s>>>(rb.key_a, rb.key_b, rb.val_a, rb.val_b, rb.desc, rb.sdesc, plan, rb.work, rb.capacity);
     if (hook) hook->end(hook->user);
     launches++;
     return launches;
+}
+
+// sharded: between the walk and the descriptor sort (see runs_pack_kernel). The box headers are cleared here.
+int launch_runs_pack(cudaStream_t s, size_t max_runs, BatchPlan* plan, const RunBuffers& rb, u64* records, const u64* splitters, u32 rank, u32 world,
+                     const ShardBoxes& boxes, int num_sms) {
+    cudaMemset2DAsync(boxes.out, size_t(boxes.words) * 8, 0, 16, world, s);
+    max_runs = std::min<size_t>(rb.capacity, max_runs);
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(blocks_for((u32)max_runs), size_t(num_sms) * 8));
+    runs_pack_kernel<<<grid, RUN_THREADS, 0, s>>>(records, rb.key_a, rb.desc, plan, splitters, rank, world, boxes.out, boxes.words);
+    return 1;
+}
+
+int launch_runs_ingest(cudaStream_t s, BatchPlan* plan, const RunBuffers& rb, u64* records, u32 rec_capacity, u32 rank, u32 world, const ShardBoxes& boxes) {
+    runs_ingest_kernel<<<dim3(16, world), RUN_THREADS, 0, s>>>(records, rec_capacity, rb.key_a, rb.val_a, rb.desc, rb.capacity, plan, rank, world, boxes.in,
+                                                                boxes.words);
+    return 1;
 }
 
 int launch_runs_fold(cudaStream_t s, const u64* records, const RunBuffers& rb, BatchPlan* plan, const ChunkTable& t, int num_sms) {

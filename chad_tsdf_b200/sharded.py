@@ -1,14 +1,10 @@
-"""One TSDF map sharded across GPUs by contiguous Morton ranges.
+"""ONE TSDF map on several GPUs, one process per GPU (torch.distributed is plumbing only).
 
-One process per GPU (torch.distributed, NCCL over NVLink). Every rank receives every scan (3 MB), runs the small point
-stage on the whole batch, enumerates the band voxels of its 1/world slice of the sorted rays and sends each update to
-the rank that owns the voxel (`all_to_all_single` of 16-byte tuples {Morton key, sorted-point rank, sd}). The receiver
-bins / sorts / folds the tuples into its shard; the rank carried by every tuple restores the reference's fold order, so
-the union of the shards is bit-identical to the single-GPU map. At a submap switch the shards' leaf chunks are
-all-gathered (rank order == Morton order) and every rank builds the identical global DAG.
-
-The numerical work is behind a small engine interface: `CudaShardEngine` drives the C ABI (chad_shard_*); the CPU tests
-plug in a numpy/oracle engine to exercise this file's host logic (submap rule, batching, splits, exchange) with gloo.
+* Morton-range sharding (north_star): the map is cut into `world` contiguous Morton ranges and the C++ library
+  does everything, including the NCCL exchanges (chad_create_sharded, csrc/shard.cu, csrc/runs.cu, csrc/context.cu). This file only
+  hands the communicator id around (`create_sharded_map`) and gathers the shards' state for parity checks (`sharded_digest`).
+* Submap-parallel mode (`SubmapParallelTSDFMap`): the map's submaps -- independent octrees -- are integrated on different ranks and
+  only their sorted leaf chunks travel; kept as the second decomposition.
 """
 from __future__ import annotations
 
@@ -19,7 +15,6 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-TUPLE_WORDS = 2  # a tuple is 2 x int64 on the wire: (key, rank | sd << 32)
 CELL_WORDS = 8   # a leaf chunk's cells: 8 x (sd bits, weight) = 8 x int64
 
 
@@ -56,20 +51,6 @@ class CudaShardEngine:
         torch.cuda.current_stream(self.device).synchronize()  # the engine works on its own stream
         return xyz.contiguous()
 
-    def front(self, xyz: torch.Tensor, offsets: np.ndarray, poses: np.ndarray, rank: int, world: int, new_submap: bool):
-        counts = np.zeros(8, np.uint64)
-        offsets = np.ascontiguousarray(offsets, np.uint32)
-        poses = np.ascontiguousarray(poses, np.float32)
-        self._keep = xyz  # until the next batch: the engine copies out of it asynchronously
-        self.map._check(self._lib.chad_shard_front(self._h, C.c_void_p(xyz.data_ptr()), offsets.ctypes.data_as(C.c_void_p),
-                                                   poses.ctypes.data_as(C.c_void_p), len(offsets) - 1, rank, world, int(new_submap),
-                                                   counts.ctypes.data_as(C.c_void_p)))
-        p = C.c_void_p()
-        self.map._check(self._lib.chad_shard_send_buffer(self._h, C.byref(p)))
-        counts = [int(c) for c in counts[:world]]
-        send = device_tensor(p.value or 0, sum(counts) * TUPLE_WORDS, self.device).view(-1, TUPLE_WORDS)
-        return counts, send
-
     # the ordinary single-GPU insert path (SubmapParallelTSDFMap): host memory, or a tensor on this device
     def insert(self, points, position) -> None:
         if isinstance(points, torch.Tensor) and points.is_cuda:
@@ -79,10 +60,6 @@ class CudaShardEngine:
 
     def flush(self) -> None:
         self.map.flush()
-
-    def ingest(self, tuples: torch.Tensor) -> None:
-        tuples = tuples.contiguous()
-        self.map._check(self._lib.chad_shard_ingest(self._h, C.c_void_p(tuples.data_ptr()), tuples.shape[0]))
 
     def export_chunks(self):
         n, k, c = C.c_size_t(), C.c_void_p(), C.c_void_p()
@@ -124,104 +101,57 @@ class CudaShardEngine:
         self.map.close()
 
 
-class ShardedTSDFMap:
-    """chad::TSDFMap semantics (insert / submap rule / finalize) over `world` Morton-range shards."""
+def create_sharded_map(sdf_res: float, sdf_trunc: float, device: int, group=None, max_batch_scans: int = 0):
+    """Rank `dist.get_rank(group)` of ONE chad::TSDFMap cut into `world` Morton ranges (chad_create_sharded, include/chad_b200.h).
+    torch.distributed only carries the 256-byte communicator id from rank 0 to the others; every exchange of the map itself is issued
+    by the C++ library (NCCL send / recv on its own streams)."""
+    from .tsdf_map import TSDFMap
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [TSDFMap.shard_unique_id() if rank == 0 and world > 1 else None]
+    if world > 1:
+        src = 0 if group is None else dist.get_global_rank(group, 0)
+        dist.broadcast_object_list(box, src=src, group=group)
+    return TSDFMap(sdf_res, sdf_trunc, device=device, max_batch_scans=max_batch_scans, shard=(rank, world, box[0]) if world > 1 else None)
 
-    def __init__(self, engine, group=None, max_batch_scans: int = 16):
-        self.engine = engine
-        self.group = group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
-        self.max_batch = max(1, min(int(max_batch_scans), 64))
-        self._scans: list = []   # (points, pose) of the batch being assembled
-        self._first_pose: np.ndarray | None = None
-        self._new_submap = True
-        self.exchanged_tuples = 0
-        self.phase_s = {"stage": 0.0, "front": 0.0, "exchange": 0.0, "ingest": 0.0, "close": 0.0}  # host wall clock per phase
 
-    # -- the reference's API --
-    def insert(self, points, position) -> None:
-        """points: (n, 3) float32 as a numpy array, a page-locked CPU tensor or a tensor on the engine's device."""
-        pts = points if isinstance(points, torch.Tensor) else np.ascontiguousarray(points, np.float32).reshape(-1, 3)
-        pos = np.ascontiguousarray(position, np.float32).reshape(3)
-        # tsdf.cpp:46-61: strictly more than 5 m from the submap's first pose, fp32 ((dx*dx + dy*dy) + dz*dz, then sqrt)
-        if self._first_pose is None:
-            self._first_pose = pos.copy()
-        else:
-            d = self._first_pose - pos
-            t = d * d
-            if np.sqrt(np.float32(np.float32(t[0] + t[1]) + t[2])) > np.float32(5.0):
-                self._close_submap()
-                self._first_pose = pos.copy()
-        if len(pts):
-            self._scans.append((pts, pos))
-        if len(self._scans) >= self.max_batch:
-            self._process_batch()
+def gather_voxels(local, group=None):
+    """(keys, sd_bits, weights) of every rank, concatenated in rank order on rank 0 (None elsewhere). The ranges ascend with the rank,
+    so the result is the whole active submap in ascending Morton order -- asserted here, because it is what makes the shards ONE map."""
+    if not dist.is_initialized():  # a single process holds the whole map
+        parts, rank = [tuple(np.ascontiguousarray(a) for a in local)], 0
+    else:
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        parts = [None] * world if rank == 0 else None
+        dst = 0 if group is None else dist.get_global_rank(group, 0)
+        dist.gather_object(tuple(np.ascontiguousarray(a) for a in local), parts, dst=dst, group=group)
+    if rank != 0:
+        return None
+    keys = np.concatenate([p[0] for p in parts])
+    if len(keys) > 1 and not np.all(keys[1:] > keys[:-1]):
+        raise AssertionError("the ranks' voxel ranges overlap or are out of order: the shards do not form one map")
+    return keys, np.concatenate([p[1] for p in parts]), np.concatenate([p[2] for p in parts])
 
-    def flush(self) -> None:
-        self._process_batch()
 
-    def finalize_active(self) -> None:
-        """The part of TSDFMap::save before meshing (tsdf.cpp:78-81)."""
-        if self._first_pose is not None:
-            self._close_submap()
-            self._first_pose = None
+def sharded_digest(m, group=None, with_dag: bool = True):
+    """The digest of oracle.bindings.map_digest (active voxels, the 21 DAG levels, counters, roots) of a sharded map, on rank 0 (None
+    elsewhere): voxels gathered from all ranks, the DAG read from rank 0, which holds it. Collective."""
+    import hashlib
 
-    # -- internals --
-    def _process_batch(self) -> None:
-        if not self._scans:
-            return
-        t0 = time.perf_counter()
-        xyz = self.engine.concat([p for p, _ in self._scans])
-        offsets = np.concatenate([[0], np.cumsum([len(p) for p, _ in self._scans])]).astype(np.uint32)
-        poses = np.stack([q for _, q in self._scans]).astype(np.float32)
-        self._scans = []
-        self.phase_s["stage"] += time.perf_counter() - t0
-        t0 = time.perf_counter()
-        counts, send = self.engine.front(xyz, offsets, poses, self.rank, self.world, self._new_submap)
-        t1 = time.perf_counter()
-        self._new_submap = False
-        send_counts = self.engine.empty((self.world,))
-        send_counts.copy_(torch.tensor(counts, dtype=torch.int64))
-        recv_counts = torch.empty_like(send_counts)
-        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
-        recv_list = [int(c) for c in recv_counts.tolist()]
-        recv = self.engine.empty((sum(recv_list), TUPLE_WORDS))
-        dist.all_to_all_single(recv, send, output_split_sizes=recv_list, input_split_sizes=counts, group=self.group)
-        self.exchanged_tuples += sum(c for r, c in enumerate(counts) if r != self.rank)
-        self.engine.sync()
-        t2 = time.perf_counter()
-        self.engine.ingest(recv)
-        t3 = time.perf_counter()
-        self.phase_s["front"] += t1 - t0
-        self.phase_s["exchange"] += t2 - t1
-        self.phase_s["ingest"] += t3 - t2
+    def h(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
-    def _close_submap(self) -> None:
-        self._process_batch()
-        t0 = time.perf_counter()
-        keys, cells = self.engine.export_chunks()
-        n = self.engine.empty((1,))
-        n.fill_(keys.shape[0])
-        all_n = self.engine.empty((self.world,))
-        dist.all_gather_into_tensor(all_n, n, group=self.group)
-        counts = [int(c) for c in all_n.tolist()]
-        pad = max(max(counts), 1)
-        kbuf = self.engine.empty((pad,))
-        cbuf = self.engine.empty((pad, CELL_WORDS))
-        kbuf[: keys.shape[0]] = keys
-        cbuf[: keys.shape[0]] = cells
-        all_k = self.engine.empty((self.world * pad,))
-        all_c = self.engine.empty((self.world * pad, CELL_WORDS))
-        dist.all_gather_into_tensor(all_k, kbuf, group=self.group)
-        dist.all_gather_into_tensor(all_c, cbuf, group=self.group)
-        # rank order == ascending Morton order (contiguous ranges)
-        gk = torch.cat([all_k[r * pad: r * pad + c] for r, c in enumerate(counts)])
-        gc = torch.cat([all_c[r * pad: r * pad + c] for r, c in enumerate(counts)])
-        self.engine.sync()
-        self.engine.finalize_from(gk, gc)
-        self._new_submap = True
-        self.phase_s["close"] += time.perf_counter() - t0
+    vox = gather_voxels(m.voxels(), group)
+    roots = m.roots()
+    if vox is None:
+        return None
+    k, sd, w = vox
+    out = {"voxels_n": int(len(k)), "voxels_keys": h(k), "voxels_sd_bits": h(sd), "voxels_weights": h(w), "weight_sum": int(w.astype(np.uint64).sum()),
+           "roots": [list(r) for r in roots], "levels": []}
+    if with_dag:
+        for lv in range(21):
+            arr, u, d = m.level(lv)
+            out["levels"].append({"words": int(len(arr)), "uniques": int(u), "dupes": int(d), "sha256": h(arr)})
+    return out
 
 
 class SubmapParallelTSDFMap:

@@ -13,16 +13,40 @@ from . import capi
 
 
 class TSDFMap:
-    def __init__(self, sdf_res: float = 0.05, sdf_trunc: float = 0.1, device: int = 0, max_batch_scans: int = 0, pair_path: int | None = None):
+    def __init__(self, sdf_res: float = 0.05, sdf_trunc: float = 0.1, device: int = 0, max_batch_scans: int = 0, pair_path: int | None = None,
+                 shard: tuple[int, int, bytes] | None = None):
+        """shard = (rank, world, id): this object is rank `rank` of ONE map cut into `world` Morton ranges, one GPU each (collective: every
+        rank constructs it with the id rank 0 got from shard_unique_id(), and then makes the same calls with the same scans)."""
         self._lib = capi.load()
         self._h = C.c_void_p()
-        rc = self._lib.chad_create(sdf_res, sdf_trunc, device, max_batch_scans, C.byref(self._h))
+        self.shard_rank, self.shard_world = (shard[0], shard[1]) if shard else (0, 1)
+        if shard and shard[1] > 1:
+            ident = C.create_string_buffer(bytes(shard[2]), capi.SHARD_ID_BYTES)
+            rc = self._lib.chad_create_sharded(sdf_res, sdf_trunc, device, max_batch_scans, shard[0], shard[1], ident, C.byref(self._h))
+        else:
+            rc = self._lib.chad_create(sdf_res, sdf_trunc, device, max_batch_scans, C.byref(self._h))
         if rc != capi.CHAD_OK:
             raise capi.ChadError(rc, self._lib.chad_last_error(None).decode())
         self._sdf_res, self._sdf_trunc = float(sdf_res), float(sdf_trunc)
         self.sdf_res, self.sdf_trunc = self._sdf_res, self._sdf_trunc
         if pair_path is not None:
             self.set_pair_path(pair_path)
+
+    @staticmethod
+    def shard_unique_id() -> bytes:
+        """Rank 0: the id every rank of a sharded map passes to the constructor (hand it over with any transport)."""
+        lib = capi.load()
+        ident = C.create_string_buffer(capi.SHARD_ID_BYTES)
+        rc = lib.chad_shard_unique_id(ident)
+        if rc != capi.CHAD_OK:
+            raise capi.ChadError(rc, lib.chad_last_error(None).decode())
+        return ident.raw
+
+    def shard_info(self) -> dict:
+        r, w = C.c_int(), C.c_int()
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.chad_shard_info(self._h, C.byref(r), C.byref(w), C.byref(a), C.byref(b), C.byref(c)))
+        return {"rank": r.value, "world": w.value, "sent_runs": a.value, "sent_records": b.value, "exchanges": c.value}
 
     # -- lifetime --
     def close(self) -> None:

@@ -145,25 +145,28 @@ int chad_upload(chad_ctx* ctx, void* device_dst, const void* host_src, size_t by
 int chad_timer_begin(chad_ctx* ctx);
 int chad_timer_end(chad_ctx* ctx, float* milliseconds);
 
-/* ---- Morton-range sharding across GPUs ----------------------------------
- * One context per rank / GPU; the map is cut into `world` contiguous Morton ranges of 8x8x8-voxel blocks. Every rank
- * calls these with the SAME batch; between the calls the caller exchanges device buffers (NCCL all-to-all / all-gather;
- * chad_tsdf_b200/sharded.py does it with torch.distributed). An update travels as a 16-byte tuple
- * {u64 Morton key, u32 sorted-point rank, u32 sd bits}; the rank restores the reference's fold order on the receiver.
- *   chad_shard_front        host points of <= 64 scans (scan_offsets[n_scans+1], poses[n_scans][3]) -> point stage on the
- *                           whole batch, band enumeration of this rank's slice of the sorted rays, tuples grouped by
- *                           destination in the send buffer; send_counts[world] = tuples per destination. new_submap != 0
- *                           recomputes the range splitters (identically on every rank, from the batch's sorted points).
- *   chad_shard_send_buffer  device pointer of the send buffer
- *   chad_shard_ingest       received tuples (device memory, any order) -> bin, sort, fold into this rank's shard
- *   chad_shard_export_chunks  this rank's leaf chunks, ascending: device pointers to n x u64 chunk keys and n x 64 B cells
- *   chad_shard_finalize_from  Submap::finalize from a device-resident, ascending chunk stream -- the concatenation (rank order = Morton
- *                           order) of all ranks' chunks, or a whole submap integrated by another rank -- queued on the finalize stream;
- *                           every rank ends up with the identical DAG; clear_local != 0 also clears the local shard */
-int chad_shard_front(chad_ctx* ctx, const float* xyz, const uint32_t* scan_offsets, const float* poses, int n_scans, int rank, int world,
-                     int new_submap, uint64_t* send_counts);
-int chad_shard_send_buffer(chad_ctx* ctx, void** tuples_device);
-int chad_shard_ingest(chad_ctx* ctx, const void* tuples_device, size_t n_tuples);
+/* ---- ONE map on several GPUs: Morton-range sharding (north_star) ---------------
+ * The reference has a single map object (one octree + one NodeLevels, /root/reference/include/chad/tsdf.hpp:166-170); here the map
+ * is cut into `world` contiguous Morton ranges of 8x8x8-voxel blocks and rank g -- one context, one GPU, one host thread or
+ * process -- holds the voxels of range g. EVERY rank makes the SAME sequence of calls with the SAME scans (chad_insert* /
+ * chad_flush / chad_finalize_active / chad_reset): a rank sorts, estimates normals for and walks only the points of its own
+ * range; the few band voxels a ray adds beyond the range travel to their owner once per batch (NCCL send / recv of fixed-size
+ * boxes, counts inside -- no host round trip); at a submap's close the ranks' sorted leaf chunks are gathered on rank 0, which
+ * runs Submap::finalize (submap.hpp:10-106) and holds the DAG (chad_level_* / chad_export_level / chad_query_voxels: rank 0
+ * only; chad_submap_roots: every rank). chad_export_voxels returns the rank's own range (ascending; the concatenation in rank
+ * order is the whole active submap). The union of the ranks' state is bit-identical to the single-GPU map.
+ *   chad_shard_unique_id   rank 0: fill `id` (CHAD_SHARD_ID_BYTES) and hand it to every rank by any means (file, MPI, torch.distributed)
+ *   chad_create_sharded    collective: every rank calls it with the same id; world == 1 is chad_create
+ *   chad_shard_info        rank / world and what this rank has sent to the others so far (runs, 8-byte update records, exchanges) */
+#define CHAD_SHARD_ID_BYTES 256
+int chad_shard_unique_id(void* id);
+int chad_create_sharded(float sdf_res, float sdf_trunc, int device, int max_batch_scans, int rank, int world, const void* id, chad_ctx** out);
+int chad_shard_info(chad_ctx* ctx, int* rank, int* world, uint64_t* sent_runs, uint64_t* sent_records, uint64_t* exchanges);
+
+/* ---- a submap integrated on another GPU (submap-parallel mode): chunk stream out, chunk stream in -----
+ *   chad_shard_export_chunks  this context's leaf chunks, ascending: device pointers to n x u64 chunk keys and n x 64 B cells
+ *   chad_shard_finalize_from  Submap::finalize from a device-resident, ascending chunk stream (a whole submap integrated by another
+ *                           context), queued on the finalize stream; clear_local != 0 also clears the local table */
 int chad_shard_export_chunks(chad_ctx* ctx, size_t* n_chunks, void** keys_device, void** cells_device);
 int chad_shard_finalize_from(chad_ctx* ctx, const uint64_t* keys_device, const void* cells_device, size_t n_chunks, int clear_local);
 /* Forget the active submap's voxels and first pose (octree.clear(), tsdf.cpp:57) without finalising anything here: the submap-parallel

@@ -1,5 +1,7 @@
-"""GPU: the Morton-range sharded map (chad_shard_* + chad_tsdf_b200/sharded.py over NCCL) against the CPU oracle.
-world = 1 runs everywhere; world = 2 needs two GPUs (`gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu`)."""
+"""GPU: ONE map on several GPUs against the CPU oracle -- the Morton-range sharded map (chad_create_sharded: C++ library + NCCL) and
+the submap-parallel mode (chad_tsdf_b200/sharded.py). world = 1 runs everywhere; world = 2 needs two GPUs
+(`gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu`); bench.py --gpus N re-checks the sharded map against the
+reference's golden pins at every N (its `parity_checked` field), which is what the driver's multi-GPU run exercises."""
 import json
 import os
 import subprocess
@@ -12,44 +14,68 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(world, tmp_path, mode="morton"):
+def _launch(world, tmp_path, mode):
     port = 29700 + os.getpid() % 200
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "sharded_worker.py"), str(tmp_path), mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    res = [json.load(open(tmp_path / f"result{i}.json")) for i in range(world)]
+    return [json.load(open(tmp_path / f"result{i}.json")) for i in range(world)]
+
+
+def _run_morton(world, tmp_path, case=""):
+    res = _launch(world, tmp_path, "morton:" + case)
+    r0 = res[0]
+    assert r0["voxels_match"] and r0["roots_match"] and r0["dag_matches_oracle"], r0
+    assert r0["submaps"] >= 1 and all(r["roots"] == r0["roots"] for r in res)  # every rank learns the roots; the levels live on rank 0
+    assert sum(r["local_voxels"] for r in res) == r0["voxels_n"]
+    return res
+
+
+def _run_submaps(world, tmp_path):
+    res = _launch(world, tmp_path, "submaps")
     shards = [np.load(tmp_path / f"shard{i}.npz") for i in range(world)]
     o = np.load(tmp_path / "oracle.npz")
     for r_ in res:
         assert r_["roots_match"] and r_["dag_matches_oracle"], r_  # every rank holds the identical, exact DAG
-    keys = np.concatenate([s["keys"] for s in shards])
-    assert np.array_equal(keys, o["keys"])  # shards are disjoint ascending ranges whose union is the single map
+    assert np.array_equal(np.concatenate([s["keys"] for s in shards]), o["keys"])
     assert np.array_equal(np.concatenate([s["sd"] for s in shards]), o["sd"])
     assert np.array_equal(np.concatenate([s["w"] for s in shards]), o["w"])
     return res
 
 
-def test_sharded_world1(chad_lib, oracle_lib, tmp_path):
-    _run(1, tmp_path)
-
-
-def test_sharded_world2(chad_lib, oracle_lib, tmp_path):
+def _gpus():
     import torch
-    if torch.cuda.device_count() < 2:
+    return torch.cuda.device_count()
+
+
+def test_sharded_world1(chad_lib, oracle_lib, tmp_path):
+    _run_morton(1, tmp_path)
+
+
+@pytest.mark.parametrize("case", ["", "fine"])
+def test_sharded_world2(chad_lib, oracle_lib, tmp_path, case):
+    if _gpus() < 2:
         pytest.skip("needs 2 GPUs")
-    res = _run(2, tmp_path)
-    assert all(r["exchanged"] > 0 for r in res)  # updates really crossed NVLink
+    res = _run_morton(2, tmp_path, case)
+    assert all(r["local_voxels"] > 0 for r in res)
+    assert sum(r["info"]["sent_records"] for r in res) > 0  # updates really crossed NVLink
+
+
+def test_sharded_world4(chad_lib, oracle_lib, tmp_path):
+    if _gpus() < 4:
+        pytest.skip("needs 4 GPUs")
+    res = _run_morton(4, tmp_path)
+    assert sum(r["info"]["sent_records"] for r in res) > 0
 
 
 def test_submap_parallel_world1(chad_lib, oracle_lib, tmp_path):
-    _run(1, tmp_path, "submaps")
+    _run_submaps(1, tmp_path)
 
 
 def test_submap_parallel_world2(chad_lib, oracle_lib, tmp_path):
     """The map's submaps integrated on alternating GPUs, closed submaps broadcast over NCCL: same voxels, same DAG."""
-    import torch
-    if torch.cuda.device_count() < 2:
+    if _gpus() < 2:
         pytest.skip("needs 2 GPUs")
-    res = _run(2, tmp_path, "submaps")
+    res = _run_submaps(2, tmp_path)
     assert all(r["exchanged"] > 0 for r in res)
