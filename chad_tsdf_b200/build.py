@@ -52,6 +52,17 @@ def build_facade_overloads(verbose: bool = False) -> str:
     return out
 
 
+def build_facade_persist(verbose: bool = False) -> str:
+    """tests/cpp/facade_persist.cpp: save -> load -> continue, the leaf iterator (host cursor and device), page-locked vectors."""
+    out = os.path.join(ROOT, "tests", "cpp", "facade_persist")
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++20", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "cpp", "shims"),
+           os.path.join(ROOT, "tests", "cpp", "facade_persist.cpp"), "-o", out, "-L", PKG, "-lchad_b200", f"-Wl,-rpath,{PKG}"]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return out
+
+
 def build_dag_reader(verbose: bool = False) -> str:
     """tests/cpp/dag_reader.cpp: chad::load_dag + HostNodeLevels::query (host-only code of the library; runs without a GPU)."""
     out = os.path.join(ROOT, "tests", "cpp", "dag_reader")

@@ -32,6 +32,13 @@ class Stats(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class DagImage(C.Structure):
+    """chad_dag_image of include/chad_b200.h."""
+    _fields_ = [("node_words", C.c_void_p * 20), ("node_word_count", C.c_size_t * 20), ("cluster_words", C.c_void_p), ("cluster_word_count", C.c_size_t),
+                ("uniques", C.c_uint32 * NUM_LEVELS), ("dupes", C.c_uint32 * NUM_LEVELS), ("roots", C.c_void_p), ("n_submaps", C.c_uint32),
+                ("positions", C.c_void_p), ("position_counts", C.c_void_p)]
+
+
 # every symbol include/chad_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -59,6 +66,10 @@ SYMBOLS = {
     "chad_stage_pairs": (C.c_int, [_P, _P, _P, C.c_size_t, _P, _P, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "chad_stage_sort": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int]),
     "chad_stage_morton": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "chad_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    "chad_host_free": (C.c_int, [_P]),
+    "chad_host_register": (C.c_int, [_P, C.c_size_t]),
+    "chad_host_unregister": (C.c_int, [_P]),
     "chad_device_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "chad_device_free": (C.c_int, [_P, _P]),
     "chad_upload": (C.c_int, [_P, _P, _P, C.c_size_t]),
@@ -71,6 +82,9 @@ SYMBOLS = {
     "chad_shard_finalize_from": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int]),
     "chad_shard_clear": (C.c_int, [_P]),
     "chad_query_voxels": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t, _P]),
+    "chad_iterate_leaves": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "chad_submap_positions": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "chad_import_dag": (C.c_int, [_P, _P]),
     "chad_profile_timeline": (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "chad_morton_encode": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32]),
     "chad_morton_decode": (None, [C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

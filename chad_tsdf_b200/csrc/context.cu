@@ -75,6 +75,8 @@ struct chad_ctx {
     bool has_pose = false;
     float first_pose[3] = {0, 0, 0};
     std::vector<std::array<u32, 2>> roots;
+    std::vector<std::vector<std::array<float, 3>>> positions;  // Submap::positions (submap.hpp:110) of every closed submap, in closing order
+    std::vector<std::array<float, 3>> active_positions;        // ... and of the active one
 
     // batch assembly
     size_t cap_points = 0, cap_pairs = 0;
@@ -1097,6 +1099,8 @@ int finalize_finish(chad_ctx* ctx) {
 int finalize_submap(chad_ctx* ctx, bool lazy) {
     TRY(process_front(ctx));
     ctx->sh.need_splitters = true;  // (sharded) the next submap's ranges follow its own first scan
+    ctx->positions.push_back(std::move(ctx->active_positions));  // closing order == the order the roots arrive in
+    ctx->active_positions.clear();
     if (ctx->n_pend) {
         ctx->pend[ctx->n_pend - 1].close = true;  // the submap's last batch: the finalize begins right after its fold
         if (lazy) return CHAD_OK;
@@ -1116,6 +1120,7 @@ int begin_scan(chad_ctx* ctx, size_t n, const float position[3], bool* skip) {
     TRY(poll_folds(ctx));
     // tsdf.cpp:46-61: a pose more than 5 m (strictly) from the submap's FIRST pose finalises the submap;
     // the triggering scan goes entirely into the new one
+    const std::array<float, 3> pose{position[0], position[1], position[2]};
     if (!ctx->has_pose) {
         ctx->has_pose = true;
         std::memcpy(ctx->first_pose, position, 12);
@@ -1129,6 +1134,7 @@ int begin_scan(chad_ctx* ctx, size_t n, const float position[3], bool* skip) {
             std::memcpy(ctx->first_pose, position, 12);
         }
     }
+    ctx->active_positions.push_back(pose);  // tsdf.cpp:48,56,60: every scan's pose joins the (possibly new) active submap
     ctx->stats.scans++;
     ctx->stats.points += n;
     if (n == 0) { *skip = true; return CHAD_OK; }
@@ -1647,6 +1653,8 @@ int chad_reset(chad_ctx* ctx) {
     ctx->table_count_known = 0;
     ctx->has_pose = false;
     ctx->roots.clear();
+    ctx->positions.clear();
+    ctx->active_positions.clear();
     ctx->stats.resident_clusters = 0;
     return CHAD_OK;
 }
@@ -1732,6 +1740,143 @@ int chad_reset_stats(chad_ctx* ctx) {
     const uint64_t resident = ctx->stats.resident_clusters;
     ctx->stats = chad_stats{};
     ctx->stats.resident_clusters = resident;
+    return CHAD_OK;
+}
+
+// ---- read path and persistence ---------------------------------------------
+int chad_submap_positions(chad_ctx* ctx, uint32_t submap, float* xyz, size_t capacity, size_t* count) {
+    if (!ctx || !count) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(settle(ctx));
+    if (submap > ctx->roots.size()) return fail(ctx, CHAD_ERR_INVALID, "submap index out of range");
+    const std::vector<std::array<float, 3>> none;
+    const auto& p = submap == ctx->roots.size() ? ctx->active_positions : (submap < ctx->positions.size() ? ctx->positions[submap] : none);
+    *count = p.size();
+    if (!xyz) return CHAD_OK;
+    if (capacity < p.size()) return fail(ctx, CHAD_ERR_INVALID, "position capacity too small");
+    if (!p.empty()) std::memcpy(xyz, p.data(), p.size() * 12);
+    return CHAD_OK;
+}
+
+int chad_iterate_leaves(chad_ctx* ctx, uint32_t submap, uint64_t* keys, uint8_t* bytes, size_t capacity, size_t* count) {
+    if (!ctx || !count || (keys && !bytes)) return CHAD_ERR_INVALID;
+    if (ctx->sh.rank != 0) return fail(ctx, CHAD_ERR_INVALID, "sharded map: the DAG levels live on rank 0");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(settle(ctx));
+    if (submap >= ctx->roots.size()) return fail(ctx, CHAD_ERR_INVALID, "submap index out of range");
+    cudaStream_t s = ctx->stream;
+    const u32 root = ctx->roots[submap][0];
+    int rc = CHAD_OK;
+    // the widest frontier is the submap's number of leaf clusters, unknown before the walk: grow the work arrays until nothing overflows
+    for (size_t cap = 1u << 20; rc == CHAD_OK; cap *= 2) {
+        if (cap >= (1ull << 31)) { rc = fail(ctx, CHAD_ERR_CAPACITY, "chad_iterate_leaves: tree too wide"); break; }
+        DevBuf addr[2], prefix[2], counts, offsets, ws, scal, dkeys, dbytes;
+        auto release = [&]() { for (DevBuf* b : {&addr[0], &addr[1], &prefix[0], &prefix[1], &counts, &offsets, &ws, &scal, &dkeys, &dbytes}) dev_free(*b); };
+        for (int q = 0; q < 2 && rc == CHAD_OK; q++) { rc = dev_ensure(ctx, addr[q], cap * 4); if (rc == CHAD_OK) rc = dev_ensure(ctx, prefix[q], cap * 8); }
+        if (rc == CHAD_OK) rc = dev_ensure(ctx, counts, cap * 4);
+        if (rc == CHAD_OK) rc = dev_ensure(ctx, offsets, cap * 4);
+        if (rc == CHAD_OK) rc = dev_ensure(ctx, ws, scan_workspace_bytes(cap));
+        if (rc == CHAD_OK) rc = dev_ensure(ctx, scal, 256);
+        if (rc == CHAD_OK && keys) { rc = dev_ensure(ctx, dkeys, (capacity ? capacity : 1) * 8); if (rc == CHAD_OK) rc = dev_ensure(ctx, dbytes, capacity ? capacity : 1); }
+        if (rc != CHAD_OK) { release(); break; }
+        u32* d = scal.as<u32>();  // [0 .. 20] frontier sizes by depth, [21] voxels, [22] overflow
+        const u32 init[2] = {1u, 0u};
+        const u64 zero = 0;
+        cudaMemsetAsync(d, 0, 256, s);
+        cudaMemcpyAsync(d, &init[0], 4, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(addr[0].p, &root, 4, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(prefix[0].p, &zero, 8, cudaMemcpyHostToDevice, s);
+        u64 launches = 0;
+        int cur = 0;
+        for (int depth = 0; depth < 20; depth++, cur ^= 1)
+            launches += launch_iter_expand(s, ctx->levels[depth].raw.as<u32>(), addr[cur].as<u32>(), prefix[cur].as<u64>(), d + depth, (u32)cap, counts.as<u32>(),
+                                           offsets.as<u32>(), ws.p, addr[cur ^ 1].as<u32>(), prefix[cur ^ 1].as<u64>(), d + depth + 1, d + 22);
+        // a frontier wider than `cap` was cut: its size (d[depth]) still says so, and so does the overflow flag
+        launches += launch_iter_leaves(s, ctx->levels[CHAD_LEVEL_CLUSTERS].raw.as<u64>(), addr[cur].as<u32>(), prefix[cur].as<u64>(), d + 20, (u32)cap,
+                                       counts.as<u32>(), offsets.as<u32>(), ws.p, (u32)std::min<size_t>(capacity, 0xFFFFFFFFu), keys ? dkeys.as<u64>() : nullptr,
+                                       keys ? dbytes.as<u8>() : nullptr, d + 21);
+        ctx->stats.kernel_launches += launches;
+        u32 h[24] = {0};
+        cudaError_t e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { release(); rc = fail(ctx, CHAD_ERR_CUDA, std::string("chad_iterate_leaves: ") + cudaGetErrorString(e)); break; }
+        bool cut = h[22] != 0;
+        for (int depth = 0; depth <= 20; depth++) cut |= h[depth] > cap;
+        if (cut) { release(); continue; }
+        *count = h[21];
+        if (keys) {
+            if (capacity < h[21]) { release(); rc = fail(ctx, CHAD_ERR_INVALID, "leaf capacity too small"); break; }
+            e = cudaMemcpy(keys, dkeys.p, size_t(h[21]) * 8, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(bytes, dbytes.p, h[21], cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) rc = fail(ctx, CHAD_ERR_CUDA, std::string("chad_iterate_leaves: ") + cudaGetErrorString(e));
+        }
+        release();
+        break;
+    }
+    return rc;
+}
+
+int chad_import_dag(chad_ctx* ctx, const chad_dag_image* img) {
+    if (!ctx || !img) return CHAD_ERR_INVALID;
+    if (ctx->sh.world > 1) return fail(ctx, CHAD_ERR_INVALID, "chad_import_dag: not on a sharded map");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(settle(ctx));
+    if (!ctx->roots.empty() || ctx->has_pose || ctx->levels[CHAD_LEVEL_CLUSTERS].uniques != 0)
+        return fail(ctx, CHAD_ERR_INVALID, "chad_import_dag: the map must be empty (fresh, or after chad_reset)");
+    if (img->n_submaps && (!img->roots)) return fail(ctx, CHAD_ERR_INVALID, "chad_import_dag: roots missing");
+    cudaStream_t s = ctx->fin_stream;
+    LevelCounters counters[CHAD_NUM_LEVELS];
+    std::vector<u32> starts;
+    for (int lv = 0; lv < CHAD_NUM_LEVELS; lv++) {
+        const bool cluster = lv == CHAD_LEVEL_CLUSTERS;
+        Level& L = ctx->levels[lv];
+        const size_t words = cluster ? img->cluster_word_count : img->node_word_count[lv];
+        const void* src = cluster ? static_cast<const void*>(img->cluster_words) : static_cast<const void*>(img->node_words[lv]);
+        if (words == 0 || !src) return fail(ctx, CHAD_ERR_INVALID, "chad_import_dag: a level is missing (every level holds at least its reserved word 0)");
+        if (words >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "chad_import_dag: level exceeds 2^31 words");
+        u32 records = 0;
+        starts.clear();
+        if (cluster) {
+            records = (u32)(words - 1);  // addresses 1 .. uniques
+        } else {  // records follow each other from address 1: [mask, children ...] (levels.hpp:57-88)
+            const u32* w = img->node_words[lv];
+            size_t a = 1;
+            while (a < words) {
+                starts.push_back((u32)a);
+                a += 1 + (size_t)__builtin_popcount(w[a] & 0xFFu);
+            }
+            if (a != words) return fail(ctx, CHAD_ERR_INVALID, "chad_import_dag: a node level does not end on a record boundary");
+            records = (u32)starts.size();
+        }
+        if (records != img->uniques[lv]) return fail(ctx, CHAD_ERR_INVALID, "chad_import_dag: a level's unique count does not match its records");
+        L.uniques = 0; L.dupes = 0; L.occupied = cluster ? 0 : 1;
+        TRY(level_reserve(ctx, L, cluster, size_t(records) + 1024));
+        if (size_t(words) > L.raw_cap) return fail(ctx, CHAD_ERR_CAPACITY, "chad_import_dag: level buffer too small");
+        CUDA_TRY(ctx, cudaMemcpyAsync(L.raw.p, src, words * (cluster ? 8 : 4), cudaMemcpyHostToDevice, s));
+        DevBuf dstarts;
+        if (!cluster && records) {
+            TRY(dev_ensure(ctx, dstarts, size_t(records) * 4));
+            CUDA_TRY(ctx, cudaMemcpyAsync(dstarts.p, starts.data(), size_t(records) * 4, cudaMemcpyHostToDevice, s));
+        }
+        ctx->stats.kernel_launches += launch_dedup_restore(s, L.table, cluster, L.raw.p, dstarts.as<u32>(), records);
+        CUDA_TRY(ctx, cudaStreamSynchronize(s));  // (`starts` and the staging buffer are reused by the next level)
+        dev_free(dstarts);
+        L.uniques = img->uniques[lv];
+        L.dupes = img->dupes[lv];
+        L.occupied = cluster ? 0 : (u32)words;
+        counters[lv] = LevelCounters{cluster ? 0u : (u32)words, L.uniques, L.dupes, 0u};
+    }
+    CUDA_TRY(ctx, cudaMemcpy(ctx->f_counters.p, counters, sizeof(counters), cudaMemcpyHostToDevice));
+    const float* pos = img->positions;
+    for (u32 i = 0; i < img->n_submaps; i++) {
+        ctx->roots.push_back({img->roots[2 * i], img->roots[2 * i + 1]});
+        std::vector<std::array<float, 3>> p;
+        const u32 np = (img->position_counts && pos) ? img->position_counts[i] : 0u;
+        for (u32 q = 0; q < np; q++, pos += 3) p.push_back({pos[0], pos[1], pos[2]});
+        ctx->positions.push_back(std::move(p));
+    }
+    ctx->stats.submaps = ctx->roots.size();
     return CHAD_OK;
 }
 
@@ -1919,6 +2064,29 @@ int chad_shard_finalize_from(chad_ctx* ctx, const uint64_t* keys_device, const v
         ctx->stats.resident_clusters = 0;
     }
     return finalize_begin(ctx, (u32)n_chunks, true, ctx->stream);
+}
+
+int chad_host_alloc(size_t bytes, void** host_ptr) {
+    if (!host_ptr) return CHAD_ERR_INVALID;
+    *host_ptr = nullptr;
+    const cudaError_t e = cudaHostAlloc(host_ptr, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(nullptr, CHAD_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    return CHAD_OK;
+}
+int chad_host_free(void* host_ptr) {
+    if (!host_ptr) return CHAD_OK;
+    return cudaFreeHost(host_ptr) == cudaSuccess ? CHAD_OK : CHAD_ERR_CUDA;
+}
+int chad_host_register(void* host_ptr, size_t bytes) {
+    if (!host_ptr || !bytes) return CHAD_ERR_INVALID;
+    const cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, CHAD_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+    return CHAD_OK;
+}
+int chad_host_unregister(void* host_ptr) {
+    if (!host_ptr) return CHAD_ERR_INVALID;
+    if (cudaHostUnregister(host_ptr) != cudaSuccess) { cudaGetLastError(); return CHAD_ERR_CUDA; }
+    return CHAD_OK;
 }
 
 int chad_device_alloc(chad_ctx* ctx, size_t bytes, void** device_ptr) {

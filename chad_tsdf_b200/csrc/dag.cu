@@ -381,6 +381,100 @@ __global__ void __launch_bounds__(DAG_THREADS) dag_query_kernel(DagReadArgs a, u
     out[i] = byte;
 }
 
+// ------------------------------------------------------------------------------------------
+// Restoring a saved map: the level arrays come back from a file, the dedup sets are rebuilt from them so that later
+// Submap::finalize calls deduplicate against everything the saved map ever added (levels.hpp:90-93,141-143: the sets
+// are never cleared). Every stored record is distinct, so insertion is a plain first-free probe.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DAG_THREADS) restore_clusters_kernel(u64* entries, u64 capacity, const u64* __restrict__ raw, u32 uniques) {
+    const u32 a = blockIdx.x * DAG_THREADS + threadIdx.x + 1;  // address 0 is reserved (levels.hpp:119-120)
+    if (a > uniques) return;
+    const u32 tag = (u32)(mix64(raw[a]) >> 32);
+    const u64 mask = capacity - 1;
+    u64 slot = tag & mask;
+    const u64 ent = (u64(tag) << 32) | a;
+    for (u64 probes = 0; probes < capacity; probes++) {
+        if (atomicCAS(&entries[slot], 0ull, ent) == 0ull) return;
+        slot = (slot + 1) & mask;
+    }
+}
+__global__ void __launch_bounds__(DAG_THREADS) restore_nodes_kernel(u64* entries, u64 capacity, const u32* __restrict__ raw, const u32* __restrict__ starts,
+                                                                    u32 n_records) {
+    const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (i >= n_records) return;
+    const u32 a = starts[i];
+    u32 rec[9];
+    rec[0] = raw[a] & 0xFFu;
+    const u32 nchild = __popc(rec[0]);
+#pragma unroll
+    for (u32 q = 1; q < 9; q++) rec[q] = (q <= nchild) ? raw[a + q] : 0u;  // the probe's candidate records are zero padded
+    const u32 tag = node_tag(rec);
+    const u64 mask = capacity - 1;
+    u64 slot = tag & mask;
+    const u64 ent = (u64(tag) << 32) | a;
+    for (u64 probes = 0; probes < capacity; probes++) {
+        if (atomicCAS(&entries[slot], 0ull, ent) == 0ull) return;
+        slot = (slot + 1) & mask;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Leaf iterator over a finalised submap's tree on the device (the reader the reference sketches but never finishes:
+// tsdf.hpp:120-155, tsdf.cpp:88-159 walk root -> first leaf cluster with get_child_addr / try_get_lc). Data-parallel
+// form: the tree is expanded one depth at a time; a node's children are appended in child order behind an exclusive
+// prefix sum of the popcounts, so every frontier -- and finally the voxel list -- is in ascending Morton order.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DAG_THREADS) iter_count_kernel(const u32* __restrict__ raw, const u32* __restrict__ addr, const u32* __restrict__ d_n,
+                                                                 u32 max_n, u32* __restrict__ counts) {
+    const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (i >= max_n) return;
+    counts[i] = (i < *d_n) ? (u32)__popc(raw[addr[i]] & 0xFFu) : 0u;
+}
+__global__ void __launch_bounds__(DAG_THREADS) iter_expand_kernel(const u32* __restrict__ raw, const u32* __restrict__ addr, const u64* __restrict__ prefix,
+                                                                  const u32* __restrict__ d_n, const u32* __restrict__ offsets, u32 capacity,
+                                                                  u32* __restrict__ addr_next, u64* __restrict__ prefix_next, u32* d_overflow) {
+    const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (i >= *d_n) return;
+    const u32 a = addr[i];
+    const u32 mask = raw[a] & 0xFFu;
+    u32 out = offsets[i], c = 0;
+    for (u32 child = 0; child < 8; child++) {
+        if (!(mask & (1u << child))) continue;
+        c++;
+        if (out < capacity) { addr_next[out] = raw[a + c]; prefix_next[out] = (prefix[i] << 3) | child; }
+        else atomicOr(d_overflow, 1u);
+        out++;
+    }
+}
+// frontier of leaf clusters (address, cluster id = key >> 3) -> per cluster the number of present voxels
+__global__ void __launch_bounds__(DAG_THREADS) iter_leaf_count_kernel(const u64* __restrict__ clusters, const u32* __restrict__ addr, const u32* __restrict__ d_n,
+                                                                      u32 max_n, u32* __restrict__ counts) {
+    const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (i >= max_n) return;
+    u32 c = 0;
+    if (i < *d_n) {
+        const u64 v = clusters[addr[i]];
+#pragma unroll
+        for (int s = 0; s < 8; s++) c += (((v >> (8 * s)) & 0xFFull) != 0xFFull) ? 1u : 0u;
+    }
+    counts[i] = c;
+}
+__global__ void __launch_bounds__(DAG_THREADS) iter_leaf_emit_kernel(const u64* __restrict__ clusters, const u32* __restrict__ addr, const u64* __restrict__ prefix,
+                                                                     const u32* __restrict__ d_n, const u32* __restrict__ offsets, u32 capacity,
+                                                                     u64* __restrict__ keys, u8* __restrict__ bytes) {
+    const u32 i = blockIdx.x * DAG_THREADS + threadIdx.x;
+    if (i >= *d_n) return;
+    const u64 v = clusters[addr[i]];
+    u32 out = offsets[i];
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        const u8 b = (u8)(v >> (8 * s));
+        if (b == 0xFF) continue;
+        if (out < capacity) { keys[out] = (prefix[i] << 3) | (u64)s; bytes[out] = b; }
+        out++;
+    }
+}
+
 __global__ void __launch_bounds__(DAG_THREADS) dedup_rehash_kernel(const u64* __restrict__ from, u64 from_capacity, u64* to, u64 to_capacity) {
     const u64 mask = to_capacity - 1;
     for (u64 s = u64(blockIdx.x) * DAG_THREADS + threadIdx.x; s < from_capacity; s += u64(gridDim.x) * DAG_THREADS) {
@@ -466,6 +560,35 @@ int launch_dag_levels(cudaStream_t s, const LevelsArgs& args, int num_sms) {
     // coop_ok == 0 (CHAD_LEVELS_COOP=0): the round-1 plain launch, kept for A/B timing only
     dag_levels_kernel<<<grid, threads, 0, s>>>(args);
     return 1;
+}
+
+int launch_dedup_restore(cudaStream_t s, const DedupTable& t, bool cluster, const void* raw, const u32* starts, u32 n_records) {
+    launch_dedup_clear(s, t);
+    if (!n_records) return 0;
+    if (cluster) restore_clusters_kernel<<<blocks_for(n_records), DAG_THREADS, 0, s>>>(t.entries, t.capacity, static_cast<const u64*>(raw), n_records);
+    else restore_nodes_kernel<<<blocks_for(n_records), DAG_THREADS, 0, s>>>(t.entries, t.capacity, static_cast<const u32*>(raw), starts, n_records);
+    return 1;
+}
+
+// One depth of the leaf iterator: frontier (addr, prefix)[*d_n] at node level `raw` -> the children, in order. counts / offsets: work
+// arrays of `capacity` u32; *d_n_next = number of children. Returns the kernels queued.
+int launch_iter_expand(cudaStream_t s, const u32* raw, const u32* addr, const u64* prefix, const u32* d_n, u32 capacity, u32* counts, u32* offsets,
+                       void* scan_ws, u32* addr_next, u64* prefix_next, u32* d_n_next, u32* d_overflow) {
+    iter_count_kernel<<<blocks_for(capacity), DAG_THREADS, 0, s>>>(raw, addr, d_n, capacity, counts);
+    int launches = 1 + exclusive_scan<u32, u32>(s, counts, offsets, capacity, scan_ws, d_n_next);
+    iter_expand_kernel<<<blocks_for(capacity), DAG_THREADS, 0, s>>>(raw, addr, prefix, d_n, offsets, capacity, addr_next, prefix_next, d_overflow);
+    return launches + 1;
+}
+// the last depth: frontier of leaf clusters -> (Morton key, quantised byte) of every present voxel, ascending; *d_total = their number
+int launch_iter_leaves(cudaStream_t s, const u64* clusters, const u32* addr, const u64* prefix, const u32* d_n, u32 capacity, u32* counts, u32* offsets,
+                       void* scan_ws, u32 out_capacity, u64* keys, u8* bytes, u32* d_total) {
+    iter_leaf_count_kernel<<<blocks_for(capacity), DAG_THREADS, 0, s>>>(clusters, addr, d_n, capacity, counts);
+    int launches = 1 + exclusive_scan<u32, u32>(s, counts, offsets, capacity, scan_ws, d_total);
+    if (keys) {
+        iter_leaf_emit_kernel<<<blocks_for(capacity), DAG_THREADS, 0, s>>>(clusters, addr, prefix, d_n, offsets, out_capacity, keys, bytes);
+        launches++;
+    }
+    return launches;
 }
 
 int launch_dag_query(cudaStream_t s, const DagReadArgs& args, u32 root, const u64* keys, u32 n, u8* out) {

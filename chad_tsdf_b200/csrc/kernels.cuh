@@ -164,6 +164,14 @@ int launch_dag_levels(cudaStream_t s, const LevelsArgs& args, int num_sms);
 struct DagReadArgs { const u32* raw[20]; const u64* clusters; };
 int launch_dag_query(cudaStream_t s, const DagReadArgs& args, u32 root, const u64* keys, u32 n, u8* out);
 int launch_dedup_clear(cudaStream_t s, const DedupTable& t);
+// rebuild a level's dedup set from its stored records (restore of a saved map): cluster level: raw = u64 values, addresses 1 .. n_records;
+// node level: raw = u32 words, starts[i] = address of record i
+int launch_dedup_restore(cudaStream_t s, const DedupTable& t, bool cluster, const void* raw, const u32* starts, u32 n_records);
+// leaf iterator over a finalised submap's tree, one depth per call (see dag.cu)
+int launch_iter_expand(cudaStream_t s, const u32* raw, const u32* addr, const u64* prefix, const u32* d_n, u32 capacity, u32* counts, u32* offsets,
+                       void* scan_ws, u32* addr_next, u64* prefix_next, u32* d_n_next, u32* d_overflow);
+int launch_iter_leaves(cudaStream_t s, const u64* clusters, const u32* addr, const u64* prefix, const u32* d_n, u32 capacity, u32* counts, u32* offsets,
+                       void* scan_ws, u32 out_capacity, u64* keys, u8* bytes, u32* d_total);
 int launch_dedup_rehash(cudaStream_t s, const DedupTable& from, const DedupTable& to, int num_sms);
 // the chunk count is read from device memory (*d_chunks <= max_chunks): finalize part 1 runs without a host round trip
 int launch_cluster_build(cudaStream_t s, const void* gathered_cells, const u32* d_chunks, u32 max_chunks, const MapParams& mp, u64* tsdf_values);

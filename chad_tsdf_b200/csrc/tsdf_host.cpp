@@ -6,6 +6,7 @@
 #include <bit>
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <stdexcept>
 #include <unordered_map>
 
@@ -55,109 +56,211 @@ HostNodeLevels TSDFMap::node_levels() {
     return out;
 }
 
-// Flat little-endian dump: "CHADDAG1", f32 sdf_res, f32 sdf_trunc, u32 n_submaps, n_submaps x (u32 root_tsdf,
-// u32 root_weight), then for level 0..19: u64 n_words + n_words x u32, then u64 n_clusters + n x u64.
-void TSDFMap::save(const std::string& filename) {
-    check(_ctx, chad_finalize_active(_ctx), "save");  // tsdf.cpp:78-81
-    const HostNodeLevels levels = node_levels();
+// Flat little-endian dump: "CHADDAG2", f32 sdf_res, f32 sdf_trunc, u32 n_submaps, per submap
+// (u32 root_tsdf, u32 root_weight, u32 n_poses, n_poses x 3 f32), then for level 0..19: u32 uniques, u32 dupes, u64 n_words,
+// n_words x u32, then for the cluster level: u32 uniques, u32 dupes, u64 n_clusters, n x u64.
+void save_dag(const SavedMap& m, const std::string& filename) {
     std::FILE* f = std::fopen(filename.c_str(), "wb");
-    if (!f) throw std::runtime_error("chad::TSDFMap::save: cannot open " + filename);
-    auto put = [&](const void* p, size_t n) { if (std::fwrite(p, 1, n, f) != n) { std::fclose(f); throw std::runtime_error("chad::TSDFMap::save: write failed"); } };
-    put("CHADDAG1", 8);
-    put(&_sdf_res, 4);
-    put(&_sdf_trunc, 4);
-    const uint32_t n_sub = (uint32_t)submap_count();
+    if (!f) throw std::runtime_error("chad::save_dag: cannot open " + filename);
+    auto put = [&](const void* p, size_t n) { if (n && std::fwrite(p, 1, n, f) != n) { std::fclose(f); throw std::runtime_error("chad::save_dag: write failed"); } };
+    put("CHADDAG2", 8);
+    put(&m.sdf_res, 4);
+    put(&m.sdf_trunc, 4);
+    const uint32_t n_sub = (uint32_t)m.roots.size();
     put(&n_sub, 4);
-    for (uint32_t i = 0; i < n_sub; i++) { auto r = submap_roots(i); put(r.data(), 8); }
-    for (const auto& lv : levels.nodes) { const uint64_t n = lv.size(); put(&n, 8); put(lv.data(), n * 4); }
-    const uint64_t n = levels.leaf_clusters.size();
-    put(&n, 8);
-    put(levels.leaf_clusters.data(), n * 8);
+    for (uint32_t i = 0; i < n_sub; i++) {
+        put(m.roots[i].data(), 8);
+        const uint32_t np = i < m.positions.size() ? (uint32_t)m.positions[i].size() : 0u;
+        put(&np, 4);
+        if (np) put(m.positions[i].data(), size_t(np) * 12);
+    }
+    for (size_t lv = 0; lv <= HostNodeLevels::MAX_DEPTH; lv++) {
+        put(&m.uniques[lv], 4);
+        put(&m.dupes[lv], 4);
+        if (lv < HostNodeLevels::MAX_DEPTH) { const uint64_t n = m.levels.nodes[lv].size(); put(&n, 8); put(m.levels.nodes[lv].data(), n * 4); }
+        else { const uint64_t n = m.levels.leaf_clusters.size(); put(&n, 8); put(m.levels.leaf_clusters.data(), n * 8); }
+    }
     std::fclose(f);
 }
 
-// The reference's ChadGrid constructor (lvr2.cpp:32-130) + ChadGrid::saveGrid (lvr2.cpp:170-200) on the host copy of the DAG.
+void TSDFMap::save(const std::string& filename) {
+    check(_ctx, chad_finalize_active(_ctx), "save");  // tsdf.cpp:78-81
+    SavedMap m;
+    m.sdf_res = _sdf_res;
+    m.sdf_trunc = _sdf_trunc;
+    m.levels = node_levels();
+    m.has_counters = true;
+    for (int lv = 0; lv < CHAD_NUM_LEVELS; lv++) check(_ctx, chad_level_counters(_ctx, lv, &m.uniques[lv], &m.dupes[lv]), "save");
+    const size_t n_sub = submap_count();
+    for (size_t i = 0; i < n_sub; i++) {
+        m.roots.push_back(submap_roots(i));
+        m.positions.push_back(submap_positions(i));
+    }
+    save_dag(m, filename);
+}
+
+void TSDFMap::load(const std::string& filename) {
+    const SavedMap m = load_dag(filename);
+    if (m.sdf_res != _sdf_res || m.sdf_trunc != _sdf_trunc) throw std::runtime_error("chad::TSDFMap::load: " + filename + " was saved with another voxel size / truncation");
+    if (!m.has_counters) throw std::runtime_error("chad::TSDFMap::load: " + filename + " is a CHADDAG1 dump (no dedup counters): readable with load_dag, not restorable");
+    chad_dag_image img{};
+    for (size_t lv = 0; lv < HostNodeLevels::MAX_DEPTH; lv++) { img.node_words[lv] = m.levels.nodes[lv].data(); img.node_word_count[lv] = m.levels.nodes[lv].size(); }
+    img.cluster_words = m.levels.leaf_clusters.data();
+    img.cluster_word_count = m.levels.leaf_clusters.size();
+    for (int lv = 0; lv < CHAD_NUM_LEVELS; lv++) { img.uniques[lv] = m.uniques[lv]; img.dupes[lv] = m.dupes[lv]; }
+    std::vector<uint32_t> roots, counts;
+    std::vector<float> poses;
+    for (size_t i = 0; i < m.roots.size(); i++) {
+        roots.push_back(m.roots[i][0]);
+        roots.push_back(m.roots[i][1]);
+        counts.push_back(i < m.positions.size() ? (uint32_t)m.positions[i].size() : 0u);
+        if (i < m.positions.size()) for (const auto& p : m.positions[i]) poses.insert(poses.end(), p.begin(), p.end());
+    }
+    img.roots = roots.data();
+    img.n_submaps = (uint32_t)m.roots.size();
+    img.positions = poses.data();
+    img.position_counts = counts.data();
+    check(_ctx, chad_import_dag(_ctx, &img), "load");
+}
+
+std::vector<std::array<float, 3>> TSDFMap::submap_positions(size_t submap) {
+    size_t n = 0;
+    check(_ctx, chad_submap_positions(_ctx, (uint32_t)submap, nullptr, 0, &n), "submap_positions");
+    std::vector<std::array<float, 3>> out(n);
+    if (n) check(_ctx, chad_submap_positions(_ctx, (uint32_t)submap, out[0].data(), n, &n), "submap_positions");
+    return out;
+}
+
+// ---- leaf iterator ------------------------------------------------------------------------------------
+namespace {
+Leaf make_leaf(uint64_t key, uint8_t byte, float sdf_res, float sdf_trunc) {
+    int32_t x, y, z;
+    chad_morton_decode(key, &x, &y, &z);
+    float sd = float(byte) - 127.0f;  // TSDFs::try_get, cluster.hpp:46-50
+    sd *= float(1.0 / 127.0f);
+    sd *= sdf_trunc;
+    return Leaf{float(x) * sdf_res, float(y) * sdf_res, float(z) * sdf_res, sd, byte, key};
+}
+}  // namespace
+
+LeafCursor::LeafCursor(const HostNodeLevels& levels, uint32_t root_addr): _levels(&levels) {
+    _addr[0] = root_addr;
+    _leaf_i = 7;  // "behind the last voxel of a cluster": next() starts with the first cluster
+    _cluster = ~0ull;
+    if (root_addr == 0 || root_addr >= levels.nodes[0].size()) { _done = true; return; }
+    next();
+}
+// depth-first, children in index order: the clusters come in ascending Morton order (submap.hpp:10-106 writes them in that order)
+bool LeafCursor::next_cluster() {
+    while (true) {
+        if (_child[_depth] == 8) {  // this node is exhausted
+            if (_depth == 0) return false;
+            _depth--;
+            continue;
+        }
+        const uint8_t c = _child[_depth]++;
+        if (_depth + 1 < HostNodeLevels::MAX_DEPTH) {
+            const uint32_t a = _levels->get_child_addr(_depth, _addr[_depth], c);
+            if (a == 0) continue;
+            _depth++;
+            _addr[_depth] = a;
+            _child[_depth] = 0;
+        } else if (_levels->try_get_lc(_addr[_depth], c, _cluster)) {
+            _cluster_key = 0;  // the path IS the key: child index d-th triple from the top (octree.hpp:44-56)
+            for (uint32_t d = 0; d < HostNodeLevels::MAX_DEPTH; d++) _cluster_key = (_cluster_key << 3) | uint64_t(_child[d] - 1);
+            return true;
+        }
+    }
+}
+void LeafCursor::next() {
+    if (_done) return;
+    while (true) {
+        if (_leaf_i == 7) {
+            if (!next_cluster()) { _done = true; return; }
+            _leaf_i = 0;
+        } else {
+            _leaf_i++;
+        }
+        if (byte() != 0xFF) return;  // 0xFF = no voxel (cluster.hpp:29-32)
+    }
+}
+Leaf LeafCursor::leaf(float sdf_res, float sdf_trunc) const { return make_leaf(key(), byte(), sdf_res, sdf_trunc); }
+
+TSDFMap::LeafRange TSDFMap::leaves(size_t submap) {
+    check(_ctx, chad_flush(_ctx), "leaves");
+    if (submap >= submap_count()) throw std::runtime_error("chad::TSDFMap::leaves: no such submap");
+    return LeafRange{node_levels(), submap_roots(submap)[0], _sdf_res, _sdf_trunc};
+}
+std::vector<Leaf> TSDFMap::collect_leaves(size_t submap) {
+    size_t n = 0;
+    check(_ctx, chad_iterate_leaves(_ctx, (uint32_t)submap, nullptr, nullptr, 0, &n), "collect_leaves");
+    std::vector<uint64_t> keys(n);
+    std::vector<uint8_t> bytes(n);
+    if (n) check(_ctx, chad_iterate_leaves(_ctx, (uint32_t)submap, keys.data(), bytes.data(), n, &n), "collect_leaves");
+    std::vector<Leaf> out;
+    out.reserve(n);
+    for (size_t i = 0; i < n; i++) out.push_back(make_leaf(keys[i], bytes[i], _sdf_res, _sdf_trunc));
+    return out;
+}
+
+// ---- .grid file ------------------------------------------------------------------------------------------
 void TSDFMap::save_grid(const std::string& filename, size_t submap) {
     check(_ctx, chad_finalize_active(_ctx), "save_grid");  // tsdf.cpp:78-81
     if (submap >= submap_count()) throw std::runtime_error("chad::TSDFMap::save_grid: no such submap");
     write_grid(node_levels(), submap_roots(submap)[0], _sdf_res, _sdf_trunc, filename);
 }
 
-void write_grid(const HostNodeLevels& levels, uint32_t root, float _sdf_res, float _sdf_trunc, const std::string& filename) {
+// File format of lvr2's ChadGrid::saveGrid (lvr2.cpp:170-200): the header float (the truncation distance, under the name voxel_res:
+// SURVEY.md section 9 Q15), the counts, one (x, y, z, sd) query point per voxel and eight query-point indices per complete cell. The
+// content follows from the leaf iterator: voxels in ascending Morton order are the query points; voxel v is corner j of the cell at
+// v + corner_offset[j] (the corner numbering of lvr2.cpp:88-98); a cell with a missing corner is dropped (lvr2.cpp:115-129).
+void write_grid(const HostNodeLevels& levels, uint32_t root, float sdf_res, float sdf_trunc, const std::string& filename) {
     struct QueryPoint { float x, y, z, sd; };
-    std::vector<QueryPoint> query_points;
-    constexpr uint32_t INVALID = 0xFFFFFFFFu;  // lvr2 FastBox::INVALID_INDEX
+    constexpr uint32_t NO_POINT = 0xFFFFFFFFu;  // lvr2 FastBox::INVALID_INDEX
+    static const int32_t corner_offset[8][3] = { {0, 0, 0}, {-1, 0, 0}, {-1, -1, 0}, {0, -1, 0}, {0, 0, -1}, {-1, 0, -1}, {-1, -1, -1}, {0, -1, -1} };
+    std::vector<QueryPoint> points;
     std::unordered_map<uint64_t, std::array<uint32_t, 8>> cells;
-    static const int32_t cell_offsets[8][3] = { {0, 0, 0}, {-1, 0, 0}, {-1, -1, 0}, {0, -1, 0}, {0, 0, -1}, {-1, 0, -1}, {-1, -1, -1}, {0, -1, -1} };  // lvr2.cpp:88-98
-    std::array<uint8_t, HostNodeLevels::MAX_DEPTH> path_child{};
-    std::array<uint32_t, HostNodeLevels::MAX_DEPTH> path_addr{};
-    path_addr[0] = root;
-    uint32_t depth = 0;
-    while (true) {  // lvr2.cpp:33-113
-        const uint8_t child_i = path_child[depth]++;
-        if (child_i == 8) {
-            if (depth > 0) depth--;
-            else break;
-        } else if (depth < HostNodeLevels::MAX_DEPTH - 1) {
-            const uint32_t child_addr = levels.get_child_addr(depth, path_addr[depth], child_i);
-            if (child_addr > 0) {
-                depth++;
-                path_child[depth] = 0;
-                path_addr[depth] = child_addr;
-            }
-        } else {
-            uint64_t cluster;
-            if (!levels.try_get_lc(path_addr[depth], child_i, cluster)) continue;
-            uint64_t code = 0;  // Morton code of the cluster from the path (lvr2.cpp:59-65)
-            for (uint64_t k = 0; k < 63 / 3 - 1; k++) code |= uint64_t(path_child[k] - 1) << uint64_t(60 - k * 3);
-            int32_t cx, cy, cz;
-            chad_morton_decode(code, &cx, &cy, &cz);
-            uint32_t leaf_i = 0;
-            for (int32_t z = 0; z <= 1; z++) for (int32_t y = 0; y <= 1; y++) for (int32_t x = 0; x <= 1; x++, leaf_i++) {
-                const uint64_t bits = (cluster >> (leaf_i * 8)) & 0xFF;  // TSDFs::try_get, cluster.hpp:34-52
-                if (bits == 0xFF) continue;
-                float sd = float(bits) - 127.0f;
-                sd *= float(1.0 / 127.0f);
-                sd *= _sdf_trunc;
-                const int32_t lx = cx + x, ly = cy + y, lz = cz + z;
-                const uint32_t qi = (uint32_t)query_points.size();
-                query_points.push_back({ float(lx) * _sdf_res, float(ly) * _sdf_res, float(lz) * _sdf_res, sd });
-                for (size_t i = 0; i < 8; i++) {
-                    const uint64_t cell = chad_morton_encode(lx + cell_offsets[i][0], ly + cell_offsets[i][1], lz + cell_offsets[i][2]);
-                    auto [it, fresh] = cells.try_emplace(cell);
-                    if (fresh) it->second.fill(INVALID);
-                    it->second[i] = qi;
-                }
-            }
+    for (LeafCursor it(levels, root); !it.done(); it.next()) {
+        const Leaf v = it.leaf(sdf_res, sdf_trunc);
+        int32_t vx, vy, vz;
+        chad_morton_decode(v.morton, &vx, &vy, &vz);
+        const uint32_t index = (uint32_t)points.size();
+        points.push_back({v.x, v.y, v.z, v.signed_distance});
+        for (size_t j = 0; j < 8; j++) {
+            auto [cell, fresh] = cells.try_emplace(chad_morton_encode(vx + corner_offset[j][0], vy + corner_offset[j][1], vz + corner_offset[j][2]));
+            if (fresh) cell->second.fill(NO_POINT);
+            cell->second[j] = index;
         }
     }
-    std::vector<uint64_t> complete;  // lvr2.cpp:115-129: cells with a missing corner are culled
-    for (const auto& [code, verts] : cells)
-        if (std::find(verts.begin(), verts.end(), INVALID) == verts.end()) complete.push_back(code);
+    std::vector<uint64_t> complete;
+    for (const auto& [code, corners] : cells)
+        if (std::find(corners.begin(), corners.end(), NO_POINT) == corners.end()) complete.push_back(code);
     std::sort(complete.begin(), complete.end());
     std::FILE* f = std::fopen(filename.c_str(), "wb");
     if (!f) throw std::runtime_error("chad::write_grid: cannot open " + filename);
     auto put = [&](const void* p, size_t n) { if (n && std::fwrite(p, 1, n, f) != n) { std::fclose(f); throw std::runtime_error("chad::write_grid: write failed"); } };
-    const float header = _sdf_trunc;  // the reference writes m_truncsize under the name voxel_res (lvr2.cpp:176-177)
-    const size_t nq = query_points.size(), nc = complete.size();
-    put(&header, sizeof(float));
+    const size_t nq = points.size(), nc = complete.size();
+    put(&sdf_trunc, sizeof(float));
     put(&nq, sizeof(size_t));
     put(&nc, sizeof(size_t));
-    put(query_points.data(), nq * sizeof(QueryPoint));
+    put(points.data(), nq * sizeof(QueryPoint));
     for (uint64_t code : complete) put(cells[code].data(), 8 * sizeof(uint32_t));
     std::fclose(f);
 }
 
+// ---- DAG readers ---------------------------------------------------------------------------------------
 uint32_t HostNodeLevels::get_child_addr(uint32_t depth, uint32_t parent_addr, uint8_t child_i) const {
-    const uint32_t child_mask = nodes[depth][parent_addr];
+    const std::vector<uint32_t>& level = nodes[depth];
+    if (parent_addr == 0 || parent_addr >= level.size()) return 0;
+    const uint32_t child_mask = level[parent_addr];
     const uint32_t child_bit = 1u << child_i;
     if (!(child_mask & child_bit)) return 0;
-    const uint32_t before = (uint32_t)std::popcount(uint8_t(child_mask & (child_bit - 1)));
-    return nodes[depth][parent_addr + before + 1];
+    const size_t at = size_t(parent_addr) + 1 + (size_t)std::popcount(uint8_t(child_mask & (child_bit - 1)));
+    return at < level.size() ? level[at] : 0;
 }
 bool HostNodeLevels::try_get_lc(uint32_t parent_addr, uint8_t child_i, uint64_t& cluster) const {
     const uint32_t addr = get_child_addr(MAX_DEPTH - 1, parent_addr, child_i);
-    if (addr == 0) return false;
+    if (addr == 0 || addr >= leaf_clusters.size()) return false;
     cluster = leaf_clusters[addr];
     return true;
 }
@@ -174,40 +277,85 @@ uint8_t HostNodeLevels::query(uint32_t root_addr, uint64_t morton_key) const {
     if (!try_get_lc(addr, uint8_t((morton_key >> 3) & 7), cluster)) return 0xFF;
     return uint8_t(cluster >> (8 * (morton_key & 7)));
 }
+bool HostNodeLevels::consistent(std::string* why) const {
+    auto no = [&](const std::string& w) { if (why) *why = w; return false; };
+    if (leaf_clusters.empty()) return no("the cluster level lacks its reserved word 0");
+    for (size_t d = 0; d < MAX_DEPTH; d++) {
+        const std::vector<uint32_t>& level = nodes[d];
+        if (level.empty()) return no("node level " + std::to_string(d) + " lacks its reserved word 0");
+        const size_t below = d + 1 < MAX_DEPTH ? nodes[d + 1].size() : leaf_clusters.size();
+        size_t a = 1;
+        while (a < level.size()) {
+            const size_t n = (size_t)std::popcount(uint8_t(level[a] & 0xFF));
+            if (a + n >= level.size()) return no("a record of node level " + std::to_string(d) + " runs past the end of the level");
+            for (size_t q = 1; q <= n; q++)
+                if (level[a + q] == 0 || level[a + q] >= below) return no("a record of node level " + std::to_string(d) + " points outside the level below");
+            a += 1 + n;
+        }
+        if (a != level.size()) return no("node level " + std::to_string(d) + " does not end on a record boundary");
+    }
+    return true;
+}
 
 SavedMap load_dag(const std::string& filename) {
     std::FILE* f = std::fopen(filename.c_str(), "rb");
     if (!f) throw std::runtime_error("chad::load_dag: cannot open " + filename);
-    auto fail = [&](const char* what) { std::fclose(f); throw std::runtime_error("chad::load_dag: " + filename + ": " + what); };
+    auto fail = [&](const std::string& what) { std::fclose(f); throw std::runtime_error("chad::load_dag: " + filename + ": " + what); };
     auto get = [&](void* p, size_t n) { if (n && std::fread(p, 1, n, f) != n) fail("truncated file"); };
     std::fseek(f, 0, SEEK_END);
     const uint64_t file_bytes = (uint64_t)std::ftell(f);
     std::fseek(f, 0, SEEK_SET);
     char magic[8];
     get(magic, 8);
-    if (std::memcmp(magic, "CHADDAG1", 8) != 0) fail("not a CHADDAG1 file");
+    const bool v2 = std::memcmp(magic, "CHADDAG2", 8) == 0;
+    if (!v2 && std::memcmp(magic, "CHADDAG1", 8) != 0) fail("not a CHADDAG file");
     SavedMap m;
+    m.has_counters = v2;
     uint32_t n_sub = 0;
     get(&m.sdf_res, 4);
     get(&m.sdf_trunc, 4);
     get(&n_sub, 4);
     if (uint64_t(n_sub) * 8 > file_bytes) fail("submap count exceeds the file size");
     m.roots.resize(n_sub);
-    for (auto& r : m.roots) get(r.data(), 8);
-    for (auto& lv : m.levels.nodes) {
+    m.positions.resize(n_sub);
+    for (uint32_t i = 0; i < n_sub; i++) {
+        get(m.roots[i].data(), 8);
+        if (v2) {
+            uint32_t np = 0;
+            get(&np, 4);
+            if (uint64_t(np) * 12 > file_bytes) fail("pose count exceeds the file size");
+            m.positions[i].resize(np);
+            if (np) get(m.positions[i].data(), size_t(np) * 12);
+        }
+    }
+    for (size_t lv = 0; lv <= HostNodeLevels::MAX_DEPTH; lv++) {
+        if (v2) { get(&m.uniques[lv], 4); get(&m.dupes[lv], 4); }
         uint64_t n = 0;
         get(&n, 8);
-        if (n > file_bytes / 4) fail("level size exceeds the file size");
-        lv.resize(n);
-        get(lv.data(), n * 4);
+        if (lv < HostNodeLevels::MAX_DEPTH) {
+            if (n > file_bytes / 4) fail("level size exceeds the file size");
+            m.levels.nodes[lv].resize(n);
+            get(m.levels.nodes[lv].data(), n * 4);
+        } else {
+            if (n > file_bytes / 8) fail("cluster count exceeds the file size");
+            m.levels.leaf_clusters.resize(n);
+            get(m.levels.leaf_clusters.data(), n * 8);
+        }
     }
-    uint64_t n = 0;
-    get(&n, 8);
-    if (n > file_bytes / 8) fail("cluster count exceeds the file size");
-    m.levels.leaf_clusters.resize(n);
-    get(m.levels.leaf_clusters.data(), n * 8);
     if ((uint64_t)std::ftell(f) != file_bytes) fail("trailing bytes");
+    std::string why;
+    if (!m.levels.consistent(&why)) fail("inconsistent DAG: " + why);
+    for (const auto& r : m.roots)
+        for (uint32_t a : r)
+            if (a == 0 || a >= m.levels.nodes[0].size()) fail("a submap root lies outside the root level");
     std::fclose(f);
     return m;
 }
+
+void* pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (chad_host_alloc(bytes, &p) != CHAD_OK || !p) throw std::bad_alloc();
+    return p;
+}
+void pinned_free(void* p) noexcept { chad_host_free(p); }
 }  // namespace chad

@@ -122,6 +122,53 @@ class TSDFMap:
         self._check(self._lib.chad_query_voxels(self._h, submap, capi.ptr(k), k.shape[0], capi.ptr(out)))
         return out
 
+    def iterate_leaves(self, submap: int):
+        """Every voxel of finalised submap `submap` as (Morton keys ascending, quantised bytes): the device-side leaf iterator."""
+        n = C.c_size_t()
+        self._check(self._lib.chad_iterate_leaves(self._h, submap, None, None, 0, C.byref(n)))
+        keys, b = np.empty(n.value, np.uint64), np.empty(n.value, np.uint8)
+        if n.value:
+            self._check(self._lib.chad_iterate_leaves(self._h, submap, capi.ptr(keys), capi.ptr(b), n.value, C.byref(n)))
+        return keys, b
+
+    def submap_positions(self, submap: int) -> np.ndarray:
+        """Submap::positions (submap.hpp:110): poses of the scans of finalised submap `submap` (== number of submaps: the active one)."""
+        n = C.c_size_t()
+        self._check(self._lib.chad_submap_positions(self._h, submap, None, 0, C.byref(n)))
+        out = np.empty((n.value, 3), np.float32)
+        if n.value:
+            self._check(self._lib.chad_submap_positions(self._h, submap, capi.ptr(out), n.value, C.byref(n)))
+        return out
+
+    def export_image(self) -> dict:
+        """Everything chad_import_dag needs to continue this map elsewhere: level arrays, counters, roots, poses (after finalize_active)."""
+        levels = [self.level(lv) for lv in range(capi.NUM_LEVELS)]
+        roots = self.roots()
+        return {"levels": [a for a, _, _ in levels], "uniques": [u for _, u, _ in levels], "dupes": [d for _, _, d in levels], "roots": roots,
+                "positions": [self.submap_positions(i) for i in range(len(roots))]}
+
+    def import_image(self, image: dict) -> None:
+        """chad_import_dag: restore a saved map into this (empty) map; inserts continue from there."""
+        img = capi.DagImage()
+        keep = []
+        for lv in range(20):
+            a = np.ascontiguousarray(image["levels"][lv], np.uint32)
+            keep.append(a)
+            img.node_words[lv] = a.ctypes.data_as(C.c_void_p)
+            img.node_word_count[lv] = len(a)
+        cl = np.ascontiguousarray(image["levels"][20], np.uint64)
+        keep.append(cl)
+        img.cluster_words, img.cluster_word_count = cl.ctypes.data_as(C.c_void_p), len(cl)
+        for lv in range(capi.NUM_LEVELS):
+            img.uniques[lv], img.dupes[lv] = image["uniques"][lv], image["dupes"][lv]
+        roots = np.ascontiguousarray(np.array(image["roots"], np.uint32).reshape(-1, 2))
+        counts = np.array([len(p) for p in image["positions"]], np.uint32)
+        poses = np.ascontiguousarray(np.concatenate([np.asarray(p, np.float32).reshape(-1, 3) for p in image["positions"]]) if len(counts) else np.zeros((0, 3), np.float32))
+        keep += [roots, counts, poses]
+        img.roots, img.n_submaps = roots.ctypes.data_as(C.c_void_p), len(roots)
+        img.positions, img.position_counts = poses.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p)
+        self._check(self._lib.chad_import_dag(self._h, C.byref(img)))
+
     def level(self, level: int):
         n = C.c_size_t()
         self._check(self._lib.chad_level_words(self._h, level, C.byref(n)))

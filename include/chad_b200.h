@@ -101,6 +101,31 @@ int chad_export_level(chad_ctx* ctx, int level, void* dst, size_t capacity_words
  * 0xFF where the voxel does not exist. Decode: (byte - 127) / 127 * sdf_trunc. */
 int chad_query_voxels(chad_ctx* ctx, uint32_t submap, const uint64_t* keys, size_t n, uint8_t* bytes);
 
+/* Leaf iterator over finalised submap `submap`'s TSDF tree on the device -- the reader the reference sketches but never finishes
+ * (tsdf.hpp:120-155; tsdf.cpp:88-159 walks root -> first leaf cluster with get_child_addr / try_get_lc): every voxel of the submap in
+ * ascending Morton order as (key, quantised byte). Two-call protocol: keys == NULL returns the count. */
+int chad_iterate_leaves(chad_ctx* ctx, uint32_t submap, uint64_t* keys, uint8_t* bytes, size_t capacity, size_t* count);
+/* Submap::positions (submap.hpp:110): the poses of the scans inserted into finalised submap `submap` (submap == chad_submap_count:
+ * the active one), n x 3 floats. xyz == NULL returns the count. */
+int chad_submap_positions(chad_ctx* ctx, uint32_t submap, float* xyz, size_t capacity, size_t* count);
+
+/* Restoring a saved map (the reference has no persistence): the 21 level arrays exactly as chad_export_level
+ * returned them, their counters (chad_level_counters), the submaps' roots and poses. The context must be empty; afterwards it behaves as
+ * if it had built those submaps itself: the dedup sets are rebuilt from the arrays, so later submaps deduplicate against the restored
+ * ones and receive the addresses an uninterrupted run would have given them. chad::TSDFMap::save / load wrap this with a file format. */
+typedef struct chad_dag_image {
+    const uint32_t* node_words[20];     /* NodeLevel::_raw_data[0.._occupied_n) per level */
+    size_t node_word_count[20];
+    const uint64_t* cluster_words;      /* LeafClusterLevel::_raw_data[0.._uniques_n] */
+    size_t cluster_word_count;
+    uint32_t uniques[CHAD_NUM_LEVELS], dupes[CHAD_NUM_LEVELS];
+    const uint32_t* roots;              /* n_submaps x (root_addr_tsdf, root_addr_weight) */
+    uint32_t n_submaps;
+    const float* positions;             /* the submaps' poses, concatenated (x, y, z); may be NULL */
+    const uint32_t* position_counts;    /* poses per submap; may be NULL */
+} chad_dag_image;
+int chad_import_dag(chad_ctx* ctx, const chad_dag_image* image);
+
 /* How the band-voxel updates of a batch are grouped per voxel before the fold: 2 = tile runs + fused per-block sort and fold (default: runs.cu), 0 = block-binned (hashed
  * 8x8x8-voxel blocks + shared-memory sort), 1 = global onesweep radix sort. All give bit-identical results. */
 int chad_set_pair_path(chad_ctx* ctx, int mode);
@@ -133,6 +158,15 @@ int chad_stage_pairs(chad_ctx* ctx, const float* xyz_sorted, const float* normal
 int chad_stage_sort(chad_ctx* ctx, uint64_t* keys, uint32_t* values, size_t n, int nbits);
 /* Morton encode (morton.hpp:21-28) on the device, n voxel coordinates (x,y,z int32 AoS). */
 int chad_stage_morton(chad_ctx* ctx, const int32_t* voxels, size_t n, uint64_t* keys);
+
+/* Input adaptors without copies. chad_insert DMAs page-locked memory straight from the caller's buffer (pageable
+ * memory goes through a pinned staging ring): chad_host_alloc / chad_host_free hand out page-locked memory (chad::pinned_allocator wraps
+ * them for std::vector<glm::vec3> / <Eigen::Vector3f> / <std::array<float,3>>), chad_host_register / chad_host_unregister page-lock
+ * a buffer the caller already owns (e.g. a LiDAR driver's ring) for as long as it lives. */
+int chad_host_alloc(size_t bytes, void** host_ptr);
+int chad_host_free(void* host_ptr);
+int chad_host_register(void* host_ptr, size_t bytes);
+int chad_host_unregister(void* host_ptr);
 
 /* Raw device pointer + CUDA stream used by the context, for callers that place inputs on the
  * device themselves (bench `value` leg). */

@@ -2,6 +2,8 @@
 // chad::HostNodeLevels::query -- the walk the reference's readers make (levels.hpp:147-192).
 // usage: dag_reader <file.chad> <submap> <keys.u64> <out.u8>   -> prints "res trunc n_submaps root_tsdf root_weight n_keys"
 //        dag_reader grid <file.chad> <submap> <out.grid>      -> the reference's hashgrid.grid (lvr2.cpp:170-200) of that submap
+//        dag_reader leaves <file.chad> <submap> <keys.u64> <bytes.u8>  -> every voxel of the submap through chad::LeafCursor
+//        dag_reader resave <in.chad> <out.chad>               -> load_dag + save_dag (CHADDAG2)
 #include <cstdio>
 #include <cstdlib>
 #include <exception>
@@ -16,6 +18,44 @@ int main(int argc, char** argv) {
             const size_t submap = std::strtoul(argv[3], nullptr, 10);
             if (submap >= m.roots.size()) { std::fprintf(stderr, "no such submap\n"); return 3; }
             chad::write_grid(m.levels, m.roots[submap][0], m.sdf_res, m.sdf_trunc, argv[4]);
+            return 0;
+        } catch (const std::exception& e) {
+            std::fprintf(stderr, "%s\n", e.what());
+            return 1;
+        }
+    }
+    if (argc == 6 && std::string(argv[1]) == "leaves") {  // dag_reader leaves <file.chad> <submap> <out_keys.u64> <out_bytes.u8>: the leaf iterator
+        try {
+            const chad::SavedMap m = chad::load_dag(argv[2]);
+            const size_t submap = std::strtoul(argv[3], nullptr, 10);
+            if (submap >= m.roots.size()) { std::fprintf(stderr, "no such submap\n"); return 3; }
+            std::vector<uint64_t> keys;
+            std::vector<uint8_t> bytes;
+            double checksum = 0.0;  // also exercises Leaf: position and decoded distance
+            for (chad::LeafCursor it(m.levels, m.roots[submap][0]); !it.done(); it.next()) {
+                keys.push_back(it.key());
+                bytes.push_back(it.byte());
+                const chad::Leaf v = it.leaf(m.sdf_res, m.sdf_trunc);
+                checksum += double(v.x) + double(v.y) + double(v.z) + double(v.signed_distance);
+            }
+            std::FILE* fk = std::fopen(argv[4], "wb");
+            std::FILE* fb = std::fopen(argv[5], "wb");
+            if (!fk || !fb) return 5;
+            if (!keys.empty() && (std::fwrite(keys.data(), 8, keys.size(), fk) != keys.size() || std::fwrite(bytes.data(), 1, bytes.size(), fb) != bytes.size())) return 5;
+            std::fclose(fk);
+            std::fclose(fb);
+            std::printf("%zu %.9g %zu\n", keys.size(), checksum, m.positions[submap].size());
+            return 0;
+        } catch (const std::exception& e) {
+            std::fprintf(stderr, "%s\n", e.what());
+            return 1;
+        }
+    }
+    if (argc == 4 && std::string(argv[1]) == "resave") {  // dag_reader resave <in.chad> <out.chad>: load_dag -> save_dag
+        try {
+            chad::SavedMap m = chad::load_dag(argv[2]);
+            chad::save_dag(m, argv[3]);
+            std::printf("%d %zu\n", m.has_counters ? 1 : 0, m.roots.size());
             return 0;
         } catch (const std::exception& e) {
             std::fprintf(stderr, "%s\n", e.what());

@@ -154,3 +154,88 @@ def test_grid_file_of_a_loaded_map_matches_the_oracle(chad_lib, oracle_lib, tmp_
     complete = sorted((lib.chad_morton_encode(*c), corners) for c, corners in expect.items() if corners is not None)
     assert nc == len(complete) and nc > 0
     assert np.array_equal(cells, np.array([c for _, c in complete], np.uint32))  # ascending Morton order of the cell
+
+
+def _write_chaddag2(path, m, res, trunc, positions):
+    """Independent writer of the CHADDAG2 format: roots + poses per submap, counters + words per level."""
+    with open(path, "wb") as f:
+        f.write(b"CHADDAG2")
+        roots = m.roots()
+        f.write(struct.pack("<ffI", res, trunc, len(roots)))
+        for r, p in zip(roots, positions):
+            f.write(struct.pack("<III", r[0], r[1], len(p)))
+            f.write(np.ascontiguousarray(p, dtype="<f4").tobytes())
+        for lv in range(21):
+            arr, u, d = m.level(lv)
+            f.write(struct.pack("<IIQ", u, d, len(arr)))
+            f.write(np.ascontiguousarray(arr, dtype="<u4" if lv < 20 else "<u8").tobytes())
+
+
+def _two_submaps(oracle_lib):
+    w = synth.Workload("persist", synth.BOX_ROOM, 32, 3, 0.0, 3.0, 0.05, 0.10)  # scans 3 m apart: the third one opens a second submap
+    o = oracle_lib.OracleMap(w.sdf_res, w.sdf_trunc)
+    per_submap, poses = [], [[], []]
+    for s in range(3):
+        pts, pos = w.scan(s)
+        before = o.voxels()
+        if o.insert(pts, pos) == 1 and not per_submap:
+            per_submap.append(before)
+        poses[len(per_submap)].append(pos)
+    per_submap.append(o.voxels())
+    o.finalize_active()
+    assert len(o.roots()) == 2 and [len(p) for p in poses] == [2, 1]
+    return w, o, per_submap, poses
+
+
+def test_leaf_cursor_walks_every_voxel_in_morton_order(chad_lib, oracle_lib, tmp_path):
+    """chad::LeafCursor -- the leaf iterator the reference sketches (tsdf.hpp:120-155, tsdf.cpp:88-159) -- over a saved map: exactly the
+    submap's voxels, ascending, each with the byte cluster.hpp quantises its distance to."""
+    from chad_tsdf_b200 import build
+    exe = build.build_dag_reader()
+    w, o, per_submap, poses = _two_submaps(oracle_lib)
+    chad_file = tmp_path / "m.chad"
+    _write_chaddag2(chad_file, o, w.sdf_res, w.sdf_trunc, poses)
+    o.close()
+    for submap, (keys, sd_bits, _) in enumerate(per_submap):
+        kf, bf = tmp_path / "lk.u64", tmp_path / "lb.u8"
+        r = subprocess.run([exe, "leaves", str(chad_file), str(submap), str(kf), str(bf)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        n, _, npos = r.stdout.split()
+        assert int(n) == len(keys) and int(npos) == len(poses[submap])
+        assert np.array_equal(np.fromfile(kf, np.uint64), keys)
+        assert np.array_equal(np.fromfile(bf, np.uint8), _quantise(sd_bits, w.sdf_trunc))
+
+
+def test_chaddag2_survives_a_load_and_save(chad_lib, oracle_lib, tmp_path):
+    """save_dag(load_dag(file)) reproduces the file byte for byte: poses (submap.hpp:110), dedup counters (levels.hpp:90-91,141) and all."""
+    from chad_tsdf_b200 import build
+    exe = build.build_dag_reader()
+    w, o, _, poses = _two_submaps(oracle_lib)
+    a, b = tmp_path / "a.chad", tmp_path / "b.chad"
+    _write_chaddag2(a, o, w.sdf_res, w.sdf_trunc, poses)
+    o.close()
+    r = subprocess.run([exe, "resave", str(a), str(b)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.split() == ["1", "2"], r.stdout + r.stderr
+    assert open(a, "rb").read() == open(b, "rb").read()
+
+
+def test_a_child_address_outside_its_level_is_rejected(chad_lib, oracle_lib, tmp_path):
+    """A crafted / corrupt file must not become an out-of-bounds read in the readers: load_dag validates every address once."""
+    from chad_tsdf_b200 import build
+    exe = build.build_dag_reader()
+    w, o, _, poses = _two_submaps(oracle_lib)
+    good = tmp_path / "good.chad"
+    _write_chaddag2(good, o, w.sdf_res, w.sdf_trunc, poses)
+    blob = bytearray(open(good, "rb").read())
+    # the first child address of the first record of level 19 (word 2 of the level) -> far beyond the cluster level
+    at = 8 + 12 + sum(12 + 12 * len(p) for p in poses)
+    for lv in range(19):
+        (n,) = struct.unpack_from("<Q", blob, at + 8)
+        at += 16 + 4 * n
+    struct.pack_into("<I", blob, at + 16 + 4 * 2, 0x7FFFFFF0)
+    o.close()
+    bad = tmp_path / "bad.chad"
+    open(bad, "wb").write(bytes(blob))
+    (tmp_path / "k.u64").write_bytes(b"")
+    r = subprocess.run([exe, str(bad), "0", str(tmp_path / "k.u64"), str(tmp_path / "o.u8")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "inconsistent DAG" in r.stderr, r.stderr

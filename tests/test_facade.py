@@ -36,7 +36,7 @@ def test_facade_demo_runs_on_gpu(chad_lib, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "roots (1, 10)" in r.stdout
     blob = open(tmp_path / "facade_demo.chad", "rb").read()
-    assert blob[:8] == b"CHADDAG1"
+    assert blob[:8] == b"CHADDAG2"
     res, trunc, nsub = struct.unpack_from("<ffI", blob, 8)
     assert (np.float32(res), np.float32(trunc), nsub) == (np.float32(0.05), np.float32(0.1), 1)
     # the reference's .grid file (lvr2.cpp:170-200): header, query points (leaf corner position + decoded distance), complete cells
@@ -69,3 +69,20 @@ def test_facade_overloads_build_the_identical_map(chad_lib, tmp_path):
     r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "10 maps" in r.stdout and "identical: yes" in r.stdout
+
+
+@pytest.mark.gpu
+def test_facade_persistence_iterator_and_pinned_vectors(chad_lib, tmp_path):
+    """SURVEY.md section 8f through the C++ class: a map saved, loaded into a new object and continued equals the map that never stopped
+    (byte-identical dump, poses included); the leaf iterator gives the same voxels on the host copy and on the device; vectors with
+    chad::pinned_allocator build the identical map."""
+    from chad_tsdf_b200 import build
+    exe = build.build_facade_persist()
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count(": yes") == 4 and "NO" not in r.stdout, r.stdout
+
+
+def test_facade_persist_program_compiles(chad_lib):
+    from chad_tsdf_b200 import build
+    assert os.path.exists(build.build_facade_persist())
