@@ -13,7 +13,9 @@
 // Optional (CHAD_OVERLAP_WALK=1, off by default -- measured no gain, profiles/ab_overlap_r01.md): the ray walk on its own
 // stream beside the next batch's point stage, with three plan slots instead of two.
 #include <array>
+#include <chrono>
 #include <cmath>
+#include <cstdarg>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
@@ -210,6 +212,20 @@ struct chad_ctx {
 };
 
 namespace {
+
+// CHAD_TRACE=1: host-side milestones (rank, milliseconds since the first one) on stderr -- for diagnosing a stalled multi-rank run
+void trace(const chad_ctx* ctx, const char* fmt, ...) {
+    static const bool on = [] { const char* e = std::getenv("CHAD_TRACE"); return e && std::atoi(e) != 0; }();
+    if (!on) return;
+    static const auto t0 = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    char buf[256];
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    std::fprintf(stderr, "[chad r%d %9.3f] %s\n", ctx ? ctx->sh.rank : -1, ms, buf);
+}
 
 int fail(chad_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->error = msg; else g_create_error = msg;
@@ -449,6 +465,7 @@ int complete_one_fold(chad_ctx* ctx, bool block, bool* launched) {
     for (int q = 0; q + 1 < ctx->n_pend; q++) ctx->pend[q] = ctx->pend[q + 1];
     ctx->n_pend--;
     *launched = true;
+    trace(ctx, "fold of slot %d (close %d)", slot, (int)pf.close);
     account_fold_stats(ctx, slot);  // the pair stage of this batch waited for the fold that used this slot before
     BatchPlan plan = ctx->h_plan[slot];
     const bool runs = pf.runs;
@@ -583,6 +600,7 @@ void queue_point_stage(chad_ctx* ctx, int slot, int b, u32 n, u32 ns, const Batc
 // walk and the descriptor sort). One grouped send / receive of fixed-size boxes per batch: the counts travel inside the boxes, so the
 // host never learns (or waits for) them.
 int queue_shard_exchange(chad_ctx* ctx, int slot) {
+    trace(ctx, "exchange %llu (slot %d)", (unsigned long long)ctx->sh.exchanges, slot);
     cudaStream_t gs = ctx->group_stream;
     chad_ctx::Shard& sh = ctx->sh;
     const ShardBoxes boxes{sh.box_out.as<u64>(), sh.box_in.as<u64>(), sh.box_words};
@@ -609,6 +627,7 @@ int queue_shard_exchange(chad_ctx* ctx, int slot) {
 // otherwise: ~50 launches per batch against ~2 ms of kernels).
 int process_front(chad_ctx* ctx) {
     if (ctx->batch_scans == 0) return CHAD_OK;
+    trace(ctx, "front: %u scans, %u points, slot %d", ctx->batch_scans, ctx->batch_points, ctx->plan_slot);
     const int b = ctx->cur;
     const int slot = ctx->plan_slot;
     const u32 n = ctx->batch_points, ns = ctx->batch_scans;
@@ -994,6 +1013,7 @@ int finalize_part2(chad_ctx* ctx) {
         // must be known on the host). Queued here, collected by finalize_gather -- nobody waits.
         chad_ctx::Shard& sh = ctx->sh;
         ctx->fin_chunks = C;
+        trace(ctx, "finalize: own chunk count %u known, all-gather of the counts", C);
         u32* d = sh.scalars.as<u32>();
         ctx->h_fin->h2d[1] = C;
         CUDA_TRY(ctx, cudaMemcpyAsync(d + 8, &ctx->h_fin->h2d[1], 4, cudaMemcpyHostToDevice, fs));
@@ -1022,6 +1042,7 @@ int finalize_gather(chad_ctx* ctx) {
     u64 offset[SHARD_WORLD_MAX + 1];
     for (int g = 0; g < sh.world; g++) { offset[g] = total; total += sh.h_counts[g]; }
     const u32 own = sh.h_counts[sh.rank];
+    trace(ctx, "finalize: counts arrived (total %llu), gather on rank 0", (unsigned long long)total);
     if (total >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
     if (sh.rank == 0) {
         TRY(finalize_dag(ctx, (u32)total, true, [&]() -> int {
@@ -1063,6 +1084,7 @@ int finalize_gather(chad_ctx* ctx) {
 
 int finalize_finish(chad_ctx* ctx) {
     ctx->fin_state = chad_ctx::FIN_IDLE;
+    trace(ctx, "finalize: done, submap %zu", ctx->roots.size());
     const u32* hs = ctx->h_fin->scalars;
     if (hs[SC_ERR]) return error_from_flags(ctx, hs[SC_ERR]);
     const u32 C = ctx->fin_chunks;
@@ -1333,11 +1355,53 @@ static int create_impl(float sdf_res, float sdf_trunc, int device, int max_batch
         // two communicators: the per-batch exchange (group stream) and the per-submap gather (finalize stream) are queued from points of
         // the host code that are not ordered against each other, and NCCL wants one issue order per communicator
         const ncclUniqueId* ids = static_cast<const ncclUniqueId*>(shard_id);
+        // NCCL sets up the connections an operation needs when the operation is first issued, and that handshake blocks the HOST until the
+        // peer issues the matching call. Later the exchanges and gathers are queued from wherever a rank's poll finds their inputs ready
+        // -- at different program points on different ranks -- so a blocking first use there can deadlock (rank A waits inside NCCL for
+        // rank B, which waits for a batch exchange rank A has not issued yet). Hence: connect eagerly, and issue every kind of operation
+        // once here, where all ranks are inside the same collective call.
+        setenv("NCCL_RUNTIME_CONNECT", "0", 0);
         ncclResult_t n1 = nccl->CommInitRank(&sh.comm_x, world, ids[0], rank);
         ncclResult_t n2 = n1 == ncclSuccess ? nccl->CommInitRank(&sh.comm_f, world, ids[1], rank) : n1;
         if (n1 != ncclSuccess || n2 != ncclSuccess) {
             ctx->error = std::string("ncclCommInitRank: ") + nccl->GetErrorString(n1 != ncclSuccess ? n1 : n2);
             return bail(CHAD_ERR_CUDA);
+        }
+        {
+            auto warm = [&]() -> ncclResult_t {
+                ncclResult_t n;
+                u64* out = sh.box_out.as<u64>();
+                u64* in = sh.box_in.as<u64>();
+                u32* d = sh.scalars.as<u32>();
+                const size_t w = sh.box_words;
+                cudaStream_t st = ctx->stream;
+                if ((n = nccl->GroupStart()) != ncclSuccess) return n;  // the per-batch exchange: every pair, full boxes
+                for (int g = 0; g < world; g++) {
+                    if (g == rank) continue;
+                    if ((n = nccl->Send(out + size_t(g) * w, w, ncclUint64, g, sh.comm_x, st)) != ncclSuccess) return n;
+                    if ((n = nccl->Recv(in + size_t(g) * w, w, ncclUint64, g, sh.comm_x, st)) != ncclSuccess) return n;
+                }
+                if ((n = nccl->GroupEnd()) != ncclSuccess) return n;
+                if ((n = nccl->AllGather(d + 8, d + 16, 1, ncclUint32, sh.comm_f, st)) != ncclSuccess) return n;      // chunk counts
+                if ((n = nccl->Broadcast(d, d, 2, ncclUint32, 0, sh.comm_f, st)) != ncclSuccess) return n;           // roots
+                if ((n = nccl->GroupStart()) != ncclSuccess) return n;                                               // chunk gather on rank 0
+                for (int g = 1; g < world; g++) {
+                    if (rank == 0) {
+                        if ((n = nccl->Recv(in + size_t(g) * w, w, ncclUint64, g, sh.comm_f, st)) != ncclSuccess) return n;
+                        if ((n = nccl->Recv(in + size_t(g) * w, 8, ncclUint64, g, sh.comm_f, st)) != ncclSuccess) return n;
+                    } else if (g == rank) {
+                        if ((n = nccl->Send(out, w, ncclUint64, 0, sh.comm_f, st)) != ncclSuccess) return n;
+                        if ((n = nccl->Send(out, 8, ncclUint64, 0, sh.comm_f, st)) != ncclSuccess) return n;
+                    }
+                }
+                return nccl->GroupEnd();
+            };
+            CREATE_TRY(cudaMemset(sh.box_out.p, 0, size_t(world) * sh.box_words * 8));
+            const ncclResult_t n = warm();
+            if (n != ncclSuccess) { ctx->error = std::string("NCCL warm-up: ") + nccl->GetErrorString(n); return bail(CHAD_ERR_CUDA); }
+            CREATE_TRY(cudaStreamSynchronize(ctx->stream));
+            CREATE_TRY(cudaMemset(sh.box_in.p, 0, size_t(world) * sh.box_words * 8));
+            CREATE_TRY(cudaMemset(sh.scalars.p, 0, 256));
         }
     }
 #undef CREATE_TRY
