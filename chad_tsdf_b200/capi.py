@@ -32,6 +32,15 @@ class Stats(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class Memory(C.Structure):
+    """chad_memory of include/chad_b200.h."""
+    _fields_ = [(n, C.c_uint64) for n in ("dag_words_bytes", "dag_arena_bytes", "dedup_bytes", "dedup_records", "dedup_max_load_permille", "chunk_table_bytes",
+                                           "batch_buffer_bytes", "grow_events", "grow_bytes", "grow_host_us", "device_used_bytes", "device_total_bytes")]
+
+    def as_dict(self) -> dict:
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
 class DagImage(C.Structure):
     """chad_dag_image of include/chad_b200.h."""
     _fields_ = [("node_words", C.c_void_p * 20), ("node_word_count", C.c_size_t * 20), ("cluster_words", C.c_void_p), ("cluster_word_count", C.c_size_t),
@@ -47,6 +56,7 @@ SYMBOLS = {
     "chad_last_error": (C.c_char_p, [_P]),
     "chad_insert": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "chad_insert_async": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "chad_insert_many": (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_int]),
     "chad_insert_device": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "chad_flush": (C.c_int, [_P]),
     "chad_finalize_active": (C.c_int, [_P]),
@@ -61,6 +71,7 @@ SYMBOLS = {
     "chad_pipeline_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "chad_reset": (C.c_int, [_P]),
     "chad_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "chad_memory_info": (C.c_int, [_P, C.POINTER(Memory)]),
     "chad_reset_stats": (C.c_int, [_P]),
     "chad_stage_points": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P, _P, _P]),
     "chad_stage_pairs": (C.c_int, [_P, _P, _P, C.c_size_t, _P, _P, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -187,6 +187,12 @@ struct chad_ctx {
         cudaEvent_t counts_done = nullptr;
         u64 sent_runs = 0, sent_records = 0, exchanges = 0;
     } sh;
+    // growth of the never-freed DAG arenas and the chunk tables (VirtualArray, virtual_array.hpp:12-104, becomes explicit device buffers):
+    // a buffer that has been outgrown is parked here instead of freed -- cudaFree synchronises the whole device, i.e. stalls every
+    // stream of the pipeline -- and released at the next drain
+    std::vector<void*> graveyard;
+    u64 grow_events = 0, grow_bytes = 0;
+    double grow_host_ms = 0.0;
     u32 burst_batches = 0;              // batches queued since the last drain (sharded: the batch boundaries must not depend on timing)
 
     // finalize work buffers
@@ -348,6 +354,7 @@ int table_alloc(chad_ctx* ctx, ChunkTable& t, DevBuf& keys, DevBuf& cells, DevBu
 }
 int table_reserve(chad_ctx* ctx, u64 need_chunks) {
     if (need_chunks * 2 <= ctx->table.capacity) return CHAD_OK;
+    const auto t_grow = std::chrono::steady_clock::now();
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));  // a fold may still be writing the table
     ctx->fold_in_flight = false;
@@ -360,6 +367,9 @@ int table_reserve(chad_ctx* ctx, u64 need_chunks) {
     dev_free(ctx->t_keys); dev_free(ctx->t_cells); dev_free(ctx->t_count); dev_free(ctx->t_list);
     ctx->t_keys = nk; ctx->t_cells = nc; ctx->t_count = ncount; ctx->t_list = nlist;
     ctx->table = nt;
+    ctx->grow_events++;
+    ctx->grow_bytes += new_cap * 76;
+    ctx->grow_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_grow).count();
     return CHAD_OK;
 }
 
@@ -754,6 +764,11 @@ int drain(chad_ctx* ctx) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));
     ctx->fold_in_flight = false;
     ctx->burst_batches = 0;
+    if (!ctx->graveyard.empty() && ctx->fin_state == chad_ctx::FIN_IDLE) {  // (a finalize still in flight may be copying out of a parked buffer)
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fin_stream));
+        for (void* q : ctx->graveyard) cudaFree(q);
+        ctx->graveyard.clear();
+    }
     fold_bounds_reset(ctx);
     account_fold_stats(ctx);
     prof_resolve(ctx);
@@ -826,16 +841,20 @@ int level_reserve(chad_ctx* ctx, Level& L, bool cluster, size_t new_records) {
     if (need_words >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "DAG level exceeds 2^31 words");
     if (need_words > L.raw_cap) {
         const size_t cap = next_pow2(need_words);  // (the callers' record counts are generous upper bounds already)
+        const auto t_grow = std::chrono::steady_clock::now();
         void* np = nullptr;
         CUDA_TRY(ctx, cudaMalloc(&np, cap * word));
         if (L.raw.p) {
+            // stream order is enough: every later reader / writer of the level runs on fin_stream behind this copy
             CUDA_TRY(ctx, cudaMemcpyAsync(np, L.raw.p, L.raw.bytes, cudaMemcpyDeviceToDevice, s));
-            CUDA_TRY(ctx, cudaStreamSynchronize(s));
-            CUDA_TRY(ctx, cudaFree(L.raw.p));
+            ctx->graveyard.push_back(L.raw.p);
         }
         L.raw.p = np;
         L.raw.bytes = cap * word;
         L.raw_cap = cap;
+        ctx->grow_events++;
+        ctx->grow_bytes += cap * word;
+        ctx->grow_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_grow).count();
     }
     const size_t need_slots = (size_t(L.uniques) + new_records) * 2;
     if (need_slots > L.table.capacity) {
@@ -846,7 +865,11 @@ int level_reserve(chad_ctx* ctx, Level& L, bool cluster, size_t new_records) {
         DedupTable nt{static_cast<u64*>(ne), static_cast<u32*>(nf), cap};
         if (L.table.capacity) {
             ctx->stats.kernel_launches += launch_dedup_rehash(s, L.table, nt, ctx->num_sms);
-            CUDA_TRY(ctx, cudaStreamSynchronize(s));
+            ctx->graveyard.push_back(L.entries.p);
+            ctx->graveyard.push_back(L.first.p);
+            L.entries = DevBuf{}; L.first = DevBuf{};
+            ctx->grow_events++;
+            ctx->grow_bytes += cap * 12;
         } else {
             launch_dedup_clear(s, nt);
         }
@@ -1467,6 +1490,7 @@ void chad_destroy(chad_ctx* ctx) {
                       &ctx->f_slot_of, &ctx->f_is_new, &ctx->f_rank, &ctx->f_radix_ws, &ctx->f_scan_ws, &ctx->f_scalars};
     for (DevBuf* b : bufs) dev_free(*b);
     for (auto& L : ctx->levels) { dev_free(L.raw); dev_free(L.entries); dev_free(L.first); }
+    for (void* q : ctx->graveyard) cudaFree(q);
     for (int b = 0; b < 2; b++) {
         if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
         if (ctx->h_scans_pinned[b]) cudaFreeHost(ctx->h_scans_pinned[b]);
@@ -1533,6 +1557,15 @@ static int insert_host(chad_ctx* ctx, const float* xyz, size_t n, const float po
 
 int chad_insert(chad_ctx* ctx, const float* xyz, size_t n, const float position[3]) { return insert_host(ctx, xyz, n, position, true); }
 int chad_insert_async(chad_ctx* ctx, const float* xyz, size_t n, const float position[3]) { return insert_host(ctx, xyz, n, position, false); }
+
+// The host loop of a C++ caller (for (scan : trajectory) map.insert(scan.points, scan.pose);) behind one call, for callers whose own
+// loop is slow (a ctypes call costs ~6 us; 100 scans per 9 ms step make that 6 % of the step)
+int chad_insert_many(chad_ctx* ctx, const float* const* xyz, const size_t* n, const float* positions, size_t count, int wait_for_copy) {
+    if (!ctx) return CHAD_ERR_INVALID;
+    if (count && (!xyz || !n || !positions)) return fail(ctx, CHAD_ERR_INVALID, "NULL argument");
+    for (size_t i = 0; i < count; i++) TRY(insert_host(ctx, xyz[i], n[i], positions + 3 * i, wait_for_copy != 0));
+    return CHAD_OK;
+}
 
 int chad_insert_device(chad_ctx* ctx, const float* xyz_device, size_t n, const float position[3]) {
     if (!ctx) return CHAD_ERR_INVALID;
@@ -1790,6 +1823,33 @@ int chad_profile_timeline(chad_ctx* ctx, int* classes, float* begin_ms, float* e
         begin_ms[i] = ctx->timeline[i].t0;
         end_ms[i] = ctx->timeline[i].t1;
     }
+    return CHAD_OK;
+}
+
+int chad_memory_info(chad_ctx* ctx, chad_memory* out) {
+    if (!ctx || !out) return CHAD_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(settle(ctx));
+    chad_memory m{};
+    double worst = 0.0;
+    for (int lv = 0; lv < CHAD_NUM_LEVELS; lv++) {
+        const Level& L = ctx->levels[lv];
+        const bool cluster = lv == CHAD_LEVEL_CLUSTERS;
+        m.dag_words_bytes += cluster ? (u64(L.uniques) + 1) * 8 : u64(L.occupied) * 4;
+        m.dag_arena_bytes += L.raw.bytes;
+        m.dedup_bytes += L.entries.bytes + L.first.bytes;
+        m.dedup_records += L.uniques;
+        if (L.table.capacity) worst = std::max(worst, double(L.uniques) / double(L.table.capacity));
+    }
+    m.dedup_max_load_permille = (u64)(worst * 1000.0 + 0.5);
+    m.chunk_table_bytes = (ctx->table.capacity + ctx->table2.capacity) * 76;
+    m.batch_buffer_bytes = ctx->cap_pairs * 8 * 2 + ctx->cap_points * (12 * 2 + 8 * 3 + 4 * 6 + 12 * 2);
+    m.grow_events = ctx->grow_events;
+    m.grow_bytes = ctx->grow_bytes;
+    m.grow_host_us = (u64)(ctx->grow_host_ms * 1000.0);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) { m.device_used_bytes = total_b - free_b; m.device_total_bytes = total_b; } else cudaGetLastError();
+    *out = m;
     return CHAD_OK;
 }
 

@@ -82,6 +82,25 @@ class TSDFMap:
         f = self._lib.chad_insert if wait_for_copy else self._lib.chad_insert_async
         self._check(f(self._h, p, n, capi.ptr(pos)))
 
+    def insert_many(self, scans, wait_for_copy: bool = True):
+        """The caller's loop over TSDFMap::insert behind one C call (chad_insert_many). scans: [(points, pose)], points = host arrays /
+        tensors as for insert(). Returns the prepared argument block; pass it back as `scans` to skip the marshalling next time."""
+        if not isinstance(scans, tuple):
+            k = len(scans)
+            ptrs, counts, poses, keep = (C.c_void_p * k)(), (C.c_size_t * k)(), np.empty((k, 3), np.float32), []
+            for i, (pts, pos) in enumerate(scans):
+                if hasattr(pts, "data_ptr"):
+                    ptrs[i], counts[i] = pts.data_ptr(), pts.numel() // 3
+                else:
+                    pts = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 3)
+                    ptrs[i], counts[i] = pts.ctypes.data, pts.shape[0]
+                keep.append(pts)
+                poses[i] = np.asarray(pos, np.float32).reshape(3)
+            scans = (ptrs, counts, poses, k, keep)
+        ptrs, counts, poses, k, _ = scans
+        self._check(self._lib.chad_insert_many(self._h, ptrs, counts, capi.ptr(poses), k, 1 if wait_for_copy else 0))
+        return scans
+
     def insert_device(self, device_ptr: int, n: int, position) -> None:
         pos = np.ascontiguousarray(position, dtype=np.float32).reshape(3)
         self._check(self._lib.chad_insert_device(self._h, C.c_void_p(device_ptr), n, capi.ptr(pos)))
@@ -182,6 +201,12 @@ class TSDFMap:
         s = capi.Stats()
         self._check(self._lib.chad_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def memory(self) -> dict:
+        """Device memory behind the map and its growth so far (chad_memory_info)."""
+        m = capi.Memory()
+        self._check(self._lib.chad_memory_info(self._h, C.byref(m)))
+        return m.as_dict()
 
     def set_pair_path(self, mode: int) -> None:
         """2 = tile runs + streaming fold (default), 0 = block-binned grouping of the voxel updates, 1 = global radix sort. Identical results."""

@@ -50,6 +50,24 @@ typedef struct chad_stats {
     uint64_t resident_clusters; /* leaf chunks (2x2x2 voxels) in the active submap's table (as of last flush) */
 } chad_stats;
 
+/* Device memory behind the map and how it has grown. The reference reserves 352 GiB of virtual memory and lets the page faults do the
+ * growing (virtual_array.hpp:12-38, levels.hpp:50,117; never freed: levels.hpp:92,142); here the DAG arenas, their dedup sets and the
+ * chunk tables are device buffers that double when they fill up -- on the finalize stream, without synchronising the insert streams. */
+typedef struct chad_memory {
+    uint64_t dag_words_bytes;        /* bytes of the 21 levels actually in use (what save() writes) */
+    uint64_t dag_arena_bytes;        /* bytes reserved for them */
+    uint64_t dedup_bytes;            /* bytes of the 21 dedup sets */
+    uint64_t dedup_records;          /* records in them (sum of the levels' unique counts) */
+    uint64_t dedup_max_load_permille;/* fullest dedup set: records / slots x 1000 (kept <= 500) */
+    uint64_t chunk_table_bytes;      /* the two resident chunk tables (active submap, submap being finalised) */
+    uint64_t batch_buffer_bytes;     /* per-batch work buffers (points, update records) */
+    uint64_t grow_events;            /* buffer doublings since creation (DAG arenas, dedup sets, chunk tables) */
+    uint64_t grow_bytes;             /* bytes allocated by them */
+    uint64_t grow_host_us;           /* host time spent in them (cudaMalloc + waits) */
+    uint64_t device_used_bytes, device_total_bytes; /* cudaMemGetInfo */
+} chad_memory;
+int chad_memory_info(chad_ctx* ctx, chad_memory* out);
+
 /* ---- lifetime ------------------------------------------------------------------------- */
 /* Replaces TSDFMap::TSDFMap(float sdf_res, float sdf_trunc) (tsdf.cpp:27-31). `device` is the CUDA
  * ordinal. `max_batch_scans` >= 1: how many consecutive scans of one submap may be fused into one
@@ -72,6 +90,9 @@ int chad_insert(chad_ctx* ctx, const float* xyz, size_t n, const float position[
  * the link's full rate (a caller that recycles one buffer per scan needs chad_insert). `xyz` must stay valid and unchanged until
  * the next chad_flush (or any other synchronising call). Fails with CHAD_ERR_INVALID for pageable memory. */
 int chad_insert_async(chad_ctx* ctx, const float* xyz, size_t n, const float position[3]);
+/* `count` consecutive chad_insert (wait_for_copy != 0) or chad_insert_async (== 0) calls behind one entry point: xyz[i] = points of scan
+ * i, n[i] their number, positions = count x 3 floats. For callers whose own loop is slow (Python); a C++ caller just loops. */
+int chad_insert_many(chad_ctx* ctx, const float* const* xyz, const size_t* n, const float* positions, size_t count, int wait_for_copy);
 /* Same, but `xyz_device` already lives in this context's device memory (no host copy). */
 int chad_insert_device(chad_ctx* ctx, const float* xyz_device, size_t n, const float position[3]);
 /* Wait until every queued insert has been applied; reports deferred device errors. */
