@@ -302,7 +302,9 @@ int dev_ensure(chad_ctx* ctx, DevBuf& b, size_t bytes, bool preserve = false) {
     if (b.p) {
         if (preserve) CUDA_TRY(ctx, cudaMemcpyAsync(np, b.p, b.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        CUDA_TRY(ctx, cudaFree(b.p));
+        // parked, not freed: cudaFree synchronises the whole DEVICE. Beside stalling every stream, on a sharded map that is a deadlock:
+        // an NCCL kernel of this rank may be waiting for a peer whose host waits for an exchange this (blocked) host has yet to issue
+        ctx->graveyard.push_back(b.p);
     }
     b.p = np;
     b.bytes = nb;
@@ -364,7 +366,7 @@ int table_reserve(chad_ctx* ctx, u64 need_chunks) {
     TRY(table_alloc(ctx, nt, nk, nc, ncount, nlist, new_cap));
     ctx->stats.kernel_launches += launch_table_rehash(ctx->stream, ctx->table, nt, ctx->num_sms);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx->t_keys); dev_free(ctx->t_cells); dev_free(ctx->t_count); dev_free(ctx->t_list);
+    for (DevBuf* b : {&ctx->t_keys, &ctx->t_cells, &ctx->t_count, &ctx->t_list}) ctx->graveyard.push_back(b->p);  // (see dev_ensure)
     ctx->t_keys = nk; ctx->t_cells = nc; ctx->t_count = ncount; ctx->t_list = nlist;
     ctx->table = nt;
     ctx->grow_events++;

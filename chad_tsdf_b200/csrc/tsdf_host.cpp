@@ -4,6 +4,10 @@
 
 #include <algorithm>
 #include <bit>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -19,18 +23,124 @@ void check(chad_ctx* ctx, int rc, const char* what) {
 }
 }  // namespace
 
+// ---- several GPUs behind the same class -------------------------------------------------------------------
+// One worker thread per device, each owning the context of one Morton range (a context is single-threaded, like the reference's
+// class). A collective call hands the same job to every worker and waits for all of them: every rank makes the same calls with the
+// same arguments, which is what chad_create_sharded asks for.
+struct TSDFMap::Group {
+    std::vector<chad_ctx*> ctx;
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    std::function<int(chad_ctx*&, int)> job;
+    uint64_t generation = 0;
+    int pending = 0;
+    bool quit = false;
+    std::vector<int> rc;
+
+    explicit Group(size_t n): ctx(n, nullptr), rc(n, CHAD_OK) {
+        for (size_t r = 0; r < n; r++) threads.emplace_back([this, r] { work((int)r); });
+    }
+    ~Group() {
+        { std::lock_guard<std::mutex> lk(m); quit = true; }
+        cv_job.notify_all();
+        for (auto& t : threads) t.join();
+    }
+    void work(int r) {
+        uint64_t seen = 0;
+        while (true) {
+            std::function<int(chad_ctx*&, int)> f;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_job.wait(lk, [&] { return quit || generation != seen; });
+                if (quit) return;
+                seen = generation;
+                f = job;
+            }
+            const int res = f(ctx[r], r);
+            { std::lock_guard<std::mutex> lk(m); rc[r] = res; pending--; }
+            cv_done.notify_all();
+        }
+    }
+    // run f on every rank; returns the first failing rank (or -1)
+    int run(std::function<int(chad_ctx*&, int)> f) {
+        std::unique_lock<std::mutex> lk(m);
+        job = std::move(f);
+        pending = (int)threads.size();
+        generation++;
+        cv_job.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+        for (size_t r = 0; r < rc.size(); r++) if (rc[r] != CHAD_OK) return (int)r;
+        return -1;
+    }
+};
+
+namespace {
+std::vector<int> devices_from_env() {
+    std::vector<int> out;
+    if (const char* env = std::getenv("CHAD_DEVICES")) {
+        std::string tok;
+        for (const char* p = env;; p++) {
+            if (*p == ',' || *p == 0) { if (!tok.empty()) out.push_back(std::atoi(tok.c_str())); tok.clear(); if (!*p) break; }
+            else tok.push_back(*p);
+        }
+    }
+    return out;
+}
+}  // namespace
+
 TSDFMap::TSDFMap(float sdf_res, float sdf_trunc): _sdf_res(sdf_res), _sdf_trunc(sdf_trunc), _ctx(nullptr) {
-    int device = 0;
-    if (const char* env = std::getenv("CHAD_DEVICE")) device = std::atoi(env);
+    const std::vector<int> devices = devices_from_env();
+    if (devices.size() > 1) {
+        alignas(8) unsigned char id[CHAD_SHARD_ID_BYTES];
+        check(nullptr, chad_shard_unique_id(id), "TSDFMap");
+        _group = new Group(devices.size());
+        std::vector<std::string> errors(devices.size());
+        const int world = (int)devices.size();
+        const int bad = _group->run([&](chad_ctx*& c, int r) {
+            const int rc = chad_create_sharded(sdf_res, sdf_trunc, devices[r], 0, r, world, id, &c);
+            if (rc != CHAD_OK) errors[r] = chad_last_error(nullptr);  // (thread-local: must be read on the worker)
+            return rc;
+        });
+        if (bad >= 0) {
+            const std::string why = errors[bad];
+            _group->run([](chad_ctx*& c, int) { chad_destroy(c); c = nullptr; return CHAD_OK; });
+            delete _group;
+            _group = nullptr;
+            throw std::runtime_error("chad::TSDFMap::TSDFMap: rank " + std::to_string(bad) + ": " + why);
+        }
+        _ctx = _group->ctx[0];
+        return;
+    }
+    int device = devices.size() == 1 ? devices[0] : 0;
+    if (devices.empty()) if (const char* env = std::getenv("CHAD_DEVICE")) device = std::atoi(env);
     check(nullptr, chad_create(sdf_res, sdf_trunc, device, 0, &_ctx), "TSDFMap");
 }
-TSDFMap::~TSDFMap() { chad_destroy(_ctx); }
+TSDFMap::~TSDFMap() {
+    if (_group) {
+        _group->run([](chad_ctx*& c, int) { chad_flush(c); return CHAD_OK; });  // every rank quiescent before any communicator goes away
+        _group->run([](chad_ctx*& c, int) { chad_destroy(c); c = nullptr; return CHAD_OK; });
+        delete _group;
+    } else {
+        chad_destroy(_ctx);
+    }
+}
+
+// a call every rank must make (insert, flush, finalize): forwarded to all workers, or made directly on the single context
+void TSDFMap::collective(const char* what, int (*call)(chad_ctx*, const void*), const void* arg) {
+    if (!_group) { check(_ctx, call(_ctx, arg), what); return; }
+    const int bad = _group->run([&](chad_ctx*& c, int) { return call(c, arg); });
+    if (bad >= 0) check(_group->ctx[bad], CHAD_ERR_INVALID, what);
+}
 
 void TSDFMap::insert(const float* points_p, size_t points_count, const float* position_p) {
-    check(_ctx, chad_insert(_ctx, points_p, points_count, position_p), "insert");
+    struct Args { const float* p; size_t n; const float* pos; } a{points_p, points_count, position_p};
+    collective("insert", [](chad_ctx* c, const void* v) { const Args* a = static_cast<const Args*>(v); return chad_insert(c, a->p, a->n, a->pos); }, &a);
 }
-void TSDFMap::flush() { check(_ctx, chad_flush(_ctx), "flush"); }
+void TSDFMap::flush() { collective("flush", [](chad_ctx* c, const void*) { return chad_flush(c); }, nullptr); }
+void TSDFMap::finalize_active() { collective("save", [](chad_ctx* c, const void*) { return chad_finalize_active(c); }, nullptr); flush(); }
 size_t TSDFMap::submap_count() {
+    if (_group) flush();  // (a read settles the context it is made on; on a sharded map every rank has to)
     uint32_t n = 0;
     check(_ctx, chad_submap_count(_ctx, &n), "submap_count");
     return n;
@@ -41,6 +151,7 @@ std::array<uint32_t, 2> TSDFMap::submap_roots(size_t i) {
     return r;
 }
 HostNodeLevels TSDFMap::node_levels() {
+    if (_group) flush();
     HostNodeLevels out;
     for (int level = 0; level < CHAD_NUM_LEVELS; level++) {
         size_t words = 0;
@@ -84,7 +195,7 @@ void save_dag(const SavedMap& m, const std::string& filename) {
 }
 
 void TSDFMap::save(const std::string& filename) {
-    check(_ctx, chad_finalize_active(_ctx), "save");  // tsdf.cpp:78-81
+    finalize_active();  // tsdf.cpp:78-81 (on every rank of a sharded map)
     SavedMap m;
     m.sdf_res = _sdf_res;
     m.sdf_trunc = _sdf_trunc;
@@ -100,6 +211,7 @@ void TSDFMap::save(const std::string& filename) {
 }
 
 void TSDFMap::load(const std::string& filename) {
+    if (_group) throw std::runtime_error("chad::TSDFMap::load: a saved map is restored into a single-GPU map (unset CHAD_DEVICES)");
     const SavedMap m = load_dag(filename);
     if (m.sdf_res != _sdf_res || m.sdf_trunc != _sdf_trunc) throw std::runtime_error("chad::TSDFMap::load: " + filename + " was saved with another voxel size / truncation");
     if (!m.has_counters) throw std::runtime_error("chad::TSDFMap::load: " + filename + " is a CHADDAG1 dump (no dedup counters): readable with load_dag, not restorable");
@@ -187,11 +299,12 @@ void LeafCursor::next() {
 Leaf LeafCursor::leaf(float sdf_res, float sdf_trunc) const { return make_leaf(key(), byte(), sdf_res, sdf_trunc); }
 
 TSDFMap::LeafRange TSDFMap::leaves(size_t submap) {
-    check(_ctx, chad_flush(_ctx), "leaves");
+    flush();
     if (submap >= submap_count()) throw std::runtime_error("chad::TSDFMap::leaves: no such submap");
     return LeafRange{node_levels(), submap_roots(submap)[0], _sdf_res, _sdf_trunc};
 }
 std::vector<Leaf> TSDFMap::collect_leaves(size_t submap) {
+    if (_group) flush();
     size_t n = 0;
     check(_ctx, chad_iterate_leaves(_ctx, (uint32_t)submap, nullptr, nullptr, 0, &n), "collect_leaves");
     std::vector<uint64_t> keys(n);
@@ -205,7 +318,7 @@ std::vector<Leaf> TSDFMap::collect_leaves(size_t submap) {
 
 // ---- .grid file ------------------------------------------------------------------------------------------
 void TSDFMap::save_grid(const std::string& filename, size_t submap) {
-    check(_ctx, chad_finalize_active(_ctx), "save_grid");  // tsdf.cpp:78-81
+    finalize_active();  // tsdf.cpp:78-81
     if (submap >= submap_count()) throw std::runtime_error("chad::TSDFMap::save_grid: no such submap");
     write_grid(node_levels(), submap_roots(submap)[0], _sdf_res, _sdf_trunc, filename);
 }

@@ -213,6 +213,13 @@ namespace chad {
         const float _sdf_trunc;
 
     private:
-        chad_ctx* _ctx;
+        // CHAD_DEVICES=0,1,... (environment, read by the constructor): ONE map cut into Morton ranges over those GPUs (chad_create_sharded,
+        // one worker thread per GPU; insert / flush / save are forwarded to every rank, reads go to rank 0, which holds the DAG). Unset or
+        // a single ordinal: the plain single-GPU map on CHAD_DEVICE (default 0).
+        struct Group;
+        Group* _group = nullptr;
+        void collective(const char* what, int (*call)(chad_ctx*, const void*), const void* arg);
+        void finalize_active();
+        chad_ctx* _ctx;   // the map (rank 0's shard when sharded)
     };
 }
