@@ -185,6 +185,14 @@ struct chad_ctx {
         DevBuf scalars;                 // u32: [0..1] sample sort (n, nbits) | [8] own chunk count | [16 .. 16 + world) all chunk counts
         u32* h_counts = nullptr;        // pinned [SHARD_WORLD_MAX]: chunk counts of the submap being closed
         cudaEvent_t counts_done = nullptr;
+        // The gather of a closed submap's chunks is issued at a point of the call sequence that is the same on every rank (the
+        // n_slots-th batch after the closing one, the next submap switch, or a flush -- whichever comes first), never from a poll: an
+        // NCCL kernel that waits on the device for a peer whose HOST has not got there yet blocks this rank's other NCCL traffic, and the
+        // peer's host may be waiting for exactly that traffic.
+        bool gather_pending = false;
+        int gather_countdown = 0;
+        u32* h_roots = nullptr;         // pinned staging of the root broadcast
+        size_t roots_synced = 0;        // submaps whose roots this rank knows (rank 0: has broadcast)
         u64 sent_runs = 0, sent_records = 0, exchanges = 0;
     } sh;
     // growth of the never-freed DAG arenas and the chunk tables (VirtualArray, virtual_array.hpp:12-104, becomes explicit device buffers):
@@ -357,6 +365,7 @@ int table_alloc(chad_ctx* ctx, ChunkTable& t, DevBuf& keys, DevBuf& cells, DevBu
 int table_reserve(chad_ctx* ctx, u64 need_chunks) {
     if (need_chunks * 2 <= ctx->table.capacity) return CHAD_OK;
     const auto t_grow = std::chrono::steady_clock::now();
+    trace(ctx, "chunk table grows: %llu chunks needed, capacity %llu", (unsigned long long)need_chunks, (unsigned long long)ctx->table.capacity);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->fold_stream));  // a fold may still be writing the table
     ctx->fold_in_flight = false;
@@ -371,6 +380,7 @@ int table_reserve(chad_ctx* ctx, u64 need_chunks) {
     ctx->table = nt;
     ctx->grow_events++;
     ctx->grow_bytes += new_cap * 76;
+    trace(ctx, "chunk table grown");
     ctx->grow_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_grow).count();
     return CHAD_OK;
 }
@@ -441,6 +451,7 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
 }
 
 int finalize_begin(chad_ctx* ctx, u32 max_chunks, bool external, cudaStream_t count_stream);
+int shard_gather_now(chad_ctx* ctx);
 
 // device mirror of the node levels' counters: NodeLevel's constructor reserves index 0 (levels.hpp:52-54)
 int level_counters_reset(chad_ctx* ctx) {
@@ -472,6 +483,7 @@ int complete_one_fold(chad_ctx* ctx, bool block, bool* launched) {
         if (q == cudaErrorNotReady) { cudaGetLastError(); return CHAD_OK; }
         CUDA_TRY(ctx, q);
     } else {
+        trace(ctx, "wait: front of slot %d", slot);
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->front_done[slot]));
     }
     for (int q = 0; q + 1 < ctx->n_pend; q++) ctx->pend[q] = ctx->pend[q + 1];
@@ -657,6 +669,7 @@ int process_front(chad_ctx* ctx) {
     // (which follows its ray walk and its descriptor sort) must have been launched ...
     while (ctx->n_pend && ctx->pend[0].slot == slot) { bool launched; TRY(complete_one_fold(ctx, true, &launched)); }
     if (ctx->n_pend == ctx->n_slots) { bool launched; TRY(complete_one_fold(ctx, true, &launched)); }
+    if (ctx->sh.gather_pending && --ctx->sh.gather_countdown <= 0) TRY(shard_gather_now(ctx));  // the closing batch's fold has been launched by now
     // ... and the device waits for it (on fold_stream) before touching the slot
     if (ctx->fold_done_valid[slot]) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->fold_done[slot], 0));
     if (ctx->scans_uploaded_valid[b]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->scans_uploaded[b]));  // (two batches ago: long done)
@@ -754,8 +767,10 @@ int process_front(chad_ctx* ctx) {
 int finalize_part2(chad_ctx* ctx);
 
 int drain(chad_ctx* ctx) {
+    trace(ctx, "drain (%d folds pending, finalize state %d)", ctx->n_pend, ctx->fin_state);
     TRY(process_front(ctx));
     TRY(complete_pending_fold(ctx));
+    if (ctx->sh.gather_pending) TRY(shard_gather_now(ctx));
     if (ctx->fin_state == chad_ctx::FIN_PART1) {  // let part 2 of an in-flight finalize overlap the tail of the compute stream
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->fin_p1_done));
         TRY(finalize_part2(ctx));
@@ -906,8 +921,7 @@ int finalize_finish(chad_ctx* ctx);
 int finalize_gather(chad_ctx* ctx);
 // non-blocking progress of an in-flight finalize (called from every API entry)
 int finalize_poll(chad_ctx* ctx) {
-    if (ctx->fin_state == chad_ctx::FIN_PART1 && cudaEventQuery(ctx->fin_p1_done) == cudaSuccess) TRY(finalize_part2(ctx));
-    if (ctx->fin_state == chad_ctx::FIN_COUNTS && cudaEventQuery(ctx->sh.counts_done) == cudaSuccess) TRY(finalize_gather(ctx));
+    if (ctx->sh.world == 1 && ctx->fin_state == chad_ctx::FIN_PART1 && cudaEventQuery(ctx->fin_p1_done) == cudaSuccess) TRY(finalize_part2(ctx));
     if (ctx->fin_state == chad_ctx::FIN_PART2 && cudaEventQuery(ctx->fin_done) == cudaSuccess) TRY(finalize_finish(ctx));
     cudaGetLastError();  // cudaErrorNotReady is not an error
     return CHAD_OK;
@@ -915,12 +929,9 @@ int finalize_poll(chad_ctx* ctx) {
 // blocking completion
 int finalize_wait(chad_ctx* ctx) {
     if (ctx->fin_state == chad_ctx::FIN_PART1) {
+        if (ctx->sh.world > 1) return fail(ctx, CHAD_ERR_INVALID, "internal: a sharded finalize was waited for before its gather point");
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->fin_p1_done));
         TRY(finalize_part2(ctx));
-    }
-    if (ctx->fin_state == chad_ctx::FIN_COUNTS) {
-        CUDA_TRY(ctx, cudaEventSynchronize(ctx->sh.counts_done));
-        TRY(finalize_gather(ctx));
     }
     if (ctx->fin_state == chad_ctx::FIN_PART2) {
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->fin_done));
@@ -935,6 +946,7 @@ int finalize_wait(chad_ctx* ctx) {
 // table counter were queued on) -- by the next API call that finds it there, or by whoever needs the DAG.
 // external = true (sharded mode): f_ids[0] / f_cells already hold `max_chunks` globally sorted chunks.
 int finalize_begin(chad_ctx* ctx, u32 max_chunks, bool external, cudaStream_t count_stream) {
+    trace(ctx, "finalize_begin (previous finalize in state %d)", ctx->fin_state);
     TRY(finalize_wait(ctx));  // one finalize in flight at a time
     cudaStream_t fs = ctx->fin_stream;
     CUDA_TRY(ctx, cudaEventRecord(ctx->submap_closed, ctx->stream));
@@ -1033,22 +1045,7 @@ int finalize_tail(chad_ctx* ctx, bool clear_table2) {
 int finalize_part2(chad_ctx* ctx) {
     cudaStream_t fs = ctx->fin_stream;
     const u32 C = ctx->fin_external ? ctx->fin_max_chunks : *ctx->h_table_count2;
-    if (ctx->sh.world > 1 && !ctx->fin_external) {
-        // sharded: rank 0 builds the DAG from all ranks' chunks, so every rank first learns every rank's count (the sizes of the gather
-        // must be known on the host). Queued here, collected by finalize_gather -- nobody waits.
-        chad_ctx::Shard& sh = ctx->sh;
-        ctx->fin_chunks = C;
-        trace(ctx, "finalize: own chunk count %u known, all-gather of the counts", C);
-        u32* d = sh.scalars.as<u32>();
-        ctx->h_fin->h2d[1] = C;
-        CUDA_TRY(ctx, cudaMemcpyAsync(d + 8, &ctx->h_fin->h2d[1], 4, cudaMemcpyHostToDevice, fs));
-        NCCL_TRY(ctx, sh.nccl->AllGather(d + 8, d + 16, 1, ncclUint32, sh.comm_f, fs));
-        CUDA_TRY(ctx, cudaMemcpyAsync(sh.h_counts, d + 16, size_t(sh.world) * 4, cudaMemcpyDeviceToHost, fs));
-        CUDA_TRY(ctx, cudaEventRecord(sh.counts_done, fs));
-        ctx->stats.kernel_launches += 1;
-        ctx->fin_state = chad_ctx::FIN_COUNTS;
-        return CHAD_OK;
-    }
+    if (ctx->sh.world > 1 && !ctx->fin_external) return fail(ctx, CHAD_ERR_INVALID, "internal: sharded finalize outside its gather point");
     TRY(finalize_dag(ctx, C, ctx->fin_external, [&]() -> int {
         if (C && !ctx->fin_external) TRY(queue_sorted_chunks(ctx, fs, ctx->table2, C));
         return CHAD_OK;
@@ -1056,13 +1053,34 @@ int finalize_part2(chad_ctx* ctx) {
     return finalize_tail(ctx, !ctx->fin_external);
 }
 
-// sharded: every rank's chunk count has arrived. The ranges ascend with the rank, so the concatenation of the ranks' sorted chunks in
+// sharded, at the gather point of a closed submap (see Shard::gather_pending). The ranges ascend with the rank, so the concatenation of the ranks' sorted chunks in
 // rank order is the submap's chunk stream in ascending Morton order (submap.hpp:10-106 walks the octree in that order): every rank
 // sorts its chunks and sends them to rank 0, which receives them behind its own and runs the DAG stage; the two root addresses
-// (submap.hpp:108-109) are broadcast back.
+// (submap.hpp:108-109) reach the other ranks at the next flush.
 int finalize_gather(chad_ctx* ctx) {
     cudaStream_t fs = ctx->fin_stream;
     chad_ctx::Shard& sh = ctx->sh;
+    {   // every rank's chunk count (the sizes of the gather must be known on the host). Blocking, but every rank is at the same point of
+        // its call sequence: nobody waits for more than the others' skew
+        if (ctx->fin_state != chad_ctx::FIN_PART1) return fail(ctx, CHAD_ERR_INVALID, "internal: gather without a closed submap");
+        // No batch exchange of this rank may be in flight beside the gather: an NCCL kernel spins on the device until its peer kernel runs,
+        // and CUDA maps streams onto a limited number of hardware queues (CUDA_DEVICE_MAX_CONNECTIONS), so a spinning kernel can hold back
+        // kernels of OTHER streams -- with two communicators that is a cycle (A's receive waits for B's send, queued behind B's exchange,
+        // which waits for A's exchange, queued behind A's receive). Hence the two kinds of transfer never overlap on a rank: the exchanges
+        // issued so far are waited for here, and the gather's own transfers are waited for below.
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->fin_p1_done));
+        const u32 C = *ctx->h_table_count2;
+        trace(ctx, "gather point: own chunk count %u, all-gather of the counts", C);
+        u32* d = sh.scalars.as<u32>();
+        ctx->h_fin->h2d[1] = C;
+        CUDA_TRY(ctx, cudaMemcpyAsync(d + 8, &ctx->h_fin->h2d[1], 4, cudaMemcpyHostToDevice, fs));
+        NCCL_TRY(ctx, sh.nccl->AllGather(d + 8, d + 16, 1, ncclUint32, sh.comm_f, fs));
+        CUDA_TRY(ctx, cudaMemcpyAsync(sh.h_counts, d + 16, size_t(sh.world) * 4, cudaMemcpyDeviceToHost, fs));
+        CUDA_TRY(ctx, cudaStreamSynchronize(fs));
+        ctx->stats.kernel_launches += 1;
+    }
+    sh.gather_pending = false;
     u64 total = 0;
     u64 offset[SHARD_WORLD_MAX + 1];
     for (int g = 0; g < sh.world; g++) { offset[g] = total; total += sh.h_counts[g]; }
@@ -1085,8 +1103,10 @@ int finalize_gather(chad_ctx* ctx) {
                 NCCL_TRY(ctx, sh.nccl->GroupEnd());
                 ctx->stats.kernel_launches += 1;
             }
+            CUDA_TRY(ctx, cudaEventRecord(sh.counts_done, fs));  // the transfers are complete here; the DAG stage behind them runs on
             return CHAD_OK;
         }));
+        CUDA_TRY(ctx, cudaEventSynchronize(sh.counts_done));
     } else {
         ctx->fin_chunks = own;
         ctx->fin_state = chad_ctx::FIN_IDLE;
@@ -1100,11 +1120,36 @@ int finalize_gather(chad_ctx* ctx) {
             NCCL_TRY(ctx, sh.nccl->Send(ctx->f_cells.p, size_t(own) * 8, ncclUint64, 0, sh.comm_f, fs));
             NCCL_TRY(ctx, sh.nccl->GroupEnd());
             ctx->stats.kernel_launches += 1;
+            CUDA_TRY(ctx, cudaStreamSynchronize(fs));
         }
     }
-    NCCL_TRY(ctx, sh.nccl->Broadcast(scalar32(ctx, SC_ROOT), scalar32(ctx, SC_ROOT), 2, ncclUint32, 0, sh.comm_f, fs));
-    ctx->stats.kernel_launches += 1;
+    // (the roots reach the other ranks at the next flush: shard_sync_roots)
+    trace(ctx, "finalize: gather + DAG stage queued");
     return finalize_tail(ctx, true);
+}
+
+// sharded, collective (chad_flush / chad_finalize_active): the roots of the submaps closed since the last flush, from rank 0 to all
+int shard_sync_roots(chad_ctx* ctx) {
+    chad_ctx::Shard& sh = ctx->sh;
+    const size_t n = ctx->roots.size();  // the same on every rank: closes are counted by the common call sequence
+    if (sh.world == 1 || n == sh.roots_synced) return CHAD_OK;
+    const size_t fresh = n - sh.roots_synced;
+    if (fresh > 4096) return fail(ctx, CHAD_ERR_CAPACITY, "more than 4096 submaps closed between two flushes of a sharded map");
+    cudaStream_t fs = ctx->fin_stream;
+    DevBuf d;
+    TRY(dev_ensure(ctx, d, fresh * 8));
+    if (sh.rank == 0) {
+        for (size_t i = 0; i < fresh; i++) { sh.h_roots[2 * i] = ctx->roots[sh.roots_synced + i][0]; sh.h_roots[2 * i + 1] = ctx->roots[sh.roots_synced + i][1]; }
+        CUDA_TRY(ctx, cudaMemcpyAsync(d.p, sh.h_roots, fresh * 8, cudaMemcpyHostToDevice, fs));
+    }
+    NCCL_TRY(ctx, sh.nccl->Broadcast(d.p, d.p, fresh * 2, ncclUint32, 0, sh.comm_f, fs));
+    if (sh.rank != 0) CUDA_TRY(ctx, cudaMemcpyAsync(sh.h_roots, d.p, fresh * 8, cudaMemcpyDeviceToHost, fs));
+    CUDA_TRY(ctx, cudaStreamSynchronize(fs));
+    if (sh.rank != 0)
+        for (size_t i = 0; i < fresh; i++) ctx->roots[sh.roots_synced + i] = {sh.h_roots[2 * i], sh.h_roots[2 * i + 1]};
+    sh.roots_synced = n;
+    ctx->graveyard.push_back(d.p);
+    return CHAD_OK;
 }
 
 int finalize_finish(chad_ctx* ctx) {
@@ -1143,8 +1188,11 @@ int finalize_finish(chad_ctx* ctx) {
 // Close the active submap. lazy = true (submap switch inside insert): if a batch of the submap is still in flight, only
 // mark it; its fold and the finalize are queued by the next process_front / drain, so the host never waits for the
 // device here. lazy = false (chad_finalize_active): queue everything now.
+int shard_gather_now(chad_ctx* ctx);
 int finalize_submap(chad_ctx* ctx, bool lazy) {
+    if (ctx->sh.gather_pending) TRY(shard_gather_now(ctx));  // (a submap shorter than n_slots batches: its gather point is the next switch)
     TRY(process_front(ctx));
+    if (ctx->sh.world > 1) { ctx->sh.gather_pending = true; ctx->sh.gather_countdown = ctx->n_slots; }
     ctx->sh.need_splitters = true;  // (sharded) the next submap's ranges follow its own first scan
     ctx->positions.push_back(std::move(ctx->active_positions));  // closing order == the order the roots arrive in
     ctx->active_positions.clear();
@@ -1158,6 +1206,17 @@ int finalize_submap(chad_ctx* ctx, bool lazy) {
     TRY(finalize_begin(ctx, 0, false, ctx->last_fold_stream ? ctx->last_fold_stream : ctx->stream));
     ctx->stats.resident_clusters = 0;
     return CHAD_OK;
+}
+
+// the gather point of the closed submap: its last fold must have been launched (which begins the finalize: tables swapped, count copy
+// queued); then every rank exchanges counts and chunks (finalize_gather)
+int shard_gather_now(chad_ctx* ctx) {
+    if (ctx->fin_state == chad_ctx::FIN_IDLE || ctx->fin_state == chad_ctx::FIN_PART2) {
+        // the closing batch's fold is still pending (the finalize of the submap BEFORE may be in flight: finalize_begin waits for it)
+        TRY(complete_pending_fold(ctx));
+    }
+    if (ctx->fin_state != chad_ctx::FIN_PART1) return fail(ctx, CHAD_ERR_INVALID, "internal: no closed submap at a gather point");
+    return finalize_gather(ctx);
 }
 
 int begin_scan(chad_ctx* ctx, size_t n, const float position[3], bool* skip) {
@@ -1375,6 +1434,7 @@ static int create_impl(float sdf_res, float sdf_trunc, int device, int max_batch
         CREATE_TRY(cudaMemset(sh.scalars.p, 0, 256));
         CREATE_TRY(cudaMemset(sh.box_in.p, 0, size_t(world) * sh.box_words * 8));
         CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&sh.h_counts), SHARD_WORLD_MAX * sizeof(u32)));
+        CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&sh.h_roots), 4096 * 2 * sizeof(u32)));
         CREATE_TRY(cudaEventCreateWithFlags(&sh.counts_done, cudaEventDisableTiming));
         if (const char* env = std::getenv("CHAD_SHARD_RANK0_SHARE")) { const int v = std::atoi(env); if (v >= 0 && v <= 256) sh.first_share_256 = (u32)v; }
         // two communicators: the per-batch exchange (group stream) and the per-submap gather (finalize stream) are queued from points of
@@ -1477,6 +1537,7 @@ void chad_destroy(chad_ctx* ctx) {
                           &ctx->sh.box_in, &ctx->sh.scalars})
             dev_free(*b);
         if (ctx->sh.h_counts) cudaFreeHost(ctx->sh.h_counts);
+        if (ctx->sh.h_roots) cudaFreeHost(ctx->sh.h_roots);
         if (ctx->sh.counts_done) cudaEventDestroy(ctx->sh.counts_done);
     }
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -1586,17 +1647,20 @@ int chad_flush(chad_ctx* ctx) {
     if (!ctx) return CHAD_ERR_INVALID;
     if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    return settle(ctx);
+    TRY(settle(ctx));
+    return shard_sync_roots(ctx);
 }
 
 int chad_finalize_active(chad_ctx* ctx) {
     if (!ctx) return CHAD_ERR_INVALID;
     if (ctx->sticky_error != CHAD_OK) return ctx->sticky_error;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (!ctx->has_pose) return settle(ctx);
+    if (!ctx->has_pose) { TRY(settle(ctx)); return shard_sync_roots(ctx); }
     TRY(finalize_submap(ctx, false));
     ctx->has_pose = false;
-    return CHAD_OK;
+    if (ctx->sh.world == 1) return CHAD_OK;
+    TRY(settle(ctx));  // sharded: collective anyway -- gather, DAG and roots are complete when the call returns
+    return shard_sync_roots(ctx);
 }
 
 int chad_submap_count(chad_ctx* ctx, uint32_t* count) {
@@ -1724,6 +1788,8 @@ int chad_reset(chad_ctx* ctx) {
     ctx->n_pend = 0;
     for (bool& f : ctx->fold_stats_pending) f = false;
     ctx->sh.need_splitters = true;
+    ctx->sh.gather_pending = false;
+    ctx->sh.roots_synced = 0;
     ctx->burst_batches = 0;
     ctx->sh.sent_runs = ctx->sh.sent_records = ctx->sh.exchanges = 0;
     if (ctx->sh.world > 1 && ctx->sh.filter_mem.p) CUDA_TRY(ctx, cudaMemsetAsync(ctx->sh.filter_mem.p, 0, ctx->sh.filter_mem.bytes, ctx->stream));

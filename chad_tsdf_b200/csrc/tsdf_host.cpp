@@ -146,6 +146,7 @@ size_t TSDFMap::submap_count() {
     return n;
 }
 std::array<uint32_t, 2> TSDFMap::submap_roots(size_t i) {
+    if (_group) flush();
     std::array<uint32_t, 2> r{};
     check(_ctx, chad_submap_roots(_ctx, (uint32_t)i, &r[0], &r[1]), "submap_roots");
     return r;
@@ -236,6 +237,7 @@ void TSDFMap::load(const std::string& filename) {
 }
 
 std::vector<std::array<float, 3>> TSDFMap::submap_positions(size_t submap) {
+    if (_group) flush();
     size_t n = 0;
     check(_ctx, chad_submap_positions(_ctx, (uint32_t)submap, nullptr, 0, &n), "submap_positions");
     std::vector<std::array<float, 3>> out(n);

@@ -4,6 +4,8 @@ import json
 import os
 import sys
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before CUDA starts: see bench.py
+
 import numpy as np
 import torch
 import torch.distributed as dist

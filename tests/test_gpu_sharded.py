@@ -79,3 +79,21 @@ def test_submap_parallel_world2(chad_lib, oracle_lib, tmp_path):
         pytest.skip("needs 2 GPUs")
     res = _run_submaps(2, tmp_path)
     assert all(r["exchanged"] > 0 for r in res)
+
+
+def test_cpp_class_on_two_gpus_builds_the_identical_map(chad_lib, tmp_path):
+    """chad::TSDFMap with CHAD_DEVICES=0,1 (one worker thread per GPU inside the class, chad_create_sharded underneath): the README-style
+    sphere demo must write byte-identical files (DAG dump with roots, poses and counters; .grid) on one and on two GPUs."""
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    from chad_tsdf_b200 import build
+    exe = build.build_facade_demo()
+    outs = {}
+    for name, env in (("one", {}), ("two", {"CHAD_DEVICES": "0,1"})):
+        d = tmp_path / name
+        d.mkdir()
+        r = subprocess.run([exe, "150000"], cwd=d, capture_output=True, text=True, timeout=240, env={**os.environ, **env})
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[name] = (open(d / "facade_demo.chad", "rb").read(), open(d / "facade_demo.grid", "rb").read(), r.stdout)
+    assert outs["one"][0] == outs["two"][0] and outs["one"][1] == outs["two"][1]
+    assert len(outs["one"][0]) > 100000
