@@ -191,6 +191,7 @@ struct chad_ctx {
         // peer's host may be waiting for exactly that traffic.
         bool gather_pending = false;
         int gather_countdown = 0;
+        bool xfer_pending = false;      // counts_done marks the end of this rank's gather transfers: the next exchange waits for it
         u32* h_roots = nullptr;         // pinned staging of the root broadcast
         size_t roots_synced = 0;        // submaps whose roots this rank knows (rank 0: has broadcast)
         u64 sent_runs = 0, sent_records = 0, exchanges = 0;
@@ -597,9 +598,8 @@ void queue_point_stage(chad_ctx* ctx, int slot, int b, u32 n, u32 ns, const Batc
             // every rank samples and sorts the same points (the submap's first scan), so every rank derives the same ranges: no communication
             ctx->sh.split_set ^= 1;
             ctx->sh.need_splitters = false;
-            PROF(ctx, PC_PLAN, launch_shard_splitters(s, xyz, h.offset[1], ctx->mp, (u32)ctx->sh.world, ctx->sh.first_share_256, ctx->pk_a.as<u64>(),
-                                                      ctx->pv_a.as<u32>(), ctx->pk_b.as<u64>(), ctx->pv_b.as<u32>(), ctx->sh.scalars.as<u32>(), ctx->rws,
-                                                      ctx->num_sms, const_cast<u64*>(shard_splitters(ctx, ctx->sh.split_set))));
+            PROF(ctx, PC_PLAN, launch_shard_splitters(s, xyz, h.offset[1], ctx->mp, (u32)ctx->sh.world, ctx->sh.first_share_256,
+                                                      const_cast<u64*>(shard_splitters(ctx, ctx->sh.split_set))));
         }
         ctx->sh.slot_split[slot] = ctx->sh.split_set;
         PROF(ctx, PC_POINT_KEYS, launch_shard_filter(s, xyz, n, ns, ctx->sh.batch_scans[slot].as<BatchScans>(), ctx->mp, plan, tsb, shard_gbits(ctx),
@@ -628,6 +628,10 @@ int queue_shard_exchange(chad_ctx* ctx, int slot) {
     cudaStream_t gs = ctx->group_stream;
     chad_ctx::Shard& sh = ctx->sh;
     const ShardBoxes boxes{sh.box_out.as<u64>(), sh.box_in.as<u64>(), sh.box_words};
+    if (sh.xfer_pending) {  // (see finalize_gather: no exchange overtakes the chunk gather)
+        CUDA_TRY(ctx, cudaStreamWaitEvent(gs, sh.counts_done, 0));
+        sh.xfer_pending = false;
+    }
     u64 launches = 0;
     launches += launch_runs_pack(gs, ctx->rb[slot].capacity, plan_ptr(ctx, slot), ctx->rb[slot], slot_records(ctx, slot), shard_splitters(ctx, sh.slot_split[slot]),
                                  (u32)sh.rank, (u32)sh.world, boxes, ctx->num_sms);
@@ -1063,12 +1067,13 @@ int finalize_gather(chad_ctx* ctx) {
     {   // every rank's chunk count (the sizes of the gather must be known on the host). Blocking, but every rank is at the same point of
         // its call sequence: nobody waits for more than the others' skew
         if (ctx->fin_state != chad_ctx::FIN_PART1) return fail(ctx, CHAD_ERR_INVALID, "internal: gather without a closed submap");
-        // No batch exchange of this rank may be in flight beside the gather: an NCCL kernel spins on the device until its peer kernel runs,
-        // and CUDA maps streams onto a limited number of hardware queues (CUDA_DEVICE_MAX_CONNECTIONS), so a spinning kernel can hold back
-        // kernels of OTHER streams -- with two communicators that is a cycle (A's receive waits for B's send, queued behind B's exchange,
-        // which waits for A's exchange, queued behind A's receive). Hence the two kinds of transfer never overlap on a rank: the exchanges
-        // issued so far are waited for here, and the gather's own transfers are waited for below.
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->group_stream));
+        // An NCCL kernel spins on the device until its peer kernel runs, and CUDA maps streams onto a limited number of hardware queues
+        // (CUDA_DEVICE_MAX_CONNECTIONS), so a spinning kernel can hold back kernels submitted LATER to other streams. With two
+        // communicators that can close a cycle: A's receive waits for B's send, queued behind B's next batch exchange, which waits for A's
+        // next exchange, queued behind A's receive. Work submitted EARLIER cannot be held back, and every rank submits the gather at the
+        // same point of the exchange sequence, so the one thing to forbid is a LATER exchange overtaking the gather: the group stream
+        // waits (on the device, see queue_shard_exchange) for this rank's part of the gather before the next exchange. The host waits
+        // only for the counts.
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->fin_p1_done));
         const u32 C = *ctx->h_table_count2;
         trace(ctx, "gather point: own chunk count %u, all-gather of the counts", C);
@@ -1104,9 +1109,9 @@ int finalize_gather(chad_ctx* ctx) {
                 ctx->stats.kernel_launches += 1;
             }
             CUDA_TRY(ctx, cudaEventRecord(sh.counts_done, fs));  // the transfers are complete here; the DAG stage behind them runs on
+            sh.xfer_pending = true;
             return CHAD_OK;
         }));
-        CUDA_TRY(ctx, cudaEventSynchronize(sh.counts_done));
     } else {
         ctx->fin_chunks = own;
         ctx->fin_state = chad_ctx::FIN_IDLE;
@@ -1120,7 +1125,8 @@ int finalize_gather(chad_ctx* ctx) {
             NCCL_TRY(ctx, sh.nccl->Send(ctx->f_cells.p, size_t(own) * 8, ncclUint64, 0, sh.comm_f, fs));
             NCCL_TRY(ctx, sh.nccl->GroupEnd());
             ctx->stats.kernel_launches += 1;
-            CUDA_TRY(ctx, cudaStreamSynchronize(fs));
+            CUDA_TRY(ctx, cudaEventRecord(sh.counts_done, fs));
+            sh.xfer_pending = true;
         }
     }
     // (the roots reach the other ranks at the next flush: shard_sync_roots)
@@ -1789,6 +1795,7 @@ int chad_reset(chad_ctx* ctx) {
     for (bool& f : ctx->fold_stats_pending) f = false;
     ctx->sh.need_splitters = true;
     ctx->sh.gather_pending = false;
+    ctx->sh.xfer_pending = false;
     ctx->sh.roots_synced = 0;
     ctx->burst_batches = 0;
     ctx->sh.sent_runs = ctx->sh.sent_records = ctx->sh.exchanges = 0;

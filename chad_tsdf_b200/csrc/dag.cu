@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) dag_levels_kernel(LevelsArgs a)
     int cur = 0;
     auto sync = [&]() { if (nctas == 1) __syncthreads(); else grid_barrier(a.bar, phase, gridDim.x); };
     for (int d = 19; d >= 0; d--) {
-        if (nctas > 1 && n <= LV_SOLO) {  // uniform over the grid: n comes from memory written before the last barrier
+        if (nctas > 1 && n <= a.solo) {  // uniform over the grid: n comes from memory written before the last barrier
             if (cta != 0) return;
             nctas = 1;
         }
@@ -520,7 +520,10 @@ int launch_cluster_dedup(cudaStream_t s, const DedupTable& t, const u64* tsdf_va
     return launches + 2;
 }
 
-int launch_dag_levels(cudaStream_t s, const LevelsArgs& args, int num_sms) {
+int launch_dag_levels(cudaStream_t s, const LevelsArgs& args_in, int num_sms) {
+    LevelsArgs args = args_in;
+    static const u32 env_solo = [] { const char* e = std::getenv("CHAD_LEVELS_SOLO"); const long v = e ? std::atol(e) : 0; return (u32)(v > 0 ? v : LV_SOLO); }();
+    args.solo = env_solo;  // children from which ONE block finishes the remaining levels alone (no grid barriers)
     cudaMemsetAsync(args.bar, 0, 4, s);
     static const int env_ctas = [] { const char* e = std::getenv("CHAD_LEVELS_CTAS"); return e ? std::atoi(e) : 0; }();
     // one CTA of 512 threads per SM: the CTAs spin at the grid barriers while the insert kernels of the next submap run beside them, so

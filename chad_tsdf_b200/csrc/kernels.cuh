@@ -66,6 +66,7 @@ struct ShardFilter {    // work arrays of the ownership filter
     u32* scan_own;      // [MAX_BATCH_SCANS + 1] points of scan s this rank owns (zero between batches)
     u32* scan_lower;    // [MAX_BATCH_SCANS + 1] points of scan s owned by lower ranks
     u32* tile_cnt;      // [max_tiles] owned points per 256-point tile of the batch -> their exclusive prefix
+    u32* own_bits;      // [max_tiles * 8] per warp of 32 consecutive points: which of them this rank owns
     u32 max_tiles;
 };
 size_t shard_filter_bytes(size_t max_points);
@@ -73,7 +74,6 @@ ShardFilter shard_filter_carve(void* mem, size_t max_points);
 int launch_plan_reset(cudaStream_t s, BatchPlan* plan, u32 n_points, u32 n_scans);
 // splitters[0 .. world] (block ids = Morton key >> 9; [0] = 0, [world] = ~0) from a sorted sample of the submap's first scan
 int launch_shard_splitters(cudaStream_t s, const float* xyz_first_scan, u32 n_first_scan, const MapParams& mp, u32 world, u32 first_share_256,
-                           u64* keys_a, u32* vals_a, u64* keys_b, u32* vals_b, u32* d_scalars, const RadixWorkspace& rws, int num_sms,
                            u64* splitters);
 // plan + ownership filter of a batch (replaces launch_plan + launch_point_keys): plan->n_points = owned points, own_scans = their scan table
 int launch_shard_filter(cudaStream_t s, const float* xyz, u32 n_points, u32 n_scans, const BatchScans* scans, const MapParams& mp, BatchPlan* plan,
@@ -158,6 +158,7 @@ struct LevelsArgs {
     u64* partial;              // [2][1024]
     u32* bar;                  // grid barrier counter
     u32* d_error; u32* root_out; u32* level_nodes;
+    u32 solo;                  // set by launch_dag_levels
 };
 int launch_dag_levels(cudaStream_t s, const LevelsArgs& args, int num_sms);
 // device-side DAG reader: bytes of the queried voxels in the TSDF tree rooted at `root` (0xFF = absent)

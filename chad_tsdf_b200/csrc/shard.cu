@@ -29,37 +29,50 @@ __device__ __forceinline__ u32 owner_of(u64 blk, const u64* __restrict__ splitte
     return g;
 }
 
-// every `stride`-th point of the submap's first scan -> block id (full Morton key >> 9); *d_n = sample size, *d_nbits = 54
-__global__ void __launch_bounds__(PT_THREADS) shard_sample_kernel(const float* __restrict__ xyz, u32 n_points, u32 stride, float recip,
-                                                                  u64* __restrict__ keys, u32* __restrict__ d_n, u32* __restrict__ d_nbits) {
-    const u32 j = blockIdx.x * PT_THREADS + threadIdx.x;
-    const u32 ns = (n_points + stride - 1) / stride;
-    if (j == 0) { *d_n = ns; *d_nbits = 54; }
-    if (j >= ns) return;
-    const size_t i = size_t(j) * stride;
-    i32 vx, vy, vz;
-    voxel_of(__ldg(&xyz[i * 3]), __ldg(&xyz[i * 3 + 1]), __ldg(&xyz[i * 3 + 2]), recip, vx, vy, vz);  // (out of range -> origin; reported by the count kernel)
-    keys[j] = morton_encode(vx, vy, vz) >> 9;
-}
-
-// quantiles of the sorted sample -> range starts. first_share_256: share of rank 0 relative to the others' 256 (rank 0 also builds the
-// DAG of every closed submap, so it may be given fewer rays)
-__global__ void shard_splitters_kernel(const u64* __restrict__ keys_a, const u64* __restrict__ keys_b, const u32* __restrict__ d_n, u32 world,
-                                       u32 first_share_256, u64* __restrict__ splitters) {
+// Range starts of a new submap from its first scan, in ONE block: 4096 evenly spaced points of the scan -> block ids (full Morton key
+// >> 9), bitonic sort in shared memory, quantiles. first_share_256: share of rank 0 relative to the others' 256 (rank 0 also builds
+// the DAG of every closed submap, so it may be given fewer rays). Every rank runs this on the same points: identical ranges, no
+// communication.
+constexpr u32 SH_SAMPLES = 4096;
+__global__ void __launch_bounds__(SH_SCAN_THREADS) shard_splitters_kernel(const float* __restrict__ xyz, u32 n_points, float recip, u32 world,
+                                                                          u32 first_share_256, u64* __restrict__ splitters) {
+    __shared__ u64 s_key[SH_SAMPLES];
+    const u32 ns = min(n_points, SH_SAMPLES);
+    for (u32 j = threadIdx.x; j < SH_SAMPLES; j += SH_SCAN_THREADS) {
+        u64 key = ~0ull;  // padding sorts last
+        if (j < ns) {
+            const size_t i = (size_t)((u64)j * n_points / ns);
+            i32 vx, vy, vz;
+            voxel_of(__ldg(&xyz[i * 3]), __ldg(&xyz[i * 3 + 1]), __ldg(&xyz[i * 3 + 2]), recip, vx, vy, vz);  // (out of range -> origin; reported by the count kernel)
+            key = morton_encode(vx, vy, vz) >> 9;
+        }
+        s_key[j] = key;
+    }
+    __syncthreads();
+    for (u32 k = 2; k <= SH_SAMPLES; k <<= 1) {
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            for (u32 t = threadIdx.x; t < SH_SAMPLES; t += SH_SCAN_THREADS) {
+                const u32 partner = t ^ j;
+                if (partner > t) {
+                    const u64 a = s_key[t], b = s_key[partner];
+                    const bool up = (t & k) == 0;
+                    if ((a > b) == up) { s_key[t] = b; s_key[partner] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
     const u32 g = threadIdx.x;
     if (g > world) return;
-    const u64* __restrict__ sorted = radix_result_in_alt(54) ? keys_b : keys_a;
-    const u32 ns = *d_n;
     u64 v;
     if (g == 0) v = 0ull;
-    else if (g == world) v = ~0ull;
-    else if (ns == 0) v = ~0ull;  // nothing to go by: everything belongs to rank 0
+    else if (g == world || ns == 0) v = ~0ull;  // (nothing to go by: everything belongs to rank 0)
     else {
         const u64 total = u64(first_share_256) + 256ull * (world - 1);
         const u64 cum = u64(first_share_256) + 256ull * (g - 1);
         u64 idx = u64(ns) * cum / total;
         if (idx >= ns) idx = ns - 1;
-        v = sorted[idx];
+        v = s_key[idx];
     }
     splitters[g] = v;
 }
@@ -69,14 +82,16 @@ __global__ void shard_splitters_kernel(const u64* __restrict__ keys_a, const u64
 __global__ void __launch_bounds__(PT_THREADS) shard_count_kernel(const float* __restrict__ xyz, u32 n_points, const BatchScans* __restrict__ scans,
                                                                  u32 n_scans, float recip, BatchPlan* plan, const u64* __restrict__ splitters,
                                                                  u32 rank, u32 world, u32* __restrict__ tile_cnt, u32* __restrict__ scan_own,
-                                                                 u32* __restrict__ scan_lower) {
+                                                                 u32* __restrict__ scan_lower, u32* __restrict__ own_bits) {
     __shared__ __align__(16) float s_xyz[PT_THREADS * 3];
     __shared__ u32 s_r[PT_THREADS / 32], s_e[PT_THREADS / 32];
     __shared__ u32 s_cnt[4];  // own / lower of the tile's first scan, own / lower of the next one
     __shared__ u32 s_first;
     const u32 tile_base = blockIdx.x * PT_THREADS;
+    __shared__ u64 s_split[SHARD_WORLD_MAX + 1];
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_first = scan_of(scans, n_scans, tile_base);
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + SHARD_WORLD_MAX + 1) s_split[threadIdx.x - 32] = (threadIdx.x - 32 <= world) ? splitters[threadIdx.x - 32] : ~0ull;
     load_xyz_tile(xyz, tile_base, n_points, s_xyz);  // (ends with __syncthreads)
     const u32 i = tile_base + threadIdx.x, lane = threadIdx.x & 31;
     const u32 s_first_scan = s_first;
@@ -89,7 +104,7 @@ __global__ void __launch_bounds__(PT_THREADS) shard_count_kernel(const float* __
         i32 vx, vy, vz;
         if (!voxel_of(px, py, pz, recip, vx, vy, vz)) err = (isfinite(px) && isfinite(py) && isfinite(pz)) ? ERRF_RANGE : ERRF_NUMERIC;
         r = max(rcode(vx), max(rcode(vy), rcode(vz)));
-        const u32 g = owner_of(morton_encode(vx, vy, vz) >> 9, splitters, world);
+        const u32 g = owner_of(morton_encode(vx, vy, vz) >> 9, s_split, world);
         own = g == rank;
         lower = g < rank;
         u32 s = s_first_scan;
@@ -113,6 +128,7 @@ __global__ void __launch_bounds__(PT_THREADS) shard_count_kernel(const float* __
         if (lower) atomicAdd(&scan_lower[s_first_scan + rel], 1u);
     }
     const u32 own_all = __ballot_sync(0xffffffffu, own);
+    if (lane == 0) own_bits[i >> 5] = own_all;  // (i is a multiple of 32 here; warps beyond the batch write zero into the padding)
     __shared__ u32 s_own_total;
     if (threadIdx.x == 0) s_own_total = 0;
     __syncthreads();
@@ -172,33 +188,24 @@ __global__ void __launch_bounds__(SH_SCAN_THREADS) shard_plan_kernel(BatchPlan* 
 }
 
 // The owned points' sort keys, compacted in input order: key = (scan | ~compact Morton) with the BATCH index of the point below it
-// (point_gather_kernel fetches the coordinates through it), or a separate index array when the key has no room.
+// (point_gather_kernel fetches the coordinates through it), or a separate index array when the key has no room. Only the owned
+// points (the count kernel left one ownership ballot per warp) are read again: the pass costs 1 / world of the batch.
 __global__ void __launch_bounds__(PT_THREADS) shard_scatter_kernel(const float* __restrict__ xyz, u32 n_points, const BatchScans* __restrict__ scans,
-                                                                   float recip, const BatchPlan* __restrict__ plan, const u64* __restrict__ splitters,
-                                                                   u32 rank, u32 world, const u32* __restrict__ tile_off, u64* __restrict__ sortkeys,
-                                                                   u32* __restrict__ index) {
-    __shared__ __align__(16) float s_xyz[PT_THREADS * 3];
+                                                                   float recip, const BatchPlan* __restrict__ plan, const u32* __restrict__ own_bits,
+                                                                   const u32* __restrict__ tile_off, u64* __restrict__ sortkeys, u32* __restrict__ index) {
     __shared__ u32 s_wcnt[PT_THREADS / 32];
-    const u32 tile_base = blockIdx.x * PT_THREADS;
-    load_xyz_tile(xyz, tile_base, n_points, s_xyz);
-    const u32 i = tile_base + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    bool own = false;
-    u64 full = 0;
-    if (i < n_points) {
-        i32 vx, vy, vz;
-        voxel_of(s_xyz[threadIdx.x * 3], s_xyz[threadIdx.x * 3 + 1], s_xyz[threadIdx.x * 3 + 2], recip, vx, vy, vz);
-        full = morton_encode(vx, vy, vz);
-        own = owner_of(full >> 9, splitters, world) == rank;
-    }
-    const u32 b = __ballot_sync(0xffffffffu, own);
+    const u32 i = blockIdx.x * PT_THREADS + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 b = own_bits[i >> 5];
     if (lane == 0) s_wcnt[warp] = (u32)__popc(b);
     __syncthreads();
-    if (!own) return;
+    if (!((b >> lane) & 1u)) return;
     u32 before = 0;
 #pragma unroll
     for (u32 w = 0; w < PT_THREADS / 32; w++) before += (w < warp) ? s_wcnt[w] : 0u;
     const u32 pos = tile_off[blockIdx.x] + before + (u32)__popc(b & ((1u << lane) - 1u));
-    const u64 sk = point_sort_key(full, plan->k, scan_of(scans, plan->n_scans, i));
+    i32 vx, vy, vz;
+    voxel_of(__ldg(&xyz[size_t(i) * 3]), __ldg(&xyz[size_t(i) * 3 + 1]), __ldg(&xyz[size_t(i) * 3 + 2]), recip, vx, vy, vz);
+    const u64 sk = point_sort_key(morton_encode(vx, vy, vz), plan->k, scan_of(scans, plan->n_scans, i));
     if (plan->point_shift) sortkeys[pos] = (sk << POINT_INDEX_BITS) | (u64)i;
     else { sortkeys[pos] = sk; index[pos] = i; }
 }
@@ -207,7 +214,10 @@ inline unsigned blocks_for(u32 n) { return (n + PT_THREADS - 1) / PT_THREADS; }
 
 }  // namespace
 
-size_t shard_filter_bytes(size_t max_points) { return (((max_points + PT_THREADS - 1) / PT_THREADS) + 2 * (MAX_BATCH_SCANS + 1) + 64) * sizeof(u32); }
+size_t shard_filter_bytes(size_t max_points) {
+    const size_t tiles = (max_points + PT_THREADS - 1) / PT_THREADS;
+    return (tiles + tiles * (PT_THREADS / 32) + 2 * (MAX_BATCH_SCANS + 1) + 64) * sizeof(u32);
+}
 
 ShardFilter shard_filter_carve(void* mem, size_t max_points) {
     ShardFilter f;
@@ -216,25 +226,15 @@ ShardFilter shard_filter_carve(void* mem, size_t max_points) {
     f.scan_lower = p + (MAX_BATCH_SCANS + 1);
     f.tile_cnt = p + 2 * (MAX_BATCH_SCANS + 1) + 30;  // (keeps tile_cnt 16-byte aligned: 2 * 65 + 30 = 160 words)
     f.max_tiles = (u32)((max_points + PT_THREADS - 1) / PT_THREADS);
+    f.own_bits = f.tile_cnt + f.max_tiles;  // one ballot per warp of the count kernel (whole tiles: PT_THREADS / 32 words each)
     return f;
 }
 
-// splitters of a new submap from its first scan (device pointer into the batch buffer); sorts with the point sort's buffers
+// splitters of a new submap from its first scan (device pointer into the batch buffer)
 int launch_shard_splitters(cudaStream_t s, const float* xyz_first_scan, u32 n_first_scan, const MapParams& mp, u32 world, u32 first_share_256,
-                           u64* keys_a, u32* vals_a, u64* keys_b, u32* vals_b, u32* d_scalars, const RadixWorkspace& rws, int num_sms,
                            u64* splitters) {
-    const u32 stride = n_first_scan > (1u << 18) ? 16u : 8u;
-    const u32 ns = (n_first_scan + stride - 1) / stride;
-    int launches = 0;
-    if (ns) {
-        shard_sample_kernel<<<blocks_for(ns), PT_THREADS, 0, s>>>(xyz_first_scan, n_first_scan, stride, mp.recip, keys_a, d_scalars, d_scalars + 1);
-        launches++;
-        launches += radix_sort_pairs(s, keys_a, vals_a, keys_b, vals_b, d_scalars, d_scalars + 1, ns, 7, rws, num_sms);
-    } else {
-        cudaMemsetAsync(d_scalars, 0, 8, s);
-    }
-    shard_splitters_kernel<<<1, 32, 0, s>>>(keys_a, keys_b, d_scalars, world, first_share_256, splitters);
-    return launches + 1;
+    shard_splitters_kernel<<<1, SH_SCAN_THREADS, 0, s>>>(xyz_first_scan, n_first_scan, mp.recip, world, first_share_256, splitters);
+    return 1;
 }
 
 // plan + ownership filter of a batch: replaces launch_plan + launch_point_keys of the single-GPU point stage
@@ -246,13 +246,13 @@ int launch_shard_filter(cudaStream_t s, const float* xyz, u32 n_points, u32 n_sc
     const u32 n_tiles = blocks_for(n_points);
     if (n_points) {
         shard_count_kernel<<<n_tiles, PT_THREADS, 0, s>>>(xyz, n_points, scans, n_scans, mp.recip, plan, splitters, rank, world, f.tile_cnt, f.scan_own,
-                                                         f.scan_lower);
+                                                         f.scan_lower, f.own_bits);
         launches++;
     }
     shard_plan_kernel<<<1, SH_SCAN_THREADS, 0, s>>>(plan, mp.band_margin, tsb, gbits, scans, n_scans, f.tile_cnt, n_tiles, f.scan_own, f.scan_lower, own_scans);
     launches++;
     if (n_points) {
-        shard_scatter_kernel<<<n_tiles, PT_THREADS, 0, s>>>(xyz, n_points, scans, mp.recip, plan, splitters, rank, world, f.tile_cnt, sortkeys, index);
+        shard_scatter_kernel<<<n_tiles, PT_THREADS, 0, s>>>(xyz, n_points, scans, mp.recip, plan, f.own_bits, f.tile_cnt, sortkeys, index);
         launches++;
     }
     return launches;

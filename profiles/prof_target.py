@@ -1,5 +1,6 @@
-"""Profiling target for ncu: one submap of the bench workload (21 scans of cfg1, batches of 16 + 5) followed
-by Submap::finalize, run twice in-process (first run = warm-up). Usage: python profiles/prof_target.py [scans]"""
+"""Profiling target for ncu: one submap of the bench workload (21 scans of cfg1 = ONE batch at the library's default of 24 scans per
+batch, i.e. the batch shape bench.py times) followed by Submap::finalize, run twice in-process (first run = warm-up).
+Usage: python profiles/prof_target.py [scans] [max_batch_scans]"""
 import os
 import sys
 
@@ -11,7 +12,7 @@ from chad_tsdf_b200 import TSDFMap, synth  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 21
 w = synth.WORKLOADS["cfg1_traj100_128beam"]
 scans = [w.scan(s) for s in range(n)]
-m = TSDFMap(w.sdf_res, w.sdf_trunc, max_batch_scans=16)
+m = TSDFMap(w.sdf_res, w.sdf_trunc, max_batch_scans=int(sys.argv[2]) if len(sys.argv) > 2 else 24)
 for rep in range(2):
     m.reset()
     m.reset_stats()

@@ -63,7 +63,7 @@ def test_a_restored_map_continues_like_an_uninterrupted_one(chad_lib, oracle_lib
     for x, y in zip(b.voxels(), o.voxels()):
         assert np.array_equal(x, y)
     b.finalize_active(); o.finalize_active()
-    assert b.roots() == o.roots() and len(b.roots()) >= 4
+    assert b.roots() == o.roots() and len(b.roots()) >= 3
     for lv in range(21):
         ga, gu, gd = b.level(lv)
         oa, ou, od = o.level(lv)
