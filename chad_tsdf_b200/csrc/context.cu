@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cstdint>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -95,7 +96,7 @@ struct chad_ctx {
     BatchPlan* h_plan = nullptr;  // pinned BatchPlan[MAX_SLOTS]
     int plan_slot = 0;            // slot of the batch being assembled
     int n_slots = 2;              // slots in use: 2, or 3 with overlap_walk (a batch's walk, descriptor sort and fold then span two point stages)
-    struct PendingFold { int slot; bool runs; u32 max_pairs; bool close; };
+    struct PendingFold { int slot; bool runs; u32 max_pairs; bool close; u64 close_index; };
     PendingFold pend[MAX_SLOTS];  // batches whose front is queued but whose fold is not (oldest first): the fold needs the batch's block
     int n_pend = 0;               // count on the host (table sizing), so it is launched as soon as the front's read-back has arrived --
                                   // by any later API call that finds it there, at the latest when the batch's plan slot is needed again
@@ -185,12 +186,14 @@ struct chad_ctx {
         DevBuf scalars;                 // u32: [0..1] sample sort (n, nbits) | [8] own chunk count | [16 .. 16 + world) all chunk counts
         u32* h_counts = nullptr;        // pinned [SHARD_WORLD_MAX]: chunk counts of the submap being closed
         cudaEvent_t counts_done = nullptr;
-        // The gather of a closed submap's chunks is issued at a point of the call sequence that is the same on every rank (the
-        // n_slots-th batch after the closing one, the next submap switch, or a flush -- whichever comes first), never from a poll: an
+        // The gather of a closed submap's chunks is issued at a point of the BATCH sequence that is the same on every rank (in front of
+        // the n_slots-th batch after the closing one, or at a flush -- whichever comes first), never from a poll: every rank has then
+        // issued the same batch exchanges, so the two kinds of transfer meet in the same order everywhere. Reason: an
         // NCCL kernel that waits on the device for a peer whose HOST has not got there yet blocks this rank's other NCCL traffic, and the
         // peer's host may be waiting for exactly that traffic.
-        bool gather_pending = false;
-        int gather_countdown = 0;
+        std::deque<u64> gather_at;      // per closed, not yet gathered submap: the batch (sequence number) in front of which its gather is issued
+        u64 front_seq = 0;              // batches queued so far
+        u64 closes_marked = 0, closes_gathered = 0;
         bool xfer_pending = false;      // counts_done marks the end of this rank's gather transfers: the next exchange waits for it
         u32* h_roots = nullptr;         // pinned staging of the root broadcast
         size_t roots_synced = 0;        // submaps whose roots this rank knows (rank 0: has broadcast)
@@ -487,6 +490,15 @@ int complete_one_fold(chad_ctx* ctx, bool block, bool* launched) {
         trace(ctx, "wait: front of slot %d", slot);
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->front_done[slot]));
     }
+    if (pf.close && ctx->sh.world > 1) {
+        // this fold ends a submap, i.e. swaps the tables: the submap closed BEFORE must have left the spare table, which its gather does.
+        // From a poll the fold simply waits for it; the blocking callers sit at fixed points of the batch sequence, where the gather
+        // may be issued (see Shard::gather_at)
+        while (ctx->sh.closes_gathered + 1 < pf.close_index) {
+            if (!block) return CHAD_OK;
+            TRY(shard_gather_now(ctx));
+        }
+    }
     for (int q = 0; q + 1 < ctx->n_pend; q++) ctx->pend[q] = ctx->pend[q + 1];
     ctx->n_pend--;
     *launched = true;
@@ -673,7 +685,8 @@ int process_front(chad_ctx* ctx) {
     // (which follows its ray walk and its descriptor sort) must have been launched ...
     while (ctx->n_pend && ctx->pend[0].slot == slot) { bool launched; TRY(complete_one_fold(ctx, true, &launched)); }
     if (ctx->n_pend == ctx->n_slots) { bool launched; TRY(complete_one_fold(ctx, true, &launched)); }
-    if (ctx->sh.gather_pending && --ctx->sh.gather_countdown <= 0) TRY(shard_gather_now(ctx));  // the closing batch's fold has been launched by now
+    // the gathers due in front of this batch (the closing batch's fold has been launched by now: it used this slot, or an older one)
+    while (!ctx->sh.gather_at.empty() && ctx->sh.gather_at.front() <= ctx->sh.front_seq) TRY(shard_gather_now(ctx));
     // ... and the device waits for it (on fold_stream) before touching the slot
     if (ctx->fold_done_valid[slot]) CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->fold_done[slot], 0));
     if (ctx->scans_uploaded_valid[b]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->scans_uploaded[b]));  // (two batches ago: long done)
@@ -760,7 +773,8 @@ int process_front(chad_ctx* ctx) {
     ctx->stats.kernel_launches += launches;
     ctx->stats.batches++;
     ctx->burst_batches++;
-    ctx->pend[ctx->n_pend++] = chad_ctx::PendingFold{slot, use_runs, (u32)max_pairs, false};
+    ctx->pend[ctx->n_pend++] = chad_ctx::PendingFold{slot, use_runs, (u32)max_pairs, false, 0};
+    ctx->sh.front_seq++;
     ctx->plan_slot = (ctx->plan_slot + 1) % ctx->n_slots;
     ctx->cur ^= 1;
     ctx->batch_points = 0;
@@ -774,7 +788,7 @@ int drain(chad_ctx* ctx) {
     trace(ctx, "drain (%d folds pending, finalize state %d)", ctx->n_pend, ctx->fin_state);
     TRY(process_front(ctx));
     TRY(complete_pending_fold(ctx));
-    if (ctx->sh.gather_pending) TRY(shard_gather_now(ctx));
+    while (!ctx->sh.gather_at.empty()) TRY(shard_gather_now(ctx));
     if (ctx->fin_state == chad_ctx::FIN_PART1) {  // let part 2 of an in-flight finalize overlap the tail of the compute stream
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->fin_p1_done));
         TRY(finalize_part2(ctx));
@@ -1057,7 +1071,7 @@ int finalize_part2(chad_ctx* ctx) {
     return finalize_tail(ctx, !ctx->fin_external);
 }
 
-// sharded, at the gather point of a closed submap (see Shard::gather_pending). The ranges ascend with the rank, so the concatenation of the ranks' sorted chunks in
+// sharded, at the gather point of a closed submap (see Shard::gather_at). The ranges ascend with the rank, so the concatenation of the ranks' sorted chunks in
 // rank order is the submap's chunk stream in ascending Morton order (submap.hpp:10-106 walks the octree in that order): every rank
 // sorts its chunks and sends them to rank 0, which receives them behind its own and runs the DAG stage; the two root addresses
 // (submap.hpp:108-109) reach the other ranks at the next flush.
@@ -1085,7 +1099,8 @@ int finalize_gather(chad_ctx* ctx) {
         CUDA_TRY(ctx, cudaStreamSynchronize(fs));
         ctx->stats.kernel_launches += 1;
     }
-    sh.gather_pending = false;
+    sh.gather_at.pop_front();
+    sh.closes_gathered++;
     u64 total = 0;
     u64 offset[SHARD_WORLD_MAX + 1];
     for (int g = 0; g < sh.world; g++) { offset[g] = total; total += sh.h_counts[g]; }
@@ -1194,34 +1209,30 @@ int finalize_finish(chad_ctx* ctx) {
 // Close the active submap. lazy = true (submap switch inside insert): if a batch of the submap is still in flight, only
 // mark it; its fold and the finalize are queued by the next process_front / drain, so the host never waits for the
 // device here. lazy = false (chad_finalize_active): queue everything now.
-int shard_gather_now(chad_ctx* ctx);
 int finalize_submap(chad_ctx* ctx, bool lazy) {
-    if (ctx->sh.gather_pending) TRY(shard_gather_now(ctx));  // (a submap shorter than n_slots batches: its gather point is the next switch)
     TRY(process_front(ctx));
-    if (ctx->sh.world > 1) { ctx->sh.gather_pending = true; ctx->sh.gather_countdown = ctx->n_slots; }
+    const u64 close_index = ++ctx->sh.closes_marked;
+    if (ctx->sh.world > 1) ctx->sh.gather_at.push_back(ctx->sh.front_seq - 1 + (u64)ctx->n_slots);  // the closing batch is number front_seq - 1
     ctx->sh.need_splitters = true;  // (sharded) the next submap's ranges follow its own first scan
     ctx->positions.push_back(std::move(ctx->active_positions));  // closing order == the order the roots arrive in
     ctx->active_positions.clear();
     if (ctx->n_pend) {
         ctx->pend[ctx->n_pend - 1].close = true;  // the submap's last batch: the finalize begins right after its fold
+        ctx->pend[ctx->n_pend - 1].close_index = close_index;
         if (lazy) return CHAD_OK;
         return complete_pending_fold(ctx);  // waits for the front of the last batch, queues its fold, begins the finalize
     }
     // every fold of the submap has been launched already: the copy of the table counter that followed the last one is in flight on
     // that fold's stream (or has arrived); the finalize is queued when it is there -- no host wait here either
+    while (ctx->sh.world > 1 && ctx->sh.closes_gathered + 1 < close_index) TRY(shard_gather_now(ctx));  // (the tables are about to be swapped)
     TRY(finalize_begin(ctx, 0, false, ctx->last_fold_stream ? ctx->last_fold_stream : ctx->stream));
     ctx->stats.resident_clusters = 0;
     return CHAD_OK;
 }
 
-// the gather point of the closed submap: its last fold must have been launched (which begins the finalize: tables swapped, count copy
-// queued); then every rank exchanges counts and chunks (finalize_gather)
+// the gather of the oldest closed submap: its last fold has been launched (which began the finalize: tables swapped, count copy queued)
 int shard_gather_now(chad_ctx* ctx) {
-    if (ctx->fin_state == chad_ctx::FIN_IDLE || ctx->fin_state == chad_ctx::FIN_PART2) {
-        // the closing batch's fold is still pending (the finalize of the submap BEFORE may be in flight: finalize_begin waits for it)
-        TRY(complete_pending_fold(ctx));
-    }
-    if (ctx->fin_state != chad_ctx::FIN_PART1) return fail(ctx, CHAD_ERR_INVALID, "internal: no closed submap at a gather point");
+    if (ctx->sh.gather_at.empty() || ctx->fin_state != chad_ctx::FIN_PART1) return fail(ctx, CHAD_ERR_INVALID, "internal: no closed submap at a gather point");
     return finalize_gather(ctx);
 }
 
@@ -1794,7 +1805,8 @@ int chad_reset(chad_ctx* ctx) {
     ctx->n_pend = 0;
     for (bool& f : ctx->fold_stats_pending) f = false;
     ctx->sh.need_splitters = true;
-    ctx->sh.gather_pending = false;
+    ctx->sh.gather_at.clear();
+    ctx->sh.front_seq = ctx->sh.closes_marked = ctx->sh.closes_gathered = 0;
     ctx->sh.xfer_pending = false;
     ctx->sh.roots_synced = 0;
     ctx->burst_batches = 0;

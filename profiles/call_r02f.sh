@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call f (2 GPUs): sharded map with device-side ordering of gather vs exchange, one-kernel splitters, sparse scatter
-TAG=${1:-r02f}
+TAG=${1:-r02g}
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_sharded.py tests/test_gpu_readers.py -m gpu -q -k "world2 or readers or two_gpus" > gpurun_out/t_${TAG}.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/t_${TAG}.log
 for share in 256 176; do
