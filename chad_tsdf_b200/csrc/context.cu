@@ -1442,7 +1442,7 @@ static int create_impl(float sdf_res, float sdf_trunc, int device, int max_batch
         r = dev_ensure(ctx, sh.splitters, 2 * (SHARD_WORLD_MAX + 1) * sizeof(u64));
         for (int q = 0; q < MAX_SLOTS; q++) if (r == CHAD_OK) r = dev_ensure(ctx, sh.batch_scans[q], sizeof(BatchScans));
         if (r == CHAD_OK) r = dev_ensure(ctx, sh.scalars, 256);
-        size_t box_mb = 4;
+        size_t box_mb = world <= 2 ? 4 : (world <= 4 ? 2 : 1);  // the boundary a pair of ranks shares shrinks as the ranges do
         if (const char* env = std::getenv("CHAD_SHARD_BOX_MB")) { const long v = std::atol(env); if (v >= 1 && v <= 1024) box_mb = (size_t)v; }
         sh.box_words = (u32)(box_mb * (1u << 20) / 8);
         if (r == CHAD_OK) r = dev_ensure(ctx, sh.box_out, size_t(world) * sh.box_words * 8);

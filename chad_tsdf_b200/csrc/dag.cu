@@ -166,7 +166,8 @@ __device__ __forceinline__ u32 node_tag(const u32* __restrict__ rec) {
 // and nothing waits for the host. Once a level has few children left, CTA 0 finishes the remaining levels alone.
 // ------------------------------------------------------------------------------------------
 constexpr int LV_THREADS = 1024;
-constexpr u32 LV_SOLO = 8192;  // children from which one CTA takes over
+constexpr u32 LV_SOLO = 1024;  // children from which one CTA takes over (sweep r02h / r02i: 131 072 / 32 768 / 8 192 / 2 048 / 512 -> 6.4 / 6.4 / 4.8 / 4.2 / 3.9 ms of
+                               // finalize per bench step: the one-block tail is the slow part, the grid barriers are cheap)
 
 __device__ __forceinline__ void grid_barrier(u32* bar, u32& phase, u32 nctas) {
     __syncthreads();

@@ -683,9 +683,9 @@ cudaError_t runs_init() {
     int per_sm = 0;  // the fold is persistent (blocks are handed out by ticket): launch exactly what is resident
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, runs_fold_kernel, RF_THREADS, 0);
     if (e != cudaSuccess) return e;
-    // ... but not more than 3 CTAs (12 warps) per SM: at 64 registers per thread the 7 that fit would take 57 k of the SM's 64 k registers
+    // ... but not more than 4 CTAs (16 warps) per SM: at 64 registers per thread the 7 that fit would take 57 k of the SM's 64 k registers
     // and the next batch's front, which runs concurrently on the main stream, could not place a single CTA beside them
-    g_fold_ctas_per_sm = per_sm > 3 ? 3 : (per_sm > 0 ? per_sm : 1);
+    g_fold_ctas_per_sm = per_sm > 4 ? 4 : (per_sm > 0 ? per_sm : 1);  // (round 2 sweep, profiles/sweep_r02h.md: 2 / 3 / 4 / 5 CTAs -> 9.41 / 9.31 / 9.15 / 9.11 ms per step)
     if (const char* e = std::getenv("CHAD_FOLD_CTAS")) { const int v = std::atoi(e); if (v >= 1 && v <= per_sm) g_fold_ctas_per_sm = v; }
     return cudaSuccess;
 }
