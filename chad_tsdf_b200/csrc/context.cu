@@ -194,6 +194,12 @@ struct chad_ctx {
         std::deque<u64> gather_at;      // per closed, not yet gathered submap: the batch (sequence number) in front of which its gather is issued
         u64 front_seq = 0;              // batches queued so far
         u64 closes_marked = 0, closes_gathered = 0;
+        // A close = table swap + begin of the finalize. It needs the spare table back (the gather of the submap closed before) and the
+        // finalize work buffers (the finalize before finished). A sharded rank never makes a poll wait for either: the closing batch's
+        // fold is launched at once, the close itself is deferred until it can go through -- at the latest in front of the next fold.
+        bool close_deferred = false;
+        u64 deferred_index = 0;
+        cudaStream_t deferred_count_stream = nullptr;
         bool xfer_pending = false;      // counts_done marks the end of this rank's gather transfers: the next exchange waits for it
         u32* h_roots = nullptr;         // pinned staging of the root broadcast
         size_t roots_synced = 0;        // submaps whose roots this rank knows (rank 0: has broadcast)
@@ -456,6 +462,9 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
 
 int finalize_begin(chad_ctx* ctx, u32 max_chunks, bool external, cudaStream_t count_stream);
 int shard_gather_now(chad_ctx* ctx);
+int try_deferred_close(chad_ctx* ctx, bool block);
+int finalize_poll(chad_ctx* ctx);
+int finalize_wait(chad_ctx* ctx);
 
 // device mirror of the node levels' counters: NodeLevel's constructor reserves index 0 (levels.hpp:52-54)
 int level_counters_reset(chad_ctx* ctx) {
@@ -490,14 +499,9 @@ int complete_one_fold(chad_ctx* ctx, bool block, bool* launched) {
         trace(ctx, "wait: front of slot %d", slot);
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->front_done[slot]));
     }
-    if (pf.close && ctx->sh.world > 1) {
-        // this fold ends a submap, i.e. swaps the tables: the submap closed BEFORE must have left the spare table, which its gather does.
-        // From a poll the fold simply waits for it; the blocking callers sit at fixed points of the batch sequence, where the gather
-        // may be issued (see Shard::gather_at)
-        while (ctx->sh.closes_gathered + 1 < pf.close_index) {
-            if (!block) return CHAD_OK;
-            TRY(shard_gather_now(ctx));
-        }
+    if (ctx->sh.close_deferred) {  // this fold goes into the NEXT submap's table: the swap must have happened
+        TRY(try_deferred_close(ctx, block));
+        if (ctx->sh.close_deferred) return CHAD_OK;  // (from a poll: not yet possible; the fold waits)
     }
     for (int q = 0; q + 1 < ctx->n_pend; q++) ctx->pend[q] = ctx->pend[q + 1];
     ctx->n_pend--;
@@ -563,10 +567,35 @@ int complete_one_fold(chad_ctx* ctx, bool block, bool* launched) {
     CUDA_TRY(ctx, cudaGetLastError());
     if (pf.close) {  // that was the submap's last batch: swap tables and start its asynchronous finalize
         if (count_bound >= (1ull << 31)) return fail(ctx, CHAD_ERR_CAPACITY, "submap exceeds 2^31 leaf chunks");
-        TRY(finalize_begin(ctx, 0, false, fold_on));
+        if (ctx->sh.world > 1) {
+            ctx->sh.close_deferred = true;
+            ctx->sh.deferred_index = pf.close_index;
+            ctx->sh.deferred_count_stream = fold_on;
+            TRY(try_deferred_close(ctx, false));
+        } else {
+            TRY(finalize_begin(ctx, 0, false, fold_on));
+        }
         ctx->stats.resident_clusters = 0;
     }
     return CHAD_OK;
+}
+
+// sharded: perform the deferred close if it can go through (block = false), or make it go through (block = true: only from the fixed
+// points of the batch sequence, where a gather may be issued)
+int try_deferred_close(chad_ctx* ctx, bool block) {
+    chad_ctx::Shard& sh = ctx->sh;
+    if (!sh.close_deferred) return CHAD_OK;
+    while (sh.closes_gathered + 1 < sh.deferred_index) {  // the submap closed before still sits in the spare table
+        if (!block) return CHAD_OK;
+        TRY(shard_gather_now(ctx));
+    }
+    TRY(finalize_poll(ctx));
+    if (ctx->fin_state != chad_ctx::FIN_IDLE) {  // the finalize before still uses the work buffers
+        if (!block) return CHAD_OK;
+        TRY(finalize_wait(ctx));
+    }
+    sh.close_deferred = false;
+    return finalize_begin(ctx, 0, false, sh.deferred_count_stream);
 }
 
 // every pending fold, waiting for the fronts
@@ -788,7 +817,10 @@ int drain(chad_ctx* ctx) {
     trace(ctx, "drain (%d folds pending, finalize state %d)", ctx->n_pend, ctx->fin_state);
     TRY(process_front(ctx));
     TRY(complete_pending_fold(ctx));
-    while (!ctx->sh.gather_at.empty()) TRY(shard_gather_now(ctx));
+    while (!ctx->sh.gather_at.empty() || ctx->sh.close_deferred) {
+        if (ctx->sh.close_deferred) TRY(try_deferred_close(ctx, true));
+        if (!ctx->sh.gather_at.empty()) TRY(shard_gather_now(ctx));
+    }
     if (ctx->fin_state == chad_ctx::FIN_PART1) {  // let part 2 of an in-flight finalize overlap the tail of the compute stream
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->fin_p1_done));
         TRY(finalize_part2(ctx));
@@ -1224,6 +1256,7 @@ int finalize_submap(chad_ctx* ctx, bool lazy) {
     }
     // every fold of the submap has been launched already: the copy of the table counter that followed the last one is in flight on
     // that fold's stream (or has arrived); the finalize is queued when it is there -- no host wait here either
+    if (ctx->sh.close_deferred) TRY(try_deferred_close(ctx, true));
     while (ctx->sh.world > 1 && ctx->sh.closes_gathered + 1 < close_index) TRY(shard_gather_now(ctx));  // (the tables are about to be swapped)
     TRY(finalize_begin(ctx, 0, false, ctx->last_fold_stream ? ctx->last_fold_stream : ctx->stream));
     ctx->stats.resident_clusters = 0;
@@ -1232,6 +1265,7 @@ int finalize_submap(chad_ctx* ctx, bool lazy) {
 
 // the gather of the oldest closed submap: its last fold has been launched (which began the finalize: tables swapped, count copy queued)
 int shard_gather_now(chad_ctx* ctx) {
+    if (ctx->sh.close_deferred && ctx->sh.deferred_index == ctx->sh.closes_gathered + 1) TRY(try_deferred_close(ctx, true));  // (it IS the oldest ungathered close)
     if (ctx->sh.gather_at.empty() || ctx->fin_state != chad_ctx::FIN_PART1) return fail(ctx, CHAD_ERR_INVALID, "internal: no closed submap at a gather point");
     return finalize_gather(ctx);
 }
@@ -1806,6 +1840,7 @@ int chad_reset(chad_ctx* ctx) {
     for (bool& f : ctx->fold_stats_pending) f = false;
     ctx->sh.need_splitters = true;
     ctx->sh.gather_at.clear();
+    ctx->sh.close_deferred = false;
     ctx->sh.front_seq = ctx->sh.closes_marked = ctx->sh.closes_gathered = 0;
     ctx->sh.xfer_pending = false;
     ctx->sh.roots_synced = 0;
