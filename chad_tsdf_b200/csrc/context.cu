@@ -194,9 +194,14 @@ struct chad_ctx {
         std::deque<u64> gather_at;      // per closed, not yet gathered submap: the batch (sequence number) in front of which its gather is issued
         u64 front_seq = 0;              // batches queued so far
         u64 closes_marked = 0, closes_gathered = 0;
-        // A close = table swap + begin of the finalize. It needs the spare table back (the gather of the submap closed before) and the
-        // finalize work buffers (the finalize before finished). A sharded rank never makes a poll wait for either: the closing batch's
-        // fold is launched at once, the close itself is deferred until it can go through -- at the latest in front of the next fold.
+        // A close = table swap. It needs the spare table back, i.e. the gather of the submap closed before must have been issued. A
+        // sharded rank never makes a poll wait for that: the closing batch's fold is launched at once, the close itself is deferred until
+        // it can go through -- at the latest in front of the next fold.
+        bool closed_waiting = false;    // the spare table holds a closed submap whose gather has not been issued yet. (On a sharded rank this is
+                                        // NOT ctx->fin_state: the DAG stage of the submap closed before may still be running on rank 0 while
+                                        // the next submap closes -- only the gather of submap j + 1 waits for the finalize of submap j)
+        cudaEvent_t table_free = nullptr;  // the closed submap's chunks have left the spare table and it has been cleared (finalize stream)
+        bool table_free_valid = false;
         bool close_deferred = false;
         u64 deferred_index = 0;
         cudaStream_t deferred_count_stream = nullptr;
@@ -588,11 +593,6 @@ int try_deferred_close(chad_ctx* ctx, bool block) {
     while (sh.closes_gathered + 1 < sh.deferred_index) {  // the submap closed before still sits in the spare table
         if (!block) return CHAD_OK;
         TRY(shard_gather_now(ctx));
-    }
-    TRY(finalize_poll(ctx));
-    if (ctx->fin_state != chad_ctx::FIN_IDLE) {  // the finalize before still uses the work buffers
-        if (!block) return CHAD_OK;
-        TRY(finalize_wait(ctx));
     }
     sh.close_deferred = false;
     return finalize_begin(ctx, 0, false, sh.deferred_count_stream);
@@ -997,7 +997,18 @@ int finalize_wait(chad_ctx* ctx) {
 // external = true (sharded mode): f_ids[0] / f_cells already hold `max_chunks` globally sorted chunks.
 int finalize_begin(chad_ctx* ctx, u32 max_chunks, bool external, cudaStream_t count_stream) {
     trace(ctx, "finalize_begin (previous finalize in state %d)", ctx->fin_state);
-    TRY(finalize_wait(ctx));  // one finalize in flight at a time
+    const bool sharded = ctx->sh.world > 1 && !external;
+    if (sharded) {
+        // the spare table is free as soon as the submap closed before has been gathered out of it (device: table_free); its DAG stage may
+        // still be running -- it works on the gathered chunk stream
+        if (ctx->sh.closed_waiting) return fail(ctx, CHAD_ERR_INVALID, "internal: close while the spare table still holds a closed submap");
+        if (ctx->sh.table_free_valid) {
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->fold_stream, ctx->sh.table_free, 0));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->sh.table_free, 0));
+        }
+    } else {
+        TRY(finalize_wait(ctx));  // one finalize in flight at a time
+    }
     cudaStream_t fs = ctx->fin_stream;
     CUDA_TRY(ctx, cudaEventRecord(ctx->submap_closed, ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(fs, ctx->submap_closed, 0));
@@ -1020,6 +1031,7 @@ int finalize_begin(chad_ctx* ctx, u32 max_chunks, bool external, cudaStream_t co
     ctx->table_count_known = 0;
     fold_bounds_reset(ctx);
     CUDA_TRY(ctx, cudaEventRecord(ctx->fin_p1_done, count_stream));
+    if (sharded) { ctx->sh.closed_waiting = true; return CHAD_OK; }
     ctx->fin_state = chad_ctx::FIN_PART1;
     return CHAD_OK;
 }
@@ -1112,7 +1124,8 @@ int finalize_gather(chad_ctx* ctx) {
     chad_ctx::Shard& sh = ctx->sh;
     {   // every rank's chunk count (the sizes of the gather must be known on the host). Blocking, but every rank is at the same point of
         // its call sequence: nobody waits for more than the others' skew
-        if (ctx->fin_state != chad_ctx::FIN_PART1) return fail(ctx, CHAD_ERR_INVALID, "internal: gather without a closed submap");
+        if (!sh.closed_waiting) return fail(ctx, CHAD_ERR_INVALID, "internal: gather without a closed submap");
+        TRY(finalize_wait(ctx));  // the DAG stage of the submap before: its work buffers and the host mirrors of the level counters are needed now
         // An NCCL kernel spins on the device until its peer kernel runs, and CUDA maps streams onto a limited number of hardware queues
         // (CUDA_DEVICE_MAX_CONNECTIONS), so a spinning kernel can hold back kernels submitted LATER to other streams. With two
         // communicators that can close a cycle: A's receive waits for B's send, queued behind B's next batch exchange, which waits for A's
@@ -1133,6 +1146,13 @@ int finalize_gather(chad_ctx* ctx) {
     }
     sh.gather_at.pop_front();
     sh.closes_gathered++;
+    sh.closed_waiting = false;
+    auto release_table = [&]() -> int {  // octree.clear(), tsdf.cpp:57 -- as soon as the chunks are out, so that the next close can swap
+        launch_table_clear(fs, ctx->table2);
+        CUDA_TRY(ctx, cudaEventRecord(sh.table_free, fs));
+        sh.table_free_valid = true;
+        return CHAD_OK;
+    };
     u64 total = 0;
     u64 offset[SHARD_WORLD_MAX + 1];
     for (int g = 0; g < sh.world; g++) { offset[g] = total; total += sh.h_counts[g]; }
@@ -1142,6 +1162,7 @@ int finalize_gather(chad_ctx* ctx) {
     if (sh.rank == 0) {
         TRY(finalize_dag(ctx, (u32)total, true, [&]() -> int {
             if (own) TRY(queue_sorted_chunks(ctx, fs, ctx->table2, own));
+            TRY(release_table());
             bool any = false;
             for (int g = 1; g < sh.world; g++) any |= sh.h_counts[g] != 0;
             if (any) {
@@ -1165,8 +1186,9 @@ int finalize_gather(chad_ctx* ctx) {
         TRY(ensure_finalize_capacity(ctx, own));
         if (ctx->profiling) cudaEventRecord(ctx->fin_t0, fs);
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->f_scalars.p, 0, 256, fs));
+        if (own) TRY(queue_sorted_chunks(ctx, fs, ctx->table2, own));
+        TRY(release_table());
         if (own) {
-            TRY(queue_sorted_chunks(ctx, fs, ctx->table2, own));
             NCCL_TRY(ctx, sh.nccl->GroupStart());
             NCCL_TRY(ctx, sh.nccl->Send(ctx->f_ids[0].p, own, ncclUint64, 0, sh.comm_f, fs));
             NCCL_TRY(ctx, sh.nccl->Send(ctx->f_cells.p, size_t(own) * 8, ncclUint64, 0, sh.comm_f, fs));
@@ -1178,7 +1200,7 @@ int finalize_gather(chad_ctx* ctx) {
     }
     // (the roots reach the other ranks at the next flush: shard_sync_roots)
     trace(ctx, "finalize: gather + DAG stage queued");
-    return finalize_tail(ctx, true);
+    return finalize_tail(ctx, false);
 }
 
 // sharded, collective (chad_flush / chad_finalize_active): the roots of the submaps closed since the last flush, from rank 0 to all
@@ -1266,7 +1288,7 @@ int finalize_submap(chad_ctx* ctx, bool lazy) {
 // the gather of the oldest closed submap: its last fold has been launched (which began the finalize: tables swapped, count copy queued)
 int shard_gather_now(chad_ctx* ctx) {
     if (ctx->sh.close_deferred && ctx->sh.deferred_index == ctx->sh.closes_gathered + 1) TRY(try_deferred_close(ctx, true));  // (it IS the oldest ungathered close)
-    if (ctx->sh.gather_at.empty() || ctx->fin_state != chad_ctx::FIN_PART1) return fail(ctx, CHAD_ERR_INVALID, "internal: no closed submap at a gather point");
+    if (ctx->sh.gather_at.empty() || !ctx->sh.closed_waiting) return fail(ctx, CHAD_ERR_INVALID, "internal: no closed submap at a gather point");
     return finalize_gather(ctx);
 }
 
@@ -1487,6 +1509,7 @@ static int create_impl(float sdf_res, float sdf_trunc, int device, int max_batch
         CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&sh.h_counts), SHARD_WORLD_MAX * sizeof(u32)));
         CREATE_TRY(cudaMallocHost(reinterpret_cast<void**>(&sh.h_roots), 4096 * 2 * sizeof(u32)));
         CREATE_TRY(cudaEventCreateWithFlags(&sh.counts_done, cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&sh.table_free, cudaEventDisableTiming));
         if (const char* env = std::getenv("CHAD_SHARD_RANK0_SHARE")) { const int v = std::atoi(env); if (v >= 0 && v <= 256) sh.first_share_256 = (u32)v; }
         // two communicators: the per-batch exchange (group stream) and the per-submap gather (finalize stream) are queued from points of
         // the host code that are not ordered against each other, and NCCL wants one issue order per communicator
@@ -1590,6 +1613,7 @@ void chad_destroy(chad_ctx* ctx) {
         if (ctx->sh.h_counts) cudaFreeHost(ctx->sh.h_counts);
         if (ctx->sh.h_roots) cudaFreeHost(ctx->sh.h_roots);
         if (ctx->sh.counts_done) cudaEventDestroy(ctx->sh.counts_done);
+        if (ctx->sh.table_free) cudaEventDestroy(ctx->sh.table_free);
     }
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
@@ -1841,6 +1865,8 @@ int chad_reset(chad_ctx* ctx) {
     ctx->sh.need_splitters = true;
     ctx->sh.gather_at.clear();
     ctx->sh.close_deferred = false;
+    ctx->sh.closed_waiting = false;
+    ctx->sh.table_free_valid = false;
     ctx->sh.front_seq = ctx->sh.closes_marked = ctx->sh.closes_gathered = 0;
     ctx->sh.xfer_pending = false;
     ctx->sh.roots_synced = 0;
