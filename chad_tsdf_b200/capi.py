@@ -15,7 +15,7 @@ from .build import LIB
 CHAD_OK = 0
 NUM_LEVELS = 21
 LEVEL_CLUSTERS = 20
-SHARD_ID_BYTES = 256
+SHARD_ID_BYTES = 512
 
 
 class ChadError(RuntimeError):

@@ -172,7 +172,10 @@ struct chad_ctx {
     struct Shard {
         int rank = 0, world = 1;
         const NcclApi* nccl = nullptr;
-        ncclComm_t comm_x = nullptr, comm_f = nullptr;
+        ncclComm_t comm_x = nullptr, comm_f = nullptr, comm_c = nullptr;
+        bool slice_h2d = true;          // a scan comes over the host link once, not once per rank: every rank copies 1 / world of it and the
+                                        // slices are all-gathered over NVLink (comm_c, copy stream). CHAD_SHARD_SLICE_H2D=0: every rank copies all
+        cudaEvent_t h2d_done = nullptr;
         DevBuf splitters;               // u64[2][SHARD_WORLD_MAX + 1]: range starts (block ids), two sets used alternately by the submaps
         int split_set = 0;              // set of the active submap
         int slot_split[MAX_SLOTS] = {}; // set a plan slot's batch was filtered with (its pack kernel runs later, on the group stream)
@@ -416,7 +419,7 @@ int ensure_batch_capacity(chad_ctx* ctx, size_t points) {
         if (ctx->h_stage[b]) CUDA_TRY(ctx, cudaFreeHost(ctx->h_stage[b]));
         CUDA_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_stage[b]), np * 12));
         ctx->stage_busy[b] = false;
-        TRY(dev_ensure(ctx, ctx->d_xyz[b], np * 12, true));
+        TRY(dev_ensure(ctx, ctx->d_xyz[b], np * 12 + 1024, true));  // (+ slack: the sharded all-gather of a scan rounds the slices up)
     }
     TRY(dev_ensure(ctx, ctx->pk_a, np * 8));
     TRY(dev_ensure(ctx, ctx->pk_b, np * 8));
@@ -1522,10 +1525,13 @@ static int create_impl(float sdf_res, float sdf_trunc, int device, int max_batch
         setenv("NCCL_RUNTIME_CONNECT", "0", 0);
         ncclResult_t n1 = nccl->CommInitRank(&sh.comm_x, world, ids[0], rank);
         ncclResult_t n2 = n1 == ncclSuccess ? nccl->CommInitRank(&sh.comm_f, world, ids[1], rank) : n1;
+        if (n1 == ncclSuccess && n2 == ncclSuccess) n2 = nccl->CommInitRank(&sh.comm_c, world, ids[2], rank);
         if (n1 != ncclSuccess || n2 != ncclSuccess) {
             ctx->error = std::string("ncclCommInitRank: ") + nccl->GetErrorString(n1 != ncclSuccess ? n1 : n2);
             return bail(CHAD_ERR_CUDA);
         }
+        CREATE_TRY(cudaEventCreateWithFlags(&sh.h2d_done, cudaEventDisableTiming));
+        if (const char* env = std::getenv("CHAD_SHARD_SLICE_H2D")) sh.slice_h2d = std::atoi(env) != 0;
         {
             auto warm = [&]() -> ncclResult_t {
                 ncclResult_t n;
@@ -1542,6 +1548,7 @@ static int create_impl(float sdf_res, float sdf_trunc, int device, int max_batch
                 }
                 if ((n = nccl->GroupEnd()) != ncclSuccess) return n;
                 if ((n = nccl->AllGather(d + 8, d + 16, 1, ncclUint32, sh.comm_f, st)) != ncclSuccess) return n;      // chunk counts
+                if ((n = nccl->AllGather(out, in, 1024, ncclFloat, sh.comm_c, st)) != ncclSuccess) return n;           // scan slices
                 if ((n = nccl->Broadcast(d, d, 2, ncclUint32, 0, sh.comm_f, st)) != ncclSuccess) return n;           // roots
                 if ((n = nccl->GroupStart()) != ncclSuccess) return n;                                               // chunk gather on rank 0
                 for (int g = 1; g < world; g++) {
@@ -1578,7 +1585,7 @@ int chad_shard_unique_id(void* id) {
     const NcclApi* nccl = nccl_api(&why);
     if (!nccl) return fail(nullptr, CHAD_ERR_CUDA, std::string("chad_shard_unique_id: ") + why);
     ncclUniqueId* ids = static_cast<ncclUniqueId*>(id);
-    for (int q = 0; q < 2; q++) {
+    for (int q = 0; q < 3; q++) {  // batch exchange, chunk gather, scan slices
         const ncclResult_t n = nccl->GetUniqueId(&ids[q]);
         if (n != ncclSuccess) return fail(nullptr, CHAD_ERR_CUDA, std::string("ncclGetUniqueId: ") + nccl->GetErrorString(n));
     }
@@ -1604,9 +1611,11 @@ void chad_destroy(chad_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->sh.world > 1) {
-        for (cudaStream_t st : {ctx->group_stream, ctx->fin_stream}) if (st) cudaStreamSynchronize(st);
+        for (cudaStream_t st : {ctx->group_stream, ctx->fin_stream, ctx->copy_stream}) if (st) cudaStreamSynchronize(st);
         if (ctx->sh.comm_x) ctx->sh.nccl->CommDestroy(ctx->sh.comm_x);
         if (ctx->sh.comm_f) ctx->sh.nccl->CommDestroy(ctx->sh.comm_f);
+        if (ctx->sh.comm_c) ctx->sh.nccl->CommDestroy(ctx->sh.comm_c);
+        if (ctx->sh.h2d_done) cudaEventDestroy(ctx->sh.h2d_done);
         for (DevBuf* b : {&ctx->sh.splitters, &ctx->sh.filter_mem, &ctx->sh.batch_scans[0], &ctx->sh.batch_scans[1], &ctx->sh.batch_scans[2], &ctx->sh.box_out,
                           &ctx->sh.box_in, &ctx->sh.scalars})
             dev_free(*b);
@@ -1673,6 +1682,38 @@ static int insert_host(chad_ctx* ctx, const float* xyz, size_t n, const float po
     TRY(guard_batch_buffer(ctx));
     const int b = ctx->cur;
     float* dst = ctx->d_xyz[b].as<float>() + size_t(ctx->batch_points) * 3;
+    if (ctx->sh.world > 1 && ctx->sh.slice_h2d && n >= 4096) {
+        // Sharded: every rank is handed the whole scan, but the host link is the scarce resource (N ranks x 3 MB per scan through one
+        // host's memory) and NVLink is not: this rank copies slice `rank` of the scan, the all-gather assembles the scan on every rank.
+        // Issued at every insert, i.e. at the same point of the call sequence on every rank. Slices are whole
+        // multiples of 4 floats; the gather may write up to 4 * world floats beyond the scan: into the next scan's place (filled later,
+        // in stream order) or the buffer's slack.
+        chad_ctx::Shard& sh = ctx->sh;
+        const size_t total = n * 3;
+        size_t c = (total + (size_t)sh.world - 1) / (size_t)sh.world;
+        c = (c + 3) & ~size_t(3);
+        const size_t lo = std::min(total, c * (size_t)sh.rank), hi = std::min(total, lo + c);
+        if (hi > lo) {
+            const float* src = xyz + lo;
+            if (!pinned) {
+                if (ctx->stage_busy[b] && ctx->batch_scans == 0) {
+                    CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_copied[b]));
+                    ctx->stage_busy[b] = false;
+                }
+                float* stage = ctx->h_stage[b] + size_t(ctx->batch_points) * 3 + lo;
+                std::memcpy(stage, src, (hi - lo) * 4);
+                src = stage;
+                ctx->stage_busy[b] = true;
+            }
+            CUDA_TRY(ctx, cudaMemcpyAsync(dst + lo, src, (hi - lo) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
+        CUDA_TRY(ctx, cudaEventRecord(sh.h2d_done, ctx->copy_stream));
+        NCCL_TRY(ctx, sh.nccl->AllGather(dst + c * (size_t)sh.rank, dst, c, ncclFloat, sh.comm_c, ctx->copy_stream));
+        ctx->stats.kernel_launches += 1;
+        if (pinned && wait_for_copy) CUDA_TRY(ctx, cudaEventSynchronize(sh.h2d_done));  // (the caller's buffer has been read; the gather runs on)
+        ctx->stats.h2d_bytes += (hi - lo) * 4;
+        return end_scan(ctx, n, position);
+    }
     if (pinned) {
         // page-locked caller memory: DMA straight from it. chad_insert waits for the copy, so the caller may reuse the buffer at once
         // (one 3 MB transfer at a time reaches 36-44 of the link's 55 GB/s on an idle GPU: profiles/h2d_probe.py); chad_insert_async

@@ -103,7 +103,7 @@ class CudaShardEngine:
 
 def create_sharded_map(sdf_res: float, sdf_trunc: float, device: int, group=None, max_batch_scans: int = 0):
     """Rank `dist.get_rank(group)` of ONE chad::TSDFMap cut into `world` Morton ranges (chad_create_sharded, include/chad_b200.h).
-    torch.distributed only carries the 256-byte communicator id from rank 0 to the others; every exchange of the map itself is issued
+    torch.distributed only carries the 512-byte communicator id from rank 0 to the others; every exchange of the map itself is issued
     by the C++ library (NCCL send / recv on its own streams)."""
     from .tsdf_map import TSDFMap
     rank, world = dist.get_rank(group), dist.get_world_size(group)

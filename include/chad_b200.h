@@ -204,7 +204,8 @@ int chad_timer_end(chad_ctx* ctx, float* milliseconds);
  * The reference has a single map object (one octree + one NodeLevels, /root/reference/include/chad/tsdf.hpp:166-170); here the map
  * is cut into `world` contiguous Morton ranges of 8x8x8-voxel blocks and rank g -- one context, one GPU, one host thread or
  * process -- holds the voxels of range g. EVERY rank makes the SAME sequence of calls with the SAME scans (chad_insert* /
- * chad_flush / chad_finalize_active / chad_reset): a rank sorts, estimates normals for and walks only the points of its own
+ * chad_flush / chad_finalize_active / chad_reset). A host scan crosses the host link once: each rank copies 1 / world of it and the
+ * slices are all-gathered over NVLink. A rank sorts, estimates normals for and walks only the points of its own
  * range; the few band voxels a ray adds beyond the range travel to their owner once per batch (NCCL send / recv of fixed-size
  * boxes, counts inside -- no host round trip); at a submap's close the ranks' sorted leaf chunks are gathered on rank 0, which
  * runs Submap::finalize (submap.hpp:10-106) and holds the DAG (chad_level_* / chad_export_level / chad_query_voxels: rank 0
@@ -213,7 +214,7 @@ int chad_timer_end(chad_ctx* ctx, float* milliseconds);
  *   chad_shard_unique_id   rank 0: fill `id` (CHAD_SHARD_ID_BYTES) and hand it to every rank by any means (file, MPI, torch.distributed)
  *   chad_create_sharded    collective: every rank calls it with the same id; world == 1 is chad_create
  *   chad_shard_info        rank / world and what this rank has sent to the others so far (runs, 8-byte update records, exchanges) */
-#define CHAD_SHARD_ID_BYTES 256
+#define CHAD_SHARD_ID_BYTES 512
 int chad_shard_unique_id(void* id);
 int chad_create_sharded(float sdf_res, float sdf_trunc, int device, int max_batch_scans, int rank, int world, const void* id, chad_ctx** out);
 int chad_shard_info(chad_ctx* ctx, int* rank, int* world, uint64_t* sent_runs, uint64_t* sent_records, uint64_t* exchanges);
