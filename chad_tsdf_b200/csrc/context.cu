@@ -1111,6 +1111,7 @@ int finalize_part2(chad_ctx* ctx) {
     cudaStream_t fs = ctx->fin_stream;
     const u32 C = ctx->fin_external ? ctx->fin_max_chunks : *ctx->h_table_count2;
     if (ctx->sh.world > 1 && !ctx->fin_external) return fail(ctx, CHAD_ERR_INVALID, "internal: sharded finalize outside its gather point");
+    trace(ctx, "finalize: submap %zu has %u chunks", ctx->roots.size(), C);
     TRY(finalize_dag(ctx, C, ctx->fin_external, [&]() -> int {
         if (C && !ctx->fin_external) TRY(queue_sorted_chunks(ctx, fs, ctx->table2, C));
         return CHAD_OK;

@@ -32,9 +32,14 @@ constexpr u32 RUN_BLK_SHIFT = 9;           // 8^3 voxels per block
 constexpr u32 RUN_RANK_BITS = 23;          // sorted-point rank inside the batch
 constexpr u64 RUN_EMPTY = ~0ull;
 constexpr u32 RUN_BIG_BLOCK = 2048;        // updates from which a block is scheduled ahead of the others
-constexpr u32 RUN_STASH_BITS = 50;         // a descriptor key of at most this many bits carries its run's record count above them
-                                           // (the radix sort ignores -- and carries along -- the bits above the sorted width)
-__device__ __forceinline__ u64 run_key_mask(u32 nbits_blocks) { return nbits_blocks <= RUN_STASH_BITS ? ((1ull << RUN_STASH_BITS) - 1ull) : ~0ull; }
+constexpr u32 RUN_STASH_BITS = 50;         // a descriptor key carries its run's record count from this bit up when the radix sort does not look there
+// The sort works in whole 8-bit digits: with nbits key bits it orders bits [0, 8 * ceil(nbits / 8)), so the count may only sit above
+// THAT width (48 for nbits <= 48), not above nbits. Round 1 tested `nbits <= 50`: at 49 or 50 key bits -- voxel coordinates beyond
+// +-8192 in batches of 5 to 16 scans -- the last digit then contained six bits of the count, the runs of a block were no longer
+// adjacent after the sort, several warps folded the same block and chunks were inserted twice. Found by bench.py's hash check on the
+// 1000-scan urban drive (profiles/probe_cfg3_r02.md); no shorter test reaches those widths.
+__device__ __forceinline__ bool run_stash(u32 nbits_blocks) { return radix_num_passes(nbits_blocks) * RS_RADIX_BITS <= RUN_STASH_BITS; }
+__device__ __forceinline__ u64 run_key_mask(u32 nbits_blocks) { return run_stash(nbits_blocks) ? ((1ull << RUN_STASH_BITS) - 1ull) : ~0ull; }
 
 constexpr int RF_THREADS = 128;             // fold: four independent warps per CTA, one block per warp at a time
 constexpr u32 RF_VOXELS = 512;
@@ -263,7 +268,7 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_emit_kernel(const float* __r
     const u32 gbase = s_gbase;
     if (gbase != 0xFFFFFFFFu) {
         const u32 k = plan->k, tbits = plan->tile_bits;
-        const bool stash = plan->nbits_blocks <= RUN_STASH_BITS;
+        const bool stash = run_stash(plan->nbits_blocks);
         for (u32 t = tid; t < nslots; t += RUN_THREADS) {
             const u32 hs = s_list[t];
             const u32 d = s_dbase + t;
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_group_kernel(const u64* __re
     const u32* __restrict__ vals = alt ? dvals_b : dvals_a;
     const u32 tbits = plan->tile_bits;
     const u64 kmask = run_key_mask(plan->nbits_blocks);
-    const bool stash = plan->nbits_blocks <= RUN_STASH_BITS;
+    const bool stash = run_stash(plan->nbits_blocks);
     const u32 lane = threadIdx.x & 31;
     for (u32 q0 = blockIdx.x * RUN_THREADS; q0 < n; q0 += gridDim.x * RUN_THREADS) {  // uniform per CTA
         const u32 p = q0 + threadIdx.x;
@@ -659,7 +664,7 @@ __global__ void __launch_bounds__(RUN_THREADS) runs_ingest_kernel(u64* __restric
     }
     if (bad) return;
     const u64* __restrict__ box = in + size_t(src) * words;
-    const bool stash = plan->nbits_blocks <= RUN_STASH_BITS;
+    const bool stash = run_stash(plan->nbits_blocks);
     for (u32 j = blockIdx.x * RUN_THREADS + threadIdx.x; j < my_nd; j += gridDim.x * RUN_THREADS) {
         const u64 key = box[2 + 2 * j], fl = box[3 + 2 * j];
         const u32 first = (u32)fl, len = (u32)(fl >> 32);

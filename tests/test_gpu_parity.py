@@ -240,3 +240,30 @@ def test_scan_beyond_the_tile_run_rank_range_then_ordinary_scans(chad_lib, oracl
     _assert_same_state(g, o)
     assert g.stats()["points"] == len(pts)
     g.close(); o.close()
+
+
+@pytest.mark.parametrize("beams,want_bits", [(32, 49), (64, 50)])
+def test_run_descriptor_keys_of_49_and_50_bits(chad_lib, oracle_lib, monkeypatch, beams, want_bits):
+    """The widths at which a run descriptor's key reaches into the sort digit that used to hold the stashed record count: voxel coordinates
+    beyond +-8192 (k = 14: 36 block bits) in ONE batch of 24 scans (5 scan bits) of 65 536 / 131 072 points (8 / 9 tile bits). Round 1's
+    `nbits <= 50` let the last radix digit order the runs by six bits of the count: the runs of a block were no longer adjacent, several
+    warps folded the same block, chunks were inserted twice -- found by bench.py's hash check on the 1000-scan urban drive (no shorter
+    test reached these widths). 24 scans 0.1 m apart 500 m down the street: one submap, one batch."""
+    from chad_tsdf_b200 import TSDFMap
+    from oracle import bindings as ob
+    monkeypatch.setenv("CHAD_FIRST_BATCH", "64")  # the whole burst in one batch
+    w = synth.Workload("t", synth.URBAN, beams, 24, 500.0, 0.1, 0.05, 0.10, seed=31)
+    g, o = TSDFMap(w.sdf_res, w.sdf_trunc, max_batch_scans=24), ob.OracleMap(w.sdf_res, w.sdf_trunc)
+    for s in range(w.scans):
+        pts, pos = w.scan(s)
+        g.insert(pts, pos)
+        o.insert(pts, pos)
+    g.flush()
+    st = g.stats()
+    assert st["batches"] == 1 and st["key_bits_pairs"] == 45, st  # k = 14
+    tiles = -(-max(len(w.scan(s)[0]) for s in range(3)) // 256)
+    assert 3 * 14 - 6 + 5 + (tiles - 1).bit_length() == want_bits
+    _assert_same_state(g, o, check_levels=False)
+    g.finalize_active(); o.finalize_active()
+    _assert_same_state(g, o)
+    g.close(); o.close()
