@@ -176,6 +176,8 @@ struct chad_ctx {
         bool slice_h2d = true;          // a scan comes over the host link once, not once per rank: every rank copies 1 / world of it and the
                                         // slices are all-gathered over NVLink (comm_c, copy stream). CHAD_SHARD_SLICE_H2D=0: every rank copies all
         cudaEvent_t h2d_done = nullptr;
+        struct Slice { float* dst; size_t count; };
+        std::vector<Slice> slices;      // scans of the batch being assembled that arrived as slices: {place in the batch buffer, floats per rank}
         DevBuf splitters;               // u64[2][SHARD_WORLD_MAX + 1]: range starts (block ids), two sets used alternately by the submaps
         int split_set = 0;              // set of the active submap
         int slot_split[MAX_SLOTS] = {}; // set a plan slot's batch was filtered with (its pack kernel runs later, on the group stream)
@@ -705,6 +707,14 @@ int process_front(chad_ctx* ctx) {
     const u32 n = ctx->batch_points, ns = ctx->batch_scans;
     cudaStream_t s = ctx->stream;
     ctx->h_scans.offset[ns] = n;
+    if (!ctx->sh.slices.empty()) {  // scans that came as 1 / world slices over the host link (insert_host): assemble them, one launch
+        chad_ctx::Shard& sh = ctx->sh;
+        NCCL_TRY(ctx, sh.nccl->GroupStart());
+        for (const auto& sl : sh.slices) NCCL_TRY(ctx, sh.nccl->AllGather(sl.dst + sl.count * (size_t)sh.rank, sl.dst, sl.count, ncclFloat, sh.comm_c, ctx->copy_stream));
+        NCCL_TRY(ctx, sh.nccl->GroupEnd());
+        sh.slices.clear();
+        ctx->stats.kernel_launches += 1;
+    }
     CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[b], ctx->copy_stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->copy_done[b], 0));
     if (ctx->stage_busy[b]) CUDA_TRY(ctx, cudaEventRecord(ctx->stage_copied[b], ctx->copy_stream));
@@ -1685,34 +1695,34 @@ static int insert_host(chad_ctx* ctx, const float* xyz, size_t n, const float po
     float* dst = ctx->d_xyz[b].as<float>() + size_t(ctx->batch_points) * 3;
     if (ctx->sh.world > 1 && ctx->sh.slice_h2d && n >= 4096) {
         // Sharded: every rank is handed the whole scan, but the host link is the scarce resource (N ranks x 3 MB per scan through one
-        // host's memory) and NVLink is not: this rank copies slice `rank` of the scan, the all-gather assembles the scan on every rank.
-        // Issued at every insert, i.e. at the same point of the call sequence on every rank. Slices are whole
-        // multiples of 4 floats; the gather may write up to 4 * world floats beyond the scan: into the next scan's place (filled later,
-        // in stream order) or the buffer's slack.
+        // host's memory) and NVLink is not: this rank copies slice `rank` of the scan (plus the few floats left over after the division
+        // into `world` equal slices of whole float4s, which every rank copies); ONE grouped all-gather per batch, issued when the batch
+        // is closed (process_front: the same point of the call sequence on every rank), assembles the scans on
+        // every rank. (An all-gather per scan cost ~60 us of latency on the copy stream, 100 times per step: profiles/bench_r02_final_n2_sliced_h2d.json.)
         chad_ctx::Shard& sh = ctx->sh;
         const size_t total = n * 3;
-        size_t c = (total + (size_t)sh.world - 1) / (size_t)sh.world;
-        c = (c + 3) & ~size_t(3);
-        const size_t lo = std::min(total, c * (size_t)sh.rank), hi = std::min(total, lo + c);
-        if (hi > lo) {
-            const float* src = xyz + lo;
-            if (!pinned) {
-                if (ctx->stage_busy[b] && ctx->batch_scans == 0) {
-                    CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_copied[b]));
-                    ctx->stage_busy[b] = false;
-                }
-                float* stage = ctx->h_stage[b] + size_t(ctx->batch_points) * 3 + lo;
-                std::memcpy(stage, src, (hi - lo) * 4);
-                src = stage;
-                ctx->stage_busy[b] = true;
+        const size_t c = (total / (size_t)sh.world) & ~size_t(3);
+        const size_t lo = c * (size_t)sh.rank, tail = c * (size_t)sh.world;
+        const float* src = xyz;
+        if (!pinned) {
+            if (ctx->stage_busy[b] && ctx->batch_scans == 0) {
+                CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_copied[b]));
+                ctx->stage_busy[b] = false;
             }
-            CUDA_TRY(ctx, cudaMemcpyAsync(dst + lo, src, (hi - lo) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+            float* stage = ctx->h_stage[b] + size_t(ctx->batch_points) * 3;
+            std::memcpy(stage + lo, xyz + lo, c * 4);
+            if (total > tail) std::memcpy(stage + tail, xyz + tail, (total - tail) * 4);
+            src = stage;
+            ctx->stage_busy[b] = true;
         }
-        CUDA_TRY(ctx, cudaEventRecord(sh.h2d_done, ctx->copy_stream));
-        NCCL_TRY(ctx, sh.nccl->AllGather(dst + c * (size_t)sh.rank, dst, c, ncclFloat, sh.comm_c, ctx->copy_stream));
-        ctx->stats.kernel_launches += 1;
-        if (pinned && wait_for_copy) CUDA_TRY(ctx, cudaEventSynchronize(sh.h2d_done));  // (the caller's buffer has been read; the gather runs on)
-        ctx->stats.h2d_bytes += (hi - lo) * 4;
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst + lo, src + lo, c * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (total > tail) CUDA_TRY(ctx, cudaMemcpyAsync(dst + tail, src + tail, (total - tail) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        sh.slices.push_back({dst, c});
+        if (pinned && wait_for_copy) {  // (the caller's buffer has been read; the gather follows at the batch's close)
+            CUDA_TRY(ctx, cudaEventRecord(sh.h2d_done, ctx->copy_stream));
+            CUDA_TRY(ctx, cudaEventSynchronize(sh.h2d_done));
+        }
+        ctx->stats.h2d_bytes += (c + total - tail) * 4;
         return end_scan(ctx, n, position);
     }
     if (pinned) {
@@ -1905,6 +1915,7 @@ int chad_reset(chad_ctx* ctx) {
     ctx->n_pend = 0;
     for (bool& f : ctx->fold_stats_pending) f = false;
     ctx->sh.need_splitters = true;
+    ctx->sh.slices.clear();
     ctx->sh.gather_at.clear();
     ctx->sh.close_deferred = false;
     ctx->sh.closed_waiting = false;
