@@ -204,8 +204,8 @@ int chad_timer_end(chad_ctx* ctx, float* milliseconds);
  * The reference has a single map object (one octree + one NodeLevels, /root/reference/include/chad/tsdf.hpp:166-170); here the map
  * is cut into `world` contiguous Morton ranges of 8x8x8-voxel blocks and rank g -- one context, one GPU, one host thread or
  * process -- holds the voxels of range g. EVERY rank makes the SAME sequence of calls with the SAME scans (chad_insert* /
- * chad_flush / chad_finalize_active / chad_reset). A host scan crosses the host link once: each rank copies 1 / world of it and the
- * slices are all-gathered over NVLink. A rank sorts, estimates normals for and walks only the points of its own
+ * chad_flush / chad_finalize_active / chad_reset). A host scan crosses the host link once: each rank copies 1 / world of it and
+ * one grouped all-gather per batch assembles the slices over NVLink (CHAD_SHARD_SLICE_H2D=0: every rank copies all). A rank sorts, estimates normals for and walks only the points of its own
  * range; the few band voxels a ray adds beyond the range travel to their owner once per batch (NCCL send / recv of fixed-size
  * boxes, counts inside -- no host round trip); at a submap's close the ranks' sorted leaf chunks are gathered on rank 0, which
  * runs Submap::finalize (submap.hpp:10-106) and holds the DAG (chad_level_* / chad_export_level / chad_query_voxels: rank 0
