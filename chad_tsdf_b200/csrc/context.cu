@@ -147,8 +147,7 @@ struct chad_ctx {
     // asynchronous Submap::finalize (see finalize_begin): part 1 and part 2 run on fin_stream
     cudaStream_t fin_stream = nullptr;
     enum FinState { FIN_IDLE = 0, FIN_PART1 = 1 /* tables swapped, waiting for the closed submap's exact chunk count */,
-                    FIN_PART2 = 2 /* everything queued on fin_stream */,
-                    FIN_COUNTS = 3 /* sharded: own count known, waiting for the all-gather of every rank's count */ };
+                    FIN_PART2 = 2 /* everything queued on fin_stream */ };
     int fin_state = FIN_IDLE;
     u32 fin_max_chunks = 0;       // host upper bound of the chunk count of the submap being finalised
     u32 fin_chunks = 0;           // exact count (known after part 1)
