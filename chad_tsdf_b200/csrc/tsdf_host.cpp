@@ -5,7 +5,9 @@
 #include <algorithm>
 #include <bit>
 #include <condition_variable>
+#include <cmath>
 #include <functional>
+#include <limits>
 #include <mutex>
 #include <thread>
 #include <cstdio>
@@ -361,6 +363,99 @@ void write_grid(const HostNodeLevels& levels, uint32_t root, float sdf_res, floa
     put(points.data(), nq * sizeof(QueryPoint));
     for (uint64_t code : complete) put(cells[code].data(), 8 * sizeof(uint32_t));
     std::fclose(f);
+}
+
+// ---- ray cast --------------------------------------------------------------------------------------------
+namespace {
+// Root-to-leaf walk for one voxel that also says how large the hole is where the voxel does not exist: `empty_shift` = s means that
+// the whole aligned cube of 2^s voxels per axis around the voxel is absent (s = 20 - depth for a missing child of a depth-`depth`
+// node, 1 for a missing leaf cluster, 0 for a missing voxel of an existing cluster).
+uint8_t descend(const HostNodeLevels& levels, uint32_t root, uint64_t key, uint32_t& empty_shift) {
+    uint32_t addr = root;
+    for (uint32_t depth = 0; depth + 1 < HostNodeLevels::MAX_DEPTH; depth++) {
+        addr = levels.get_child_addr(depth, addr, uint8_t((key >> (3 * (20 - depth))) & 7));
+        if (addr == 0) { empty_shift = 20 - depth; return 0xFF; }
+    }
+    uint64_t cluster;
+    if (!levels.try_get_lc(addr, uint8_t((key >> 3) & 7), cluster)) { empty_shift = 1; return 0xFF; }
+    empty_shift = 0;
+    return uint8_t(cluster >> (8 * (key & 7)));
+}
+}  // namespace
+
+RayHit raycast(const HostNodeLevels& levels, uint32_t root, const std::array<float, 3>& origin, const std::array<float, 3>& direction,
+               float max_distance, float sdf_res, float sdf_trunc, std::vector<Leaf>* along) {
+    const double len = std::sqrt(double(direction[0]) * direction[0] + double(direction[1]) * direction[1] + double(direction[2]) * direction[2]);
+    if (!(len > 0.0)) throw std::invalid_argument("chad::raycast: zero direction");
+    if (!(sdf_res > 0.0f)) throw std::invalid_argument("chad::raycast: voxel size must be positive");
+    RayHit out;
+    if (root == 0 || root >= levels.nodes[0].size()) return out;
+    constexpr double INF = std::numeric_limits<double>::infinity();
+    constexpr int64_t BIAS = 1 << 20;  // morton.hpp:21-28: 21 bits per axis around 2^20
+    const double res = double(sdf_res), limit = double(max_distance);
+    double d[3], t_next[3], t_step[3];
+    int64_t v[3];
+    int step[3];
+    for (int a = 0; a < 3; a++) {
+        d[a] = double(direction[a]) / len;
+        v[a] = (int64_t)std::floor(double(origin[a]) / res);
+        step[a] = d[a] > 0.0 ? 1 : (d[a] < 0.0 ? -1 : 0);
+        t_step[a] = step[a] ? res / std::fabs(d[a]) : INF;
+        t_next[a] = step[a] ? (double(v[a] + (step[a] > 0 ? 1 : 0)) * res - double(origin[a])) / d[a] : INF;  // where the ray leaves the voxel along a
+    }
+    bool have_prev = false, in_hole = false;
+    double t_prev = 0.0, sd_prev = 0.0, t_enter = 0.0;
+    Leaf leaf_prev{};
+    int64_t hole[3] = {0, 0, 0};
+    uint32_t hole_shift = 0;
+    while (t_enter < limit) {
+        if (v[0] < -BIAS || v[0] >= BIAS || v[1] < -BIAS || v[1] >= BIAS || v[2] < -BIAS || v[2] >= BIAS) break;  // outside the key space
+        const int axis = t_next[0] < t_next[1] ? (t_next[0] < t_next[2] ? 0 : 2) : (t_next[1] < t_next[2] ? 1 : 2);
+        const double t_exit = t_next[axis];
+        out.voxels_walked++;
+        if (in_hole && (((v[0] + BIAS) >> hole_shift) != hole[0] || ((v[1] + BIAS) >> hole_shift) != hole[1] || ((v[2] + BIAS) >> hole_shift) != hole[2])) in_hole = false;
+        if (!in_hole) {
+            const uint64_t key = chad_morton_encode((int32_t)v[0], (int32_t)v[1], (int32_t)v[2]);
+            uint32_t shift;
+            const uint8_t byte = descend(levels, root, key, shift);
+            out.tree_descents++;
+            if (byte == 0xFF) {
+                if (shift) {  // an absent octant: no descents until the ray has left it
+                    in_hole = true;
+                    hole_shift = shift;
+                    for (int a = 0; a < 3; a++) hole[a] = (v[a] + BIAS) >> shift;
+                }
+            } else {
+                out.voxels_found++;
+                const Leaf leaf = make_leaf(key, byte, sdf_res, sdf_trunc);
+                if (along) along->push_back(leaf);
+                // the distance was measured at the voxel's lower corner (octree.hpp:157): the sample sits where that corner projects onto the ray
+                const double t = (double(v[0]) * res - double(origin[0])) * d[0] + (double(v[1]) * res - double(origin[1])) * d[1] + (double(v[2]) * res - double(origin[2])) * d[2];
+                const double sd = double(leaf.signed_distance);
+                if (have_prev && sd_prev > 0.0 && sd <= 0.0) {
+                    const double t_hit = std::max(0.0, t_prev + (t - t_prev) * (sd_prev / (sd_prev - sd)));
+                    if (t_hit <= limit) {
+                        out.hit = true;
+                        out.distance = float(t_hit);
+                        out.x = float(double(origin[0]) + t_hit * d[0]);
+                        out.y = float(double(origin[1]) + t_hit * d[1]);
+                        out.z = float(double(origin[2]) + t_hit * d[2]);
+                        out.before = leaf_prev;
+                        out.after = leaf;
+                    }
+                    return out;
+                }
+                have_prev = true;
+                t_prev = t;
+                sd_prev = sd;
+                leaf_prev = leaf;
+            }
+        }
+        t_enter = t_exit;
+        t_next[axis] += t_step[axis];
+        v[axis] += step[axis];
+    }
+    return out;
 }
 
 // ---- DAG readers ---------------------------------------------------------------------------------------

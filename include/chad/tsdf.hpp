@@ -77,6 +77,26 @@ namespace chad {
         bool _done = false;
     };
 
+    // A ray through the tree under `root_addr_tsdf` -- the second reader on the reference's list (tsdf.hpp:157-160: "raycast to retrieve
+    // leaves along it + physics hit"). The ray is walked voxel by voxel (Amanatides-Woo, the walk octree.hpp:120-152 makes for the
+    // truncation band, here in double precision from `origin` to `max_distance`); octants the tree does not hold are crossed without
+    // descending into them. The hit is the first place where the signed distance goes from > 0 (in front of the surface) to <= 0, its
+    // distance interpolated linearly between the two samples (a voxel's distance was measured at its lower corner, octree.hpp:157: the
+    // sample sits where that corner projects onto the ray).
+    struct RayHit {
+        bool hit = false;
+        float distance = 0.0f;             // metres along the ray
+        float x = 0.0f, y = 0.0f, z = 0.0f;  // origin + distance * direction / |direction|
+        Leaf before{}, after{};            // the voxels around the crossing (before: signed distance > 0, after: <= 0)
+        size_t voxels_walked = 0;          // voxels the ray went through
+        size_t voxels_found = 0;           // ... of which the tree holds this many
+        size_t tree_descents = 0;          // root-to-leaf walks made (one per found voxel and one per empty octant entered)
+    };
+    // `along` (optional) receives every voxel of the tree the ray goes through, in ray order, up to and including `after`.
+    // Throws std::invalid_argument for a zero direction or a non-positive voxel size.
+    RayHit raycast(const HostNodeLevels& levels, uint32_t root_addr_tsdf, const std::array<float, 3>& origin, const std::array<float, 3>& direction,
+                   float max_distance, float sdf_res, float sdf_trunc, std::vector<Leaf>* along = nullptr);
+
     // What TSDFMap::save writes (flat CHADDAG2 dump): map parameters, per finalised submap its roots
     // (submap.hpp:108-109) and poses (submap.hpp:110), the host copy of the DAG and the levels' dedup counters (levels.hpp:90-91,141).
     // Pure host code: no GPU needed to read a map back (CHADDAG1 files of round 1 -- no poses, no counters -- are still read).

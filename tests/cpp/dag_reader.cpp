@@ -4,6 +4,8 @@
 //        dag_reader grid <file.chad> <submap> <out.grid>      -> the reference's hashgrid.grid (lvr2.cpp:170-200) of that submap
 //        dag_reader leaves <file.chad> <submap> <keys.u64> <bytes.u8>  -> every voxel of the submap through chad::LeafCursor
 //        dag_reader resave <in.chad> <out.chad>               -> load_dag + save_dag (CHADDAG2)
+//        dag_reader ray <file.chad> <submap> <rays.f32> <out.f64> <along.u64>  -> chad::raycast per ray (7 floats: origin, direction, max distance);
+//                   per ray 9 doubles: hit, distance, x, y, z, voxels walked, voxels found, tree descents, voxels in `along`
 #include <cstdio>
 #include <cstdlib>
 #include <exception>
@@ -45,6 +47,43 @@ int main(int argc, char** argv) {
             std::fclose(fk);
             std::fclose(fb);
             std::printf("%zu %.9g %zu\n", keys.size(), checksum, m.positions[submap].size());
+            return 0;
+        } catch (const std::exception& e) {
+            std::fprintf(stderr, "%s\n", e.what());
+            return 1;
+        }
+    }
+    if (argc == 7 && std::string(argv[1]) == "ray") {
+        try {
+            const chad::SavedMap m = chad::load_dag(argv[2]);
+            const size_t submap = std::strtoul(argv[3], nullptr, 10);
+            if (submap >= m.roots.size()) { std::fprintf(stderr, "no such submap\n"); return 3; }
+            std::FILE* fr = std::fopen(argv[4], "rb");
+            if (!fr) return 4;
+            std::fseek(fr, 0, SEEK_END);
+            const size_t n = (size_t)std::ftell(fr) / 28;
+            std::fseek(fr, 0, SEEK_SET);
+            std::vector<float> rays(n * 7);
+            if (n && std::fread(rays.data(), 28, n, fr) != n) return 4;
+            std::fclose(fr);
+            std::vector<double> out;
+            std::vector<uint64_t> keys;
+            for (size_t i = 0; i < n; i++) {
+                const float* r = &rays[i * 7];
+                std::vector<chad::Leaf> along;
+                const chad::RayHit h = chad::raycast(m.levels, m.roots[submap][0], {r[0], r[1], r[2]}, {r[3], r[4], r[5]}, r[6], m.sdf_res, m.sdf_trunc, &along);
+                for (const chad::Leaf& v : along) keys.push_back(v.morton);
+                for (double x : {double(h.hit), double(h.distance), double(h.x), double(h.y), double(h.z), double(h.voxels_walked), double(h.voxels_found),
+                                 double(h.tree_descents), double(along.size())}) out.push_back(x);
+                if (h.hit && (along.empty() || along.back().morton != h.after.morton || !(h.before.signed_distance > 0.0f) || h.after.signed_distance > 0.0f)) return 6;
+            }
+            std::FILE* fo = std::fopen(argv[5], "wb");
+            std::FILE* fk = std::fopen(argv[6], "wb");
+            if (!fo || !fk) return 5;
+            if (!out.empty() && std::fwrite(out.data(), 8, out.size(), fo) != out.size()) return 5;
+            if (!keys.empty() && std::fwrite(keys.data(), 8, keys.size(), fk) != keys.size()) return 5;
+            std::fclose(fo);
+            std::fclose(fk);
             return 0;
         } catch (const std::exception& e) {
             std::fprintf(stderr, "%s\n", e.what());

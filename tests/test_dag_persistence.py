@@ -239,3 +239,103 @@ def test_a_child_address_outside_its_level_is_rejected(chad_lib, oracle_lib, tmp
     (tmp_path / "k.u64").write_bytes(b"")
     r = subprocess.run([exe, str(bad), "0", str(tmp_path / "k.u64"), str(tmp_path / "o.u8")], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "inconsistent DAG" in r.stderr, r.stderr
+
+
+def _ray_walk_here(voxels, origin, direction, max_distance, res, trunc):
+    """Independent restatement of chad::raycast: voxel-by-voxel walk with a dictionary instead of the tree (no octant skipping)."""
+    import math
+    o = [float(np.float32(c)) for c in origin]
+    dr = [float(np.float32(c)) for c in direction]
+    length = math.sqrt(dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2])
+    d = [c / length for c in dr]
+    res, limit = float(np.float32(res)), float(np.float32(max_distance))
+    v = [math.floor(o[a] / res) for a in range(3)]
+    step = [1 if d[a] > 0 else (-1 if d[a] < 0 else 0) for a in range(3)]
+    t_step = [res / abs(d[a]) if step[a] else math.inf for a in range(3)]
+    t_next = [((v[a] + (1 if step[a] > 0 else 0)) * res - o[a]) / d[a] if step[a] else math.inf for a in range(3)]
+    walked, along, prev, t_enter = 0, [], None, 0.0
+    while t_enter < limit:
+        if any(c < -(1 << 20) or c >= (1 << 20) for c in v):
+            break
+        axis = (0 if t_next[0] < t_next[2] else 2) if t_next[0] < t_next[1] else (1 if t_next[1] < t_next[2] else 2)
+        walked += 1
+        byte = voxels.get(tuple(v))
+        if byte is not None:
+            along.append(tuple(v))
+            sd = float((np.float32(byte) - np.float32(127.0)) * np.float32(1.0 / 127.0) * np.float32(trunc))  # cluster.hpp:46-50
+            t = (v[0] * res - o[0]) * d[0] + (v[1] * res - o[1]) * d[1] + (v[2] * res - o[2]) * d[2]
+            if prev is not None and prev[1] > 0.0 and sd <= 0.0:
+                t_hit = max(0.0, prev[0] + (t - prev[0]) * (prev[1] / (prev[1] - sd)))
+                return (t_hit <= limit), t_hit, walked, along
+            prev = (t, sd)
+        t_enter = t_next[axis]
+        t_next[axis] += t_step[axis]
+        v[axis] += step[axis]
+    return False, 0.0, walked, along
+
+
+def test_ray_cast_through_a_saved_map(chad_lib, oracle_lib, tmp_path):
+    """chad::raycast -- "raycast to retrieve leaves along it + physics hit", the reader the reference lists after the leaf iterator
+    (tsdf.hpp:157-160) -- on a map read back with load_dag: the voxels along each ray and the hit must equal an independent walk
+    over the oracle's voxel set made here; rays from the sensor towards the measured points hit the surface where it was measured;
+    empty octants are crossed without descending into them."""
+    from chad_tsdf_b200 import build, capi
+    exe = build.build_dag_reader()
+    lib = capi.load()
+    w = synth.Workload("ray", synth.BOX_ROOM, 32, 1, 0.0, 0.0, 0.05, 0.10)
+    pts, pos = w.scan(0)
+    o = oracle_lib.OracleMap(w.sdf_res, w.sdf_trunc)
+    o.insert(pts, pos)
+    keys, sd_bits, _ = o.voxels()
+    o.finalize_active()
+    chad_file = tmp_path / "m.chad"
+    _write_chaddag1(chad_file, o, w.sdf_res, w.sdf_trunc)
+    o.close()
+    byte = _quantise(sd_bits, w.sdf_trunc)
+    voxels = {}
+    for k, b in zip(keys.tolist(), byte.tolist()):
+        x, y, z = (C.c_int32(), C.c_int32(), C.c_int32())
+        lib.chad_morton_decode(int(k), C.byref(x), C.byref(y), C.byref(z))
+        voxels[(x.value, y.value, z.value)] = b
+    rng = np.random.default_rng(11)
+    pick = rng.choice(len(pts), 120, replace=False)
+    rays = []
+    for i in pick:  # towards measured points, from the sensor: must hit close to the measured range
+        rays.append([*pos, *(pts[i] - pos), 150.0])
+    for _ in range(40):  # arbitrary rays from arbitrary places, axis-parallel ones included
+        d = rng.normal(size=3)
+        if rng.random() < 0.3:
+            d[rng.integers(3)] = 0.0
+        if rng.random() < 0.2:
+            d = np.eye(3)[rng.integers(3)] * rng.choice([-1.0, 1.0])
+        rays.append([*rng.uniform(-15, 15, 3), *d, float(rng.uniform(5, 60))])
+    rays.append([0.0, 0.0, 500.0, 0.0, 0.0, 1.0, 50.0])  # far from everything: a handful of descents for 1000 voxels
+    rays = np.asarray(rays, np.float32)
+    rf, of, kf = tmp_path / "rays.f32", tmp_path / "hits.f64", tmp_path / "along.u64"
+    rays.tofile(rf)
+    r = subprocess.run([exe, "ray", str(chad_file), "0", str(rf), str(of), str(kf)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(of, np.float64).reshape(len(rays), 9)
+    along_keys = np.fromfile(kf, np.uint64)
+    at = 0
+    hits_towards_points = 0
+    for i, ray in enumerate(rays):
+        hit, t_hit, walked, along = _ray_walk_here(voxels, ray[:3], ray[3:6], ray[6], w.sdf_res, w.sdf_trunc)
+        n_along = int(got[i, 8])
+        assert (bool(got[i, 0]), int(got[i, 5]), int(got[i, 6]), n_along) == (hit, walked, len(along), len(along)), (i, got[i], hit, walked, len(along))
+        expect_keys = [lib.chad_morton_encode(*v) for v in along]
+        assert along_keys[at:at + n_along].tolist() == expect_keys
+        at += n_along
+        assert got[i, 7] <= got[i, 5]  # never more descents than voxels
+        if hit:
+            assert abs(got[i, 1] - t_hit) <= 1e-6 * max(1.0, t_hit)  # (float32 in the struct)
+            d = ray[3:6].astype(np.float64) / np.linalg.norm(ray[3:6].astype(np.float64))
+            assert np.allclose(got[i, 2:5], ray[:3] + t_hit * d, atol=1e-4)
+        if i < len(pick):
+            measured = float(np.linalg.norm((pts[pick[i]] - pos).astype(np.float64)))
+            if hit and abs(t_hit - measured) < 2.0 * w.sdf_res:
+                hits_towards_points += 1
+    assert at == len(along_keys)
+    assert hits_towards_points >= 0.9 * len(pick), hits_towards_points  # the surface is found where the scan measured it (to two voxels)
+    far = got[-1]
+    assert not far[0] and far[5] >= 999 and far[6] == 0 and far[7] <= 8, far  # 1000 voxels of empty space: a few descents
